@@ -1,0 +1,179 @@
+/* libprotoclip_b200 — C ABI of the B200-native Proto-CLIP few-shot inference hot path.
+ *
+ * The reference (IRVLUTD/Proto-CLIP) has no FFI: its seams are Python call sites. Every entry point below
+ * names the reference interface it stands in for (file:line relative to the reference tree); the Python
+ * shells in proto-clip_b200/ (clip/, model.py, utils.py, main.py) bind these with ctypes and keep the
+ * reference's names, argument meaning and error behaviour. INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - return 0 on success, a negative PC_ERR_* otherwise; pc_last_error() gives a thread-local message.
+ *     Nothing throws or exits across this boundary.
+ *   - every pointer is a DEVICE pointer unless noted; the caller owns all buffers including workspaces
+ *     (16-byte aligned; cudaMalloc / torch allocations qualify). The library owns only the context
+ *     (weight views plus two small re-laid-out weight copies made at bind time).
+ *   - all work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*); no hidden
+ *     synchronisation or allocation on the hot path.
+ *   - fp16 storage, fp32 accumulation / statistics, with the reference's fp16 rounding points
+ *     (clip/model.py:373-394 convert_weights semantics).
+ *   - a context is bound to one device and is not thread-safe: one context per rank.
+ *   - sm_100 only: pc_ctx_create refuses any other device (no fallback path exists).
+ */
+#ifndef PROTOCLIP_B200_H_
+#define PROTOCLIP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PC_VERSION 100
+
+enum {
+  PC_OK = 0,
+  PC_ERR_ARG = -1,       /* bad shape / null pointer / unsupported size */
+  PC_ERR_ALIGN = -2,     /* pointer or leading dimension not aligned for TMA / vector access */
+  PC_ERR_ARCH = -3,      /* device is not sm_100 */
+  PC_ERR_CUDA = -4,      /* CUDA runtime / driver error */
+  PC_ERR_STATE = -5,     /* weights not bound, wrong device, ... */
+  PC_ERR_WORKSPACE = -6  /* workspace too small */
+};
+
+enum { PC_TOWER_VISUAL = 0, PC_TOWER_TEXT = 1 };
+enum { PC_IMG_F32 = 0, PC_IMG_F16 = 1 };
+/* nn.Linear epilogues (pc_linear_forward) */
+enum { PC_EPI_BIAS = 0, PC_EPI_BIAS_QUICKGELU = 1, PC_EPI_BIAS_RESIDUAL = 2, PC_EPI_F32 = 3 };
+
+typedef struct pc_ctx pc_ctx;
+
+int pc_version(void);
+const char* pc_last_error(void);
+
+/* One context per device / rank. Replaces the module-global CUDA state the reference gets from
+ * `clip.load(...)` + `.cuda()` (clip/clip.py:92-139, main.py:495-496). */
+int pc_ctx_create(int device, pc_ctx** out);
+void pc_ctx_destroy(pc_ctx* ctx);
+
+/* Parameters of one ResidualAttentionBlock, in the reference state-dict layout and dtype
+ * (clip/model.py:169-181; fp16 Linear/MHA tensors, fp32 LayerNorm tensors after convert_weights). */
+typedef struct {
+  const void* ln_1_weight;      /* f32 [d]     */
+  const void* ln_1_bias;        /* f32 [d]     */
+  const void* in_proj_weight;   /* f16 [3d, d] rows = [Wq; Wk; Wv] */
+  const void* in_proj_bias;     /* f16 [3d]    */
+  const void* out_proj_weight;  /* f16 [d, d]  */
+  const void* out_proj_bias;    /* f16 [d]     */
+  const void* ln_2_weight;      /* f32 [d]     */
+  const void* ln_2_bias;        /* f32 [d]     */
+  const void* c_fc_weight;      /* f16 [4d, d] */
+  const void* c_fc_bias;        /* f16 [4d]    */
+  const void* c_proj_weight;    /* f16 [d, 4d] */
+  const void* c_proj_bias;      /* f16 [d]     */
+} pc_resblock_weights;
+
+/* VisionTransformer (clip/model.py:204-238). heads = width / 64 (clip/model.py:273). */
+typedef struct {
+  int image_resolution, patch_size, width, layers, heads, embed_dim;
+  const void* conv1_weight;          /* f16 [width, 3, p, p], no bias */
+  const void* class_embedding;       /* f32 [width] */
+  const void* positional_embedding;  /* f32 [(res/p)^2 + 1, width] */
+  const void* ln_pre_weight;         /* f32 [width] */
+  const void* ln_pre_bias;
+  const void* ln_post_weight;        /* f32 [width] */
+  const void* ln_post_bias;
+  const void* proj;                  /* f16 [width, embed_dim] */
+  const pc_resblock_weights* blocks; /* HOST array of `layers` entries (device pointers inside) */
+} pc_vit_weights;
+
+/* Text tower (clip/model.py:277-291, 341-354). heads = width / 64 (clip/model.py:418). */
+typedef struct {
+  int context_length, vocab_size, width, layers, heads, embed_dim;
+  const void* token_embedding;       /* f32 [vocab, width] */
+  const void* positional_embedding;  /* f32 [context_length, width] */
+  const void* ln_final_weight;       /* f32 [width] */
+  const void* ln_final_bias;
+  const void* text_projection;       /* f16 [width, embed_dim] */
+  const pc_resblock_weights* blocks; /* HOST array */
+} pc_text_weights;
+
+/* Bind tower weights (views; the tensors must outlive the context). Stands in for build_model +
+ * load_state_dict (clip/model.py:397-434). Synchronous; may allocate (bind time only). */
+int pc_vit_bind_weights(pc_ctx* ctx, const pc_vit_weights* w);
+int pc_text_bind_weights(pc_ctx* ctx, const pc_text_weights* w);
+
+/* CLIP.encode_image (clip/model.py:338-339 -> 221-238) [+ the `/= norm` of utils.py:352 when l2norm != 0].
+ * images: [B, 3, res, res] f32 or f16 (NCHW, already normalised); feat_out: f16 [B, embed_dim].
+ * The batch is walked in micro-batches of `micro_batch` images (0 = library default) so activations stay
+ * L2-resident; workspace must hold pc_encode_image_workspace_bytes(ctx, micro_batch). */
+size_t pc_encode_image_workspace_bytes(const pc_ctx* ctx, int micro_batch);
+int pc_encode_image(pc_ctx* ctx, const void* images, int img_dtype, int B, void* feat_out, int l2norm,
+                    int micro_batch, void* workspace, size_t workspace_bytes, void* stream);
+
+/* CLIP.encode_text (clip/model.py:341-354). tokens: int64 [P, context_length] (clip.tokenize output,
+ * clip/clip.py:194-230); out: f16 [P, embed_dim]. */
+size_t pc_encode_text_workspace_bytes(const pc_ctx* ctx, int micro_batch);
+int pc_encode_text(pc_ctx* ctx, const int64_t* tokens, int P, void* out, int l2norm, int micro_batch,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ResidualAttentionBlock.forward (clip/model.py:187-190) of layer `layer` of a bound tower, in place on
+ * x: f16 token-major [B*L, d] (the reference's [L, B, d] permuted to batch-first; the Python shell does the
+ * permute). workspace >= pc_resblock_workspace_bytes(ctx, tower, B, L). */
+size_t pc_resblock_workspace_bytes(const pc_ctx* ctx, int tower, int B, int L);
+int pc_resblock_forward(pc_ctx* ctx, int tower, int layer, void* x, int B, int L, int causal, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* Building blocks, exposed because the reference's nn.Modules are (and the parity tests probe them):
+ * nn.Linear / F.linear: out[M,N] = x[M,K] @ w[N,K]^T (+ bias) with the epilogues above. */
+int pc_linear_forward(const void* x, int ldx, const void* w, int ldw, const void* bias, const void* residual,
+                      int ldr, void* out, int ldo, int M, int N, int K, int epilogue, void* stream);
+/* clip.model.LayerNorm.forward (clip/model.py:155-161): f16 in/out, f32 gamma/beta, eps 1e-5. */
+int pc_layernorm_forward(const void* x, void* y, const void* gamma, const void* beta, int rows, int d,
+                         void* stream);
+/* nn.MultiheadAttention core (clip/model.py:173,183-185): packed qkv f16 [B*L, 3d] -> f16 [B*L, d]. */
+int pc_attention_forward(const void* qkv, void* out, int B, int L, int heads, int causal, void* stream);
+/* x / x.norm(dim=-1, keepdim=True) on f16 rows (utils.py:267,319,352; main.py:400-409). */
+int pc_l2_normalize(const void* x, void* y, int rows, int d, void* stream);
+
+/* Adapter_FC.forward (model.py:81-95). state-dict tensors, all f16: fc.0.weight [D/4, D], fc.1.{weight,bias}
+ * [D/4], fc.2.weight [D, D/4], fc.3.{weight,bias} [D]. workspace >= pc_adapter_fc_workspace_bytes(Q, D). */
+typedef struct {
+  const void* fc0_weight;
+  const void* fc1_weight;
+  const void* fc1_bias;
+  const void* fc2_weight;
+  const void* fc3_weight;
+  const void* fc3_bias;
+  int reduction; /* 4 */
+} pc_adapter_fc_weights;
+size_t pc_adapter_fc_workspace_bytes(int Q, int D, int reduction);
+int pc_adapter_fc_forward(const pc_adapter_fc_weights* w, const void* q, void* out, int Q, int D,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* Adapter.forward (model.py:49-78), c_type 2 = 'conv-2x', 3 = 'conv-3x'. f16 tensors: conv1.weight [16,1,1,1],
+ * conv2.weight [16,16,3,3], conv3.weight [1,16,1,1], bn{1,2}.{weight,bias} [16,S,S], bn3.{weight,bias} [1,S,S],
+ * S = ceil(sqrt(D)). */
+typedef struct {
+  const void *conv1_weight, *conv2_weight, *conv3_weight;
+  const void *bn1_weight, *bn1_bias, *bn2_weight, *bn2_bias, *bn3_weight, *bn3_bias;
+} pc_adapter_conv_weights;
+int pc_adapter_conv_forward(const pc_adapter_conv_weights* w, int c_type, const void* q, void* out, int Q,
+                            int D, void* stream);
+
+/* Prototype construction (main.py:399-405; zero-shot variant main.py:173-178 with per_shot_norm = 0).
+ * V: f16 [N*K, D] class-contiguous; z: f16 [N, D]; znorm2: f32 [N] = |z|^2 of the stored fp16 values. */
+int pc_build_prototypes(const void* V, int N, int K, int D, int per_shot_norm, void* z, float* znorm2,
+                        void* stream);
+
+/* P() + argmax (utils.py:225-244, main.py:436-438): p = a*softmax(-b*|q-z_img|^2) + (1-a)*softmax(-b*|q-z_txt|^2).
+ * q: f16 [Q, D]; z_img, z_txt: f16 [N, D]; zi_n2 / zt_n2: f32 [N] (pc_build_prototypes). Outputs (each
+ * nullable): p_out f32 [Q, N], argmax int64 [Q], pmax f32 [Q]. */
+size_t pc_proto_classify_workspace_bytes(int Q, int N);
+int pc_proto_classify(const void* q, const void* z_img, const void* z_txt, const float* zi_n2,
+                      const float* zt_n2, int Q, int N, int D, float alpha, float beta, float* p_out,
+                      int64_t* argmax, float* pmax, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROTOCLIP_B200_H_ */

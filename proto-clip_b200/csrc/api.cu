@@ -1,0 +1,513 @@
+// C ABI of libprotoclip_b200 (include/protoclip_b200.h): context, weight binding and the orchestration of
+// the kernels in gemm.cu / attention.cu / rowops.cu / head.cu into the reference's hot-path functions
+// (encode_image, encode_text, ResidualAttentionBlock, Adapter*, prototypes, P).
+#include <new>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace pc;
+
+static_assert(int(PC_EPI_BIAS) == int(EPI_BIAS) && int(PC_EPI_BIAS_QUICKGELU) == int(EPI_BIAS_QGELU) &&
+                  int(PC_EPI_BIAS_RESIDUAL) == int(EPI_BIAS_RES) && int(PC_EPI_F32) == int(EPI_F32),
+              "public epilogue enum must match the kernel enum");
+
+namespace {
+
+struct Tower {
+  bool bound = false;
+  int width = 0, layers = 0, heads = 0, L = 0, embed = 0;
+  std::vector<pc_resblock_weights> blocks;
+  __half* proj_t = nullptr;  // owned: [embed, width] (transposed projection -> TN GEMM)
+};
+
+constexpr int kDefaultMicroBatch = 96;  // 96 * 197 tokens = 148 row blocks of 128: one GEMM wave per n-block
+constexpr int kClassifyChunk = 8192;    // queries per P() pass: [8192, 2N] fp32 dots stay L2-resident
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct pc_ctx {
+  int device = 0;
+  Tower vis, txt;
+  // visual stem
+  int res = 0, patch = 0, grid = 0, Kpatch = 0, Kp = 0;
+  __half* conv1_p = nullptr;  // owned: [width, Kp] zero-padded flattening of conv1.weight
+  const float *cls = nullptr, *vpos = nullptr, *ln_pre_w = nullptr, *ln_pre_b = nullptr, *ln_post_w = nullptr,
+              *ln_post_b = nullptr;
+  // text stem
+  int vocab = 0;
+  const float *tok_emb = nullptr, *tpos = nullptr, *ln_final_w = nullptr, *ln_final_b = nullptr;
+};
+
+namespace {
+
+__global__ void transpose_f16_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int rows, int cols) {
+  __shared__ __half tile[32][33];
+  const int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y)
+    if (x < cols && y0 + j < rows) tile[j][threadIdx.x] = src[static_cast<size_t>(y0 + j) * cols + x];
+  __syncthreads();
+  const int xo = blockIdx.y * 32 + threadIdx.x, yo0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y)
+    if (xo < rows && yo0 + j < cols) dst[static_cast<size_t>(yo0 + j) * rows + xo] = tile[threadIdx.x][j];
+}
+
+int make_transposed(const void* src, int rows, int cols, __half** out) {
+  if (*out) cudaFree(*out);
+  PC_CHECK_CUDA(cudaMalloc(out, static_cast<size_t>(rows) * cols * sizeof(__half)));
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  transpose_f16_kernel<<<grid, block>>>(static_cast<const __half*>(src), *out, rows, cols);
+  PC_CHECK_CUDA(cudaGetLastError());
+  PC_CHECK_CUDA(cudaDeviceSynchronize());
+  return PC_OK;
+}
+
+int check_blocks(const pc_resblock_weights* b, int layers) {
+  PC_REQUIRE(b != nullptr, PC_ERR_ARG, "bind: blocks array is null");
+  for (int i = 0; i < layers; ++i) {
+    const void* const* p = reinterpret_cast<const void* const*>(&b[i]);
+    for (size_t k = 0; k < sizeof(pc_resblock_weights) / sizeof(void*); ++k)
+      PC_REQUIRE(p[k] != nullptr, PC_ERR_ARG, "bind: resblock %d tensor %zu is null", i, k);
+  }
+  return PC_OK;
+}
+
+int use_device(const pc_ctx* ctx) {
+  PC_REQUIRE(ctx != nullptr, PC_ERR_ARG, "null context");
+  PC_CHECK_CUDA(cudaSetDevice(ctx->device));
+  return PC_OK;
+}
+
+// x += MHA(LN1(x)); x += MLP(LN2(x))  on token-major x [rows = B*L, d]. h: [rows, d], big: [rows, 4d].
+int resblock(const Tower& t, int layer, __half* x, __half* h, __half* big, int B, int L, int causal,
+             cudaStream_t s) {
+  const pc_resblock_weights& w = t.blocks[layer];
+  const int d = t.width, rows = B * L;
+  PC_TRY(launch_layernorm(x, h, static_cast<const float*>(w.ln_1_weight), static_cast<const float*>(w.ln_1_bias),
+                          rows, d, 1, s));
+  GemmArgs g{};
+  g.M = rows; g.N = 3 * d; g.K = d;
+  g.A = h; g.lda = d;
+  g.W = static_cast<const __half*>(w.in_proj_weight); g.ldw = d;
+  g.C = big; g.ldc = 3 * d;
+  g.bias = static_cast<const __half*>(w.in_proj_bias);
+  PC_TRY(launch_gemm(g, EPI_BIAS, s));
+  PC_TRY(launch_attention(big, h, B, L, t.heads, causal, s));
+  g = GemmArgs{};
+  g.M = rows; g.N = d; g.K = d;
+  g.A = h; g.lda = d;
+  g.W = static_cast<const __half*>(w.out_proj_weight); g.ldw = d;
+  g.C = x; g.ldc = d;
+  g.bias = static_cast<const __half*>(w.out_proj_bias);
+  g.residual = x; g.ldr = d;
+  PC_TRY(launch_gemm(g, EPI_BIAS_RES, s));
+  PC_TRY(launch_layernorm(x, h, static_cast<const float*>(w.ln_2_weight), static_cast<const float*>(w.ln_2_bias),
+                          rows, d, 1, s));
+  g = GemmArgs{};
+  g.M = rows; g.N = 4 * d; g.K = d;
+  g.A = h; g.lda = d;
+  g.W = static_cast<const __half*>(w.c_fc_weight); g.ldw = d;
+  g.C = big; g.ldc = 4 * d;
+  g.bias = static_cast<const __half*>(w.c_fc_bias);
+  PC_TRY(launch_gemm(g, EPI_BIAS_QGELU, s));
+  g = GemmArgs{};
+  g.M = rows; g.N = d; g.K = 4 * d;
+  g.A = big; g.lda = 4 * d;
+  g.W = static_cast<const __half*>(w.c_proj_weight); g.ldw = 4 * d;
+  g.C = x; g.ldc = d;
+  g.bias = static_cast<const __half*>(w.c_proj_bias);
+  g.residual = x; g.ldr = d;
+  PC_TRY(launch_gemm(g, EPI_BIAS_RES, s));
+  return PC_OK;
+}
+
+// workspace carve-up shared by both towers: x [rows,d] | h [rows,d] | big [rows,4d] | idx [mb] ints
+struct TowerWs {
+  __half *x, *h, *big;
+  int* idx;
+};
+size_t tower_ws_bytes(int rows, int d, int mb) {
+  return align_up(static_cast<size_t>(rows) * d * 2, 256) * 2 + align_up(static_cast<size_t>(rows) * d * 8, 256) +
+         align_up(static_cast<size_t>(mb) * 4, 256);
+}
+TowerWs carve(void* ws, int rows, int d) {
+  TowerWs t;
+  uint8_t* p = static_cast<uint8_t*>(ws);
+  const size_t a = align_up(static_cast<size_t>(rows) * d * 2, 256);
+  t.x = reinterpret_cast<__half*>(p);
+  t.h = reinterpret_cast<__half*>(p + a);
+  t.big = reinterpret_cast<__half*>(p + 2 * a);
+  t.idx = reinterpret_cast<int*>(p + 2 * a + align_up(static_cast<size_t>(rows) * d * 8, 256));
+  return t;
+}
+
+}  // namespace
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int pc_version(void) { return PC_VERSION; }
+const char* pc_last_error(void) { return get_error(); }
+
+int pc_ctx_create(int device, pc_ctx** out) {
+  PC_REQUIRE(out != nullptr, PC_ERR_ARG, "pc_ctx_create: out is null");
+  *out = nullptr;
+  int count = 0;
+  PC_CHECK_CUDA(cudaGetDeviceCount(&count));
+  PC_REQUIRE(device >= 0 && device < count, PC_ERR_ARG, "pc_ctx_create: device %d out of range (%d visible)",
+             device, count);
+  cudaDeviceProp prop;
+  PC_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  PC_REQUIRE(prop.major == 10, PC_ERR_ARCH,
+             "pc_ctx_create: device %d is sm_%d%d; libprotoclip_b200 is sm_100a-only and has no fallback",
+             device, prop.major, prop.minor);
+  PC_CHECK_CUDA(cudaSetDevice(device));
+  pc_ctx* c = new (std::nothrow) pc_ctx();
+  PC_REQUIRE(c != nullptr, PC_ERR_CUDA, "pc_ctx_create: out of host memory");
+  c->device = device;
+  *out = c;
+  return PC_OK;
+}
+
+void pc_ctx_destroy(pc_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->vis.proj_t) cudaFree(ctx->vis.proj_t);
+  if (ctx->txt.proj_t) cudaFree(ctx->txt.proj_t);
+  if (ctx->conv1_p) cudaFree(ctx->conv1_p);
+  delete ctx;
+}
+
+int pc_vit_bind_weights(pc_ctx* ctx, const pc_vit_weights* w) {
+  PC_TRY(use_device(ctx));
+  PC_REQUIRE(w != nullptr, PC_ERR_ARG, "pc_vit_bind_weights: weights are null");
+  PC_REQUIRE(w->width > 0 && w->width % 64 == 0 && w->heads * 64 == w->width, PC_ERR_ARG,
+             "pc_vit_bind_weights: width %d / heads %d (head_dim must be 64)", w->width, w->heads);
+  PC_REQUIRE(w->patch_size > 0 && w->patch_size % 2 == 0 && w->image_resolution % w->patch_size == 0,
+             PC_ERR_ARG, "pc_vit_bind_weights: resolution %d / patch %d", w->image_resolution, w->patch_size);
+  PC_REQUIRE(w->layers > 0 && w->embed_dim > 0 && w->embed_dim % 8 == 0, PC_ERR_ARG,
+             "pc_vit_bind_weights: layers %d embed_dim %d", w->layers, w->embed_dim);
+  PC_REQUIRE(w->conv1_weight && w->class_embedding && w->positional_embedding && w->ln_pre_weight &&
+                 w->ln_pre_bias && w->ln_post_weight && w->ln_post_bias && w->proj,
+             PC_ERR_ARG, "pc_vit_bind_weights: null stem tensor");
+  PC_TRY(check_blocks(w->blocks, w->layers));
+  ctx->vis.bound = false;
+  ctx->res = w->image_resolution;
+  ctx->patch = w->patch_size;
+  ctx->grid = ctx->res / ctx->patch;
+  ctx->Kpatch = 3 * ctx->patch * ctx->patch;
+  ctx->Kp = static_cast<int>(align_up(ctx->Kpatch, 8));
+  Tower& t = ctx->vis;
+  t.width = w->width; t.layers = w->layers; t.heads = w->heads; t.embed = w->embed_dim;
+  t.L = ctx->grid * ctx->grid + 1;
+  t.blocks.assign(w->blocks, w->blocks + w->layers);
+  ctx->cls = static_cast<const float*>(w->class_embedding);
+  ctx->vpos = static_cast<const float*>(w->positional_embedding);
+  ctx->ln_pre_w = static_cast<const float*>(w->ln_pre_weight);
+  ctx->ln_pre_b = static_cast<const float*>(w->ln_pre_bias);
+  ctx->ln_post_w = static_cast<const float*>(w->ln_post_weight);
+  ctx->ln_post_b = static_cast<const float*>(w->ln_post_bias);
+  // conv1.weight [d, 3, p, p] is already the [N, K] GEMM operand; re-pitch rows to Kp (16-byte TMA rows).
+  if (ctx->conv1_p) cudaFree(ctx->conv1_p);
+  PC_CHECK_CUDA(cudaMalloc(&ctx->conv1_p, static_cast<size_t>(t.width) * ctx->Kp * 2));
+  PC_CHECK_CUDA(cudaMemset(ctx->conv1_p, 0, static_cast<size_t>(t.width) * ctx->Kp * 2));
+  PC_CHECK_CUDA(cudaMemcpy2D(ctx->conv1_p, static_cast<size_t>(ctx->Kp) * 2, w->conv1_weight,
+                             static_cast<size_t>(ctx->Kpatch) * 2, static_cast<size_t>(ctx->Kpatch) * 2, t.width,
+                             cudaMemcpyDeviceToDevice));
+  PC_TRY(make_transposed(w->proj, t.width, t.embed, &t.proj_t));
+  t.bound = true;
+  return PC_OK;
+}
+
+int pc_text_bind_weights(pc_ctx* ctx, const pc_text_weights* w) {
+  PC_TRY(use_device(ctx));
+  PC_REQUIRE(w != nullptr, PC_ERR_ARG, "pc_text_bind_weights: weights are null");
+  PC_REQUIRE(w->width > 0 && w->width % 64 == 0 && w->heads * 64 == w->width, PC_ERR_ARG,
+             "pc_text_bind_weights: width %d / heads %d (head_dim must be 64)", w->width, w->heads);
+  PC_REQUIRE(w->layers > 0 && w->context_length > 0 && w->vocab_size > 0 && w->embed_dim % 8 == 0, PC_ERR_ARG,
+             "pc_text_bind_weights: bad descriptor");
+  PC_REQUIRE(w->token_embedding && w->positional_embedding && w->ln_final_weight && w->ln_final_bias &&
+                 w->text_projection,
+             PC_ERR_ARG, "pc_text_bind_weights: null stem tensor");
+  PC_TRY(check_blocks(w->blocks, w->layers));
+  Tower& t = ctx->txt;
+  t.bound = false;
+  t.width = w->width; t.layers = w->layers; t.heads = w->heads; t.embed = w->embed_dim;
+  t.L = w->context_length;
+  t.blocks.assign(w->blocks, w->blocks + w->layers);
+  ctx->vocab = w->vocab_size;
+  ctx->tok_emb = static_cast<const float*>(w->token_embedding);
+  ctx->tpos = static_cast<const float*>(w->positional_embedding);
+  ctx->ln_final_w = static_cast<const float*>(w->ln_final_weight);
+  ctx->ln_final_b = static_cast<const float*>(w->ln_final_bias);
+  PC_TRY(make_transposed(w->text_projection, t.width, t.embed, &t.proj_t));
+  t.bound = true;
+  return PC_OK;
+}
+
+size_t pc_encode_image_workspace_bytes(const pc_ctx* ctx, int micro_batch) {
+  if (!ctx || !ctx->vis.bound) return 0;
+  const int mb = micro_batch > 0 ? micro_batch : kDefaultMicroBatch;
+  return tower_ws_bytes(mb * ctx->vis.L, ctx->vis.width, mb);
+}
+
+int pc_encode_image(pc_ctx* ctx, const void* images, int img_dtype, int B, void* feat_out, int l2norm,
+                    int micro_batch, void* workspace, size_t workspace_bytes, void* stream) {
+  PC_TRY(use_device(ctx));
+  PC_REQUIRE(ctx->vis.bound, PC_ERR_STATE, "pc_encode_image: visual weights are not bound");
+  PC_REQUIRE(images && feat_out && B > 0, PC_ERR_ARG, "pc_encode_image: null buffer or empty batch");
+  PC_REQUIRE(img_dtype == PC_IMG_F32 || img_dtype == PC_IMG_F16, PC_ERR_ARG, "pc_encode_image: image dtype %d",
+             img_dtype);
+  const Tower& t = ctx->vis;
+  const int mb = micro_batch > 0 ? micro_batch : kDefaultMicroBatch;
+  PC_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, PC_ERR_ALIGN,
+             "pc_encode_image: workspace must be 256-byte aligned");
+  PC_REQUIRE(workspace_bytes >= tower_ws_bytes(mb * t.L, t.width, mb), PC_ERR_WORKSPACE,
+             "pc_encode_image: workspace %zu < %zu", workspace_bytes, tower_ws_bytes(mb * t.L, t.width, mb));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const TowerWs ws = carve(workspace, mb * t.L, t.width);
+  const int d = t.width, g2 = ctx->grid * ctx->grid;
+  const size_t img_elems = static_cast<size_t>(3) * ctx->res * ctx->res;
+  const size_t img_bytes = img_elems * (img_dtype == PC_IMG_F16 ? 2 : 4);
+  __half* feat = static_cast<__half*>(feat_out);
+  for (int b0 = 0; b0 < B; b0 += mb) {
+    const int n = (B - b0 < mb) ? (B - b0) : mb;
+    const void* img = static_cast<const uint8_t*>(images) + static_cast<size_t>(b0) * img_bytes;
+    // conv1 as a GEMM: patches [n*g2, Kp] (in `big`) x conv1_p [d, Kp]^T -> patch tokens [n*g2, d] (in `h`)
+    PC_TRY(launch_patchify(img, img_dtype == PC_IMG_F16, ws.big, n, ctx->res, ctx->patch, ctx->Kp, s));
+    GemmArgs g{};
+    g.M = n * g2; g.N = d; g.K = ctx->Kp;
+    g.A = ws.big; g.lda = ctx->Kp;
+    g.W = ctx->conv1_p; g.ldw = ctx->Kp;
+    g.C = ws.h; g.ldc = d;
+    PC_TRY(launch_gemm(g, EPI_BIAS, s));
+    PC_TRY(launch_embed_ln_pre(ws.h, ctx->cls, ctx->vpos, ctx->ln_pre_w, ctx->ln_pre_b, ws.x, n, t.L, d, s));
+    for (int l = 0; l < t.layers; ++l) PC_TRY(resblock(t, l, ws.x, ws.h, ws.big, n, t.L, 0, s));
+    // ln_post on the CLS rows, then @ proj (clip/model.py:233-236)
+    PC_TRY(launch_layernorm(ws.x, ws.h, ctx->ln_post_w, ctx->ln_post_b, n, d, t.L, s));
+    g = GemmArgs{};
+    g.M = n; g.N = t.embed; g.K = d;
+    g.A = ws.h; g.lda = d;
+    g.W = t.proj_t; g.ldw = d;
+    g.C = feat + static_cast<size_t>(b0) * t.embed; g.ldc = t.embed;
+    PC_TRY(launch_gemm(g, EPI_BIAS, s));
+    if (l2norm) {
+      __half* f = feat + static_cast<size_t>(b0) * t.embed;
+      PC_TRY(launch_l2norm(f, f, n, t.embed, s));
+    }
+  }
+  return PC_OK;
+}
+
+size_t pc_encode_text_workspace_bytes(const pc_ctx* ctx, int micro_batch) {
+  if (!ctx || !ctx->txt.bound) return 0;
+  const int mb = micro_batch > 0 ? micro_batch : 2 * kDefaultMicroBatch;
+  return tower_ws_bytes(mb * ctx->txt.L, ctx->txt.width, mb);
+}
+
+int pc_encode_text(pc_ctx* ctx, const int64_t* tokens, int P, void* out, int l2norm, int micro_batch,
+                   void* workspace, size_t workspace_bytes, void* stream) {
+  PC_TRY(use_device(ctx));
+  PC_REQUIRE(ctx->txt.bound, PC_ERR_STATE, "pc_encode_text: text weights are not bound");
+  PC_REQUIRE(tokens && out && P > 0, PC_ERR_ARG, "pc_encode_text: null buffer or empty batch");
+  const Tower& t = ctx->txt;
+  const int mb = micro_batch > 0 ? micro_batch : 2 * kDefaultMicroBatch;
+  PC_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, PC_ERR_ALIGN,
+             "pc_encode_text: workspace must be 256-byte aligned");
+  PC_REQUIRE(workspace_bytes >= tower_ws_bytes(mb * t.L, t.width, mb), PC_ERR_WORKSPACE,
+             "pc_encode_text: workspace %zu < %zu", workspace_bytes, tower_ws_bytes(mb * t.L, t.width, mb));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const TowerWs ws = carve(workspace, mb * t.L, t.width);
+  const int d = t.width;
+  __half* o = static_cast<__half*>(out);
+  for (int p0 = 0; p0 < P; p0 += mb) {
+    const int n = (P - p0 < mb) ? (P - p0) : mb;
+    const int64_t* tok = tokens + static_cast<size_t>(p0) * t.L;
+    PC_TRY(launch_text_embed(tok, ctx->tok_emb, ctx->tpos, ws.x, n, t.L, d, ctx->vocab, s));
+    for (int l = 0; l < t.layers; ++l) PC_TRY(resblock(t, l, ws.x, ws.h, ws.big, n, t.L, 1, s));
+    // ln_final is row-wise, so LN(gather(x)) == gather(LN(x)) (clip/model.py:348-352)
+    PC_TRY(launch_eot_index(tok, ws.idx, n, t.L, s));
+    PC_TRY(launch_layernorm_gather(ws.x, ws.idx, ws.h, ctx->ln_final_w, ctx->ln_final_b, n, d, s));
+    GemmArgs g{};
+    g.M = n; g.N = t.embed; g.K = d;
+    g.A = ws.h; g.lda = d;
+    g.W = t.proj_t; g.ldw = d;
+    g.C = o + static_cast<size_t>(p0) * t.embed; g.ldc = t.embed;
+    PC_TRY(launch_gemm(g, EPI_BIAS, s));
+    if (l2norm) {
+      __half* f = o + static_cast<size_t>(p0) * t.embed;
+      PC_TRY(launch_l2norm(f, f, n, t.embed, s));
+    }
+  }
+  return PC_OK;
+}
+
+size_t pc_resblock_workspace_bytes(const pc_ctx* ctx, int tower, int B, int L) {
+  if (!ctx) return 0;
+  const Tower& t = tower == PC_TOWER_TEXT ? ctx->txt : ctx->vis;
+  if (!t.bound) return 0;
+  return tower_ws_bytes(B * L, t.width, 1);
+}
+
+int pc_resblock_forward(pc_ctx* ctx, int tower, int layer, void* x, int B, int L, int causal, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  PC_TRY(use_device(ctx));
+  PC_REQUIRE(tower == PC_TOWER_VISUAL || tower == PC_TOWER_TEXT, PC_ERR_ARG, "pc_resblock_forward: tower %d", tower);
+  const Tower& t = tower == PC_TOWER_TEXT ? ctx->txt : ctx->vis;
+  PC_REQUIRE(t.bound, PC_ERR_STATE, "pc_resblock_forward: tower %d is not bound", tower);
+  PC_REQUIRE(layer >= 0 && layer < t.layers, PC_ERR_ARG, "pc_resblock_forward: layer %d of %d", layer, t.layers);
+  PC_REQUIRE(x && B > 0 && L > 0, PC_ERR_ARG, "pc_resblock_forward: null x or empty batch");
+  PC_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, PC_ERR_ALIGN,
+             "pc_resblock_forward: workspace must be 256-byte aligned");
+  PC_REQUIRE(workspace_bytes >= tower_ws_bytes(B * L, t.width, 1), PC_ERR_WORKSPACE,
+             "pc_resblock_forward: workspace %zu < %zu", workspace_bytes, tower_ws_bytes(B * L, t.width, 1));
+  const TowerWs ws = carve(workspace, B * L, t.width);
+  return resblock(t, layer, static_cast<__half*>(x), ws.h, ws.big, B, L, causal,
+                  static_cast<cudaStream_t>(stream));
+}
+
+int pc_linear_forward(const void* x, int ldx, const void* w, int ldw, const void* bias, const void* residual,
+                      int ldr, void* out, int ldo, int M, int N, int K, int epilogue, void* stream) {
+  GemmArgs g{};
+  g.M = M; g.N = N; g.K = K;
+  g.A = static_cast<const __half*>(x); g.lda = ldx;
+  g.W = static_cast<const __half*>(w); g.ldw = ldw;
+  g.C = out; g.ldc = ldo;
+  g.bias = static_cast<const __half*>(bias);
+  g.residual = static_cast<const __half*>(residual); g.ldr = ldr;
+  return launch_gemm(g, epilogue, static_cast<cudaStream_t>(stream));
+}
+
+int pc_layernorm_forward(const void* x, void* y, const void* gamma, const void* beta, int rows, int d,
+                         void* stream) {
+  PC_REQUIRE(x && y && gamma && beta, PC_ERR_ARG, "pc_layernorm_forward: null buffer");
+  return launch_layernorm(static_cast<const __half*>(x), static_cast<__half*>(y), static_cast<const float*>(gamma),
+                          static_cast<const float*>(beta), rows, d, 1, static_cast<cudaStream_t>(stream));
+}
+
+int pc_attention_forward(const void* qkv, void* out, int B, int L, int heads, int causal, void* stream) {
+  return launch_attention(static_cast<const __half*>(qkv), static_cast<__half*>(out), B, L, heads, causal,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int pc_l2_normalize(const void* x, void* y, int rows, int d, void* stream) {
+  PC_REQUIRE(x && y, PC_ERR_ARG, "pc_l2_normalize: null buffer");
+  return launch_l2norm(static_cast<const __half*>(x), static_cast<__half*>(y), rows, d,
+                       static_cast<cudaStream_t>(stream));
+}
+
+size_t pc_adapter_fc_workspace_bytes(int Q, int D, int reduction) {
+  if (Q <= 0 || D <= 0 || reduction <= 0) return 0;
+  const int H = D / reduction;
+  return align_up(static_cast<size_t>(Q) * align_up(H, 8) * 2, 256) * 2 + align_up(static_cast<size_t>(Q) * D * 2, 256);
+}
+
+int pc_adapter_fc_forward(const pc_adapter_fc_weights* w, const void* q, void* out, int Q, int D, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  PC_REQUIRE(w && q && out && Q > 0 && D > 0, PC_ERR_ARG, "pc_adapter_fc_forward: null buffer or empty batch");
+  PC_REQUIRE(w->fc0_weight && w->fc1_weight && w->fc1_bias && w->fc2_weight && w->fc3_weight && w->fc3_bias,
+             PC_ERR_ARG, "pc_adapter_fc_forward: null weight");
+  const int red = w->reduction > 0 ? w->reduction : 4;
+  PC_REQUIRE(D % red == 0 && (D / red) % 8 == 0 && D % 8 == 0, PC_ERR_ARG,
+             "pc_adapter_fc_forward: D = %d with reduction %d is not supported", D, red);
+  const int H = D / red;
+  PC_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, PC_ERR_ALIGN,
+             "pc_adapter_fc_forward: workspace must be 256-byte aligned");
+  PC_REQUIRE(workspace_bytes >= pc_adapter_fc_workspace_bytes(Q, D, red), PC_ERR_WORKSPACE,
+             "pc_adapter_fc_forward: workspace %zu < %zu", workspace_bytes, pc_adapter_fc_workspace_bytes(Q, D, red));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint8_t* p = static_cast<uint8_t*>(workspace);
+  const size_t a = align_up(static_cast<size_t>(Q) * H * 2, 256);
+  __half* h1 = reinterpret_cast<__half*>(p);
+  __half* h1n = reinterpret_cast<__half*>(p + a);
+  __half* h2 = reinterpret_cast<__half*>(p + 2 * a);
+  GemmArgs g{};
+  g.M = Q; g.N = H; g.K = D;
+  g.A = static_cast<const __half*>(q); g.lda = D;
+  g.W = static_cast<const __half*>(w->fc0_weight); g.ldw = D;
+  g.C = h1; g.ldc = H;
+  PC_TRY(launch_gemm(g, EPI_BIAS, s));
+  PC_TRY(launch_ln_f16(h1, h1n, static_cast<const __half*>(w->fc1_weight), static_cast<const __half*>(w->fc1_bias),
+                       Q, H, s));
+  g = GemmArgs{};
+  g.M = Q; g.N = D; g.K = H;
+  g.A = h1n; g.lda = H;
+  g.W = static_cast<const __half*>(w->fc2_weight); g.ldw = H;
+  g.C = h2; g.ldc = D;
+  PC_TRY(launch_gemm(g, EPI_BIAS, s));
+  PC_TRY(launch_ln_blend_f16(h2, static_cast<const __half*>(q), static_cast<__half*>(out),
+                             static_cast<const __half*>(w->fc3_weight), static_cast<const __half*>(w->fc3_bias), 0.2f,
+                             Q, D, s));
+  return PC_OK;
+}
+
+int pc_adapter_conv_forward(const pc_adapter_conv_weights* w, int c_type, const void* q, void* out, int Q, int D,
+                            void* stream) {
+  PC_REQUIRE(w && q && out, PC_ERR_ARG, "pc_adapter_conv_forward: null buffer");
+  PC_REQUIRE(c_type == 2 || c_type == 3, PC_ERR_ARG, "pc_adapter_conv_forward: c_type %d (2 = conv-2x, 3 = conv-3x)",
+             c_type);
+  PC_REQUIRE(w->conv1_weight && w->conv3_weight && w->bn1_weight && w->bn1_bias && w->bn3_weight && w->bn3_bias,
+             PC_ERR_ARG, "pc_adapter_conv_forward: null weight");
+  PC_REQUIRE(c_type == 2 || (w->conv2_weight && w->bn2_weight && w->bn2_bias), PC_ERR_ARG,
+             "pc_adapter_conv_forward: conv-3x needs conv2 / bn2");
+  AdapterConvW k;
+  k.conv1 = static_cast<const __half*>(w->conv1_weight);
+  k.conv2 = static_cast<const __half*>(w->conv2_weight);
+  k.conv3 = static_cast<const __half*>(w->conv3_weight);
+  k.bn1_w = static_cast<const __half*>(w->bn1_weight);
+  k.bn1_b = static_cast<const __half*>(w->bn1_bias);
+  k.bn2_w = static_cast<const __half*>(w->bn2_weight);
+  k.bn2_b = static_cast<const __half*>(w->bn2_bias);
+  k.bn3_w = static_cast<const __half*>(w->bn3_weight);
+  k.bn3_b = static_cast<const __half*>(w->bn3_bias);
+  return launch_adapter_conv(k, c_type == 3, static_cast<const __half*>(q), static_cast<__half*>(out), Q, D,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int pc_build_prototypes(const void* V, int N, int K, int D, int per_shot_norm, void* z, float* znorm2,
+                        void* stream) {
+  return launch_build_prototypes(static_cast<const __half*>(V), N, K, D, per_shot_norm, static_cast<__half*>(z),
+                                 znorm2, static_cast<cudaStream_t>(stream));
+}
+
+size_t pc_proto_classify_workspace_bytes(int Q, int N) {
+  if (Q <= 0 || N <= 0) return 0;
+  const int rows = Q < kClassifyChunk ? Q : kClassifyChunk;
+  return static_cast<size_t>(rows) * 2 * align_up(N, 4) * sizeof(float);
+}
+
+int pc_proto_classify(const void* q, const void* z_img, const void* z_txt, const float* zi_n2, const float* zt_n2,
+                      int Q, int N, int D, float alpha, float beta, float* p_out, int64_t* argmax, float* pmax,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  PC_REQUIRE(q && z_img && z_txt && zi_n2 && zt_n2 && Q > 0 && N > 0 && D > 0, PC_ERR_ARG,
+             "pc_proto_classify: null buffer or empty problem");
+  PC_REQUIRE(D % 8 == 0, PC_ERR_ARG, "pc_proto_classify: D = %d must be a multiple of 8", D);
+  PC_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, PC_ERR_ALIGN,
+             "pc_proto_classify: workspace must be 256-byte aligned");
+  PC_REQUIRE(workspace_bytes >= pc_proto_classify_workspace_bytes(Q, N), PC_ERR_WORKSPACE,
+             "pc_proto_classify: workspace %zu < %zu", workspace_bytes, pc_proto_classify_workspace_bytes(Q, N));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int Np = static_cast<int>(align_up(N, 4));
+  float* dots = static_cast<float*>(workspace);
+  const __half* qh = static_cast<const __half*>(q);
+  for (int q0 = 0; q0 < Q; q0 += kClassifyChunk) {
+    const int n = (Q - q0 < kClassifyChunk) ? (Q - q0) : kClassifyChunk;
+    for (int bank = 0; bank < 2; ++bank) {
+      GemmArgs g{};
+      g.M = n; g.N = N; g.K = D;
+      g.A = qh + static_cast<size_t>(q0) * D; g.lda = D;
+      g.W = static_cast<const __half*>(bank == 0 ? z_img : z_txt); g.ldw = D;
+      g.C = dots + bank * Np; g.ldc = 2 * Np;
+      PC_TRY(launch_gemm(g, EPI_F32, s));
+    }
+    PC_TRY(launch_proto_softmax(dots, 2 * Np, qh + static_cast<size_t>(q0) * D, D, zi_n2, zt_n2, n, N, alpha, beta,
+                                p_out ? p_out + static_cast<size_t>(q0) * N : nullptr,
+                                argmax ? argmax + q0 : nullptr, pmax ? pmax + q0 : nullptr, s));
+  }
+  return PC_OK;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

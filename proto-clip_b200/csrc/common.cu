@@ -1,0 +1,64 @@
+#include "common.cuh"
+
+#include <stdarg.h>
+#include <string.h>
+
+namespace pc {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows,
+                     uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  PC_REQUIRE(fn != nullptr, PC_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  PC_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, PC_ERR_ALIGN,
+             "TMA base %p is not 16-byte aligned", base);
+  PC_REQUIRE((row_stride_bytes & 15) == 0, PC_ERR_ALIGN, "TMA row stride %llu is not a multiple of 16",
+             (unsigned long long)row_stride_bytes);
+  PC_REQUIRE(box_inner * 2 == 128 && box_rows >= 1 && box_rows <= 256, PC_ERR_ARG,
+             "TMA box %ux%u unsupported", box_inner, box_rows);
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PC_REQUIRE(r == CUDA_SUCCESS, PC_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return PC_OK;
+}
+
+int device_sm_count() {
+  static int n = 0;
+  if (n) return n;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+  return n;
+}
+
+}  // namespace pc

@@ -1,0 +1,76 @@
+// Internal launcher declarations (host side). Every launcher is asynchronous on `stream`, allocates
+// nothing, and returns a pc::PC_* code. Layouts: activations are token-major [rows, width] fp16 with the
+// tokens of one image / prompt contiguous ([B, L, d]); weights keep the reference's [out, in] layout
+// (nn.Linear.weight, clip/model.py:173-179) so a GEMM is always C[M,N] = A[M,K] * W[N,K]^T ("TN").
+#pragma once
+#include "common.cuh"
+
+namespace pc {
+
+// ---------------------------------------------------------------- gemm.cu (tcgen05 + TMA)
+enum GemmEpilogue : int {
+  EPI_BIAS = 0,        // C = f16(acc + bias)
+  EPI_BIAS_QGELU = 1,  // C = quickgelu(f16(acc + bias))        (clip/model.py:164-166)
+  EPI_BIAS_RES = 2,    // C = f16(acc + bias) + residual        (clip/model.py:188-189)
+  EPI_F32 = 3          // C(fp32) = acc (+ bias)
+};
+struct GemmArgs {
+  int M, N, K;
+  const __half* A; int lda;   // [M, K] row-major, lda elements
+  const __half* W; int ldw;   // [N, K] row-major
+  void* C; int ldc;           // [M, N] fp16 (fp32 for EPI_F32)
+  const __half* bias;         // [N] or nullptr
+  const __half* residual; int ldr;  // [M, N] fp16 (EPI_BIAS_RES); may alias C
+};
+int launch_gemm(const GemmArgs& a, int epilogue, cudaStream_t stream);
+
+// ---------------------------------------------------------------- attention.cu (tcgen05 + TMA)
+// qkv: [B*L, 3*d] fp16, columns [0,d) = q, [d,2d) = k, [2d,3d) = v, head h at h*64 (nn.MultiheadAttention
+// packed in-proj order). out: [B*L, d] fp16 (heads merged). head_dim is fixed at 64 (all CLIP towers).
+int launch_attention(const __half* qkv, __half* out, int B, int L, int heads, int causal, cudaStream_t stream);
+
+// ---------------------------------------------------------------- rowops.cu
+// y[r,:] = f16(LN_fp32(x[src(r),:]) * gamma + beta); src(r) = r * row_stride_rows (gathers CLS rows when
+// row_stride_rows = L), eps = 1e-5 (clip/model.py:155-161).
+int launch_layernorm(const __half* x, __half* y, const float* gamma, const float* beta, int rows, int d,
+                     int row_stride_rows, cudaStream_t stream);
+// images [B,3,R,R] (fp32 or fp16) -> patch rows [B*g*g, Kp] fp16, column = c*p*p + i*p + j (conv1 weight
+// flattening order), zero-padded to Kp.
+int launch_patchify(const void* images, int img_is_f16, __half* out, int B, int R, int p, int Kp,
+                    cudaStream_t stream);
+// x[b,0,:] = cls + pos[0]; x[b,1+t,:] = patch[b*g2+t,:] + pos[1+t]; then ln_pre (clip/model.py:222-227).
+int launch_embed_ln_pre(const __half* patch, const float* cls, const float* pos, const float* gamma,
+                        const float* beta, __half* x, int B, int L, int d, cudaStream_t stream);
+// text: x[p,t,:] = f16(tok_emb[tokens[p,t]]) + f16(pos[t]) (clip/model.py:342-344)
+int launch_text_embed(const int64_t* tokens, const float* tok_emb, const float* pos, __half* x, int P, int L,
+                      int d, int vocab, cudaStream_t stream);
+// eot[p] = argmax_t tokens[p,t] (first max), as the row index p*L + eot into [P*L, d]
+int launch_eot_index(const int64_t* tokens, int* rows, int P, int L, cudaStream_t stream);
+// y[r,:] = LN(x[rows[r],:])
+int launch_layernorm_gather(const __half* x, const int* rows, __half* y, const float* gamma, const float* beta,
+                            int n, int d, cudaStream_t stream);
+// in-place or out-of-place row L2 normalisation in fp16 storage / fp32 math: y = x / ||x||
+int launch_l2norm(const __half* x, __half* y, int rows, int d, cudaStream_t stream);
+
+// ---------------------------------------------------------------- head.cu
+int launch_build_prototypes(const __half* V, int N, int K, int D, int per_shot_norm, __half* z, float* zn2,
+                            cudaStream_t stream);
+int launch_text_prototypes(const __half* T, int N, int D, __half* z, float* zn2, cudaStream_t stream);
+// Adapter_FC tail: y = LN(h) row-wise in fp16 semantics (model.py:84-88); blend: out = 0.2*LN(h2) + 0.8*x
+int launch_ln_f16(const __half* x, __half* y, const __half* gamma, const __half* beta, int rows, int d,
+                  cudaStream_t stream);
+int launch_ln_blend_f16(const __half* h, const __half* x_in, __half* y, const __half* gamma,
+                        const __half* beta, float ratio, int rows, int d, cudaStream_t stream);
+struct AdapterConvW {
+  const __half *conv1, *conv2, *conv3;            // [16], [16*16*9], [16]
+  const __half *bn1_w, *bn1_b, *bn2_w, *bn2_b;    // [16,S,S]
+  const __half *bn3_w, *bn3_b;                    // [S,S]
+};
+int launch_adapter_conv(const AdapterConvW& w, int three_x, const __half* q, __half* out, int Q, int D,
+                        cudaStream_t stream);
+// logits fp32 [Q, 2N] (= q . [z_img; z_txt]^T) -> p, argmax (utils.py:225-244)
+int launch_proto_softmax(const float* dots, int ld, const __half* q, int D, const float* zi_n2,
+                         const float* zt_n2, int Q, int N, float alpha, float beta, float* p_out,
+                         int64_t* argmax, float* pmax, cudaStream_t stream);
+
+}  // namespace pc

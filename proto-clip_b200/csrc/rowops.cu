@@ -1,0 +1,298 @@
+// HBM-bound row kernels around the tensor-core GEMMs: one warp per row, 16-byte vector loads, fp32
+// statistics with warp-shuffle reductions, fp16 storage. They restate
+//   LayerNorm (fp32 compute on fp16 storage)           clip/model.py:155-161
+//   patch extraction for conv1 (k = s = p, no bias)    clip/model.py:209,222-224
+//   CLS concat + positional embedding + ln_pre         clip/model.py:225-227
+//   token embedding + positional embedding             clip/model.py:342-344
+//   EOT gather (text.argmax(-1))                       clip/model.py:352
+//   feature L2 normalisation                           utils.py:352
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace pc {
+
+namespace {
+
+constexpr int ROW_WARPS = 8;   // warps (rows) per CTA
+constexpr int MAX_VEC = 8;     // 16-byte vectors per lane: d <= 32 * 8 * 8 = 2048
+
+struct RowF {  // one row slice held by a lane: up to MAX_VEC * 8 floats
+  float v[MAX_VEC][8];
+};
+
+__device__ __forceinline__ void load_row_f16(const __half* row, int d, int lane, RowF& r, int& nvec) {
+  const int vecs = d >> 3;
+  nvec = 0;
+#pragma unroll
+  for (int k = 0; k < MAX_VEC; ++k) {
+    const int vi = lane + k * 32;
+    if (vi < vecs) {
+      const uint4 u = *reinterpret_cast<const uint4*>(row + vi * 8);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h2[e]);
+        r.v[k][2 * e] = f.x;
+        r.v[k][2 * e + 1] = f.y;
+      }
+      nvec = k + 1;
+    }
+  }
+}
+
+// Normalise the row held in `r` (fp32 two-pass mean / biased variance, eps 1e-5) and store fp16.
+template <typename ParamT>
+__device__ __forceinline__ void ln_store(RowF& r, int d, int lane, const ParamT* gamma, const ParamT* beta,
+                                         __half* out) {
+  const int vecs = d >> 3;
+  float s = 0.0f;
+#pragma unroll
+  for (int k = 0; k < MAX_VEC; ++k)
+    if (lane + k * 32 < vecs)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += r.v[k][e];
+  const float mean = warp_sum(s) / static_cast<float>(d);
+  float q = 0.0f;
+#pragma unroll
+  for (int k = 0; k < MAX_VEC; ++k)
+    if (lane + k * 32 < vecs)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float c = r.v[k][e] - mean;
+        q += c * c;
+      }
+  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(d) + 1e-5f);
+#pragma unroll
+  for (int k = 0; k < MAX_VEC; ++k) {
+    const int vi = lane + k * 32;
+    if (vi < vecs) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = vi * 8 + 2 * e;
+        const float g0 = static_cast<float>(gamma[c]), g1 = static_cast<float>(gamma[c + 1]);
+        const float b0 = static_cast<float>(beta[c]), b1 = static_cast<float>(beta[c + 1]);
+        pk[e] = pack_half2((r.v[k][2 * e] - mean) * rstd * g0 + b0,
+                           (r.v[k][2 * e + 1] - mean) * rstd * g1 + b1);
+      }
+      *reinterpret_cast<uint4*>(out + vi * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, const int* __restrict__ rows_idx, int rows, int d,
+                 int row_stride_rows) {
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const size_t src = rows_idx ? static_cast<size_t>(rows_idx[row]) : static_cast<size_t>(row) * row_stride_rows;
+  RowF r;
+  int nvec;
+  load_row_f16(x + src * d, d, lane, r, nvec);
+  ln_store(r, d, lane, gamma, beta, y + static_cast<size_t>(row) * d);
+}
+
+__global__ void __launch_bounds__(256)
+patchify_kernel(const void* __restrict__ images, int img_is_f16, __half* __restrict__ out, int B, int R, int p,
+                int g, int K, int Kp) {
+  const int pairs_per_row = Kp >> 1;
+  const size_t total = static_cast<size_t>(B) * g * g * pairs_per_row;
+  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int col = static_cast<int>(t % pairs_per_row) * 2;
+    const size_t prow = t / pairs_per_row;
+    float v0 = 0.0f, v1 = 0.0f;
+    if (col < K) {
+      const int gx = static_cast<int>(prow % g);
+      const int gy = static_cast<int>((prow / g) % g);
+      const int b = static_cast<int>(prow / (static_cast<size_t>(g) * g));
+      const int c = col / (p * p);
+      const int rem = col % (p * p);
+      const int i = rem / p, j = rem % p;  // j even, p even -> (j, j+1) stay in one patch row
+      const size_t off = ((static_cast<size_t>(b) * 3 + c) * R + (gy * p + i)) * R + gx * p + j;
+      if (img_is_f16) {
+        const __half2 h = *reinterpret_cast<const __half2*>(static_cast<const __half*>(images) + off);
+        v0 = __low2float(h);
+        v1 = __high2float(h);
+      } else {
+        const float2 f = *reinterpret_cast<const float2*>(static_cast<const float*>(images) + off);
+        v0 = f.x;
+        v1 = f.y;
+      }
+    }
+    *reinterpret_cast<__half2*>(out + prow * Kp + col) = __floats2half2_rn(v0, v1);
+  }
+}
+
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+embed_ln_pre_kernel(const __half* __restrict__ patch, const float* __restrict__ cls,
+                    const float* __restrict__ pos, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, __half* __restrict__ x, int B, int L, int d) {
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= B * L) return;
+  const int lane = threadIdx.x & 31;
+  const int b = row / L, t = row % L;
+  const int vecs = d >> 3;
+  RowF r;
+#pragma unroll
+  for (int k = 0; k < MAX_VEC; ++k) {
+    const int vi = lane + k * 32;
+    if (vi < vecs) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = vi * 8 + e;
+        // token value in fp16 (conv output / cast class embedding), fp16 add of the fp16-cast position
+        const __half tok = (t == 0) ? __float2half_rn(cls[c])
+                                    : patch[(static_cast<size_t>(b) * (L - 1) + (t - 1)) * d + c];
+        const __half pe = __float2half_rn(pos[static_cast<size_t>(t) * d + c]);
+        r.v[k][e] = __half2float(__hadd(tok, pe));
+      }
+    }
+  }
+  ln_store(r, d, lane, gamma, beta, x + static_cast<size_t>(row) * d);
+}
+
+__global__ void __launch_bounds__(256)
+text_embed_kernel(const int64_t* __restrict__ tokens, const float* __restrict__ tok_emb,
+                  const float* __restrict__ pos, __half* __restrict__ x, int rows, int L, int d, int vocab) {
+  const int pairs = d >> 1;
+  const size_t total = static_cast<size_t>(rows) * pairs;
+  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(t % pairs) * 2;
+    const size_t row = t / pairs;
+    long long tok = tokens[row];
+    tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);
+    const float2 e = *reinterpret_cast<const float2*>(tok_emb + static_cast<size_t>(tok) * d + c);
+    const float2 pe = *reinterpret_cast<const float2*>(pos + static_cast<size_t>(row % L) * d + c);
+    const __half2 s = __hadd2(__floats2half2_rn(e.x, e.y), __floats2half2_rn(pe.x, pe.y));
+    *reinterpret_cast<__half2*>(x + row * d + c) = s;
+  }
+}
+
+__global__ void eot_index_kernel(const int64_t* __restrict__ tokens, int* __restrict__ rows, int P, int L) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  long long best = tokens[static_cast<size_t>(p) * L];
+  int arg = 0;
+  for (int t = 1; t < L; ++t) {
+    const long long v = tokens[static_cast<size_t>(p) * L + t];
+    if (v > best) {
+      best = v;
+      arg = t;
+    }
+  }
+  rows[p] = p * L + arg;
+}
+
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+l2norm_kernel(const __half* __restrict__ x, __half* __restrict__ y, int rows, int d) {
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  RowF r;
+  int nvec;
+  load_row_f16(x + static_cast<size_t>(row) * d, d, lane, r, nvec);
+  const int vecs = d >> 3;
+  float s = 0.0f;
+#pragma unroll
+  for (int k = 0; k < MAX_VEC; ++k)
+    if (lane + k * 32 < vecs)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += r.v[k][e] * r.v[k][e];
+  // x.norm(dim=-1) on an fp16 tensor: fp32 accumulation, fp16 result; then an fp16 division.
+  const float n = __half2float(__float2half_rn(sqrtf(warp_sum(s))));
+#pragma unroll
+  for (int k = 0; k < MAX_VEC; ++k) {
+    const int vi = lane + k * 32;
+    if (vi < vecs) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) pk[e] = pack_half2(r.v[k][2 * e] / n, r.v[k][2 * e + 1] / n);
+      *reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * d + vi * 8) =
+          make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+}
+
+int check_row_dims(const char* what, int rows, int d) {
+  PC_REQUIRE(rows > 0 && d > 0, PC_ERR_ARG, "%s: empty input (%d x %d)", what, rows, d);
+  PC_REQUIRE(d % 8 == 0 && d <= 32 * 8 * MAX_VEC, PC_ERR_ARG, "%s: width %d must be a multiple of 8 and <= %d",
+             what, d, 32 * 8 * MAX_VEC);
+  return PC_OK;
+}
+
+int grid_1d(size_t work, int block) {
+  size_t g = (work + block - 1) / block;
+  const size_t cap = static_cast<size_t>(device_sm_count()) * 16;
+  return static_cast<int>(g < cap ? (g ? g : 1) : cap);
+}
+
+}  // namespace
+
+int launch_layernorm(const __half* x, __half* y, const float* gamma, const float* beta, int rows, int d,
+                     int row_stride_rows, cudaStream_t stream) {
+  PC_TRY(check_row_dims("layernorm", rows, d));
+  layernorm_kernel<<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, stream>>>(
+      x, y, gamma, beta, nullptr, rows, d, row_stride_rows);
+  PC_CHECK_CUDA(cudaGetLastError());
+  return PC_OK;
+}
+
+int launch_layernorm_gather(const __half* x, const int* rows_idx, __half* y, const float* gamma,
+                            const float* beta, int n, int d, cudaStream_t stream) {
+  PC_TRY(check_row_dims("layernorm_gather", n, d));
+  layernorm_kernel<<<(n + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, stream>>>(x, y, gamma, beta, rows_idx,
+                                                                                  n, d, 1);
+  PC_CHECK_CUDA(cudaGetLastError());
+  return PC_OK;
+}
+
+int launch_patchify(const void* images, int img_is_f16, __half* out, int B, int R, int p, int Kp,
+                    cudaStream_t stream) {
+  PC_REQUIRE(images && out && B > 0 && p > 0 && R % p == 0 && p % 2 == 0 && R % 2 == 0, PC_ERR_ARG,
+             "patchify: bad geometry B=%d R=%d p=%d", B, R, p);
+  const int g = R / p;
+  const int K = 3 * p * p;
+  PC_REQUIRE(Kp >= K && Kp % 8 == 0, PC_ERR_ARG, "patchify: padded K %d < %d or not a multiple of 8", Kp, K);
+  const size_t total = static_cast<size_t>(B) * g * g * (Kp / 2);
+  patchify_kernel<<<grid_1d(total, 256), 256, 0, stream>>>(images, img_is_f16, out, B, R, p, g, K, Kp);
+  PC_CHECK_CUDA(cudaGetLastError());
+  return PC_OK;
+}
+
+int launch_embed_ln_pre(const __half* patch, const float* cls, const float* pos, const float* gamma,
+                        const float* beta, __half* x, int B, int L, int d, cudaStream_t stream) {
+  PC_TRY(check_row_dims("embed_ln_pre", B * L, d));
+  embed_ln_pre_kernel<<<(B * L + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, stream>>>(patch, cls, pos, gamma,
+                                                                                        beta, x, B, L, d);
+  PC_CHECK_CUDA(cudaGetLastError());
+  return PC_OK;
+}
+
+int launch_text_embed(const int64_t* tokens, const float* tok_emb, const float* pos, __half* x, int P, int L,
+                      int d, int vocab, cudaStream_t stream) {
+  PC_REQUIRE(tokens && tok_emb && pos && x && P > 0 && L > 0 && d % 2 == 0, PC_ERR_ARG, "text_embed: bad args");
+  const size_t total = static_cast<size_t>(P) * L * (d / 2);
+  text_embed_kernel<<<grid_1d(total, 256), 256, 0, stream>>>(tokens, tok_emb, pos, x, P * L, L, d, vocab);
+  PC_CHECK_CUDA(cudaGetLastError());
+  return PC_OK;
+}
+
+int launch_eot_index(const int64_t* tokens, int* rows, int P, int L, cudaStream_t stream) {
+  PC_REQUIRE(tokens && rows && P > 0 && L > 0, PC_ERR_ARG, "eot_index: bad args");
+  eot_index_kernel<<<(P + 127) / 128, 128, 0, stream>>>(tokens, rows, P, L);
+  PC_CHECK_CUDA(cudaGetLastError());
+  return PC_OK;
+}
+
+int launch_l2norm(const __half* x, __half* y, int rows, int d, cudaStream_t stream) {
+  PC_TRY(check_row_dims("l2norm", rows, d));
+  l2norm_kernel<<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, stream>>>(x, y, rows, d);
+  PC_CHECK_CUDA(cudaGetLastError());
+  return PC_OK;
+}
+
+}  // namespace pc

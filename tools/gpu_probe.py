@@ -1,0 +1,137 @@
+"""Bring-up probe: runs each primitive of libprotoclip_b200 in its own process (a trapped kernel kills only
+its case) and prints error statistics against torch fp32 on the same GPU. Not a test; tests/ holds those.
+
+    python tools/gpu_probe.py            # all cases
+    python tools/gpu_probe.py --case gemm_768
+"""
+import argparse
+import os
+import subprocess
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def stats(name, got, ref):
+    import torch
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs()
+    denom = ref.abs().max().item() + 1e-12
+    bad = (~torch.isfinite(got)).sum().item()
+    print(f"[{name}] max_abs_err={err.max().item():.4e} mean_abs_err={err.mean().item():.4e} "
+          f"ref_absmax={denom:.4e} rel={err.max().item() / denom:.4e} nonfinite={bad}", flush=True)
+    if err.max().item() / denom > 2e-2 or bad:
+        # where are the errors? (row / column histogram helps spot swizzle / descriptor mistakes)
+        e2 = err.reshape(-1, err.shape[-1])
+        rows = (e2.max(dim=1).values > 1e-2 * denom).nonzero().flatten()[:16].tolist()
+        cols = (e2.max(dim=0).values > 1e-2 * denom).nonzero().flatten()[:32].tolist()
+        print(f"[{name}]   bad rows (first 16): {rows}\n[{name}]   bad cols (first 32): {cols}", flush=True)
+        print(f"[{name}]   got[0,:8]={got.reshape(-1, got.shape[-1])[0, :8].tolist()}")
+        print(f"[{name}]   ref[0,:8]={ref.reshape(-1, ref.shape[-1])[0, :8].tolist()}")
+
+
+def case_gemm(M, N, K, epi="bias"):
+    import torch
+    from proto_clip_b200 import _native as nat
+    torch.manual_seed(0)
+    x = (torch.randn(M, K, device="cuda") * 0.5).half()
+    w = (torch.randn(N, K, device="cuda") * 0.05).half()
+    b = torch.randn(N, device="cuda").half()
+    r = torch.randn(M, N, device="cuda").half()
+    acc = x.float() @ w.float().t() + b.float()
+    if epi == "bias":
+        got, ref = nat.linear(x, w, b, nat.EPI_BIAS), acc
+    elif epi == "gelu":
+        h = acc.half().float()
+        got, ref = nat.linear(x, w, b, nat.EPI_BIAS_QUICKGELU), h * torch.sigmoid(1.702 * h)
+    elif epi == "res":
+        got, ref = nat.linear(x, w, b, nat.EPI_BIAS_RESIDUAL, residual=r), acc.half().float() + r.float()
+    elif epi == "f32":
+        got, ref = nat.linear(x, w, None, nat.EPI_F32), x.float() @ w.float().t()
+    torch.cuda.synchronize()
+    stats(f"gemm {M}x{N}x{K} {epi}", got, ref)
+    # timing
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        nat.linear(x, w, b if epi != "f32" else None, {"bias": 0, "gelu": 1, "res": 2, "f32": 3}[epi],
+                   residual=r if epi == "res" else None)
+    t0.record()
+    iters = 10
+    for _ in range(iters):
+        nat.linear(x, w, b if epi != "f32" else None, {"bias": 0, "gelu": 1, "res": 2, "f32": 3}[epi],
+                   residual=r if epi == "res" else None)
+    t1.record(); torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / iters
+    print(f"[gemm {M}x{N}x{K} {epi}] {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s", flush=True)
+
+
+def case_attn(B, L, heads, causal):
+    import torch
+    from proto_clip_b200 import _native as nat
+    torch.manual_seed(1)
+    d = heads * 64
+    qkv = (torch.randn(B * L, 3 * d, device="cuda")).half()
+    got = nat.attention(qkv, B, L, heads, causal)
+    q, k, v = [t.reshape(B, L, heads, 64).permute(0, 2, 1, 3).float() for t in qkv.split(d, dim=1)]
+    s = (q @ k.transpose(-1, -2)) * 0.125
+    if causal:
+        s = s + torch.full((L, L), float("-inf"), device="cuda").triu(1)
+    ref = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B * L, d)
+    torch.cuda.synchronize()
+    stats(f"attn B{B} L{L} h{heads} causal={causal}", got, ref)
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        nat.attention(qkv, B, L, heads, causal)
+    t0.record()
+    for _ in range(10):
+        nat.attention(qkv, B, L, heads, causal)
+    t1.record(); torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / 10
+    print(f"[attn B{B} L{L}] {ms:.3f} ms  {4.0 * B * heads * L * L * 64 / ms / 1e9:.2f} TFLOP/s", flush=True)
+
+
+def case_rows():
+    import torch
+    from proto_clip_b200 import _native as nat
+    torch.manual_seed(2)
+    for d in (512, 768, 1024):
+        x = (torch.randn(1000, d, device="cuda") * 2 + 0.3).half()
+        g = torch.randn(d, device="cuda"); b = torch.randn(d, device="cuda")
+        stats(f"layernorm d{d}", nat.layernorm(x, g, b), torch.nn.functional.layer_norm(x.float(), (d,), g, b))
+        stats(f"l2norm d{d}", nat.l2_normalize(x), x.float() / x.float().norm(dim=-1, keepdim=True))
+
+
+CASES = {
+    "gemm_small": lambda: case_gemm(128, 256, 64),
+    "gemm_k": lambda: case_gemm(128, 256, 768),
+    "gemm_n128": lambda: case_gemm(300, 128, 512),
+    "gemm_ragged": lambda: case_gemm(1000, 2000, 512, "f32"),
+    "gemm_qkv": lambda: case_gemm(96 * 197, 2304, 768),
+    "gemm_gelu": lambda: case_gemm(96 * 197, 3072, 768, "gelu"),
+    "gemm_res": lambda: case_gemm(96 * 197, 768, 3072, "res"),
+    "attn_197": lambda: case_attn(4, 197, 12, False),
+    "attn_77c": lambda: case_attn(5, 77, 8, True),
+    "attn_50": lambda: case_attn(3, 50, 12, False),
+    "attn_257": lambda: case_attn(2, 257, 16, False),
+    "attn_big": lambda: case_attn(96, 197, 12, False),
+    "rows": case_rows,
+}
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--case", default=None)
+    ap.add_argument("--timeout", type=int, default=120)
+    a = ap.parse_args()
+    if a.case:
+        CASES[a.case]()
+    else:
+        for name in CASES:
+            t = time.time()
+            try:
+                r = subprocess.run([sys.executable, __file__, "--case", name], timeout=a.timeout,
+                                   capture_output=True, text=True)
+                out = (r.stdout + r.stderr[-1500:]) if r.returncode else r.stdout
+                print(f"=== {name}: rc={r.returncode} ({time.time() - t:.1f}s)\n{out}", flush=True)
+            except subprocess.TimeoutExpired:
+                print(f"=== {name}: TIMEOUT after {a.timeout}s", flush=True)
