@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""Benchmark of the Proto-CLIP few-shot query path (BASELINE.json metric: query images/sec, ImageNet
+1000-way 16-shot ViT-B/16).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores
+
+A step = one batch of --batch synthetic 224x224 query images per rank through
+encode_image -> /norm -> Adapter_FC -> /norm -> P(alpha=0.5, beta=12) -> argmax over 1000 prototypes.
+`value` is timed with inputs resident in HBM; `e2e` goes through the public API with pinned-host inputs
+(H2D of every batch and D2H of the predictions inside the timed region). One JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ARCH = "ViT-B/16"
+N_CLASSES, K_SHOTS, N_TEMPLATES = 1000, 16, 7
+ALPHA, BETA = 0.5, 12.0
+METRIC = "query images/sec, ImageNet 1000-way 16-shot ViT-B/16"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("bf16_tflops_sustained", 1353.6), d.get("bf16_tflops", 1633.5), "measured"
+    return 1400.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def synthetic_tokens(n_prompts: int, ctx: int, vocab: int, seed: int) -> torch.Tensor:
+    """Prompt-shaped token rows (SOT, 4..12 word ids, EOT = max id, zero padding), as clip.tokenize emits."""
+    gen = torch.Generator().manual_seed(seed)
+    t = torch.zeros(n_prompts, ctx, dtype=torch.int64)
+    n = torch.randint(4, 13, (n_prompts,), generator=gen)
+    body = torch.randint(1, vocab - 2, (n_prompts, 12), generator=gen)
+    for i in range(n_prompts):
+        k = int(n[i])
+        t[i, 0] = vocab - 2
+        t[i, 1:1 + k] = body[i, :k]
+        t[i, 1 + k] = vocab - 1
+    return t
+
+
+# --------------------------------------------------------------------------------------- this repo's arm
+def run_ours(args):
+    from proto_clip_b200 import _native as nat
+    from proto_clip_b200 import dist as pdist
+    from proto_clip_b200 import pipeline, synthetic
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    rank, local_rank, world = pdist.init("nccl")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    c = synthetic.arch_config(ARCH)
+    R, D = c["image_resolution"], c["embed_dim"]
+    B, mb = args.batch, args.micro_batch
+
+    sd = synthetic.make_state_dict(ARCH, 0)
+    ctx = nat.Context(dev)
+    ctx.bind_visual(sd)
+    ctx.bind_text(sd)
+
+    # ---- head state: built on rank 0 (support + text memory), one NCCL broadcast to everyone
+    bases = synthetic.class_bases(N_CLASSES, R, seed=1, device=dev)           # same on every rank (same seed)
+    numel = pipeline.HeadState.packed_numel(N_CLASSES, D, "fc")
+    flat = None
+    if rank == 0:
+        feats = []
+        for n0 in range(0, N_CLASSES, 64):  # 64 classes x 16 shots = 1024 support images per pass
+            labels = torch.arange(n0, min(n0 + 64, N_CLASSES), device=dev).repeat_interleave(K_SHOTS)
+            imgs = synthetic.class_structured_images(bases, labels, seed=2 + n0)
+            feats.append(ctx.encode_image(imgs, l2norm=True, micro_batch=mb))   # utils.py:310,319 (augment_epoch 1)
+        V = torch.cat(feats)
+        tokens = synthetic_tokens(N_CLASSES * N_TEMPLATES, c["context_length"], c["vocab_size"], 5).to(dev)
+        te = ctx.encode_text(tokens, l2norm=True).view(N_CLASSES, N_TEMPLATES, D)  # utils.py:266-267
+        T = nat.l2_normalize(te.float().mean(dim=1).half())                      # utils.py:268-269
+        adapter = synthetic.make_adapter_state_dict("fc", D, seed=4)
+        head0 = pipeline.build_head_state(V, T, N_CLASSES, K_SHOTS, "fc", adapter, ALPHA, BETA)
+        flat = head0.pack()
+        assert flat.numel() == numel
+    flat = pdist.broadcast_flat(flat, numel, torch.float16, dev, src=0)
+    head = pipeline.HeadState.unpack(flat, N_CLASSES, D, "fc", ALPHA, BETA)
+    clf = pipeline.FewShotClassifier(ctx, head, micro_batch=mb)
+
+    # ---- query pool: 2 distinct batches per rank, class-structured, pinned host + device copies
+    pool_dev, pool_host, pool_labels = [], [], []
+    for j in range(2):
+        labels = (torch.arange(B, device=dev) * 7 + 13 * j + 101 * rank) % N_CLASSES
+        imgs = synthetic.class_structured_images(bases, labels, seed=1000 + 10 * rank + j)
+        pool_dev.append(imgs)
+        h = torch.empty(imgs.shape, dtype=torch.float32, pin_memory=True)
+        h.copy_(imgs)
+        pool_host.append(h)
+        pool_labels.append(labels)
+    del bases
+    torch.cuda.synchronize()
+
+    def step_resident(i):
+        return clf.classify(pool_dev[i % 2])[1]
+
+    # ---- value: inputs resident in HBM, CUDA events on the launching stream, barrier + sync both sides
+    for i in range(args.warmup):
+        step_resident(i)
+    torch.cuda.synchronize()
+    pdist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(args.steps):
+            pred = step_resident(i)
+        e1.record()
+        torch.cuda.synchronize()
+    pdist.barrier()
+    ms_total = pdist.max_over_ranks(e0.elapsed_time(e1), dev)
+    value = world * B * args.steps / (ms_total / 1e3)
+    acc = (pred == pool_labels[(args.steps - 1) % 2]).float().mean().item()
+
+    # ---- e2e: pinned host -> device copy of every batch (copy stream, double-buffered) + D2H of predictions
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage = [torch.empty_like(pool_dev[0]) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    out_host = torch.empty(B, dtype=torch.int64, pin_memory=True)
+
+    def e2e_run(nsteps):
+        cur = torch.cuda.current_stream(dev)
+        for k in range(2):
+            consumed[k].record(cur)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[0])
+            stage[0].copy_(pool_host[0], non_blocking=True)
+            ready[0].record(copy_stream)
+        for i in range(nsteps):
+            s = i % 2
+            if i + 1 < nsteps:
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(consumed[(i + 1) % 2])
+                    stage[(i + 1) % 2].copy_(pool_host[(i + 1) % 2], non_blocking=True)
+                    ready[(i + 1) % 2].record(copy_stream)
+            cur.wait_event(ready[s])
+            _, am, _ = clf.classify(stage[s])
+            consumed[s].record(cur)
+            out_host.copy_(am, non_blocking=True)
+        cur.synchronize()
+
+    e2e_run(max(2, args.warmup))
+    torch.cuda.synchronize()
+    pdist.barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    e2e_run(args.steps)
+    t1.record()
+    torch.cuda.synchronize()
+    pdist.barrier()
+    ms_e2e = pdist.max_over_ranks(t0.elapsed_time(t1), dev)
+    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+
+    # ---- roofline of the dominant kernel family (gemm_tn_kernel: the 4 Linears of a ResidualAttentionBlock at
+    #      the micro-batch's M), timed live with CUDA events on the launching stream
+    roof = None
+    if rank == 0:
+        roof = gemm_roofline(nat, dev, (mb or 96) * (c["image_resolution"] // c["vision_patch_size"]) ** 2 + (mb or 96),
+                             c["vision_width"])
+    cpu = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu, parity = cpu_baseline_and_parity(sd, head, pool_host[0], clf, pool_dev[0], args.cpu_sample)
+
+    if rank == 0:
+        layers = c["vision_layers"]
+        n_mb = math.ceil(B / (mb or 96))
+        launches = args.steps * (n_mb * (3 + 7 * layers + 2 + 1) + 8)
+        sustained, burst, src = measured_peaks()
+        flops_img = synthetic.vit_flops_per_image(ARCH) + 4.0 * N_CLASSES * D + 2.0 * D * D / 4 * 2
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": "imagenet 16-shot ViT-B/16 fc adapter, 1000-way eval (configs[1])",
+                       "backbone": ARCH, "n_classes": N_CLASSES, "shots": K_SHOTS, "adapter": "fc", "alpha": ALPHA,
+                       "beta": BETA, "batch_per_gpu": B, "micro_batch": mb or 96, "image": "3x224x224 fp32",
+                       "l2": "inputs larger than L2 (616 MB per batch, 2 alternating batches)",
+                       "parallelism": f"dp{world} (query shards, 1 NCCL broadcast of the head state)"},
+            "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": int(pool_host[0].numel() * 4),
+                    "d2h_bytes_per_step": int(B * 8), "ms_per_step": round(ms_e2e / args.steps, 3)},
+            "gpu_launches": launches,
+            "clocks": clocks.summary(),
+            "model_tflops": round(value * flops_img / 1e12, 1),
+            "model_frac_of_sustained_peak": round(value / world * flops_img / 1e12 / sustained, 4),
+            "accuracy_on_synthetic_queries": round(acc, 4),
+            "roofline": roof, "cpu_baseline": cpu, "parity": parity, "peaks": src,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def gemm_roofline(nat, dev, M, d):
+    """Average device time of the four GEMM launches of one ResidualAttentionBlock (QKV, out-proj, c_fc, c_proj)."""
+    sustained, burst, src = measured_peaks()
+    torch.manual_seed(0)
+    x = (torch.randn(M, d, device=dev) * 0.5).half()
+    h4 = (torch.randn(M, 4 * d, device=dev) * 0.5).half()
+    res = torch.randn(M, d, device=dev).half()
+    w_qkv = (torch.randn(3 * d, d, device=dev) * 0.03).half()
+    w_o = (torch.randn(d, d, device=dev) * 0.03).half()
+    w_fc = (torch.randn(4 * d, d, device=dev) * 0.03).half()
+    w_pr = (torch.randn(d, 4 * d, device=dev) * 0.03).half()
+    b3, b1, b4 = [torch.zeros(n * d, device=dev).half() for n in (3, 1, 4)]
+
+    def block():
+        nat.linear(x, w_qkv, b3, nat.EPI_BIAS)
+        nat.linear(x, w_o, b1, nat.EPI_BIAS_RESIDUAL, residual=res)
+        nat.linear(x, w_fc, b4, nat.EPI_BIAS_QUICKGELU)
+        nat.linear(h4, w_pr, b1, nat.EPI_BIAS_RESIDUAL, residual=res)
+
+    for _ in range(5):
+        block()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 50
+    e0.record()
+    for _ in range(iters):
+        block()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    flops = 24.0 * M * d * d
+    achieved = flops / (ms / 1e3) / 1e12
+    return {"bound": "tensor", "achieved": round(achieved, 1), "peak": sustained, "unit": "TFLOP/s",
+            "frac": round(achieved / sustained, 4), "traffic": None,
+            "kernel": f"gemm_tn_kernel<256,*>: 4 Linear launches of one ResidualAttentionBlock, M={M}, d={d}",
+            "flops_per_4_launches": flops, "ms_per_4_launches": round(ms, 4), "peak_kind": f"bf16 sustained ({src})"}
+
+
+def cpu_baseline_and_parity(sd, head, host_images, clf, dev_images, sample):
+    """The reference algorithm (oracle port, fp32 like clip.load(device='cpu')) on this box's host cores, on the
+    first `sample` queries of batch 0; also the argmax parity of the CUDA path on exactly those queries."""
+    from oracle import protoclip_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    zi, zt = head.z_img.float().cpu(), head.z_txt.float().cpu()
+    asd = {k: v.cpu() for k, v in head.adapter.items()}
+    imgs = host_images[:sample].clone()
+    bs = 32
+    with torch.no_grad():
+        O.classify_queries(sd, asd, "fc", imgs[:bs], zi, zt, ALPHA, BETA, "fp32")  # warm-up
+        best, preds, ps = float("inf"), [], []
+        for rep in range(2):
+            t = time.perf_counter()
+            preds, ps = [], []
+            for i in range(0, sample, bs):
+                p, pr, _ = O.classify_queries(sd, asd, "fc", imgs[i:i + bs], zi, zt, ALPHA, BETA, "fp32")
+                preds.append(pr)
+                ps.append(p)
+            best = min(best, time.perf_counter() - t)
+    pred_cpu, p_cpu = torch.cat(preds), torch.cat(ps)
+    p_gpu, pred_gpu, _ = clf.classify(dev_images[:sample], want_p=True)
+    top2 = p_cpu.topk(2, dim=1).values
+    mism = int((pred_gpu.cpu() != pred_cpu).sum())
+    cpu = {"value": round(sample / best, 2), "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+           "sample": f"first {sample} queries of batch 0, batch 32, fp32, best of 2 after 1 warm-up (oracle/protoclip_oracle.py)"}
+    parity = {"checked": sample, "argmax_mismatches": mism,
+              "max_abs_dp": round((p_gpu.cpu() - p_cpu).abs().max().item(), 6),
+              "min_top1_top2_margin_ref": round((top2[:, 0] - top2[:, 1]).min().item(), 6)}
+    return cpu, parity
+
+
+# --------------------------------------------------------------------------------------- reference arm (CPU)
+def run_reference(args):
+    """The reference's own CPU implementation of the path on the host cores. Uses the real reference modules
+    when /root/reference is mounted (authoring container), else the oracle port (GPU box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import protoclip_oracle as O
+    from oracle import reference_shims
+    from proto_clip_b200 import synthetic
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_grad_enabled(False)
+    c = synthetic.arch_config(ARCH)
+    R, D = c["image_resolution"], c["embed_dim"]
+    sd = synthetic.make_state_dict(ARCH, 0)
+    asd = synthetic.make_adapter_state_dict("fc", D, seed=4)
+    gen = torch.Generator().manual_seed(3)
+    zi = torch.nn.functional.normalize(torch.randn(N_CLASSES, D, generator=gen), dim=-1).half().float()
+    zt = torch.nn.functional.normalize(torch.randn(N_CLASSES, D, generator=gen), dim=-1).half().float()
+    bs = args.ref_batch
+    bases = synthetic.class_bases(8, R, seed=1)
+    imgs = synthetic.class_structured_images(bases, torch.arange(bs) % 8, seed=3)
+    kind = "port"
+    if reference_shims.available():
+        ref = reference_shims.reference()
+        model = ref.clip_model.build_model({k: v.clone() for k, v in sd.items()}).float()  # clip/clip.py:137-138
+        adapter = ref.model.Adapter_FC(D, dtype=torch.float32)
+        adapter.load_state_dict({k: v.float() for k, v in asd.items()})
+        kind = "reference"
+
+        def step():
+            f = model.encode_image(imgs)
+            f = f / f.norm(dim=-1, keepdim=True)
+            q = adapter(f)
+            q = q / q.norm(dim=-1, keepdim=True)
+            return ref.utils.P(q, zi, zt, ALPHA, BETA).max(1)[1]
+    else:
+        def step():
+            return O.classify_queries(sd, asd, "fc", imgs, zi, zt, ALPHA, BETA, "fp32")[1]
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    steps = min(args.steps, args.ref_max_steps)
+    t = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t
+    v = round(bs * steps / dt, 2)
+    sample = f"{steps} steps of {bs} synthetic queries, fp32, {os.cpu_count()} threads ({kind})"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": round(dt / steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "imagenet 16-shot ViT-B/16 fc adapter, 1000-way eval (configs[1])", "backbone": ARCH,
+                   "batch": bs, "device": "cpu"},
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": os.cpu_count(), "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="query images per rank per step (main.py:505 uses 1024)")
+    ap.add_argument("--micro-batch", type=int, default=0, help="images per encoder pass (0 = library default, 96)")
+    ap.add_argument("--cpu-sample", type=int, default=128, help="queries timed on the host CPU for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-batch", type=int, default=32)
+    ap.add_argument("--ref-max-steps", type=int, default=6)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -399,3 +399,37 @@ class Context:
                                                ws.data_ptr(), ws.numel(), stream_ptr(self.device)),
                   "pc_resblock_forward")
         return x
+
+
+# ----------------------------------------------------------------------------- adapters (functional form)
+def adapter_fc_forward(params: dict, q: torch.Tensor, reduction: int = 4) -> torch.Tensor:
+    """Adapter_FC.forward (model.py:91-95). params: state-dict tensors (f16, CUDA) keyed fc.0.weight ..."""
+    lib = load_library()
+    q = require_cuda(q, torch.float16, "q")
+    Q, D = q.shape
+    keep = [require_cuda(params[k], torch.float16, k) for k in
+            ("fc.0.weight", "fc.1.weight", "fc.1.bias", "fc.2.weight", "fc.3.weight", "fc.3.bias")]
+    w = AdapterFCWeights(*[t.data_ptr() for t in keep], reduction)
+    out = torch.empty_like(q)
+    nbytes = lib.pc_adapter_fc_workspace_bytes(Q, D, reduction)
+    ws = workspace(q.device, "adapter", nbytes)
+    with torch.cuda.device(q.device):
+        check(lib.pc_adapter_fc_forward(C.byref(w), q.data_ptr(), out.data_ptr(), Q, D, ws.data_ptr(), ws.numel(),
+                                        stream_ptr(q.device)), "pc_adapter_fc_forward")
+    return out
+
+
+def adapter_conv_forward(params: dict, c_type: str, q: torch.Tensor) -> torch.Tensor:
+    """Adapter.forward (model.py:49-78); c_type 'conv-2x' | 'conv-3x'."""
+    lib = load_library()
+    q = require_cuda(q, torch.float16, "q")
+    Q, D = q.shape
+    names = ("conv1.weight", "conv2.weight", "conv3.weight", "bn1.weight", "bn1.bias", "bn2.weight", "bn2.bias",
+             "bn3.weight", "bn3.bias")
+    keep = [require_cuda(params[k], torch.float16, k) for k in names]
+    w = AdapterConvWeights(*[t.data_ptr() for t in keep])
+    out = torch.empty_like(q)
+    with torch.cuda.device(q.device):
+        check(lib.pc_adapter_conv_forward(C.byref(w), 3 if c_type == "conv-3x" else 2, q.data_ptr(), out.data_ptr(),
+                                          Q, D, stream_ptr(q.device)), "pc_adapter_conv_forward")
+    return out

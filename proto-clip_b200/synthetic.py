@@ -1,0 +1,141 @@
+"""Deterministic synthetic weights and inputs (there is no network for checkpoints or datasets).
+
+* ``make_state_dict`` builds a CLIP state dict with the OpenAI key names and the dtypes the reference ends
+  up with after ``convert_weights`` (clip/model.py:373-394): fp16 for conv / Linear / MHA / projections, fp32
+  for LayerNorm and embeddings. Values come from a seeded CPU generator, so the same (arch, seed) gives the
+  same bytes on every box with this torch build; the reference (``build_model``) and this repo consume
+  identical tensors. Scales follow clip/model.py:297-324 so activations have realistic magnitudes.
+* ``class_structured_images`` follows SURVEY.md §8(d): per-class base pattern + 0.5 * noise, so that argmax
+  over prototypes is meaningful even with random weights.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, Tuple
+
+import torch
+
+# name -> (embed_dim, image_resolution, vision_layers, vision_width, patch, ctx, vocab, text_width, text_heads, text_layers)
+ARCHS: Dict[str, Tuple[int, ...]] = {
+    "ViT-B/32": (512, 224, 12, 768, 32, 77, 49408, 512, 8, 12),
+    "ViT-B/16": (512, 224, 12, 768, 16, 77, 49408, 512, 8, 12),
+    "ViT-L/14": (768, 224, 24, 1024, 14, 77, 49408, 768, 12, 12),
+    "ViT-L/14@336px": (768, 336, 24, 1024, 14, 77, 49408, 768, 12, 12),
+    # small towers for fast CPU oracles / golden fixtures (head_dim stays 64)
+    "tiny": (64, 32, 2, 128, 8, 77, 512, 64, 1, 2),
+    "small": (128, 64, 3, 256, 16, 77, 1024, 128, 2, 2),
+}
+
+
+def arch_config(name: str) -> dict:
+    e, r, vl, vw, p, ctx, vocab, tw, th, tl = ARCHS[name]
+    return dict(embed_dim=e, image_resolution=r, vision_layers=vl, vision_width=vw, vision_patch_size=p,
+                context_length=ctx, vocab_size=vocab, transformer_width=tw, transformer_heads=th,
+                transformer_layers=tl)
+
+
+def vit_flops_per_image(name: str) -> float:
+    """2*MAC count of one encode_image (layers*(24 L d^2 + 4 L^2 d) + 2 g^2 3p^2 d + 2 d D)."""
+    c = arch_config(name)
+    g = c["image_resolution"] // c["vision_patch_size"]
+    L, d, p = g * g + 1, c["vision_width"], c["vision_patch_size"]
+    return c["vision_layers"] * (24.0 * L * d * d + 4.0 * L * L * d) + 2.0 * g * g * 3 * p * p * d + 2.0 * d * c["embed_dim"]
+
+
+def _blocks(sd, prefix: str, width: int, layers: int, gen: torch.Generator):
+    attn_std = width ** -0.5
+    proj_std = (width ** -0.5) * ((2 * layers) ** -0.5)
+    fc_std = (2 * width) ** -0.5
+
+    def n(*shape, std=1.0):
+        return torch.randn(*shape, generator=gen) * std
+
+    for i in range(layers):
+        p = f"{prefix}{i}."
+        sd[p + "attn.in_proj_weight"] = n(3 * width, width, std=attn_std).half()
+        sd[p + "attn.in_proj_bias"] = n(3 * width, std=0.02).half()
+        sd[p + "attn.out_proj.weight"] = n(width, width, std=proj_std).half()
+        sd[p + "attn.out_proj.bias"] = n(width, std=0.02).half()
+        sd[p + "ln_1.weight"] = 1.0 + n(width, std=0.05)
+        sd[p + "ln_1.bias"] = n(width, std=0.05)
+        sd[p + "mlp.c_fc.weight"] = n(4 * width, width, std=fc_std).half()
+        sd[p + "mlp.c_fc.bias"] = n(4 * width, std=0.02).half()
+        sd[p + "mlp.c_proj.weight"] = n(width, 4 * width, std=proj_std).half()
+        sd[p + "mlp.c_proj.bias"] = n(width, std=0.02).half()
+        sd[p + "ln_2.weight"] = 1.0 + n(width, std=0.05)
+        sd[p + "ln_2.bias"] = n(width, std=0.05)
+
+
+def make_state_dict(name: str, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
+    c = arch_config(name)
+    gen = torch.Generator().manual_seed(1_000_003 * seed + 17)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    vw, p, e = c["vision_width"], c["vision_patch_size"], c["embed_dim"]
+    g = c["image_resolution"] // p
+    scale = vw ** -0.5
+
+    def n(*shape, std=1.0):
+        return torch.randn(*shape, generator=gen) * std
+
+    sd["visual.class_embedding"] = n(vw, std=scale)
+    sd["visual.positional_embedding"] = n(g * g + 1, vw, std=scale)
+    sd["visual.proj"] = n(vw, e, std=scale).half()
+    sd["visual.conv1.weight"] = n(vw, 3, p, p, std=(3 * p * p) ** -0.5).half()
+    sd["visual.ln_pre.weight"] = 1.0 + n(vw, std=0.05)
+    sd["visual.ln_pre.bias"] = n(vw, std=0.05)
+    _blocks(sd, "visual.transformer.resblocks.", vw, c["vision_layers"], gen)
+    sd["visual.ln_post.weight"] = 1.0 + n(vw, std=0.05)
+    sd["visual.ln_post.bias"] = n(vw, std=0.05)
+    tw = c["transformer_width"]
+    sd["positional_embedding"] = n(c["context_length"], tw, std=0.01)
+    sd["text_projection"] = n(tw, e, std=tw ** -0.5).half()
+    sd["logit_scale"] = torch.tensor(2.6592)
+    sd["token_embedding.weight"] = n(c["vocab_size"], tw, std=0.02)
+    _blocks(sd, "transformer.resblocks.", tw, c["transformer_layers"], gen)
+    sd["ln_final.weight"] = 1.0 + n(tw, std=0.05)
+    sd["ln_final.bias"] = n(tw, std=0.05)
+    return sd
+
+
+def make_adapter_state_dict(kind: str, D: int, seed: int = 4) -> "OrderedDict[str, torch.Tensor]":
+    """fp16 adapter parameters with the reference's state-dict keys (model.py:19-47, 84-89)."""
+    gen = torch.Generator().manual_seed(1_000_003 * seed + 29)
+
+    def n(*shape, std=1.0):
+        return torch.randn(*shape, generator=gen) * std
+
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    if kind == "fc":
+        H = D // 4
+        sd["fc.0.weight"] = n(H, D, std=D ** -0.5).half()
+        sd["fc.1.weight"] = (1.0 + n(H, std=0.05)).half()
+        sd["fc.1.bias"] = n(H, std=0.05).half()
+        sd["fc.2.weight"] = n(D, H, std=H ** -0.5).half()
+        sd["fc.3.weight"] = (1.0 + n(D, std=0.05)).half()
+        sd["fc.3.bias"] = n(D, std=0.05).half()
+    else:
+        import math
+        S = int(math.ceil(math.sqrt(D)))
+        sd["conv1.weight"] = n(16, 1, 1, 1).half()
+        sd["bn1.weight"] = (1.0 + n(16, S, S, std=0.05)).half()
+        sd["bn1.bias"] = n(16, S, S, std=0.05).half()
+        sd["conv2.weight"] = n(16, 16, 3, 3, std=(16 * 9) ** -0.5).half()
+        sd["bn2.weight"] = (1.0 + n(16, S, S, std=0.05)).half()
+        sd["bn2.bias"] = n(16, S, S, std=0.05).half()
+        sd["conv3.weight"] = n(1, 16, 1, 1, std=0.25).half()
+        sd["bn3.weight"] = (1.0 + n(1, S, S, std=0.05)).half()
+        sd["bn3.bias"] = n(1, S, S, std=0.05).half()
+    return sd
+
+
+def class_bases(num_classes: int, resolution: int, seed: int = 1, device="cpu") -> torch.Tensor:
+    """Per-class base patterns c_n ~ N(0,1), fp32 [N, 3, R, R]."""
+    gen = torch.Generator(device=device).manual_seed(1_000_003 * seed + 41)
+    return torch.randn(num_classes, 3, resolution, resolution, generator=gen, device=device)
+
+
+def class_structured_images(bases: torch.Tensor, labels: torch.Tensor, seed: int, noise: float = 0.5) -> torch.Tensor:
+    """image_i = c_{label_i} + noise * eps_i (eps from a generator on the bases' device), fp32 [B,3,R,R]."""
+    gen = torch.Generator(device=bases.device).manual_seed(1_000_003 * seed + 43)
+    eps = torch.randn((labels.numel(),) + tuple(bases.shape[1:]), generator=gen, device=bases.device)
+    return bases[labels.to(bases.device)] + noise * eps

@@ -1,0 +1,172 @@
+"""Generate the golden fixtures under tests/golden/ by running the REAL reference (imported from
+/root/reference through oracle/reference_shims.py) on seeded inputs. Run in the authoring container only:
+
+    python tests/golden/make_golden.py
+
+Weights and inputs are regenerable from seeds (proto-clip_b200/synthetic.py), so only the reference's
+OUTPUTS (plus small non-regenerable inputs such as checkpoint subsets) are stored. Every fixture records
+two reference runs: "fp32" = `clip.load(..., device="cpu")` semantics (model.float(), clip/clip.py:137-138)
+and "fp16" = the reference's GPU dtype (convert_weights fp16 modules) executed with CPU half kernels.
+"""
+import math
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import reference_shims  # noqa: E402
+from proto_clip_b200 import synthetic  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+ref = reference_shims.reference()
+torch.set_grad_enabled(False)
+
+
+def build_ref_clip(arch: str, seed: int, fp32: bool):
+    sd = synthetic.make_state_dict(arch, seed)
+    model = ref.clip_model.build_model({k: v.clone() for k, v in sd.items()})  # clip/model.py:397-434
+    return (model.float() if fp32 else model), sd
+
+
+def synth_tokens(P: int, ctx: int, vocab: int, seed: int) -> torch.Tensor:
+    """Token rows shaped like clip.tokenize output: SOT, words, EOT (= max id), zero padding."""
+    gen = torch.Generator().manual_seed(seed)
+    t = torch.zeros(P, ctx, dtype=torch.int64)
+    for i in range(P):
+        n = int(torch.randint(3, min(ctx - 2, 20), (1,), generator=gen))
+        t[i, 0] = vocab - 2
+        t[i, 1:1 + n] = torch.randint(1, vocab - 2, (n,), generator=gen)
+        t[i, 1 + n] = vocab - 1
+    return t
+
+
+def images_for(arch: str, B: int, seed: int) -> torch.Tensor:
+    c = synthetic.arch_config(arch)
+    bases = synthetic.class_bases(5, c["image_resolution"], seed=seed)
+    return synthetic.class_structured_images(bases, torch.arange(B) % 5, seed=seed + 1)
+
+
+def tower_fixture(arch: str, B: int, P: int, with_fp16: bool = True, with_blocks: bool = True):
+    c = synthetic.arch_config(arch)
+    out = {"arch": arch, "seed": 0, "B": B, "P": P, "image_seed": 7, "token_seed": 11}
+    images = images_for(arch, B, 7)
+    tokens = synth_tokens(P, c["context_length"], c["vocab_size"], 11)
+    out["tokens"] = tokens
+    for mode in (["fp32", "fp16"] if with_fp16 else ["fp32"]):
+        model, _ = build_ref_clip(arch, 0, fp32=(mode == "fp32"))
+        out[f"image_features_{mode}"] = model.encode_image(images).float()   # clip/model.py:338
+        out[f"text_features_{mode}"] = model.encode_text(tokens).float()     # clip/model.py:341
+        if with_blocks:
+            # one ResidualAttentionBlock in the reference's [L, B, d] layout (clip/model.py:187-190)
+            gen = torch.Generator().manual_seed(23)
+            L = (c["image_resolution"] // c["vision_patch_size"]) ** 2 + 1
+            x = torch.randn(L, 3, c["vision_width"], generator=gen).half().float()
+            xt = torch.randn(c["context_length"], 2, c["transformer_width"], generator=gen).half().float()
+            dt = torch.float32 if mode == "fp32" else torch.float16
+            out[f"vis_block0_{mode}"] = model.visual.transformer.resblocks[0](x.to(dt)).float()
+            out[f"txt_block0_{mode}"] = model.transformer.resblocks[0](xt.to(dt)).float()
+            out["vis_block0_in"] = x.half()
+            out["txt_block0_in"] = xt.half()
+    return out
+
+
+def adapters_fixture():
+    out = {}
+    for D in (64, 512, 768, 1024):
+        gen = torch.Generator().manual_seed(100 + D)
+        x = torch.randn(6, D, generator=gen)
+        x = (x / x.norm(dim=-1, keepdim=True)).half()
+        out[f"x_{D}"] = x
+        for kind in ("fc", "conv-2x", "conv-3x"):
+            sd = synthetic.make_adapter_state_dict(kind, D, seed=4)
+            for mode, dt in (("fp32", torch.float32), ("fp16", torch.float16)):
+                if kind == "fc":
+                    m = ref.model.Adapter_FC(D, dtype=dt)              # model.py:81
+                else:
+                    m = ref.model.Adapter(D, c_type=kind, dtype=dt)    # model.py:12
+                m.load_state_dict({k: v.to(dt) for k, v in sd.items()}, strict=False)
+                out[f"{kind}_{D}_{mode}"] = m(x.to(dt)).float()
+    return out
+
+
+def proto_statements(V, T, K, dt):
+    """main.py:399-405 verbatim semantics (tensor statements, not a function in the reference)."""
+    ndim = V.shape[-1]
+    zs_imgs = V.to(dt).view(-1, K, ndim)
+    zs_imgs = zs_imgs / zs_imgs.norm(dim=-1, keepdim=True)
+    z_img_proto = zs_imgs.mean(dim=1)
+    z_img_proto = z_img_proto / z_img_proto.norm(dim=-1, keepdim=True)
+    zs_text = T.to(dt)
+    z_text_proto = zs_text / zs_text.norm(dim=-1, keepdim=True)
+    return z_img_proto, z_text_proto
+
+
+def head_fixture():
+    gen = torch.Generator().manual_seed(5)
+    N, K, D, Q = 12, 4, 64, 9
+    centers = torch.randn(N, D, generator=gen)
+    V = (centers[:, None, :] + 0.3 * torch.randn(N, K, D, generator=gen)).reshape(N * K, D).half()
+    T = (centers + 0.3 * torch.randn(N, D, generator=gen)).half()
+    q = centers[torch.arange(Q) % N] + 0.3 * torch.randn(Q, D, generator=gen)
+    q = (q / q.norm(dim=-1, keepdim=True)).half()
+    out = {"V": V, "T": T, "q": q, "N": N, "K": K}
+    for mode, dt in (("fp32", torch.float32), ("fp16", torch.float16)):
+        zi, zt = proto_statements(V, T, K, dt)
+        out[f"z_img_{mode}"], out[f"z_txt_{mode}"] = zi.float(), zt.float()
+        for (a, b) in ((0.5, 12.0), (0.2, 5.5), (1.0, 1.0), (0.0, 20.0)):
+            p = ref.utils.P(q.to(dt), zi, zt, a, b)                    # utils.py:225
+            out[f"p_{mode}_{a}_{b}"] = p.float()
+            out[f"pred_{mode}_{a}_{b}"] = p.max(1)[1]                  # main.py:438
+    # zero-shot variant: mean without the per-shot renorm (main.py:173-176)
+    zs = V.float().view(-1, K, D).mean(dim=1)
+    out["z_img_zeroshot_fp32"] = zs / zs.norm(dim=-1, keepdim=True)
+    return out
+
+
+def ckpt_fixture(name: str, n_classes: int, kind: str, alpha: float, beta: float):
+    """Class-subset of a shipped Proto-CLIP-F checkpoint, classified by the reference head
+    (main.py:399-409,436-438) with the memory bank itself as queries (SURVEY.md §4 KAT)."""
+    d = os.path.join(reference_shims.REFERENCE_ROOT, "pretrained_ckpt", name)
+    V = torch.load(os.path.join(d, "memory_bank_v.pt"), map_location="cpu", weights_only=False).data
+    T = torch.load(os.path.join(d, "memory_bank_t.pt"), map_location="cpu", weights_only=False).data
+    A = torch.load(os.path.join(d, "query_adapter.pt"), map_location="cpu", weights_only=False)
+    K, D = 16, V.shape[1]
+    V, T = V[: n_classes * K].clone().half(), T[:n_classes].clone().half()
+    out = {"V": V, "T": T, "adapter": {k: v.clone().half() for k, v in A.items()}, "K": K, "kind": kind,
+           "alpha": alpha, "beta": beta}
+    for mode, dt in (("fp32", torch.float32), ("fp16", torch.float16)):
+        m = ref.model.Adapter_FC(D, dtype=dt) if kind == "fc" else ref.model.Adapter(D, c_type=kind, dtype=dt)
+        m.load_state_dict({k: v.to(dt) for k, v in A.items()})
+        zi, zt = proto_statements(V, T, K, dt)
+        q = m(V.to(dt))
+        q = q / q.norm(dim=-1, keepdim=True)                           # main.py:407-409
+        p = ref.utils.P(q, zi, zt, alpha, beta)
+        out[f"q_{mode}"] = q[:32].float()  # first 32 rows keep the fixture small
+        out[f"p_{mode}"] = p.float()
+        out[f"pred_{mode}"] = p.max(1)[1]
+    return out
+
+
+def main(only=None):
+    torch.manual_seed(0)
+    torch.save(tower_fixture("tiny", B=4, P=3), os.path.join(OUT, "tower_tiny.pt"))
+    print("tower_tiny done")
+    torch.save(tower_fixture("small", B=3, P=3), os.path.join(OUT, "tower_small.pt"))
+    print("tower_small done")
+    torch.save(adapters_fixture(), os.path.join(OUT, "adapters.pt"))
+    print("adapters done")
+    torch.save(head_fixture(), os.path.join(OUT, "head.pt"))
+    print("head done")
+    torch.save(ckpt_fixture("imagenet-F", 16, "conv-2x", 0.5, 12.0), os.path.join(OUT, "ckpt_imagenet_F_16.pt"))
+    torch.save(ckpt_fixture("fewsol-198-F", 24, "fc", 0.2, 12.0), os.path.join(OUT, "ckpt_fewsol_198_F_24.pt"))
+    print("ckpt subsets done")
+    for arch, B, P in (("ViT-B/32", 2, 2), ("ViT-B/16", 4, 3), ("ViT-L/14", 2, 2)):
+        fx = tower_fixture(arch, B=B, P=P, with_fp16=True, with_blocks=False)
+        torch.save(fx, os.path.join(OUT, f"tower_{arch.replace('/', '_').replace('-', '_')}.pt"))
+        print(arch, "done")
+
+
+if __name__ == "__main__":
+    main()
