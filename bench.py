@@ -118,7 +118,14 @@ def run_ours(args):
     bases = synthetic.class_bases(N_CLASSES, R, seed=1, device=dev)           # same on every rank (same seed)
     numel = pipeline.HeadState.packed_numel(N_CLASSES, D, "fc")
     flat = None
-    if rank == 0:
+    if rank == 0 and args.lite:
+        # profiling mode (ncu launch lists): random prototypes, no support / text encoding, same query path
+        g = torch.Generator(device=dev).manual_seed(9)
+        V = nat.l2_normalize(torch.randn(N_CLASSES * K_SHOTS, D, generator=g, device=dev).half())
+        T = nat.l2_normalize(torch.randn(N_CLASSES, D, generator=g, device=dev).half())
+        adapter = synthetic.make_adapter_state_dict("fc", D, seed=4, out_gain=synthetic.trained_like_gain(D))
+        flat = pipeline.build_head_state(V, T, N_CLASSES, K_SHOTS, "fc", adapter, ALPHA, BETA).pack()
+    elif rank == 0:
         feats = []
         for n0 in range(0, N_CLASSES, 64):  # 64 classes x 16 shots = 1024 support images per pass
             labels = torch.arange(n0, min(n0 + 64, N_CLASSES), device=dev).repeat_interleave(K_SHOTS)
@@ -128,7 +135,7 @@ def run_ours(args):
         tokens = synthetic_tokens(N_CLASSES * N_TEMPLATES, c["context_length"], c["vocab_size"], 5).to(dev)
         te = ctx.encode_text(tokens, l2norm=True).view(N_CLASSES, N_TEMPLATES, D)  # utils.py:266-267
         T = nat.l2_normalize(te.float().mean(dim=1).half())                      # utils.py:268-269
-        adapter = synthetic.make_adapter_state_dict("fc", D, seed=4)
+        adapter = synthetic.make_adapter_state_dict("fc", D, seed=4, out_gain=synthetic.trained_like_gain(D))
         head0 = pipeline.build_head_state(V, T, N_CLASSES, K_SHOTS, "fc", adapter, ALPHA, BETA)
         flat = head0.pack()
         assert flat.numel() == numel
@@ -169,6 +176,12 @@ def run_ours(args):
     ms_total = pdist.max_over_ranks(e0.elapsed_time(e1), dev)
     value = world * B * args.steps / (ms_total / 1e3)
     acc = (pred == pool_labels[(args.steps - 1) % 2]).float().mean().item()
+
+    if args.lite:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": round(value, 1), "unit": "images/s", "n_gpus": world,
+                              "steps": args.steps, "lite": True, "ms_per_step": round(ms_total / args.steps, 3)}), flush=True)
+        return
 
     # ---- e2e: pinned host -> device copy of every batch (copy stream, double-buffered) + D2H of predictions
     copy_stream = torch.cuda.Stream(device=dev)
@@ -335,7 +348,7 @@ def run_reference(args):
     c = synthetic.arch_config(ARCH)
     R, D = c["image_resolution"], c["embed_dim"]
     sd = synthetic.make_state_dict(ARCH, 0)
-    asd = synthetic.make_adapter_state_dict("fc", D, seed=4)
+    asd = synthetic.make_adapter_state_dict("fc", D, seed=4, out_gain=synthetic.trained_like_gain(D))
     gen = torch.Generator().manual_seed(3)
     zi = torch.nn.functional.normalize(torch.randn(N_CLASSES, D, generator=gen), dim=-1).half().float()
     zt = torch.nn.functional.normalize(torch.randn(N_CLASSES, D, generator=gen), dim=-1).half().float()
@@ -390,6 +403,7 @@ def main():
     ap.add_argument("--micro-batch", type=int, default=0, help="images per encoder pass (0 = library default, 96)")
     ap.add_argument("--cpu-sample", type=int, default=128, help="queries timed on the host CPU for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lite", action="store_true", help="profiling mode: random head state, value arm only")
     ap.add_argument("--ref-batch", type=int, default=32)
     ap.add_argument("--ref-max-steps", type=int, default=6)
     args = ap.parse_args()

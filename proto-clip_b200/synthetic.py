@@ -97,8 +97,13 @@ def make_state_dict(name: str, seed: int = 0) -> "OrderedDict[str, torch.Tensor]
     return sd
 
 
-def make_adapter_state_dict(kind: str, D: int, seed: int = 4) -> "OrderedDict[str, torch.Tensor]":
-    """fp16 adapter parameters with the reference's state-dict keys (model.py:19-47, 84-89)."""
+def make_adapter_state_dict(kind: str, D: int, seed: int = 4, out_gain: float = 1.0) -> "OrderedDict[str, torch.Tensor]":
+    """fp16 adapter parameters with the reference's state-dict keys (model.py:19-47, 84-89).
+
+    out_gain scales the last LayerNorm's affine (fc.3 / bn3). A trained adapter is a small correction on top of
+    its residual branch; out_gain = trained_like_gain(D) makes the random adapter one too (unit-variance LN output
+    would otherwise swamp the L2-normalised features, whose elements are ~D^-0.5), so synthetic queries stay
+    classifiable. The golden fixtures use out_gain = 1 to exercise the arithmetic at full magnitude."""
     gen = torch.Generator().manual_seed(1_000_003 * seed + 29)
 
     def n(*shape, std=1.0):
@@ -111,8 +116,8 @@ def make_adapter_state_dict(kind: str, D: int, seed: int = 4) -> "OrderedDict[st
         sd["fc.1.weight"] = (1.0 + n(H, std=0.05)).half()
         sd["fc.1.bias"] = n(H, std=0.05).half()
         sd["fc.2.weight"] = n(D, H, std=H ** -0.5).half()
-        sd["fc.3.weight"] = (1.0 + n(D, std=0.05)).half()
-        sd["fc.3.bias"] = n(D, std=0.05).half()
+        sd["fc.3.weight"] = (out_gain * (1.0 + n(D, std=0.05))).half()
+        sd["fc.3.bias"] = (out_gain * n(D, std=0.05)).half()
     else:
         import math
         S = int(math.ceil(math.sqrt(D)))
@@ -123,9 +128,14 @@ def make_adapter_state_dict(kind: str, D: int, seed: int = 4) -> "OrderedDict[st
         sd["bn2.weight"] = (1.0 + n(16, S, S, std=0.05)).half()
         sd["bn2.bias"] = n(16, S, S, std=0.05).half()
         sd["conv3.weight"] = n(1, 16, 1, 1, std=0.25).half()
-        sd["bn3.weight"] = (1.0 + n(1, S, S, std=0.05)).half()
-        sd["bn3.bias"] = n(1, S, S, std=0.05).half()
+        sd["bn3.weight"] = (out_gain * (1.0 + n(1, S, S, std=0.05))).half()
+        sd["bn3.bias"] = (out_gain * n(1, S, S, std=0.05)).half()
     return sd
+
+
+def trained_like_gain(D: int) -> float:
+    """Adapter output gain that keeps the random adapter a ~10 % perturbation of a unit-norm feature."""
+    return 0.5 * D ** -0.5
 
 
 def class_bases(num_classes: int, resolution: int, seed: int = 1, device="cpu") -> torch.Tensor:

@@ -189,7 +189,8 @@ def test_query_path_argmax_identical_to_oracle(nat, arch, adapter):
     c = synthetic.arch_config(arch)
     N, K, Q, D = 16, 4, 64, c["embed_dim"]
     sd = synthetic.make_state_dict(arch, 0)
-    asd = synthetic.make_adapter_state_dict(adapter, D, seed=4)
+    gain = synthetic.trained_like_gain(D) * (0.3 if adapter == "conv-3x" else 1.0)
+    asd = synthetic.make_adapter_state_dict(adapter, D, seed=4, out_gain=gain)
     bases = synthetic.class_bases(N, c["image_resolution"], seed=1)
     support = synthetic.class_structured_images(bases, torch.arange(N).repeat_interleave(K), seed=2)
     labels = torch.arange(Q) % N
@@ -220,11 +221,8 @@ def test_query_path_argmax_identical_to_oracle(nat, arch, adapter):
     print(f"{arch}/{adapter}: oracle accuracy {(pred_o == labels).float().mean():.3f}, min top1-top2 margin {margin:.3e}, "
           f"max |p - p_oracle| {(p.cpu() - p_o).abs().max():.3e}")
     assert (p.cpu() - p_o).abs().max().item() < max(2e-2, 0.0)
-    mism = (am.cpu() != pred_o).nonzero().flatten().tolist()
-    # any mismatch must be a near-tie of the reference itself (margin below the stated p tolerance)
-    for i in mism:
-        assert (top2[i, 0] - top2[i, 1]).item() < 2e-2, f"query {i}: argmax differs with margin {top2[i, 0] - top2[i, 1]}"
-    assert len(mism) == 0 or margin < 2e-2
+    assert (pred_o == labels).float().mean().item() > 0.9, "synthetic workload must be classifiable"
+    assert torch.equal(am.cpu(), pred_o), "top-1 predictions must be identical to the reference algorithm"
 
 
 # ----------------------------------------------------------------------------- properties at full size
