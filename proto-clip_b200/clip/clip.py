@@ -1,0 +1,92 @@
+"""Drop-in for the reference's clip/clip.py: ``available_models``, ``load``, ``tokenize`` (clip/clip.py:87-230).
+
+Differences, all forced by the environment or the scope:
+  * no download: there is no network, so a model name resolves to ``<download_root or ~/.cache/clip>/<file>.pt``
+    and raises RuntimeError when the file is absent (the reference would fetch it, clip/clip.py:41-70);
+  * ``name`` may also be ``synthetic:<arch>[:seed]`` (random-init weights from proto_clip_b200.synthetic), or a
+    path to a torch.save'd state dict / TorchScript archive exactly like the reference (clip/clip.py:119-133);
+  * the returned model runs only on a CUDA sm_100 device (no `model.float()` CPU branch, clip/clip.py:137-138).
+"""
+from __future__ import annotations
+
+import os
+import warnings
+from typing import List, Union
+
+import torch
+
+from .bpe_tokenizer import BPETokenizer
+from .model import build_model
+
+_MODEL_FILES = {
+    "RN50": "RN50.pt", "RN101": "RN101.pt", "RN50x4": "RN50x4.pt", "RN50x16": "RN50x16.pt",
+    "ViT-B/32": "ViT-B-32.pt", "ViT-B/16": "ViT-B-16.pt", "ViT-L/14": "ViT-L-14.pt",
+}
+_tokenizer = None
+
+
+def available_models() -> List[str]:
+    """Names accepted by ``load`` (clip/clip.py:87-89)."""
+    return list(_MODEL_FILES.keys())
+
+
+def _transform(n_px: int):
+    """Host-side preprocessing, clip/clip.py:77-84: bicubic resize, centre crop, RGB, tensor, CLIP mean/std."""
+    from torchvision.transforms import CenterCrop, Compose, InterpolationMode, Normalize, Resize, ToTensor
+    return Compose([
+        Resize(n_px, interpolation=InterpolationMode.BICUBIC),
+        CenterCrop(n_px),
+        lambda image: image.convert("RGB"),
+        ToTensor(),
+        Normalize((0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)),
+    ])
+
+
+def _read_state_dict(path: str):
+    try:
+        return torch.jit.load(path, map_location="cpu").eval().state_dict()
+    except RuntimeError:
+        sd = torch.load(path, map_location="cpu", weights_only=False)
+        return sd.state_dict() if hasattr(sd, "state_dict") else sd
+
+
+def load(name: str, device: Union[str, torch.device] = "cuda", jit: bool = False, download_root: str = None):
+    """Returns (model, preprocess) like clip/clip.py:92-139."""
+    if jit:
+        warnings.warn("jit=True is ignored: the encoders run on libprotoclip_b200, not TorchScript")
+    if name.startswith("synthetic:"):
+        from .. import synthetic
+        parts = name.split(":")
+        state_dict = synthetic.make_state_dict(parts[1], int(parts[2]) if len(parts) > 2 else 0)
+    elif name in _MODEL_FILES:
+        path = os.path.join(download_root or os.path.expanduser("~/.cache/clip"), _MODEL_FILES[name])
+        if not os.path.isfile(path):
+            raise RuntimeError(f"Model {name}: checkpoint {path} not found and this build cannot download it; "
+                               f"place the OpenAI checkpoint there or pass a state-dict path")
+        state_dict = _read_state_dict(path)
+    elif os.path.isfile(name):
+        state_dict = _read_state_dict(name)
+    else:
+        raise RuntimeError(f"Model {name} not found; available models = {available_models()}")
+    model = build_model(state_dict).to(device)
+    return model, _transform(model.visual.input_resolution)
+
+
+def tokenize(texts: Union[str, List[str]], context_length: int = 77, truncate: bool = False) -> torch.LongTensor:
+    """clip/clip.py:194-230: [SOT] + BPE(text) + [EOT], zero-padded to context_length."""
+    global _tokenizer
+    if _tokenizer is None:
+        _tokenizer = BPETokenizer()
+    if isinstance(texts, str):
+        texts = [texts]
+    sot, eot = _tokenizer.encoder["<|startoftext|>"], _tokenizer.encoder["<|endoftext|>"]
+    result = torch.zeros(len(texts), context_length, dtype=torch.long)
+    for i, text in enumerate(texts):
+        ids = [sot] + _tokenizer.encode(text) + [eot]
+        if len(ids) > context_length:
+            if not truncate:
+                raise RuntimeError(f"Input {text} is too long for context length {context_length}")
+            ids = ids[:context_length]
+            ids[-1] = eot
+        result[i, : len(ids)] = torch.tensor(ids)
+    return result

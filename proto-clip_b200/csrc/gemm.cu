@@ -10,9 +10,9 @@
 // Shape of the kernel (persistent, warp-specialised, one CTA per SM):
 //   warp 0      TMA producer  : one lane issues cp.async.bulk.tensor for the A (128x64) and W (BNx64) tiles
 //   warp 1      MMA issuer    : one lane issues 4 x tcgen05.mma (M=128, N=BN, K=16) per k-block; owns TMEM
-//   warps 2..5  epilogue      : tcgen05.ld the 128xBN fp32 accumulator (one TMEM lane quarter per warp),
+//   warps 2..9  epilogue      : tcgen05.ld the 128xBN fp32 accumulator (two warps per TMEM lane quarter),
 //                               add bias / QuickGELU / residual in the reference's rounding order, transpose
-//                               through a padded smem staging tile and write 128-byte coalesced rows.
+//                               through an XOR-swizzled smem staging tile and write 128-byte coalesced rows.
 // Two accumulator stages (2 x BN TMEM columns) let the epilogue of tile i overlap the main loop of tile i+1.
 // Tiles are walked n-fastest so the CTAs of one wave share the same A row-blocks in L2.
 #include "kernels.cuh"
@@ -25,8 +25,9 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 fp16 = 128 B = one swizzle row
 constexpr int STAGES = 4;
-constexpr int GEMM_THREADS = 192;
-constexpr int STG_ROW = 144;  // 128 B payload + 16 B pad: conflict-free for both staging passes
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
+constexpr int STG_WARP_BYTES = 32 * 128;  // 32 rows x 128 B, 16-byte chunks XOR-swizzled by (row & 7): conflict-free
 
 template <int BN>
 struct SmemLayout {
@@ -34,7 +35,7 @@ struct SmemLayout {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int OFF_STAGING = STAGES * STAGE_BYTES;
-  static constexpr int STAGING_BYTES = 4 * 32 * STG_ROW;
+  static constexpr int STAGING_BYTES = EPI_WARPS * STG_WARP_BYTES;
   static constexpr int OFF_BIAS = OFF_STAGING + STAGING_BYTES;
   static constexpr int OFF_BARS = OFF_BIAS + BN * 4;
   static constexpr int TOTAL = OFF_BARS + 128 + 1024;  // + barrier block + 1024 B alignment slack
@@ -48,13 +49,19 @@ struct Bars {
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ __half quick_gelu_f16(__half h) {
-  // x * sigmoid(1.702 * x) with an fp16 rounding after every op, as eager fp16 PyTorch does
-  // (clip/model.py:164-166).
-  const float x = __half2float(h);
-  const float t = __half2float(__float2half_rn(1.702f * x));
-  const float s = __half2float(__float2half_rn(__fdividef(1.0f, 1.0f + __expf(-t))));
-  return __float2half_rn(x * s);
+// QuickGELU x * sigmoid(1.702 x) (clip/model.py:164-166) on a packed half2, with
+// sigmoid(t) = 0.5 * tanh(t / 2) + 0.5 so one MUFU.TANH serves two elements. fp16 math throughout, as the
+// reference's eager fp16 ops; tanh.approx.f16x2 is accurate to ~2^-11, i.e. about one fp16 ulp of the result.
+__device__ __forceinline__ uint32_t quick_gelu_f16x2(uint32_t xb) {
+  const __half2 x = *reinterpret_cast<const __half2*>(&xb);
+  const __half2 t = __hmul2(x, __float2half2_rn(0.851f));
+  const uint32_t tb = *reinterpret_cast<const uint32_t*>(&t);
+  uint32_t thb;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(thb) : "r"(tb));
+  const __half2 th = *reinterpret_cast<const __half2*>(&thb);
+  const __half2 half = __float2half2_rn(0.5f);
+  const __half2 y = __hmul2(x, __hfma2(th, half, half));
+  return *reinterpret_cast<const uint32_t*>(&y);
 }
 
 template <int BN, int EPI>
@@ -87,7 +94,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&bars->tmem_full[i], 1);
-        mbar_init(&bars->tmem_empty[i], 4);  // one arrival per epilogue warp
+        mbar_init(&bars->tmem_empty[i], EPI_WARPS);  // one arrival per epilogue warp
       }
       fence_mbar_init();
     }
@@ -159,28 +166,53 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    // ------------------------------------------------------------ epilogue (warps 2..9)
+    // Two warps per TMEM lane quarter (a warp may only read lanes 32*(warp%4)..+31); the pair splits the
+    // tile's columns in halves, so every SM sub-partition always has two epilogue warps to interleave.
+    const int q = warp & 3;
+    const int chalf = (warp - 2) >> 2;
     const int ep_tid = threadIdx.x - 64;
-    uint8_t* stg = smem + L::OFF_STAGING + (warp - 2) * 32 * STG_ROW;
+    uint8_t* stg = smem + L::OFF_STAGING + (warp - 2) * STG_WARP_BYTES;
     constexpr int GRP_COLS = (EPI == EPI_F32) ? 32 : 64;  // columns per 128-byte staging row
+    constexpr int GRPS_PER_HALF = BN / GRP_COLS / 2;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / n_blks) * BM;
       const int n0 = (tile % n_blks) * BN;
-      named_bar_sync(1, 128);  // previous tile's bias fully consumed
-      for (int i = ep_tid; i < BN; i += 128) {
+      named_bar_sync(1, EPI_WARPS * 32);  // previous tile's bias fully consumed
+      for (int i = ep_tid; i < BN; i += EPI_WARPS * 32) {
         const int c = n0 + i;
         sbias[i] = (g.bias != nullptr && c < g.N) ? __half2float(g.bias[c]) : 0.0f;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, EPI_WARPS * 32);
+      const int n_grps = (min(g.N - n0, BN) + GRP_COLS - 1) / GRP_COLS;  // groups with at least one valid column
+      const int g_begin = chalf * GRPS_PER_HALF;
+      const int g_end = min(g_begin + GRPS_PER_HALF, n_grps);
       mbar_wait(&bars->tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-      int n_grps = (min(g.N - n0, BN) + GRP_COLS - 1) / GRP_COLS;
-      for (int grp = 0; grp < n_grps; ++grp) {
-        // pass 1: TMEM -> registers -> (bias, activation, round) -> staging row `lane`
+      if (g_begin >= g_end) {  // ragged N: nothing to read for this warp, still release the accumulator
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);
+      }
+      for (int grp = g_begin; grp < g_end; ++grp) {
+        // residual rows for pass 2 are requested first so their latency hides behind pass 1
+        // (C may alias the residual: every 16-byte chunk is read and written by the same thread).
+        uint4 rs[8];
+        if (EPI == EPI_BIAS_RES) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int idx = it * 32 + lane;
+            const int grow = m0 + q * 32 + (idx >> 3);
+            const int gcol = n0 + grp * 64 + (idx & 7) * 8;
+            rs[it] = make_uint4(0, 0, 0, 0);
+            if (grow < g.M && gcol < g.N)
+              rs[it] = *reinterpret_cast<const uint4*>(g.residual + static_cast<size_t>(grow) * g.ldr + gcol);
+          }
+        }
+        // pass 1: TMEM -> registers -> (bias, activation, round) -> swizzled staging row `lane`
         if (EPI == EPI_F32) {
           uint32_t v[32];
           tmem_ld_32x32(t_row + grp * 32, v);
@@ -194,7 +226,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             o.y = __uint_as_float(v[4 * j + 1]) + b.y;
             o.z = __uint_as_float(v[4 * j + 2]) + b.z;
             o.w = __uint_as_float(v[4 * j + 3]) + b.w;
-            *reinterpret_cast<float4*>(stg + lane * STG_ROW + j * 16) = o;
+            *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
           }
         } else {
 #pragma unroll
@@ -209,41 +241,35 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
                 const float4 b = b4[2 * j + e];
-                __half h0 = __float2half_rn(__uint_as_float(v[8 * j + 4 * e + 0]) + b.x);
-                __half h1 = __float2half_rn(__uint_as_float(v[8 * j + 4 * e + 1]) + b.y);
-                __half h2 = __float2half_rn(__uint_as_float(v[8 * j + 4 * e + 2]) + b.z);
-                __half h3 = __float2half_rn(__uint_as_float(v[8 * j + 4 * e + 3]) + b.w);
+                pk[2 * e + 0] = pack_half2(__uint_as_float(v[8 * j + 4 * e + 0]) + b.x,
+                                           __uint_as_float(v[8 * j + 4 * e + 1]) + b.y);
+                pk[2 * e + 1] = pack_half2(__uint_as_float(v[8 * j + 4 * e + 2]) + b.z,
+                                           __uint_as_float(v[8 * j + 4 * e + 3]) + b.w);
                 if (EPI == EPI_BIAS_QGELU) {
-                  h0 = quick_gelu_f16(h0);
-                  h1 = quick_gelu_f16(h1);
-                  h2 = quick_gelu_f16(h2);
-                  h3 = quick_gelu_f16(h3);
+                  pk[2 * e + 0] = quick_gelu_f16x2(pk[2 * e + 0]);
+                  pk[2 * e + 1] = quick_gelu_f16x2(pk[2 * e + 1]);
                 }
-                __half2 p0 = __halves2half2(h0, h1);
-                __half2 p1 = __halves2half2(h2, h3);
-                pk[2 * e + 0] = *reinterpret_cast<uint32_t*>(&p0);
-                pk[2 * e + 1] = *reinterpret_cast<uint32_t*>(&p1);
               }
-              *reinterpret_cast<uint4*>(stg + lane * STG_ROW + h * 64 + j * 16) =
+              *reinterpret_cast<uint4*>(stg + lane * 128 + (((h * 4 + j) ^ (lane & 7)) << 4)) =
                   make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
           }
         }
-        if (grp == n_grps - 1) {
-          // last TMEM read of this accumulator stage: hand it back to the MMA warp
+        if (grp == g_end - 1) {
+          // last TMEM read of this accumulator stage by this warp: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);
         }
         __syncwarp();
-        // pass 2: staging -> global, 8 lanes per 128-byte row
+        // pass 2: staging -> global, 8 lanes per 128-byte row (full-line coalesced stores)
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int idx = it * 32 + lane;
           const int r = idx >> 3;
           const int ch = idx & 7;
           const int grow = m0 + q * 32 + r;
-          uint4 val = *reinterpret_cast<const uint4*>(stg + r * STG_ROW + ch * 16);
+          uint4 val = *reinterpret_cast<const uint4*>(stg + r * 128 + ((ch ^ (r & 7)) << 4));
           if (EPI == EPI_F32) {
             const int gcol = n0 + grp * 32 + ch * 4;
             if (grow < g.M && gcol < g.N) {
@@ -254,10 +280,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int gcol = n0 + grp * 64 + ch * 8;
             if (grow < g.M && gcol < g.N) {
               if (EPI == EPI_BIAS_RES) {
-                const uint4 rs =
-                    *reinterpret_cast<const uint4*>(g.residual + static_cast<size_t>(grow) * g.ldr + gcol);
                 const __half2* a2 = reinterpret_cast<const __half2*>(&val);
-                const __half2* r2 = reinterpret_cast<const __half2*>(&rs);
+                const __half2* r2 = reinterpret_cast<const __half2*>(&rs[it]);
                 uint4 o;
                 __half2* o2 = reinterpret_cast<__half2*>(&o);
 #pragma unroll

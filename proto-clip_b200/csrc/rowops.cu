@@ -16,15 +16,17 @@ namespace {
 constexpr int ROW_WARPS = 8;   // warps (rows) per CTA
 constexpr int MAX_VEC = 8;     // 16-byte vectors per lane: d <= 32 * 8 * 8 = 2048
 
-struct RowF {  // one row slice held by a lane: up to MAX_VEC * 8 floats
-  float v[MAX_VEC][8];
+template <int NV>
+struct RowF {  // one row slice held by a lane: NV 16-byte vectors = NV * 8 floats (NV = ceil(d / 256))
+  float v[NV][8];
 };
 
-__device__ __forceinline__ void load_row_f16(const __half* row, int d, int lane, RowF& r, int& nvec) {
+template <int NV>
+__device__ __forceinline__ void load_row_f16(const __half* row, int d, int lane, RowF<NV>& r, int& nvec) {
   const int vecs = d >> 3;
   nvec = 0;
 #pragma unroll
-  for (int k = 0; k < MAX_VEC; ++k) {
+  for (int k = 0; k < NV; ++k) {
     const int vi = lane + k * 32;
     if (vi < vecs) {
       const uint4 u = *reinterpret_cast<const uint4*>(row + vi * 8);
@@ -41,20 +43,20 @@ __device__ __forceinline__ void load_row_f16(const __half* row, int d, int lane,
 }
 
 // Normalise the row held in `r` (fp32 two-pass mean / biased variance, eps 1e-5) and store fp16.
-template <typename ParamT>
-__device__ __forceinline__ void ln_store(RowF& r, int d, int lane, const ParamT* gamma, const ParamT* beta,
+template <int NV>
+__device__ __forceinline__ void ln_store(RowF<NV>& r, int d, int lane, const float* gamma, const float* beta,
                                          __half* out) {
   const int vecs = d >> 3;
   float s = 0.0f;
 #pragma unroll
-  for (int k = 0; k < MAX_VEC; ++k)
+  for (int k = 0; k < NV; ++k)
     if (lane + k * 32 < vecs)
 #pragma unroll
       for (int e = 0; e < 8; ++e) s += r.v[k][e];
   const float mean = warp_sum(s) / static_cast<float>(d);
   float q = 0.0f;
 #pragma unroll
-  for (int k = 0; k < MAX_VEC; ++k)
+  for (int k = 0; k < NV; ++k)
     if (lane + k * 32 < vecs)
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -63,23 +65,25 @@ __device__ __forceinline__ void ln_store(RowF& r, int d, int lane, const ParamT*
       }
   const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(d) + 1e-5f);
 #pragma unroll
-  for (int k = 0; k < MAX_VEC; ++k) {
+  for (int k = 0; k < NV; ++k) {
     const int vi = lane + k * 32;
     if (vi < vecs) {
       uint32_t pk[4];
+      float gm[8], bt[8];
+      *reinterpret_cast<float4*>(gm) = *reinterpret_cast<const float4*>(gamma + vi * 8);
+      *reinterpret_cast<float4*>(gm + 4) = *reinterpret_cast<const float4*>(gamma + vi * 8 + 4);
+      *reinterpret_cast<float4*>(bt) = *reinterpret_cast<const float4*>(beta + vi * 8);
+      *reinterpret_cast<float4*>(bt + 4) = *reinterpret_cast<const float4*>(beta + vi * 8 + 4);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int c = vi * 8 + 2 * e;
-        const float g0 = static_cast<float>(gamma[c]), g1 = static_cast<float>(gamma[c + 1]);
-        const float b0 = static_cast<float>(beta[c]), b1 = static_cast<float>(beta[c + 1]);
-        pk[e] = pack_half2((r.v[k][2 * e] - mean) * rstd * g0 + b0,
-                           (r.v[k][2 * e + 1] - mean) * rstd * g1 + b1);
-      }
+      for (int e = 0; e < 4; ++e)
+        pk[e] = pack_half2((r.v[k][2 * e] - mean) * rstd * gm[2 * e] + bt[2 * e],
+                           (r.v[k][2 * e + 1] - mean) * rstd * gm[2 * e + 1] + bt[2 * e + 1]);
       *reinterpret_cast<uint4*>(out + vi * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }
 }
 
+template <int NV>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ gamma,
                  const float* __restrict__ beta, const int* __restrict__ rows_idx, int rows, int d,
@@ -88,7 +92,7 @@ layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y, const flo
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const size_t src = rows_idx ? static_cast<size_t>(rows_idx[row]) : static_cast<size_t>(row) * row_stride_rows;
-  RowF r;
+  RowF<NV> r;
   int nvec;
   load_row_f16(x + src * d, d, lane, r, nvec);
   ln_store(r, d, lane, gamma, beta, y + static_cast<size_t>(row) * d);
@@ -126,6 +130,7 @@ patchify_kernel(const void* __restrict__ images, int img_is_f16, __half* __restr
   }
 }
 
+template <int NV>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 embed_ln_pre_kernel(const __half* __restrict__ patch, const float* __restrict__ cls,
                     const float* __restrict__ pos, const float* __restrict__ gamma,
@@ -135,9 +140,9 @@ embed_ln_pre_kernel(const __half* __restrict__ patch, const float* __restrict__ 
   const int lane = threadIdx.x & 31;
   const int b = row / L, t = row % L;
   const int vecs = d >> 3;
-  RowF r;
+  RowF<NV> r;
 #pragma unroll
-  for (int k = 0; k < MAX_VEC; ++k) {
+  for (int k = 0; k < NV; ++k) {
     const int vi = lane + k * 32;
     if (vi < vecs) {
 #pragma unroll
@@ -187,25 +192,26 @@ __global__ void eot_index_kernel(const int64_t* __restrict__ tokens, int* __rest
   rows[p] = p * L + arg;
 }
 
+template <int NV>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 l2norm_kernel(const __half* __restrict__ x, __half* __restrict__ y, int rows, int d) {
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  RowF r;
+  RowF<NV> r;
   int nvec;
   load_row_f16(x + static_cast<size_t>(row) * d, d, lane, r, nvec);
   const int vecs = d >> 3;
   float s = 0.0f;
 #pragma unroll
-  for (int k = 0; k < MAX_VEC; ++k)
+  for (int k = 0; k < NV; ++k)
     if (lane + k * 32 < vecs)
 #pragma unroll
       for (int e = 0; e < 8; ++e) s += r.v[k][e] * r.v[k][e];
   // x.norm(dim=-1) on an fp16 tensor: fp32 accumulation, fp16 result; then an fp16 division.
   const float n = __half2float(__float2half_rn(sqrtf(warp_sum(s))));
 #pragma unroll
-  for (int k = 0; k < MAX_VEC; ++k) {
+  for (int k = 0; k < NV; ++k) {
     const int vi = lane + k * 32;
     if (vi < vecs) {
       uint32_t pk[4];
@@ -216,6 +222,17 @@ l2norm_kernel(const __half* __restrict__ x, __half* __restrict__ y, int rows, in
     }
   }
 }
+
+// NV = ceil(d / 256): instantiate 1, 2, 3, 4 and 8 so the common widths (<= 1024) keep registers low.
+#define PC_DISPATCH_NV(d, CALL)              \
+  do {                                       \
+    const int _nv = ((d) + 255) / 256;       \
+    if (_nv <= 1) { CALL(1); }               \
+    else if (_nv == 2) { CALL(2); }          \
+    else if (_nv == 3) { CALL(3); }          \
+    else if (_nv == 4) { CALL(4); }          \
+    else { CALL(8); }                        \
+  } while (0)
 
 int check_row_dims(const char* what, int rows, int d) {
   PC_REQUIRE(rows > 0 && d > 0, PC_ERR_ARG, "%s: empty input (%d x %d)", what, rows, d);
@@ -235,8 +252,10 @@ int grid_1d(size_t work, int block) {
 int launch_layernorm(const __half* x, __half* y, const float* gamma, const float* beta, int rows, int d,
                      int row_stride_rows, cudaStream_t stream) {
   PC_TRY(check_row_dims("layernorm", rows, d));
-  layernorm_kernel<<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, stream>>>(
-      x, y, gamma, beta, nullptr, rows, d, row_stride_rows);
+#define CALL(NV) layernorm_kernel<NV><<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, stream>>>( \
+      x, y, gamma, beta, nullptr, rows, d, row_stride_rows)
+  PC_DISPATCH_NV(d, CALL);
+#undef CALL
   PC_CHECK_CUDA(cudaGetLastError());
   return PC_OK;
 }
@@ -244,8 +263,10 @@ int launch_layernorm(const __half* x, __half* y, const float* gamma, const float
 int launch_layernorm_gather(const __half* x, const int* rows_idx, __half* y, const float* gamma,
                             const float* beta, int n, int d, cudaStream_t stream) {
   PC_TRY(check_row_dims("layernorm_gather", n, d));
-  layernorm_kernel<<<(n + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, stream>>>(x, y, gamma, beta, rows_idx,
-                                                                                  n, d, 1);
+#define CALL(NV) layernorm_kernel<NV><<<(n + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, stream>>>( \
+      x, y, gamma, beta, rows_idx, n, d, 1)
+  PC_DISPATCH_NV(d, CALL);
+#undef CALL
   PC_CHECK_CUDA(cudaGetLastError());
   return PC_OK;
 }
@@ -266,8 +287,10 @@ int launch_patchify(const void* images, int img_is_f16, __half* out, int B, int 
 int launch_embed_ln_pre(const __half* patch, const float* cls, const float* pos, const float* gamma,
                         const float* beta, __half* x, int B, int L, int d, cudaStream_t stream) {
   PC_TRY(check_row_dims("embed_ln_pre", B * L, d));
-  embed_ln_pre_kernel<<<(B * L + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, stream>>>(patch, cls, pos, gamma,
-                                                                                        beta, x, B, L, d);
+#define CALL(NV) embed_ln_pre_kernel<NV><<<(B * L + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, stream>>>( \
+      patch, cls, pos, gamma, beta, x, B, L, d)
+  PC_DISPATCH_NV(d, CALL);
+#undef CALL
   PC_CHECK_CUDA(cudaGetLastError());
   return PC_OK;
 }
@@ -290,7 +313,9 @@ int launch_eot_index(const int64_t* tokens, int* rows, int P, int L, cudaStream_
 
 int launch_l2norm(const __half* x, __half* y, int rows, int d, cudaStream_t stream) {
   PC_TRY(check_row_dims("l2norm", rows, d));
-  l2norm_kernel<<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, stream>>>(x, y, rows, d);
+#define CALL(NV) l2norm_kernel<NV><<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, stream>>>(x, y, rows, d)
+  PC_DISPATCH_NV(d, CALL);
+#undef CALL
   PC_CHECK_CUDA(cudaGetLastError());
   return PC_OK;
 }
