@@ -132,9 +132,12 @@ def run_ours(args):
             imgs = synthetic.class_structured_images(bases, labels, seed=2 + n0)
             feats.append(ctx.encode_image(imgs, l2norm=True, micro_batch=mb))   # utils.py:310,319 (augment_epoch 1)
         V = torch.cat(feats)
+        # one-off text tower pass over N x 7 prompts (utils.py:256-273), timed for the record only: a random-init
+        # text tower is not class-aligned, so the classifier's textual memory is the aligned synthetic bank below
         tokens = synthetic_tokens(N_CLASSES * N_TEMPLATES, c["context_length"], c["vocab_size"], 5).to(dev)
         te = ctx.encode_text(tokens, l2norm=True).view(N_CLASSES, N_TEMPLATES, D)  # utils.py:266-267
-        T = nat.l2_normalize(te.float().mean(dim=1).half())                      # utils.py:268-269
+        _ = nat.l2_normalize(te.float().mean(dim=1).half())                       # utils.py:268-269
+        T = synthetic.aligned_text_memory(V, N_CLASSES, K_SHOTS, seed=6)
         adapter = synthetic.make_adapter_state_dict("fc", D, seed=4, out_gain=synthetic.trained_like_gain(D))
         head0 = pipeline.build_head_state(V, T, N_CLASSES, K_SHOTS, "fc", adapter, ALPHA, BETA)
         flat = head0.pack()

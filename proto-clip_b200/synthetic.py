@@ -149,3 +149,16 @@ def class_structured_images(bases: torch.Tensor, labels: torch.Tensor, seed: int
     gen = torch.Generator(device=bases.device).manual_seed(1_000_003 * seed + 43)
     eps = torch.randn((labels.numel(),) + tuple(bases.shape[1:]), generator=gen, device=bases.device)
     return bases[labels.to(bases.device)] + noise * eps
+
+
+def aligned_text_memory(V: torch.Tensor, num_classes: int, shots: int, seed: int = 6, rel_noise: float = 0.02) -> torch.Tensor:
+    """Synthetic textual memory bank [N, D] (fp16) that is ALIGNED with the visual memory, as a trained
+    Proto-CLIP-F textual memory is (main.py:352-369 saves it as a learned embedding): the per-class mean of the
+    visual memory V [N*K, D] plus a small perturbation of norm rel_noise. A random-init text tower cannot
+    produce class-aligned features, so its output is exercised by the tower tests, not by the classifier."""
+    D = V.shape[-1]
+    gen = torch.Generator(device=V.device).manual_seed(1_000_003 * seed + 47)
+    mean = V.float().view(num_classes, shots, D).mean(dim=1)
+    mean = mean / mean.norm(dim=-1, keepdim=True)
+    noise = torch.randn(num_classes, D, generator=gen, device=V.device) * (rel_noise * D ** -0.5)
+    return (mean + noise).half()

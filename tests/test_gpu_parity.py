@@ -195,24 +195,19 @@ def test_query_path_argmax_identical_to_oracle(nat, arch, adapter):
     support = synthetic.class_structured_images(bases, torch.arange(N).repeat_interleave(K), seed=2)
     labels = torch.arange(Q) % N
     queries = synthetic.class_structured_images(bases, labels, seed=3)
-    tokens = torch.zeros(N, c["context_length"], dtype=torch.int64)
-    gen = torch.Generator().manual_seed(6)
-    tokens[:, 0] = c["vocab_size"] - 2
-    tokens[:, 1:5] = torch.randint(1, c["vocab_size"] - 2, (N, 4), generator=gen)
-    tokens[:, 5] = c["vocab_size"] - 1
-    # oracle (fp32 = the reference's CPU semantics)
+    # oracle (fp32 = the reference's CPU semantics); textual memory aligned with the visual one (see synthetic.py)
     Vo = O.l2_normalize(O.encode_image(sd, support, "fp32"))
-    zi_o, zt_o = O.build_prototypes(Vo, N, K, True), O.text_prototypes(O.encode_text(sd, tokens, "fp32"))
+    T = synthetic.aligned_text_memory(Vo, N, K, seed=6)
+    zi_o, zt_o = O.build_prototypes(Vo, N, K, True), O.text_prototypes(T)
     p_o, pred_o, _ = O.classify_queries(sd, asd, adapter, queries, zi_o, zt_o, 0.5, 12.0, "fp32")
     top2 = p_o.topk(2, dim=1).values
     margin = (top2[:, 0] - top2[:, 1]).min().item()
     # CUDA path
     ctx = nat.Context(torch.device(DEV))
     ctx.bind_visual(sd)
-    ctx.bind_text(sd)
     V = ctx.encode_image(support.to(DEV), l2norm=True)
     zi, zi_n2 = nat.build_prototypes(V, N, K, True)
-    zt, zt_n2 = nat.build_prototypes(ctx.encode_text(tokens.to(DEV)), N, 1, False)
+    zt, zt_n2 = nat.build_prototypes(T.to(DEV), N, 1, False)
     f = ctx.encode_image(queries.to(DEV), l2norm=True)
     A = cuda_sd(asd)
     q = nat.adapter_fc_forward(A, f) if adapter == "fc" else nat.adapter_conv_forward(A, adapter, f)

@@ -1,0 +1,183 @@
+"""Host-side logic that needs no GPU: CLI / config overlay, adapter alias dispatch, state-dict surface,
+tokenizer, synthetic generators, head-state packing, sharding and the gloo world_size-2 path."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+import yaml
+
+from conftest import ROOT
+from oracle import reference_shims
+from proto_clip_b200 import dist as pdist
+from proto_clip_b200 import pipeline, synthetic
+
+PKG = os.path.join(ROOT, "proto-clip_b200")
+
+
+def load_main():
+    import importlib
+    return importlib.import_module("proto_clip_b200.main")
+
+
+def test_cli_overlay_and_quirks():
+    main = load_main()
+    cfg = yaml.load(open(os.path.join(PKG, "configs", "imagenet.yml")), Loader=yaml.Loader)
+    assert cfg["alpha"] == 0.5 and cfg["beta"] == 12 and cfg["adapter"] == "conv-2x" and cfg["shots"] == 16
+    a = main.get_arguments(["--config", "x.yml", "--dataset", "imagenet", "--alpha", "0", "--beta", "3.5",
+                            "--adapter", "fc", "--backbone", "ViT-B/16", "--only_test", "--shots", "4"])
+    cfg = main.populate_cfg_using_args(cfg, a)
+    assert cfg["alpha"] == 0.5          # reference quirk: `if args.alpha:` ignores 0 (main.py:56)
+    assert cfg["beta"] == 3.5 and cfg["adapter"] == "fc" and cfg["backbone"] == "ViT-B/16" and cfg["shots"] == 4
+    assert cfg["only_test"] is True     # honoured here (superset of the reference)
+    with pytest.raises(SystemExit):
+        main.get_arguments([])          # --config is required
+
+
+def test_every_reference_config_exists_with_same_keys():
+    names = ["caltech101", "dtd", "eurosat", "fewsol", "fewsol_198", "fgvc", "food101", "imagenet", "master",
+             "oxford_flowers", "oxford_pets", "stanford_cars", "sun397", "ucf101"]
+    for n in names:
+        cfg = yaml.load(open(os.path.join(PKG, "configs", f"{n}.yml")), Loader=yaml.Loader)
+        assert {"root_path", "shots", "backbone", "lr", "augment_epoch", "train_epoch", "losses"} <= set(cfg)
+        if n != "master":
+            assert {"alpha", "beta", "adapter", "dataset", "only_test", "train_vis_mem_only"} <= set(cfg)
+        if reference_shims.available():
+            ref = yaml.load(open(os.path.join(reference_shims.REFERENCE_ROOT, "configs", f"{n}.yml")), Loader=yaml.Loader)
+            assert ref == cfg, f"configs/{n}.yml differs from the reference"
+
+
+def test_alpha_beta_grid_is_11_by_29():
+    main = load_main()
+    a, b = main.alpha_beta_lists()
+    assert len(a) == 11 and len(b) == 29 and a[0] == 0 and a[-1] == 1.0 and abs(b[0] - 0.1) < 1e-9 and b[-1] == 20
+
+
+def test_adapter_state_dict_keys_match_shipped_checkpoints():
+    from proto_clip_b200.model import Adapter, Adapter_FC
+    conv = Adapter(1024, "conv-2x", dtype=torch.half)
+    fc = Adapter_FC(768, dtype=torch.half)
+    assert list(conv.state_dict()) == ["conv1.weight", "bn1.weight", "bn1.bias", "conv2.weight", "bn2.weight",
+                                       "bn2.bias", "conv3.weight", "bn3.weight", "bn3.bias"]
+    assert list(fc.state_dict()) == ["fc.0.weight", "fc.1.weight", "fc.1.bias", "fc.2.weight", "fc.3.weight",
+                                     "fc.3.bias"]
+    assert conv.bn1.weight.shape == (16, 32, 32) and Adapter(512, "conv-3x").bn3.weight.shape == (1, 23, 23)
+    if reference_shims.available():
+        d = os.path.join(reference_shims.REFERENCE_ROOT, "pretrained_ckpt")
+        conv.load_state_dict(torch.load(os.path.join(d, "imagenet-F", "query_adapter.pt"), map_location="cpu", weights_only=False))
+        fc.load_state_dict(torch.load(os.path.join(d, "fewsol-198-F", "query_adapter.pt"), map_location="cpu", weights_only=False))
+    main = load_main()
+    with pytest.raises(NameError):
+        main.make_adapter({"adapter": "mlp"}, 512)
+
+
+def test_clip_surface_on_cpu():
+    from proto_clip_b200 import _native as nat
+    from proto_clip_b200 import clip
+    assert clip.available_models() == ["RN50", "RN101", "RN50x4", "RN50x16", "ViT-B/32", "ViT-B/16", "ViT-L/14"]
+    with pytest.raises(RuntimeError):
+        clip.load("no-such-model")
+    model, preprocess = clip.load("synthetic:tiny", device="cpu")
+    assert model.dtype == torch.float16 and model.visual.input_resolution == 32
+    sd = model.state_dict()
+    ref = synthetic.make_state_dict("tiny", 0)
+    assert list(sd) == [k for k in ref] and all(torch.equal(sd[k].float(), ref[k].float()) for k in ref)
+    assert sd["visual.conv1.weight"].dtype == torch.float16 and sd["visual.ln_pre.weight"].dtype == torch.float32
+    with pytest.raises(nat.NativeError):  # no CPU execution path
+        model.encode_image(torch.zeros(1, 3, 32, 32))
+    assert callable(preprocess)
+
+
+def test_tokenizer_matches_reference():
+    from proto_clip_b200.clip import bpe_tokenizer, tokenize
+    try:
+        bpe_tokenizer.find_vocab()
+    except RuntimeError:
+        pytest.skip("CLIP BPE vocabulary not available on this box")
+    t = tokenize("a photo of a dog.")
+    assert t.shape == (1, 77) and t[0, :8].tolist() == [49406, 320, 1125, 539, 320, 1929, 269, 49407]
+    with pytest.raises(RuntimeError):
+        tokenize("word " * 100)
+    assert tokenize("word " * 100, truncate=True)[0, -1].item() == 49407
+    if reference_shims.available():
+        ref = reference_shims.reference()
+        texts = ["itap of a great white shark.", "A bad photo of the Tench, Tinca tinca!!", "don't we're 123 hello-world",
+                 "a crème brûlée &amp; naïve café", "  many   spaces\tand\nnewlines ", "a centered satellite photo of Annual Crop Land."]
+        assert torch.equal(tokenize(texts), ref.clip.tokenize(texts))
+
+
+def test_synthetic_is_deterministic_and_typed():
+    a, b = synthetic.make_state_dict("tiny", 0), synthetic.make_state_dict("tiny", 0)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    assert not torch.equal(a["visual.proj"], synthetic.make_state_dict("tiny", 1)["visual.proj"])
+    assert a["visual.transformer.resblocks.0.attn.in_proj_weight"].dtype == torch.float16
+    assert a["visual.transformer.resblocks.0.ln_1.weight"].dtype == torch.float32
+    assert abs(synthetic.vit_flops_per_image("ViT-B/16") / 35.13e9 - 1) < 0.01
+    assert abs(synthetic.vit_flops_per_image("ViT-L/14") / 162.03e9 - 1) < 0.01
+
+
+def test_head_state_pack_roundtrip():
+    N, K, D = 10, 4, 64
+    g = torch.Generator().manual_seed(0)
+    for kind in ("fc", "conv-3x"):
+        head = pipeline.HeadState(torch.randn(N, D, generator=g).half(), torch.randn(N, D, generator=g).half(),
+                                  torch.rand(N, generator=g), torch.rand(N, generator=g), kind,
+                                  synthetic.make_adapter_state_dict(kind, D), 0.5, 12.0)
+        flat = head.pack()
+        assert flat.dtype == torch.float16 and flat.numel() == pipeline.HeadState.packed_numel(N, D, kind)
+        back = pipeline.HeadState.unpack(flat, N, D, kind, 0.5, 12.0)
+        assert torch.equal(back.z_img, head.z_img) and torch.equal(back.zt_n2, head.zt_n2)
+        assert all(torch.equal(back.adapter[k], head.adapter[k]) for k in back.adapter)
+
+
+def test_shard_bounds_cover_queries_in_order():
+    for Q in (0, 1, 7, 1000, 50000):
+        for R in (1, 2, 3, 8):
+            spans = [pdist.shard_bounds(Q, r, R) for r in range(R)]
+            assert spans[0][0] == 0 and spans[-1][1] == Q
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(R - 1))
+            assert all(0 <= hi - lo <= (Q + R - 1) // R for lo, hi in spans)
+
+
+WORKER = r'''
+import os, sys, torch
+sys.path.insert(0, os.environ["REPO"])
+from proto_clip_b200 import dist as pdist, pipeline, synthetic
+rank, local, world = pdist.init("gloo")
+N, K, D, Q = 6, 2, 64, 11
+numel = pipeline.HeadState.packed_numel(N, D, "fc")
+flat = None
+if rank == 0:
+    g = torch.Generator().manual_seed(0)
+    head = pipeline.HeadState(torch.randn(N, D, generator=g).half(), torch.randn(N, D, generator=g).half(),
+                              torch.rand(N, generator=g), torch.rand(N, generator=g), "fc",
+                              synthetic.make_adapter_state_dict("fc", D), 0.5, 12.0)
+    flat = head.pack()
+flat = pdist.broadcast_flat(flat, numel, torch.float16, torch.device("cpu"))      # the single collective
+head = pipeline.HeadState.unpack(flat, N, D, "fc", 0.5, 12.0)
+lo, hi = pdist.shard_bounds(Q, rank, world)
+q = torch.randn(Q, D, generator=torch.Generator().manual_seed(1))
+local_pred = (q[lo:hi] @ head.z_img.float().t()).argmax(1)                        # stand-in for the GPU classify
+allp = pdist.gather_predictions(local_pred, Q)
+t = pdist.max_over_ranks(float(rank + 1), torch.device("cpu"))
+pdist.barrier()
+if rank == 0:
+    ref = (q @ head.z_img.float().t()).argmax(1)
+    assert torch.equal(allp, ref), (allp, ref)
+    assert t == float(world)
+    print("OK", world)
+'''
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_broadcast_shard_gather(world, tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, REPO=ROOT, MASTER_ADDR="127.0.0.1")
+    port = 29600 + world + (os.getpid() % 200)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert f"OK {world}" in r.stdout
