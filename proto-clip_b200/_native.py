@@ -157,8 +157,9 @@ def workspace(device: torch.device, tag: str, nbytes: int) -> torch.Tensor:
 
 # ----------------------------------------------------------------------------- primitive ops
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, epilogue: int = EPI_BIAS,
-           residual: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """F.linear on the tcgen05 GEMM: x [M,K] f16, w [N,K] f16 -> [M,N] f16 (f32 for EPI_F32)."""
+           residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """F.linear on the tcgen05 GEMM: x [M,K] f16, w [N,K] f16 -> [M,N] f16 (f32 for EPI_F32).
+    `out`, if given, must be a contiguous [M, ldo >= N] tensor of the output dtype (ldo a multiple of 8, 4 for f32)."""
     lib = load_library()
     x = require_cuda(x, torch.float16, "x")
     w = require_cuda(w, torch.float16, "w")
@@ -167,7 +168,13 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     out_dtype = torch.float32 if epilogue == EPI_F32 else torch.float16
     pad = 4 if epilogue == EPI_F32 else 8
     ldo = (N + pad - 1) // pad * pad
-    out = torch.empty((M, ldo), dtype=out_dtype, device=x.device)
+    if out is None:
+        out = torch.empty((M, ldo), dtype=out_dtype, device=x.device)
+    else:
+        out = require_cuda(out, out_dtype, "out")
+        if out.shape[0] != M or out.shape[1] < N or out.stride(0) % pad:
+            raise ValueError(f"out must be [M={M}, >= {N}] with a row pitch that is a multiple of {pad}")
+        ldo = out.stride(0)
     if bias is not None:
         bias = require_cuda(bias, torch.float16, "bias")
     if residual is not None:
@@ -176,7 +183,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         check(lib.pc_linear_forward(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), ptr(bias), ptr(residual),
                                     residual.stride(0) if residual is not None else 0, out.data_ptr(), ldo, M, N, K,
                                     epilogue, stream_ptr(x.device)), "pc_linear_forward")
-    return out[:, :N] if ldo != N else out
+    return out[:, :N] if out.shape[1] != N else out
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor) -> torch.Tensor:

@@ -3,6 +3,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <unordered_map>
+
 namespace pc {
 
 static thread_local char g_err[512] = "";
@@ -31,25 +33,67 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows,
-                     uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows) {
+namespace {
+
+struct TmapKey {
+  const void* base;
+  uint64_t inner, rows, stride;
+  uint32_t box_inner, box_rows, elem_bytes;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && inner == o.inner && rows == o.rows && stride == o.stride && box_inner == o.box_inner &&
+           box_rows == o.box_rows && elem_bytes == o.elem_bytes;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = reinterpret_cast<uint64_t>(k.base) * 0x9E3779B97F4A7C15ull;
+    h ^= (k.inner + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= (k.rows + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= (k.stride + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= ((static_cast<uint64_t>(k.box_inner) << 40 | static_cast<uint64_t>(k.box_rows) << 8 | k.elem_bytes) +
+          0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    return static_cast<size_t>(h);
+  }
+};
+
+}  // namespace
+
+// Descriptors are pure functions of (address, geometry): the encoder re-uses the same activation buffers and
+// weights on every call, so a small per-thread cache removes cuTensorMapEncodeTiled from the launch path.
+int make_tmap_2d(CUtensorMap* out, const void* base, uint32_t elem_bytes, uint64_t inner, uint64_t rows,
+                 uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows) {
+  static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  const TmapKey key{base, inner, rows, row_stride_bytes, box_inner, box_rows, elem_bytes};
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return PC_OK;
+  }
   EncodeTiledFn fn = get_encode_fn();
   PC_REQUIRE(fn != nullptr, PC_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  PC_REQUIRE(elem_bytes == 2 || elem_bytes == 4, PC_ERR_ARG, "TMA element size %u unsupported", elem_bytes);
   PC_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, PC_ERR_ALIGN,
              "TMA base %p is not 16-byte aligned", base);
   PC_REQUIRE((row_stride_bytes & 15) == 0, PC_ERR_ALIGN, "TMA row stride %llu is not a multiple of 16",
              (unsigned long long)row_stride_bytes);
-  PC_REQUIRE(box_inner * 2 == 128 && box_rows >= 1 && box_rows <= 256, PC_ERR_ARG,
+  PC_REQUIRE(box_inner * elem_bytes == 128 && box_rows >= 1 && box_rows <= 256, PC_ERR_ARG,
              "TMA box %ux%u unsupported", box_inner, box_rows);
   cuuint64_t dims[2] = {inner, rows};
   cuuint64_t strides[1] = {row_stride_bytes};
   cuuint32_t box[2] = {box_inner, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PC_REQUIRE(r == CUDA_SUCCESS, PC_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, *out);
   return PC_OK;
+}
+
+int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows,
+                     uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows) {
+  return make_tmap_2d(out, base, 2, inner, rows, row_stride_bytes, box_inner, box_rows);
 }
 
 int device_sm_count() {

@@ -45,6 +45,10 @@ const char* get_error();
 int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows,
                      uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows);
 
+// Generic form (elem_bytes 2 = fp16, 4 = fp32; box_inner * elem_bytes must be 128). Results are cached per thread.
+int make_tmap_2d(CUtensorMap* out, const void* base, uint32_t elem_bytes, uint64_t inner, uint64_t rows,
+                 uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows);
+
 int device_sm_count();
 
 }  // namespace pc

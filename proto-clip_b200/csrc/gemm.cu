@@ -1,5 +1,5 @@
 // C[M,N] = A[M,K] * W[N,K]^T on the 5th-gen tensor cores (tcgen05.mma, fp16 operands, fp32 accumulators
-// in TMEM), operands staged by TMA into 128B-swizzled shared memory through a 4-deep mbarrier ring.
+// in TMEM), every operand and result tile moved by TMA through 128B-swizzled shared memory.
 //
 // This is the kernel behind every Linear on the hot path: MHA in_proj / out_proj and the MLP
 // c_fc / c_proj of ResidualAttentionBlock (reference clip/model.py:169-190), the patch-embedding conv
@@ -7,14 +7,25 @@
 // Adapter_FC's two bias-free Linears (model.py:84-87) and the query x prototype contraction inside
 // P() (utils.py:230-233).
 //
-// Shape of the kernel (persistent, warp-specialised, one CTA per SM):
-//   warp 0      TMA producer  : one lane issues cp.async.bulk.tensor for the A (128x64) and W (BNx64) tiles
-//   warp 1      MMA issuer    : one lane issues 4 x tcgen05.mma (M=128, N=BN, K=16) per k-block; owns TMEM
-//   warps 2..9  epilogue      : tcgen05.ld the 128xBN fp32 accumulator (two warps per TMEM lane quarter),
-//                               add bias / QuickGELU / residual in the reference's rounding order, transpose
-//                               through an XOR-swizzled smem staging tile and write 128-byte coalesced rows.
+// Two instantiations of one persistent, warp-specialised kernel:
+//   PAIR    two CTAs on the two SMs of a TPC (cluster 2x1x1) share a 256 x 256 tile: tcgen05.mma.cta_group::2
+//           (UMMA 256x256x16). Each CTA stages its own 128 rows of A and HALF of the W tile (the tensor core
+//           reads the other half from the peer's shared memory): 32 KB per k-block per SM instead of 48 KB.
+//           The large encoder Linears run here (M >= 256 and N >= 256).
+//   SINGLE  one CTA, 128 x 128 tile (UMMA 128x128x16): small problems (projections, adapter, tails).
+// Warp roles (10 warps; the issue arbiter favours high warp ids, so the two single-lane drivers sit on top):
+//   warps 0..7  epilogue: tcgen05.ld the accumulator (lane quarter = warp % 4, column half = warp / 4), add
+//               bias / QuickGELU / residual in the reference's rounding order, write the 32-row x 128-byte
+//               block into a swizzled staging buffer and hand it to a TMA store (bulk async group); the
+//               residual block is TMA-loaded into the same buffer one block ahead. Two staging buffers per
+//               warp, so the store of block i overlaps the math of block i+1.
+//   warp 8      TMA producer: A and W tiles into a 5-deep mbarrier ring (PAIR: bytes of both CTAs are
+//               credited to the leader's `full` barrier)
+//   warp 9      MMA issuer (PAIR: leader CTA only; commits are multicast to both CTAs); owns TMEM
 // Two accumulator stages (2 x BN TMEM columns) let the epilogue of tile i overlap the main loop of tile i+1.
-// Tiles are walked n-fastest so the CTAs of one wave share the same A row-blocks in L2.
+// Tiles are walked n-fastest so concurrently running CTAs share A row-blocks in L2.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -22,32 +33,35 @@ namespace pc {
 
 namespace {
 
-constexpr int BM = 128;
-constexpr int BK = 64;  // 64 fp16 = 128 B = one swizzle row
-constexpr int STAGES = 4;
+constexpr int BM = 128;  // accumulator rows per CTA (TMEM lanes)
+constexpr int BK = 64;   // 64 fp16 = 128 B = one swizzle row
+constexpr int STAGES = 5;
 constexpr int EPI_WARPS = 8;
-constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
-constexpr int STG_WARP_BYTES = 32 * 128;  // 32 rows x 128 B, 16-byte chunks XOR-swizzled by (row & 7): conflict-free
+constexpr int TMA_WARP = EPI_WARPS;
+constexpr int MMA_WARP = EPI_WARPS + 1;
+constexpr int GEMM_THREADS = (EPI_WARPS + 2) * 32;
+constexpr int STG_BYTES = 32 * 128;  // one staging block: 32 rows x 128 B, 16-byte chunks XOR-swizzled by (row & 7)
 
-template <int BN>
-struct SmemLayout {
-  static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+struct Smem {
+  static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
+  static constexpr int B_BYTES = 128 * BK * 2;  // 16 KB: 128 W rows per CTA in both modes
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int OFF_STAGING = STAGES * STAGE_BYTES;
-  static constexpr int STAGING_BYTES = EPI_WARPS * STG_WARP_BYTES;
+  static constexpr int STAGING_BYTES = EPI_WARPS * 2 * STG_BYTES;
   static constexpr int OFF_BIAS = OFF_STAGING + STAGING_BYTES;
-  static constexpr int OFF_BARS = OFF_BIAS + BN * 4;
-  static constexpr int TOTAL = OFF_BARS + 128 + 1024;  // + barrier block + 1024 B alignment slack
+  static constexpr int OFF_BARS = OFF_BIAS + 256 * 4;
+  static constexpr int TOTAL = OFF_BARS + 512 + 1024;  // + barrier block + 1024 B alignment slack
 };
 
 struct Bars {
-  uint64_t full[STAGES];
-  uint64_t empty[STAGES];
-  uint64_t tmem_full[2];
-  uint64_t tmem_empty[2];
+  uint64_t full[STAGES];            // PAIR: used in the leader only (TMA bytes of both CTAs)
+  uint64_t empty[STAGES];           // per CTA
+  uint64_t tmem_full[2];            // per CTA
+  uint64_t tmem_empty[2];           // PAIR: leader only, 16 arrivals; SINGLE: 8 arrivals
+  uint64_t res_full[EPI_WARPS][2];  // residual block landed in staging buffer [warp][buf]
   uint32_t tmem_base;
 };
+static_assert(sizeof(Bars) <= 512, "barrier block");
 
 // QuickGELU x * sigmoid(1.702 x) (clip/model.py:164-166) on a packed half2, with
 // sigmoid(t) = 0.5 * tanh(t / 2) + 0.5 so one MUFU.TANH serves two elements. fp16 math throughout, as the
@@ -64,29 +78,51 @@ __device__ __forceinline__ uint32_t quick_gelu_f16x2(uint32_t xb) {
   return *reinterpret_cast<const uint32_t*>(&y);
 }
 
-template <int BN, int EPI>
+__device__ __forceinline__ uint32_t hadd2_u32(uint32_t a, uint32_t b) {
+  const __half2 r = __hadd2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+
+#define TRACE(slot, val)                                                                   \
+  do {                                                                                     \
+    if ((g.debug & 8) && blockIdx.x == 0 && tidx < 64) g.trace[tidx * 16 + (slot)] = (val); \
+  } while (0)
+
+template <bool PAIR, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                const GemmArgs g) {
-  using L = SmemLayout<BN>;
+  constexpr int BN = PAIR ? 256 : 128;                  // tile columns (TMEM columns per accumulator stage)
+  constexpr int TILE_M = PAIR ? 256 : 128;              // tile rows (both CTAs of a pair)
+  constexpr int GRP_COLS = (EPI == EPI_F32) ? 32 : 64;  // columns per 128-byte staging row
+  constexpr int NG = (BN / 2) / GRP_COLS;               // staging blocks per epilogue warp per tile
+  constexpr uint32_t TX_BYTES = (PAIR ? 2 : 1) * Smem::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
+  // identical carve-up in both CTAs of a pair (UMMA / commit / TMA-barrier addressing relies on equal offsets)
   uint8_t* smem =
       reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  Bars* bars = reinterpret_cast<Bars*>(smem + L::OFF_BARS);
-  float* sbias = reinterpret_cast<float*>(smem + L::OFF_BIAS);
+  Bars* bars = reinterpret_cast<Bars*>(smem + Smem::OFF_BARS);
+  float* sbias = reinterpret_cast<float*>(smem + Smem::OFF_BIAS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_blks = (g.M + BM - 1) / BM;
+  const int rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
+  const bool leader = rank == 0;
+  const int worker = PAIR ? (blockIdx.x >> 1) : blockIdx.x;  // tile-loop index of this CTA (pair)
+  const int num_workers = PAIR ? (gridDim.x >> 1) : gridDim.x;
+  const int m_blks = (g.M + TILE_M - 1) / TILE_M;
   const int n_blks = (g.N + BN - 1) / BN;
   const int k_blks = (g.K + BK - 1) / BK;
   const int num_tiles = m_blks * n_blks;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == TMA_WARP && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmC);
+    if (EPI == EPI_BIAS_RES) tma_prefetch_desc(&tmR);
   }
-  if (warp == 1) {
+  if (warp == MMA_WARP) {
     if (lane == 0) {
       for (int i = 0; i < STAGES; ++i) {
         mbar_init(&bars->full[i], 1);
@@ -94,71 +130,112 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&bars->tmem_full[i], 1);
-        mbar_init(&bars->tmem_empty[i], EPI_WARPS);  // one arrival per epilogue warp
+        mbar_init(&bars->tmem_empty[i], (PAIR ? 2 : 1) * EPI_WARPS);
+      }
+      for (int i = 0; i < EPI_WARPS; ++i) {
+        mbar_init(&bars->res_full[i][0], 1);
+        mbar_init(&bars->res_full[i][1], 1);
       }
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(&bars->tmem_base, 2 * BN);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_pair(&bars->tmem_base, 2 * BN);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(&bars->tmem_base, 2 * BN);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // barriers of BOTH CTAs initialised before any remote arrive / multicast commit
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp == 0) {
+  if (warp == TMA_WARP) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_blks) * BM;
-        const int n0 = (tile % n_blks) * BN;
+      int tidx = 0;
+      for (int tile = worker; tile < num_tiles; tile += num_workers, ++tidx) {
+        const int m0 = (tile / n_blks) * TILE_M + rank * BM;
+        const int n0 = (tile % n_blks) * BN + rank * 128;
+        long long w_empty = 0;
         for (int kb = 0; kb < k_blks; ++kb) {
+          const long long tw = clock64();
           mbar_wait(&bars->empty[stage], phase ^ 1);
-          uint8_t* sA = smem + stage * L::STAGE_BYTES;
-          uint8_t* sB = sA + L::A_BYTES;
-          mbar_arrive_expect_tx(&bars->full[stage], L::STAGE_BYTES);
-          tma_load_2d(sA, &tmA, &bars->full[stage], kb * BK, m0);
-          tma_load_2d(sB, &tmW, &bars->full[stage], kb * BK, n0);
+          w_empty += clock64() - tw;
+          uint8_t* sA = smem + stage * Smem::STAGE_BYTES;
+          uint8_t* sB = sA + Smem::A_BYTES;
+          if (g.debug & 2) {
+            if (leader) mbar_arrive(&bars->full[stage]);
+          } else if (PAIR) {
+            if (leader) mbar_arrive_expect_tx(&bars->full[stage], TX_BYTES);
+            tma_load_2d_pair(sA, &tmA, &bars->full[stage], kb * BK, m0, kEvictNormal);
+            tma_load_2d_pair(sB, &tmW, &bars->full[stage], kb * BK, n0, kEvictLast);
+          } else {
+            mbar_arrive_expect_tx(&bars->full[stage], TX_BYTES);
+            tma_load_2d_hint(sA, &tmA, &bars->full[stage], kb * BK, m0, kEvictNormal);
+            tma_load_2d_hint(sB, &tmW, &bars->full[stage], kb * BK, n0, kEvictLast);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
+        TRACE(7, w_empty);
+        TRACE(8, clock64());
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 0, 0);
+  } else if (warp == MMA_WARP) {
+    // ------------------------------------------------------------ MMA issuer (PAIR: leader CTA only)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(TILE_M, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int tidx = 0;
+      for (int tile = worker; tile < num_tiles; tile += num_workers, ++tidx) {
+        TRACE(0, clock64());
+        TRACE(9, static_cast<long long>(globaltimer_ns()));
         mbar_wait(&bars->tmem_empty[as], aphase ^ 1);
         tc_fence_after();
+        TRACE(1, clock64());
+        long long w_full = 0;
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = 0; kb < k_blks; ++kb) {
+          const long long tw = clock64();
           mbar_wait(&bars->full[stage], phase);
+          w_full += clock64() - tw;
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + L::A_BYTES;
+          const uint32_t a_addr = smem_u32(smem + stage * Smem::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + Smem::A_BYTES;
+          if (!(g.debug & 4)) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = umma_desc_kmajor_sw128(a_addr + k * 32);
-            const uint64_t db = umma_desc_kmajor_sw128(b_addr + k * 32);
-            umma_f16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t da = umma_desc_kmajor_sw128(a_addr + k * 32);
+              const uint64_t db = umma_desc_kmajor_sw128(b_addr + k * 32);
+              if (PAIR) umma_f16_ss_pair(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_f16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
-          umma_commit(&bars->empty[stage]);  // frees this smem stage once the MMAs above retire
+          // frees this smem stage (in both CTAs) once the MMAs above retire
+          if (PAIR) umma_commit_pair(&bars->empty[stage], 0x3);
+          else umma_commit(&bars->empty[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&bars->tmem_full[as]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs)
+        if (PAIR) umma_commit_pair(&bars->tmem_full[as], 0x3);
+        else umma_commit(&bars->tmem_full[as]);
+        TRACE(2, w_full);
+        TRACE(3, clock64());
+        TRACE(10, static_cast<long long>(globaltimer_ns()));
         if (++as == 2) {
           as = 0;
           aphase ^= 1;
@@ -166,178 +243,261 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..9)
-    // Two warps per TMEM lane quarter (a warp may only read lanes 32*(warp%4)..+31); the pair splits the
-    // tile's columns in halves, so every SM sub-partition always has two epilogue warps to interleave.
-    const int q = warp & 3;
-    const int chalf = (warp - 2) >> 2;
-    const int ep_tid = threadIdx.x - 64;
-    uint8_t* stg = smem + L::OFF_STAGING + (warp - 2) * STG_WARP_BYTES;
-    constexpr int GRP_COLS = (EPI == EPI_F32) ? 32 : 64;  // columns per 128-byte staging row
-    constexpr int GRPS_PER_HALF = BN / GRP_COLS / 2;
+    // ------------------------------------------------------------ epilogue (warps 0..7), this CTA's 128 rows
+    const int quarter = warp & 3;  // TMEM lanes 32 * quarter .. + 31 (hardware: warp id % 4)
+    const int chalf = warp >> 2;   // column half of the tile
+    const int ep_tid = threadIdx.x;
+    uint8_t* stg0 = smem + Smem::OFF_STAGING + warp * 2 * STG_BYTES;
+    uint64_t* res_bar = bars->res_full[warp];
+    const int row_off = rank * BM + quarter * 32;  // first row of this warp inside the tile
+    const int col_off = chalf * (BN / 2);          // first column of this warp inside the tile
+    uint32_t sg = 0;  // running staging-block counter: buffer = sg & 1, residual-barrier parity = (sg >> 1) & 1
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / n_blks) * BM;
-      const int n0 = (tile % n_blks) * BN;
-      named_bar_sync(1, EPI_WARPS * 32);  // previous tile's bias fully consumed
-      for (int i = ep_tid; i < BN; i += EPI_WARPS * 32) {
-        const int c = n0 + i;
-        sbias[i] = (g.bias != nullptr && c < g.N) ? __half2float(g.bias[c]) : 0.0f;
+
+    float bias_cur = 0.0f;  // one bias column per epilogue thread (BN <= 256 = epilogue threads), a tile ahead
+    if (worker < num_tiles) {
+      const int c = (worker % n_blks) * BN + ep_tid;
+      if (ep_tid < BN && g.bias != nullptr && c < g.N) bias_cur = __half2float(g.bias[c]);
+      if (EPI == EPI_BIAS_RES && lane == 0) {  // residual block of the very first staging block
+        mbar_arrive_expect_tx(&res_bar[0], STG_BYTES);
+        tma_load_2d(stg0, &tmR, &res_bar[0], (worker % n_blks) * BN + col_off,
+                    (worker / n_blks) * TILE_M + row_off);
       }
+    }
+    int tidx = 0;
+    for (int tile = worker; tile < num_tiles; tile += num_workers, ++tidx) {
+      const int m0 = (tile / n_blks) * TILE_M;
+      const int n0 = (tile % n_blks) * BN;
+      const int tile_next = tile + num_workers;
+      named_bar_sync(1, EPI_WARPS * 32);  // previous tile's bias fully consumed
+      if (ep_tid < BN) sbias[ep_tid] = bias_cur;
       named_bar_sync(1, EPI_WARPS * 32);
-      const int n_grps = (min(g.N - n0, BN) + GRP_COLS - 1) / GRP_COLS;  // groups with at least one valid column
-      const int g_begin = chalf * GRPS_PER_HALF;
-      const int g_end = min(g_begin + GRPS_PER_HALF, n_grps);
+      {  // next tile's bias value for this thread: in flight while this tile is processed
+        const int c = (tile_next % n_blks) * BN + ep_tid;
+        bias_cur = (tile_next < num_tiles && ep_tid < BN && g.bias != nullptr && c < g.N) ? __half2float(g.bias[c])
+                                                                                          : 0.0f;
+      }
+      if (threadIdx.x == 0) TRACE(4, clock64());
       mbar_wait(&bars->tmem_full[as], aphase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-      if (g_begin >= g_end) {  // ragged N: nothing to read for this warp, still release the accumulator
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);
-      }
-      for (int grp = g_begin; grp < g_end; ++grp) {
-        // residual rows for pass 2 are requested first so their latency hides behind pass 1
-        // (C may alias the residual: every 16-byte chunk is read and written by the same thread).
-        uint4 rs[8];
-        if (EPI == EPI_BIAS_RES) {
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int idx = it * 32 + lane;
-            const int grow = m0 + q * 32 + (idx >> 3);
-            const int gcol = n0 + grp * 64 + (idx & 7) * 8;
-            rs[it] = make_uint4(0, 0, 0, 0);
-            if (grow < g.M && gcol < g.N)
-              rs[it] = *reinterpret_cast<const uint4*>(g.residual + static_cast<size_t>(grow) * g.ldr + gcol);
-          }
-        }
-        // pass 1: TMEM -> registers -> (bias, activation, round) -> swizzled staging row `lane`
-        if (EPI == EPI_F32) {
-          uint32_t v[32];
-          tmem_ld_32x32(t_row + grp * 32, v);
+      if (threadIdx.x == 0) TRACE(5, clock64());
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + col_off;
+#pragma unroll 1
+      for (int grp = 0; grp < NG; ++grp, ++sg) {
+        uint8_t* stg = stg0 + (sg & 1) * STG_BYTES;
+        uint8_t* my_row = stg + lane * 128;
+        const int gcol0 = n0 + col_off + grp * GRP_COLS;
+        // ---- accumulator block -> registers
+        uint32_t v[2][32];
+        if (!(g.debug & 1)) {
+          tmem_ld_32x32(t_row + grp * GRP_COLS, v[0]);
+          if (EPI != EPI_F32) tmem_ld_32x32(t_row + grp * GRP_COLS + 32, v[1]);
           tmem_wait_ld();
-          const float4* b4 = reinterpret_cast<const float4*>(sbias + grp * 32);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = b4[j];
-            float4 o;
-            o.x = __uint_as_float(v[4 * j + 0]) + b.x;
-            o.y = __uint_as_float(v[4 * j + 1]) + b.y;
-            o.z = __uint_as_float(v[4 * j + 2]) + b.z;
-            o.w = __uint_as_float(v[4 * j + 3]) + b.w;
-            *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
-          }
-        } else {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t v[32];
-            tmem_ld_32x32(t_row + grp * 64 + h * 32, v);
-            tmem_wait_ld();
-            const float4* b4 = reinterpret_cast<const float4*>(sbias + grp * 64 + h * 32);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint32_t pk[4];
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const float4 b = b4[2 * j + e];
-                pk[2 * e + 0] = pack_half2(__uint_as_float(v[8 * j + 4 * e + 0]) + b.x,
-                                           __uint_as_float(v[8 * j + 4 * e + 1]) + b.y);
-                pk[2 * e + 1] = pack_half2(__uint_as_float(v[8 * j + 4 * e + 2]) + b.z,
-                                           __uint_as_float(v[8 * j + 4 * e + 3]) + b.w);
-                if (EPI == EPI_BIAS_QGELU) {
-                  pk[2 * e + 0] = quick_gelu_f16x2(pk[2 * e + 0]);
-                  pk[2 * e + 1] = quick_gelu_f16x2(pk[2 * e + 1]);
-                }
-              }
-              *reinterpret_cast<uint4*>(stg + lane * 128 + (((h * 4 + j) ^ (lane & 7)) << 4)) =
-                  make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            }
-          }
         }
-        if (grp == g_end - 1) {
-          // last TMEM read of this accumulator stage by this warp: hand it back to the MMA warp
+        if (grp == NG - 1) {  // last TMEM read of this accumulator stage by this warp: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(&bars->tmem_empty[as], 0);
+            else mbar_arrive(&bars->tmem_empty[as]);
+          }
         }
-        __syncwarp();
-        // pass 2: staging -> global, 8 lanes per 128-byte row (full-line coalesced stores)
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int idx = it * 32 + lane;
-          const int r = idx >> 3;
-          const int ch = idx & 7;
-          const int grow = m0 + q * 32 + r;
-          uint4 val = *reinterpret_cast<const uint4*>(stg + r * 128 + ((ch ^ (r & 7)) << 4));
-          if (EPI == EPI_F32) {
-            const int gcol = n0 + grp * 32 + ch * 4;
-            if (grow < g.M && gcol < g.N) {
-              float* dst = reinterpret_cast<float*>(g.C) + static_cast<size_t>(grow) * g.ldc + gcol;
-              *reinterpret_cast<uint4*>(dst) = val;
+        // ---- staging buffer management (lane 0 owns this warp's bulk groups)
+        if (lane == 0) {
+          if (EPI == EPI_BIAS_RES) {
+            tma_store_wait_read<0>();  // every earlier store has drained its buffer: the other buffer is free
+            // residual block of the NEXT staging block (possibly the first block of the next tile)
+            int nt = tile, ngrp = grp + 1;
+            if (ngrp == NG) {
+              nt = tile_next;
+              ngrp = 0;
+            }
+            if (nt < num_tiles) {
+              uint64_t* nb = &res_bar[(sg + 1) & 1];
+              mbar_arrive_expect_tx(nb, STG_BYTES);
+              tma_load_2d(stg0 + ((sg + 1) & 1) * STG_BYTES, &tmR, nb,
+                          (nt % n_blks) * BN + col_off + ngrp * GRP_COLS, (nt / n_blks) * TILE_M + row_off);
             }
           } else {
-            const int gcol = n0 + grp * 64 + ch * 8;
-            if (grow < g.M && gcol < g.N) {
-              if (EPI == EPI_BIAS_RES) {
-                const __half2* a2 = reinterpret_cast<const __half2*>(&val);
-                const __half2* r2 = reinterpret_cast<const __half2*>(&rs[it]);
-                uint4 o;
-                __half2* o2 = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) o2[e] = __hadd2(r2[e], a2[e]);
-                val = o;
-              }
-              __half* dst = reinterpret_cast<__half*>(g.C) + static_cast<size_t>(grow) * g.ldc + gcol;
-              *reinterpret_cast<uint4*>(dst) = val;
-            }
+            tma_store_wait_read<1>();  // the store issued two blocks ago has drained this buffer
           }
         }
         __syncwarp();
+        if (EPI == EPI_BIAS_RES) mbar_wait(&res_bar[sg & 1], (sg >> 1) & 1);
+        // ---- bias / activation / residual, rounded like the eager reference, into the swizzled row `lane`
+        if (!(g.debug & 1)) {
+          const float* bcol = sbias + col_off + grp * GRP_COLS;
+          if (EPI == EPI_F32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = *reinterpret_cast<const float4*>(bcol + 4 * j);
+              float4 o;
+              o.x = __uint_as_float(v[0][4 * j + 0]) + b.x;
+              o.y = __uint_as_float(v[0][4 * j + 1]) + b.y;
+              o.z = __uint_as_float(v[0][4 * j + 2]) + b.z;
+              o.w = __uint_as_float(v[0][4 * j + 3]) + b.w;
+              *reinterpret_cast<float4*>(my_row + ((j ^ (lane & 7)) << 4)) = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {  // 16-byte chunk j = columns 8j .. 8j+7 of the block
+              const uint32_t* vv = &v[j >> 2][8 * (j & 3)];
+              const float4 b0 = *reinterpret_cast<const float4*>(bcol + 8 * j);
+              const float4 b1 = *reinterpret_cast<const float4*>(bcol + 8 * j + 4);
+              uint4 pk;
+              pk.x = pack_half2(__uint_as_float(vv[0]) + b0.x, __uint_as_float(vv[1]) + b0.y);
+              pk.y = pack_half2(__uint_as_float(vv[2]) + b0.z, __uint_as_float(vv[3]) + b0.w);
+              pk.z = pack_half2(__uint_as_float(vv[4]) + b1.x, __uint_as_float(vv[5]) + b1.y);
+              pk.w = pack_half2(__uint_as_float(vv[6]) + b1.z, __uint_as_float(vv[7]) + b1.w);
+              if (EPI == EPI_BIAS_QGELU) {
+                pk.x = quick_gelu_f16x2(pk.x);
+                pk.y = quick_gelu_f16x2(pk.y);
+                pk.z = quick_gelu_f16x2(pk.z);
+                pk.w = quick_gelu_f16x2(pk.w);
+              }
+              uint4* slot = reinterpret_cast<uint4*>(my_row + ((j ^ (lane & 7)) << 4));
+              if (EPI == EPI_BIAS_RES) {  // x + f16(acc + bias): the residual chunk is already in the slot
+                const uint4 r = *slot;
+                pk.x = hadd2_u32(r.x, pk.x);
+                pk.y = hadd2_u32(r.y, pk.y);
+                pk.z = hadd2_u32(r.z, pk.z);
+                pk.w = hadd2_u32(r.w, pk.w);
+              }
+              *slot = pk;
+            }
+          }
+        }
+        fence_async_smem();  // generic-proxy writes -> visible to the TMA store
+        __syncwarp();
+        if (lane == 0) {
+          if (!(g.debug & 1) && gcol0 < g.N && m0 + row_off < g.M) tma_store_2d(&tmC, stg, gcol0, m0 + row_off);
+          tma_store_commit();
+        }
       }
+      if (threadIdx.x == 0) TRACE(6, clock64());
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
       }
     }
+    if (lane == 0) tma_store_wait_all<0>();  // results written before the CTA (and its shared memory) goes away
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
+  if (PAIR) cluster_sync_all();  // no CTA of the pair exits (or frees TMEM) while the other may still signal it
+  else __syncthreads();
+  if (warp == MMA_WARP) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    if (PAIR) tmem_dealloc_pair(tmem_base, 2 * BN);
+    else tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
-template <int BN, int EPI>
-int launch_impl(const GemmArgs& a, cudaStream_t stream) {
-  using L = SmemLayout<BN>;
+int debug_flags() {
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("PC_GEMM_DEBUG");
+    dbg = e ? atoi(e) : 0;
+  }
+  return dbg;
+}
+
+// PC_GEMM_SINGLE_CTA=1 keeps every problem on the single-CTA kernel (A/B comparisons in tools/gpu_probe.py).
+bool force_single_cta() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PC_GEMM_SINGLE_CTA");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+template <bool PAIR, int EPI>
+int launch_impl(const GemmArgs& a0, cudaStream_t stream) {
+  constexpr int BN = PAIR ? 256 : 128;
+  constexpr int TILE_M = PAIR ? 256 : 128;
   static bool configured = false;
-  auto kern = gemm_tn_kernel<BN, EPI>;
+  auto kern = gemm_tn_kernel<PAIR, EPI>;
   if (!configured) {
-    PC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    PC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::TOTAL));
     configured = true;
   }
-  CUtensorMap tmA, tmW;
-  PC_TRY(make_tmap_f16_2d(&tmA, a.A, a.K, a.M, static_cast<uint64_t>(a.lda) * 2, BK, BM));
-  PC_TRY(make_tmap_f16_2d(&tmW, a.W, a.K, a.N, static_cast<uint64_t>(a.ldw) * 2, BK, BN));
-  const int m_blks = (a.M + BM - 1) / BM;
+  GemmArgs a = a0;
+  a.debug = debug_flags();
+  CUtensorMap tmA, tmW, tmC, tmR;
+  PC_TRY(make_tmap_2d(&tmA, a.A, 2, a.K, a.M, static_cast<uint64_t>(a.lda) * 2, BK, BM));
+  PC_TRY(make_tmap_2d(&tmW, a.W, 2, a.K, a.N, static_cast<uint64_t>(a.ldw) * 2, BK, 128));
+  if (EPI == EPI_F32) {
+    PC_TRY(make_tmap_2d(&tmC, a.C, 4, a.N, a.M, static_cast<uint64_t>(a.ldc) * 4, 32, 32));
+  } else {
+    PC_TRY(make_tmap_2d(&tmC, a.C, 2, a.N, a.M, static_cast<uint64_t>(a.ldc) * 2, 64, 32));
+  }
+  if (EPI == EPI_BIAS_RES) {
+    PC_TRY(make_tmap_2d(&tmR, a.residual, 2, a.N, a.M, static_cast<uint64_t>(a.ldr) * 2, 64, 32));
+  } else {
+    tmR = tmC;
+  }
+  const int m_blks = (a.M + TILE_M - 1) / TILE_M;
   const int n_blks = (a.N + BN - 1) / BN;
   const int tiles = m_blks * n_blks;
-  const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmW, a);
-  PC_CHECK_CUDA(cudaGetLastError());
+  const int max_workers = PAIR ? device_sm_count() / 2 : device_sm_count();
+  const int workers = tiles < max_workers ? tiles : max_workers;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(PAIR ? 2 * workers : workers);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Smem::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  static long long* trace = nullptr;
+  if (a.debug & 8) {
+    if (!trace) PC_CHECK_CUDA(cudaMalloc(&trace, 64 * 16 * sizeof(long long)));
+    PC_CHECK_CUDA(cudaMemsetAsync(trace, 0, 64 * 16 * sizeof(long long), stream));
+    a.trace = trace;
+  }
+  PC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmW, tmC, tmR, a));
+  if (a.debug & 8) {
+    static int printed = 0;
+    long long h[64 * 16];
+    PC_CHECK_CUDA(cudaStreamSynchronize(stream));
+    PC_CHECK_CUDA(cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost));
+    static int trace_at = -1;
+    if (trace_at < 0) {
+      const char* e = getenv("PC_GEMM_TRACE_AT");
+      trace_at = e ? atoi(e) : 3;
+    }
+    if (printed++ == trace_at) {  // a warmed-up launch
+      const long long t0 = h[0];
+      fprintf(stderr, "[gemm trace] M=%d N=%d K=%d pair=%d epi=%d  (cycles, CTA 0)\n", a.M, a.N, a.K, (int)PAIR, EPI);
+      fprintf(stderr, "tile  mma_start tmem_wait  full_wait   mma_end | epi_wait_from epi_start  epi_end | prod_empty_wait prod_end\n");
+      int last = 0;
+      while (last + 1 < 64 && h[(last + 1) * 16 + 3]) ++last;
+      const double ns = static_cast<double>(h[last * 16 + 10] - h[9]);
+      fprintf(stderr, "mma span %lld cycles in %.0f ns -> SM clock %.0f MHz\n", h[last * 16 + 3] - t0, ns,
+              ns > 0 ? (h[last * 16 + 3] - t0) / ns * 1e3 : 0.0);
+      for (int t = 0; t < 64 && h[t * 16 + 3]; ++t) {
+        const long long* r = h + t * 16;
+        fprintf(stderr, "%4d %10lld %9lld %10lld %9lld | %13lld %9lld %8lld | %15lld %8lld\n", t, r[0] - t0, r[1] - r[0], r[2],
+                r[3] - t0, r[4] - t0, r[5] - t0, r[6] - t0, r[7], r[8] - t0);
+      }
+    }
+  }
   return PC_OK;
 }
 
-template <int BN>
+template <bool PAIR>
 int dispatch_epi(const GemmArgs& a, int epi, cudaStream_t stream) {
   switch (epi) {
-    case EPI_BIAS: return launch_impl<BN, EPI_BIAS>(a, stream);
-    case EPI_BIAS_QGELU: return launch_impl<BN, EPI_BIAS_QGELU>(a, stream);
-    case EPI_BIAS_RES: return launch_impl<BN, EPI_BIAS_RES>(a, stream);
-    case EPI_F32: return launch_impl<BN, EPI_F32>(a, stream);
+    case EPI_BIAS: return launch_impl<PAIR, EPI_BIAS>(a, stream);
+    case EPI_BIAS_QGELU: return launch_impl<PAIR, EPI_BIAS_QGELU>(a, stream);
+    case EPI_BIAS_RES: return launch_impl<PAIR, EPI_BIAS_RES>(a, stream);
+    case EPI_F32: return launch_impl<PAIR, EPI_F32>(a, stream);
     default: set_error("unknown GEMM epilogue %d", epi); return PC_ERR_ARG;
   }
 }
@@ -349,20 +509,17 @@ int launch_gemm(const GemmArgs& a, int epilogue, cudaStream_t stream) {
   PC_REQUIRE(a.A && a.W && a.C, PC_ERR_ARG, "gemm: null operand");
   PC_REQUIRE(a.K % 8 == 0 && a.lda % 8 == 0 && a.ldw % 8 == 0, PC_ERR_ALIGN,
              "gemm: K/lda/ldw (%d/%d/%d) must be multiples of 8 fp16 (16-byte TMA rows)", a.K, a.lda, a.ldw);
-  // Columns are written in 16-byte chunks; a ragged last chunk spills into the row padding, so the leading
-  // dimension must cover N rounded up to the chunk.
+  // The result leaves through a TMA store: rows of C must start on 16-byte boundaries (columns are clipped at N).
   const int chunk = (epilogue == EPI_F32) ? 4 : 8;
-  PC_REQUIRE(a.ldc % chunk == 0 && a.ldc >= (a.N + chunk - 1) / chunk * chunk &&
-                 (reinterpret_cast<uintptr_t>(a.C) & 15) == 0,
-             PC_ERR_ALIGN, "gemm: output needs a 16-byte aligned C and ldc (%d) a multiple of %d covering N (%d)",
-             a.ldc, chunk, a.N);
+  PC_REQUIRE(a.ldc % chunk == 0 && a.ldc >= a.N && (reinterpret_cast<uintptr_t>(a.C) & 15) == 0, PC_ERR_ALIGN,
+             "gemm: output needs a 16-byte aligned C and ldc (%d) >= N (%d), a multiple of %d", a.ldc, a.N, chunk);
   if (epilogue == EPI_BIAS_RES) {
-    PC_REQUIRE(a.residual != nullptr && a.ldr % 8 == 0 &&
+    PC_REQUIRE(a.residual != nullptr && a.ldr % 8 == 0 && a.ldr >= a.N &&
                    (reinterpret_cast<uintptr_t>(a.residual) & 15) == 0,
                PC_ERR_ALIGN, "gemm: residual must be non-null, 16-byte aligned, ldr %% 8 == 0");
   }
-  if (a.N > 128) return dispatch_epi<256>(a, epilogue, stream);
-  return dispatch_epi<128>(a, epilogue, stream);
+  if (a.M >= 256 && a.N >= 256 && !force_single_cta()) return dispatch_epi<true>(a, epilogue, stream);
+  return dispatch_epi<false>(a, epilogue, stream);
 }
 
 }  // namespace pc

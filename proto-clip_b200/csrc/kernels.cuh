@@ -21,6 +21,9 @@ struct GemmArgs {
   void* C; int ldc;           // [M, N] fp16 (fp32 for EPI_F32)
   const __half* bias;         // [N] or nullptr
   const __half* residual; int ldr;  // [M, N] fp16 (EPI_BIAS_RES); may alias C
+  int debug;                  // bring-up only (env PC_GEMM_DEBUG): 1 = skip epilogue body, 2 = skip TMA, 4 = skip MMA,
+                              // 8 = per-tile cycle trace of CTA 0 (printed to stderr after a device sync)
+  long long* trace;           // [tiles][16] clock64 samples when debug & 8
 };
 int launch_gemm(const GemmArgs& a, int epilogue, cudaStream_t stream);
 

@@ -31,6 +31,64 @@ def stats(name, got, ref):
         print(f"[{name}]   ref[0,:8]={ref.reshape(-1, ref.shape[-1])[0, :8].tolist()}")
 
 
+class Clocks:
+    """Median SM clock (MHz) sampled with nvidia-smi while a timed loop runs."""
+
+    def __enter__(self):
+        import threading
+        self.vals, self._stop = [], threading.Event()
+
+        def run():
+            while not self._stop.is_set():
+                try:
+                    o = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader,nounits",
+                                        "-i", "0"], capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                    self.vals.append((float(o[0]), float(o[1])))
+                except Exception:
+                    pass
+                self._stop.wait(0.05)
+        self._t = threading.Thread(target=run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def mhz(self):
+        v = sorted(x[0] for x in self.vals)
+        return v[len(v) // 2] if v else float("nan")
+
+    def watts(self):
+        v = sorted(x[1] for x in self.vals)
+        return v[len(v) // 2] if v else float("nan")
+
+
+def timed_loop(fn, flops, label, seconds=0.6):
+    """Sustained timing: run fn back to back for ~`seconds`, CUDA events around the loop, clocks sampled meanwhile."""
+    import torch
+    for _ in range(5):
+        fn()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(20):
+        fn()
+    t1.record(); torch.cuda.synchronize()
+    burst_ms = t0.elapsed_time(t1) / 20
+    iters = max(20, int(seconds * 1e3 / burst_ms))
+    with Clocks() as c:
+        t0.record()
+        for _ in range(iters):
+            fn()
+        t1.record(); torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / iters
+    tf = flops / ms / 1e9
+    mhz = c.mhz()
+    peak = 8192.0 * 148 * mhz * 1e6 / 1e12
+    print(f"[{label}] burst {burst_ms * 1e3:.1f} us ({flops / burst_ms / 1e9:.0f} TF)  sustained {ms * 1e3:.1f} us "
+          f"{tf:.0f} TFLOP/s @ {mhz:.0f} MHz {c.watts():.0f} W -> {100 * tf / peak:.1f}% of clock peak", flush=True)
+
+
 def case_gemm(M, N, K, epi="bias"):
     import torch
     from proto_clip_b200 import _native as nat
@@ -51,19 +109,10 @@ def case_gemm(M, N, K, epi="bias"):
         got, ref = nat.linear(x, w, None, nat.EPI_F32), x.float() @ w.float().t()
     torch.cuda.synchronize()
     stats(f"gemm {M}x{N}x{K} {epi}", got, ref)
-    # timing
-    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-    for _ in range(3):
-        nat.linear(x, w, b if epi != "f32" else None, {"bias": 0, "gelu": 1, "res": 2, "f32": 3}[epi],
-                   residual=r if epi == "res" else None)
-    t0.record()
-    iters = 10
-    for _ in range(iters):
-        nat.linear(x, w, b if epi != "f32" else None, {"bias": 0, "gelu": 1, "res": 2, "f32": 3}[epi],
-                   residual=r if epi == "res" else None)
-    t1.record(); torch.cuda.synchronize()
-    ms = t0.elapsed_time(t1) / iters
-    print(f"[gemm {M}x{N}x{K} {epi}] {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s", flush=True)
+    code = {"bias": 0, "gelu": 1, "res": 2, "f32": 3}[epi]
+    out = torch.empty(M, N, device="cuda", dtype=torch.float32 if epi == "f32" else torch.float16)
+    timed_loop(lambda: nat.linear(x, w, b if epi != "f32" else None, code, residual=r if epi == "res" else None, out=out),
+               2.0 * M * N * K, f"gemm {M}x{N}x{K} {epi}")
 
 
 def case_attn(B, L, heads, causal):
@@ -80,15 +129,7 @@ def case_attn(B, L, heads, causal):
     ref = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B * L, d)
     torch.cuda.synchronize()
     stats(f"attn B{B} L{L} h{heads} causal={causal}", got, ref)
-    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-    for _ in range(3):
-        nat.attention(qkv, B, L, heads, causal)
-    t0.record()
-    for _ in range(10):
-        nat.attention(qkv, B, L, heads, causal)
-    t1.record(); torch.cuda.synchronize()
-    ms = t0.elapsed_time(t1) / 10
-    print(f"[attn B{B} L{L}] {ms:.3f} ms  {4.0 * B * heads * L * L * 64 / ms / 1e9:.2f} TFLOP/s", flush=True)
+    timed_loop(lambda: nat.attention(qkv, B, L, heads, causal), 4.0 * B * heads * L * L * 64, f"attn B{B} L{L}", 0.3)
 
 
 def case_rows():
@@ -102,12 +143,27 @@ def case_rows():
         stats(f"l2norm d{d}", nat.l2_normalize(x), x.float() / x.float().norm(dim=-1, keepdim=True))
 
 
+def case_cublas():
+    """torch.matmul (cuBLAS) fp16 on the encoder's GEMM shapes: the library baseline for the same problems."""
+    import torch
+    for (M, N, K) in [(18912, 2304, 768), (18912, 768, 768), (18912, 3072, 768), (18912, 768, 3072), (8192, 8192, 8192)]:
+        x = (torch.randn(M, K, device="cuda") * 0.5).half()
+        w = (torch.randn(N, K, device="cuda") * 0.05).half()
+        out = torch.empty(M, N, device="cuda", dtype=torch.float16)
+        timed_loop(lambda: torch.matmul(x, w.t(), out=out), 2.0 * M * N * K, f"cublas {M}x{N}x{K}")
+
+
 CASES = {
     "gemm_small": lambda: case_gemm(128, 256, 64),
     "gemm_k": lambda: case_gemm(128, 256, 768),
     "gemm_n128": lambda: case_gemm(300, 128, 512),
     "gemm_ragged": lambda: case_gemm(1000, 2000, 512, "f32"),
+    "gemm_pair_small": lambda: case_gemm(256, 256, 64),
+    "gemm_pair_k": lambda: case_gemm(512, 512, 768),
+    "gemm_pair_ragged": lambda: case_gemm(1000, 1000, 512, "f32"),
+    "gemm_pair_tail": lambda: case_gemm(257, 768, 592, "res"),
     "gemm_qkv": lambda: case_gemm(96 * 197, 2304, 768),
+    "gemm_out": lambda: case_gemm(96 * 197, 768, 768, "res"),
     "gemm_gelu": lambda: case_gemm(96 * 197, 3072, 768, "gelu"),
     "gemm_res": lambda: case_gemm(96 * 197, 768, 3072, "res"),
     "attn_197": lambda: case_attn(4, 197, 12, False),
@@ -116,17 +172,21 @@ CASES = {
     "attn_257": lambda: case_attn(2, 257, 16, False),
     "attn_big": lambda: case_attn(96, 197, 12, False),
     "rows": case_rows,
+    "cublas": case_cublas,
 }
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--case", default=None)
     ap.add_argument("--timeout", type=int, default=120)
+    ap.add_argument("--only", default=None, help="substring filter on case names")
     a = ap.parse_args()
     if a.case:
         CASES[a.case]()
     else:
         for name in CASES:
+            if a.only and not any(o in name for o in a.only.split(",")):
+                continue
             t = time.time()
             try:
                 r = subprocess.run([sys.executable, __file__, "--case", name], timeout=a.timeout,
