@@ -2,16 +2,26 @@
 // (reference clip/model.py:173,183-185 -> nn.MultiheadAttention -> scaled_dot_product_attention; the text
 // tower's additive mask clip/model.py:326-332 is exactly "j > i -> -inf", i.e. the causal flag here).
 //
-// Sequence lengths are tiny and fixed (50 / 77 / 197 / 257 tokens), so one CTA owns one
-// (image, head, 128-query tile) and sees the WHOLE key axis at once: no online-softmax rescaling.
-//   warp 4 (one lane)  TMA: Q tile [128,64], K [Lp,64], V [Lp,64] straight out of the packed qkv
-//                      activation (128B swizzle); tcgen05.mma S = Q K^T into TMEM (N = Lp columns);
-//                      later tcgen05.mma O = P V (A = P from smem K-major, B = V MN-major).
-//   warps 0..3         one query row per thread (TMEM lane == row): two passes over the S row in TMEM
-//                      (max, then exp2 / sum), P written as fp16 into the swizzled K-major smem tile,
-//                      finally O * (1/sum) -> fp16 -> global.
-// P aliases the Q and K staging buffers (dead once S is complete), which keeps a CTA at ~90 KB smem /
-// 256 TMEM columns for L <= 256 so two CTAs share an SM and overlap each other's phases.
+// Persistent kernel, one CTA per SM, two independent softmax warpgroups ("WG", 128 threads = 128 query rows
+// = 128 TMEM lanes each) that ping-pong on the tensor core:
+//   warps 0-3 / 4-7   softmax WG 0 / 1, one query row per thread. S = Q K^T is read from TMEM twice (row max,
+//                     then exp2 / row sum); P is written back IN PLACE over S as packed fp16 (tcgen05.st) and
+//                     consumed by the PV MMA straight from TMEM (A operand in TMEM, tcgen05.mma "ts" form):
+//                     no shared-memory round trip and no proxy fence for P.
+//   warp 8 / 9        MMA issuer of WG 0 / 1 (one lane): S = Q K^T (Q, K from 128B-swizzled smem), then
+//                     O (+)= P V (V as the MN-major B operand). Two issuing threads, so the tensor pipe
+//                     always has the other WG's MMAs to run while one WG is inside its softmax.
+//   warp 10           TMA producer: Q tiles (one buffer per WG) and K/V blocks (two slots, shared by the WGs)
+//                     cut straight out of the packed qkv activation [B*L, 3d].
+// Work decomposition: a GROUP is one K/V stream plus the (up to) two 128-row query tiles that use it:
+//   L <= 128   ("split")  the two WGs take two different (image, head) items; a K/V slot holds both items' K/V
+//   L  > 128              the two WGs take tiles 2t, 2t+1 of the same item and share its K/V
+// Keys are processed in blocks of `kb` columns: the whole row in one block when L <= 256 (no rescaling at all:
+// 50 / 77 / 197 tokens), 192-key blocks with an online-softmax rescale of O in TMEM otherwise (257 / 577).
+// TMEM (512 columns) = one 256-column region per WG: S [0, kb), P [0, kb/2) over it, O at column 128 (single
+// block; S is dead by then) or 192 (multi block).
+#include <stdlib.h>
+
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -19,28 +29,65 @@ namespace pc {
 
 namespace {
 
-constexpr int ATT_THREADS = 160;
 constexpr int HEAD_DIM = 64;
+constexpr int MMA_WARP0 = 8;   // warps 0..7 are the two softmax warpgroups
+constexpr int TMA_WARP = 10;
+constexpr int ATT_THREADS = 11 * 32;
+constexpr int Q_BYTES = 128 * 128;  // one query tile: 128 rows x 64 fp16
+constexpr int KB_MULTI = 192;       // keys per block when the row does not fit one TMEM region
 
 struct AttnParams {
   __half* out;     // [B*L, d]
   int L;           // tokens per sequence
-  int Lp16;        // L rounded up to 16 (UMMA N / K extent)
-  int kv_box;      // rows per K/V TMA box
-  int kv_split;    // number of K/V boxes
+  int lp16;        // L rounded up to 16
   int heads;
   int d;           // heads * 64
   int causal;
+  int items;       // B * heads
   int m_tiles;     // ceil(L / 128)
-  int off_v;       // smem offset of V (bytes, 1024-aligned); Q at 0, K at 16384, P at 0
+  int split;       // 1: L <= 128, the WGs take different items
+  int ppi;         // non-split: tile pairs per item = ceil(m_tiles / 2)
+  int n_groups;
+  int n_kvb;       // key blocks per row
+  int kb;          // keys per block (multiple of 16)
+  int o_col;       // column of O inside a WG's TMEM region
+  int sub_bytes;   // split: byte offset of WG 1's K (V) inside a slot's K (V) region
+  int kreg_bytes;  // bytes of a slot's K region; the V region follows
+  int off_kv;      // smem offset of slot 0 (slot 1 follows at + 2 * kreg_bytes)
   int off_bars;
-  int tmem_cols;   // power of two >= max(Lp16, 64)
 };
 
 struct AttnBars {
-  uint64_t qk, v, s, p, o;
+  uint64_t kv_full[2];  // per slot: TMA bytes landed
+  uint64_t kv_free[2];  // per slot: both WGs' PV MMAs retired (2 arrivals)
+  uint64_t q_full[2];   // per WG
+  uint64_t q_free[2];   // per WG: last S MMA of the group retired
+  uint64_t s_full[2];   // per WG: S block in TMEM
+  uint64_t p_full[2];   // per WG: P block in TMEM (4 warp arrivals)
+  uint64_t o_full[2];   // per WG: last PV MMA of the group retired
+  uint64_t o_free[2];   // per WG: O read out, region reusable (4 warp arrivals)
   uint32_t tmem_base;
 };
+
+// job of WG `w` inside group `g`
+struct Job {
+  bool active;
+  int item;  // b * heads + h
+  int tile;  // 128-row query tile inside the sequence
+};
+__device__ __forceinline__ Job job_of(const AttnParams& p, int g, int w) {
+  Job j;
+  if (p.split) {
+    j.item = 2 * g + w;
+    j.tile = 0;
+    j.active = j.item < p.items;
+  } else {
+    j.item = g / p.ppi;
+    j.tile = 2 * (g % p.ppi) + w;
+    j.active = j.tile < p.m_tiles;
+  }
+  return j;
+}
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -48,40 +95,83 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(ATT_THREADS)
+// ---- softmax chunk helpers: 32 S columns [c0, c0+32) of this thread's row, already in registers ----------
+// Row maximum. ncv = number of valid key columns in this block (warp-uniform), cmax = last valid column of
+// THIS row (causal rows differ).
+template <bool MASK>
+__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], int c0, int ncv, int cmax, float mx) {
+#pragma unroll
+  for (int q8 = 0; q8 < 4; ++q8) {
+    if (c0 + 8 * q8 < ncv) {
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        float a = __uint_as_float(v[8 * q8 + j]), b = __uint_as_float(v[8 * q8 + j + 1]);
+        if (MASK) {
+          a = (c0 + 8 * q8 + j <= cmax) ? a : -INFINITY;
+          b = (c0 + 8 * q8 + j + 1 <= cmax) ? b : -INFINITY;
+        }
+        mx = fmaxf(mx, fmaxf(a, b));
+      }
+    }
+  }
+  return mx;
+}
+// p = exp2(s * sc - mxs) -> packed fp16 pairs; returns the fp32 sum of the (unrounded) p.
+template <bool MASK>
+__device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], uint32_t (&pk)[16], int c0, int ncv, int cmax,
+                                           float sc, float mxs) {
+  float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+  for (int q8 = 0; q8 < 4; ++q8) {
+    if (c0 + 8 * q8 < ncv) {
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        float e0 = ex2_approx(fmaf(__uint_as_float(v[8 * q8 + j]), sc, -mxs));
+        float e1 = ex2_approx(fmaf(__uint_as_float(v[8 * q8 + j + 1]), sc, -mxs));
+        if (MASK) {
+          e0 = (c0 + 8 * q8 + j <= cmax) ? e0 : 0.0f;
+          e1 = (c0 + 8 * q8 + j + 1 <= cmax) ? e1 : 0.0f;
+        }
+        s0 += e0;
+        s1 += e1;
+        pk[4 * q8 + (j >> 1)] = pack_half2(e0, e1);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pk[4 * q8 + j] = 0u;
+    }
+  }
+  return s0 + s1;
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                  const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem =
       reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + 16384;
-  uint8_t* sP = smem;
-  uint8_t* sV = smem + p.off_v;
   AttnBars* bars = reinterpret_cast<AttnBars*>(smem + p.off_bars);
-
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int mt = blockIdx.x % p.m_tiles;
-  const int bh = blockIdx.x / p.m_tiles;
-  const int h = bh % p.heads;
-  const int b = bh / p.heads;
-  const int m0 = mt * 128;
-  const int row0 = b * p.L;  // first token row of this sequence in the [B*L, .] activations
 
-  if (warp == 4) {
+  if (warp == TMA_WARP) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmKV);
-      mbar_init(&bars->qk, 1);
-      mbar_init(&bars->v, 1);
-      mbar_init(&bars->s, 1);
-      mbar_init(&bars->p, 128);
-      mbar_init(&bars->o, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&bars->kv_full[i], 1);
+        mbar_init(&bars->kv_free[i], 2);
+        mbar_init(&bars->q_full[i], 1);
+        mbar_init(&bars->q_free[i], 1);
+        mbar_init(&bars->s_full[i], 1);
+        mbar_init(&bars->p_full[i], 4);
+        mbar_init(&bars->o_full[i], 1);
+        mbar_init(&bars->o_free[i], 4);
+      }
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(&bars->tmem_base, p.tmem_cols);
+    tmem_alloc(&bars->tmem_base, 512);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -89,111 +179,222 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp == 4) {
+  if (warp == TMA_WARP) {
+    // ---------------------------------------------------------------------------------- TMA producer
     if (lane == 0) {
-      const int kv_bytes = p.kv_box * p.kv_split * 128;
-      mbar_arrive_expect_tx(&bars->qk, 16384 + kv_bytes);
-      tma_load_2d(sQ, &tmQ, &bars->qk, h * HEAD_DIM, row0 + m0);
-      for (int s = 0; s < p.kv_split; ++s)
-        tma_load_2d(sK + s * p.kv_box * 128, &tmKV, &bars->qk, p.d + h * HEAD_DIM, row0 + s * p.kv_box);
-      mbar_arrive_expect_tx(&bars->v, kv_bytes);
-      for (int s = 0; s < p.kv_split; ++s)
-        tma_load_2d(sV + s * p.kv_box * 128, &tmKV, &bars->v, 2 * p.d + h * HEAD_DIM, row0 + s * p.kv_box);
-
-      // S[128, Lp16] = Q K^T, in column chunks of <= 256 (UMMA N limit)
-      mbar_wait(&bars->qk, 0);
-      tc_fence_after();
-      const uint32_t q_addr = smem_u32(sQ);
-      const uint32_t k_addr = smem_u32(sK);
-      for (int c0 = 0; c0 < p.Lp16; c0 += 256) {
-        const int nc = min(256, p.Lp16 - c0);
-        const uint32_t idesc = umma_idesc_f16(128, nc, 0, 0);
+      uint32_t u = 0;              // K/V units loaded so far (slot = u & 1)
+      uint32_t q_cnt[2] = {0, 0};  // Q tiles loaded per WG
+      const uint32_t kv_box_bytes = static_cast<uint32_t>(p.kb) * 128;
+      for (int g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
+        const Job j0 = job_of(p, g, 0), j1 = job_of(p, g, 1);
+        for (int jb = 0; jb < p.n_kvb; ++jb, ++u) {
+          const int slot = u & 1;
+          uint8_t* kbuf = smem + p.off_kv + slot * 2 * p.kreg_bytes;
+          uint8_t* vbuf = kbuf + p.kreg_bytes;
+          mbar_wait(&bars->kv_free[slot], ((u >> 1) & 1) ^ 1);
+          if (p.split) {
+            mbar_arrive_expect_tx(&bars->kv_full[slot], 2 * kv_box_bytes * ((j0.active ? 1 : 0) + (j1.active ? 1 : 0)));
 #pragma unroll
-        for (int k = 0; k < HEAD_DIM / 16; ++k) {
-          umma_f16_ss(tmem + c0, umma_desc_kmajor_sw128(q_addr + k * 32),
-                      umma_desc_kmajor_sw128(k_addr + c0 * 128 + k * 32), idesc, k != 0 ? 1u : 0u);
+            for (int w = 0; w < 2; ++w) {
+              const Job& j = w ? j1 : j0;
+              if (!j.active) continue;
+              const int b = j.item / p.heads, h = j.item % p.heads;
+              const int row = b * p.L + jb * p.kb;
+              tma_load_2d(kbuf + w * p.sub_bytes, &tmKV, &bars->kv_full[slot], p.d + h * HEAD_DIM, row);
+              tma_load_2d(vbuf + w * p.sub_bytes, &tmKV, &bars->kv_full[slot], 2 * p.d + h * HEAD_DIM, row);
+            }
+          } else {
+            const int b = j0.item / p.heads, h = j0.item % p.heads;
+            const int row = b * p.L + jb * p.kb;
+            mbar_arrive_expect_tx(&bars->kv_full[slot], 2 * kv_box_bytes);
+            tma_load_2d(kbuf, &tmKV, &bars->kv_full[slot], p.d + h * HEAD_DIM, row);
+            tma_load_2d(vbuf, &tmKV, &bars->kv_full[slot], 2 * p.d + h * HEAD_DIM, row);
+          }
+          if (jb == 0) {
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+              const Job& j = w ? j1 : j0;
+              if (!j.active) continue;
+              const int b = j.item / p.heads, h = j.item % p.heads;
+              mbar_wait(&bars->q_free[w], (q_cnt[w] & 1) ^ 1);
+              mbar_arrive_expect_tx(&bars->q_full[w], Q_BYTES);
+              tma_load_2d(smem + w * Q_BYTES, &tmQ, &bars->q_full[w], h * HEAD_DIM, b * p.L + j.tile * 128);
+              ++q_cnt[w];
+            }
+          }
         }
       }
-      umma_commit(&bars->s);
-
-      // O[128, 64] = P V  (P: K-major 128x64 swizzled chunks; V: MN-major, 16 key rows per K step)
-      mbar_wait(&bars->p, 0);
-      mbar_wait(&bars->v, 0);
-      tc_fence_after();
-      const uint32_t p_addr = smem_u32(sP);
-      const uint32_t v_addr = smem_u32(sV);
+    }
+  } else if (warp >= MMA_WARP0) {
+    // ---------------------------------------------------------------------------------- MMA issuer of WG w
+    if (lane == 0) {
+      const int w = warp - MMA_WARP0;
+      const uint32_t region = tmem + w * 256;
+      const uint32_t q_addr = smem_u32(smem + w * Q_BYTES);
       const uint32_t idesc_o = umma_idesc_f16(128, HEAD_DIM, 0, 1);
-      const int k_steps = p.Lp16 / 16;
-      for (int kk = 0; kk < k_steps; ++kk) {
-        umma_f16_ss(tmem, umma_desc_kmajor_sw128(p_addr + (kk >> 2) * 16384 + (kk & 3) * 32),
-                    umma_desc_mnmajor_sw128(v_addr + kk * 2048, 1024), idesc_o, kk != 0 ? 1u : 0u);
+      uint32_t u = 0, q_cnt = 0, st_cnt = 0;
+      for (int g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
+        const Job j = job_of(p, g, w);
+        for (int jb = 0; jb < p.n_kvb; ++jb, ++u) {
+          const int slot = u & 1;
+          mbar_wait(&bars->kv_full[slot], (u >> 1) & 1);
+          if (!j.active) {  // this WG sits the unit out: release its share of the slot
+            mbar_arrive(&bars->kv_free[slot]);
+            continue;
+          }
+          if (jb == 0) {
+            mbar_wait(&bars->q_full[w], q_cnt & 1);
+            mbar_wait(&bars->o_free[w], (q_cnt & 1) ^ 1);
+          }
+          tc_fence_after();
+          const uint32_t k_addr =
+              smem_u32(smem + p.off_kv + slot * 2 * p.kreg_bytes + (p.split ? w * p.sub_bytes : 0));
+          const uint32_t v_addr = k_addr + p.kreg_bytes;
+          const int n_cols = min(p.kb, p.lp16 - jb * p.kb);
+          // S[128, n_cols] = Q K^T
+          const uint32_t idesc_s = umma_idesc_f16(128, n_cols, 0, 0);
+#pragma unroll
+          for (int k = 0; k < HEAD_DIM / 16; ++k) {
+            umma_f16_ss(region, umma_desc_kmajor_sw128(q_addr + k * 32), umma_desc_kmajor_sw128(k_addr + k * 32),
+                        idesc_s, k != 0 ? 1u : 0u);
+          }
+          umma_commit(&bars->s_full[w]);
+          if (jb == p.n_kvb - 1) umma_commit(&bars->q_free[w]);
+          // O[128, 64] (+)= P V : P from TMEM (8 columns per 16 keys), V MN-major (16 key rows per K step)
+          mbar_wait(&bars->p_full[w], st_cnt & 1);
+          tc_fence_after();
+          const int k_steps = n_cols >> 4;
+          for (int kk = 0; kk < k_steps; ++kk) {
+            umma_f16_ts(region + p.o_col, region + 8 * kk, umma_desc_mnmajor_sw128(v_addr + kk * 2048, 1024), idesc_o,
+                        (jb | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(&bars->kv_free[slot]);
+          if (jb == p.n_kvb - 1) umma_commit(&bars->o_full[w]);
+          ++st_cnt;
+        }
+        if (j.active) ++q_cnt;
       }
-      umma_commit(&bars->o);
     }
   } else {
-    // ---------------------------------------------------------------- softmax + output (row per thread)
-    const int r = threadIdx.x;  // 0..127 == TMEM lane
-    const int i = m0 + r;       // query index inside the sequence
-    const int jmax = p.causal ? min(i, p.L - 1) : p.L - 1;
-    const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    // ---------------------------------------------------------------------------------- softmax WG w
+    const int w = warp >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;  // row of the tile == TMEM lane
+    const uint32_t t_row = tmem + w * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
     const float sc = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-
-    mbar_wait(&bars->s, 0);
-    tc_fence_after();
-    float mx = -INFINITY;
-    for (int c0 = 0; c0 < p.Lp16; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld_32x16(t_row + c0, v);
-      tmem_wait_ld();
+    uint32_t st_cnt = 0, o_cnt = 0;
+    for (int g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
+      const Job j = job_of(p, g, w);
+      if (!j.active) continue;
+      const int i = j.tile * 128 + r;  // query index inside the sequence
+      const bool warp_live = j.tile * 128 + quarter * 32 < p.L;  // some row of this warp is a real query
+      const int jmax = p.causal ? min(i, p.L - 1) : p.L - 1;
+      float m_run = -INFINITY, sum = 0.0f;
+      for (int jb = 0; jb < p.n_kvb; ++jb, ++st_cnt) {
+        const int n_cols = min(p.kb, p.lp16 - jb * p.kb);
+        const int ncv = min(n_cols, p.L - jb * p.kb);  // valid key columns of this block
+        const int cmax = jmax - jb * p.kb;             // last valid column of this row (may be < 0)
+        const int n_chunks = (ncv + 31) >> 5;
+        mbar_wait(&bars->s_full[w], st_cnt & 1);
+        tc_fence_after();
+        if (warp_live) {
+          uint32_t va[32], vb[32];
+          // ---- pass 1: row maximum of the block
+          float mx = -INFINITY;
+          tmem_ld_32x32(t_row, va);
+          for (int c = 0; c < n_chunks; c += 2) {
+            tmem_wait_ld();
+            if (c + 1 < n_chunks) tmem_ld_32x32(t_row + (c + 1) * 32, vb);
+            if (p.causal || (c + 1) * 32 > ncv) mx = chunk_max<true>(va, c * 32, ncv, cmax, mx);
+            else mx = chunk_max<false>(va, c * 32, ncv, cmax, mx);
+            if (c + 1 < n_chunks) {
+              tmem_wait_ld();
+              if (c + 2 < n_chunks) tmem_ld_32x32(t_row + (c + 2) * 32, va);
+              if (p.causal || (c + 2) * 32 > ncv) mx = chunk_max<true>(vb, (c + 1) * 32, ncv, cmax, mx);
+              else mx = chunk_max<false>(vb, (c + 1) * 32, ncv, cmax, mx);
+            }
+          }
+          const float m_new = fmaxf(m_run, mx);
+          if (jb > 0) {
+            // online softmax: bring O and the running sum to the new maximum. s_full(jb) implies that
+            // the PV MMA of block jb-1 has retired (same issuing thread, in-order pipe), so O is stable.
+            const float alpha = ex2_approx((m_run - m_new) * sc);
+            if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+              const uint32_t t_o = t_row + p.o_col;
+              tmem_ld_32x32(t_o, va);
+              tmem_ld_32x32(t_o + 32, vb);
+              tmem_wait_ld();
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (c0 + j <= jmax) mx = fmaxf(mx, __uint_as_float(v[j]));
-    }
-    const float mxs = mx * sc;
-    float sum = 0.0f;
-    for (int c0 = 0; c0 < p.Lp16; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld_32x16(t_row + c0, v);
-      tmem_wait_ld();
-      uint32_t pk[8];
-#pragma unroll
-      for (int j = 0; j < 16; j += 2) {
-        float e0 = (c0 + j <= jmax) ? ex2_approx(fmaf(__uint_as_float(v[j]), sc, -mxs)) : 0.0f;
-        float e1 = (c0 + j + 1 <= jmax) ? ex2_approx(fmaf(__uint_as_float(v[j + 1]), sc, -mxs)) : 0.0f;
-        sum += e0 + e1;
-        pk[j >> 1] = pack_half2(e0, e1);
+              for (int e = 0; e < 32; ++e) {
+                va[e] = __float_as_uint(__uint_as_float(va[e]) * alpha);
+                vb[e] = __float_as_uint(__uint_as_float(vb[e]) * alpha);
+              }
+              tmem_st_32x32(t_o, va);
+              tmem_st_32x32(t_o + 32, vb);
+            }
+            sum *= alpha;
+          }
+          m_run = m_new;
+          // ---- pass 2: p = exp2((s - m) / 8 * log2 e), fp16 P written over S, fp32 row sum
+          const float mxs = m_new * sc;
+          uint32_t pk[16];
+          tmem_ld_32x32(t_row, va);
+          for (int c = 0; c < n_chunks; c += 2) {
+            tmem_wait_ld();
+            if (c + 1 < n_chunks) tmem_ld_32x32(t_row + (c + 1) * 32, vb);
+            if (p.causal || (c + 1) * 32 > ncv) sum += chunk_exp<true>(va, pk, c * 32, ncv, cmax, sc, mxs);
+            else sum += chunk_exp<false>(va, pk, c * 32, ncv, cmax, sc, mxs);
+            tmem_st_32x16(t_row + c * 16, pk);
+            if (c + 1 < n_chunks) {
+              tmem_wait_ld();
+              if (c + 2 < n_chunks) tmem_ld_32x32(t_row + (c + 2) * 32, va);
+              if (p.causal || (c + 2) * 32 > ncv) sum += chunk_exp<true>(vb, pk, (c + 1) * 32, ncv, cmax, sc, mxs);
+              else sum += chunk_exp<false>(vb, pk, (c + 1) * 32, ncv, cmax, sc, mxs);
+              tmem_st_32x16(t_row + (c + 1) * 16, pk);
+            }
+          }
+          // P columns of the MMA's K extent that no chunk covered (n_cols rounds ncv up to 16 only, a chunk
+          // covers 32: nothing is left) -- all of [0, n_cols / 2) is written at this point.
+          tmem_wait_st();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->p_full[w]);
       }
-      const int u = c0 >> 3;  // 16-byte unit index along the key axis
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int uu = u + e;
-        uint8_t* dst = sP + (uu >> 3) * 16384 + r * 128 + (((uu & 7) ^ (r & 7)) << 4);
-        *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * e], pk[4 * e + 1], pk[4 * e + 2], pk[4 * e + 3]);
+      // ---- O / sum -> fp16 -> out[row0 + i, h*64 .. h*64+63]
+      mbar_wait(&bars->o_full[w], o_cnt & 1);
+      ++o_cnt;
+      tc_fence_after();
+      uint32_t oa[32], ob[32];
+      if (warp_live) {
+        tmem_ld_32x32(t_row + p.o_col, oa);
+        tmem_ld_32x32(t_row + p.o_col + 32, ob);
+        tmem_wait_ld();
       }
-    }
-    fence_async_smem();  // P (generic-proxy stores) -> visible to the tensor core's async proxy
-    tc_fence_before();
-    mbar_arrive(&bars->p);
-
-    mbar_wait(&bars->o, 0);
-    tc_fence_after();
-    const float inv = __fdividef(1.0f, sum);
-    uint32_t o[4][16];
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->o_free[w]);
+      if (warp_live && i < p.L) {
+        const int b = j.item / p.heads, h = j.item % p.heads;
+        const float inv = __fdividef(1.0f, sum);
+        __half* dst = p.out + (static_cast<size_t>(b) * p.L + i) * p.d + h * HEAD_DIM;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) tmem_ld_32x16(t_row + c * 16, o[c]);
-    tmem_wait_ld();
-    if (i < p.L) {
-      __half* dst = p.out + static_cast<size_t>(row0 + i) * p.d + h * HEAD_DIM;
+        for (int e = 0; e < 4; ++e) {
+          uint4 x;
+          x.x = pack_half2(__uint_as_float(oa[8 * e + 0]) * inv, __uint_as_float(oa[8 * e + 1]) * inv);
+          x.y = pack_half2(__uint_as_float(oa[8 * e + 2]) * inv, __uint_as_float(oa[8 * e + 3]) * inv);
+          x.z = pack_half2(__uint_as_float(oa[8 * e + 4]) * inv, __uint_as_float(oa[8 * e + 5]) * inv);
+          x.w = pack_half2(__uint_as_float(oa[8 * e + 6]) * inv, __uint_as_float(oa[8 * e + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + 8 * e) = x;
+        }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          uint4 w;
-          w.x = pack_half2(__uint_as_float(o[c][8 * e + 0]) * inv, __uint_as_float(o[c][8 * e + 1]) * inv);
-          w.y = pack_half2(__uint_as_float(o[c][8 * e + 2]) * inv, __uint_as_float(o[c][8 * e + 3]) * inv);
-          w.z = pack_half2(__uint_as_float(o[c][8 * e + 4]) * inv, __uint_as_float(o[c][8 * e + 5]) * inv);
-          w.w = pack_half2(__uint_as_float(o[c][8 * e + 6]) * inv, __uint_as_float(o[c][8 * e + 7]) * inv);
-          *reinterpret_cast<uint4*>(dst + c * 16 + e * 8) = w;
+        for (int e = 0; e < 4; ++e) {
+          uint4 x;
+          x.x = pack_half2(__uint_as_float(ob[8 * e + 0]) * inv, __uint_as_float(ob[8 * e + 1]) * inv);
+          x.y = pack_half2(__uint_as_float(ob[8 * e + 2]) * inv, __uint_as_float(ob[8 * e + 3]) * inv);
+          x.z = pack_half2(__uint_as_float(ob[8 * e + 4]) * inv, __uint_as_float(ob[8 * e + 5]) * inv);
+          x.w = pack_half2(__uint_as_float(ob[8 * e + 6]) * inv, __uint_as_float(ob[8 * e + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + 32 + 8 * e) = x;
         }
       }
     }
@@ -201,9 +402,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == TMA_WARP) {
     tc_fence_after();
-    tmem_dealloc(tmem, p.tmem_cols);
+    tmem_dealloc(tmem, 512);
   }
 }
 
@@ -212,30 +413,36 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 int launch_attention(const __half* qkv, __half* out, int B, int L, int heads, int causal,
                      cudaStream_t stream) {
   PC_REQUIRE(qkv && out && B > 0 && L > 0 && heads > 0, PC_ERR_ARG, "attention: bad arguments");
-  PC_REQUIRE(L <= 512, PC_ERR_ARG,
-             "attention: L = %d > 512 needs the online-softmax variant (not built yet)", L);
+  PC_REQUIRE(L <= 4096, PC_ERR_ARG, "attention: L = %d is beyond the supported sequence length (4096)", L);
   const int d = heads * HEAD_DIM;
-  AttnParams p;
+  AttnParams p{};
   p.out = out;
   p.L = L;
-  p.Lp16 = (L + 15) / 16 * 16;
-  p.kv_split = (p.Lp16 + 255) / 256;
-  p.kv_box = ((p.Lp16 + p.kv_split - 1) / p.kv_split + 7) / 8 * 8;
+  p.lp16 = (L + 15) / 16 * 16;
   p.heads = heads;
   p.d = d;
-  p.causal = causal;
+  p.causal = causal ? 1 : 0;
+  p.items = B * heads;
   p.m_tiles = (L + 127) / 128;
-  const int kv_bytes = p.kv_box * p.kv_split * 128;
-  const int p_bytes = ((p.Lp16 + 63) / 64) * 16384;
-  int region0 = 16384 + kv_bytes;
-  if (p_bytes > region0) region0 = p_bytes;
-  region0 = (region0 + 1023) / 1024 * 1024;
-  p.off_v = region0;
-  p.off_bars = region0 + (kv_bytes + 1023) / 1024 * 1024;
-  int cols = 64;
-  while (cols < p.Lp16) cols *= 2;
-  p.tmem_cols = cols;
-  const int smem_bytes = p.off_bars + 64 + 1024;
+  p.split = p.m_tiles == 1 ? 1 : 0;
+  p.ppi = (p.m_tiles + 1) / 2;
+  p.n_groups = p.split ? (p.items + 1) / 2 : p.items * p.ppi;
+  if (p.lp16 <= 256) {
+    p.n_kvb = 1;
+    p.kb = p.lp16;
+    p.o_col = 128;
+  } else {
+    p.kb = KB_MULTI;
+    p.n_kvb = (p.lp16 + p.kb - 1) / p.kb;
+    p.o_col = 192;
+  }
+  p.sub_bytes = p.kb * 128;
+  p.kreg_bytes = (p.split ? 2 : 1) * p.kb * 128;  // kb % 8 == 0 -> 1024-byte multiples (swizzle atoms)
+  p.off_kv = 2 * Q_BYTES;
+  p.off_bars = p.off_kv + 4 * p.kreg_bytes;
+  int smem_bytes = p.off_bars + static_cast<int>(sizeof(AttnBars)) + 1024;
+  // one CTA per SM by construction (each CTA owns all 512 TMEM columns): ask for more than half the SM's smem
+  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
   PC_REQUIRE(smem_bytes <= 227 * 1024, PC_ERR_ARG, "attention: L = %d needs %d B smem", L, smem_bytes);
 
   static int configured_bytes = 0;
@@ -247,8 +454,9 @@ int launch_attention(const __half* qkv, __half* out, int B, int L, int heads, in
   CUtensorMap tmQ, tmKV;
   const uint64_t rows = static_cast<uint64_t>(B) * L;
   PC_TRY(make_tmap_f16_2d(&tmQ, qkv, 3 * d, rows, static_cast<uint64_t>(3 * d) * 2, 64, 128));
-  PC_TRY(make_tmap_f16_2d(&tmKV, qkv, 3 * d, rows, static_cast<uint64_t>(3 * d) * 2, 64, p.kv_box));
-  const int grid = B * heads * p.m_tiles;
+  PC_TRY(make_tmap_f16_2d(&tmKV, qkv, 3 * d, rows, static_cast<uint64_t>(3 * d) * 2, 64, p.kb));
+  const int sms = device_sm_count();
+  const int grid = p.n_groups < sms ? p.n_groups : sms;
   attention_kernel<<<grid, ATT_THREADS, smem_bytes, stream>>>(tmQ, tmKV, p);
   PC_CHECK_CUDA(cudaGetLastError());
   return PC_OK;

@@ -73,7 +73,10 @@ def test_linear_residual_in_place(nat):
 
 @pytest.mark.parametrize("B,L,heads,causal", [(4, 197, 12, False), (5, 77, 8, True), (3, 50, 12, False),
                                               (2, 257, 16, False), (7, 17, 2, False), (3, 77, 1, True),
-                                              (1, 1, 1, False), (2, 128, 2, True), (2, 129, 2, False)])
+                                              (1, 1, 1, False), (2, 128, 2, True), (2, 129, 2, False),
+                                              (1, 50, 1, False), (3, 256, 3, False), (2, 577, 2, False),
+                                              (1, 300, 3, True), (3, 193, 1, False), (2, 385, 1, True),
+                                              (40, 197, 12, False), (200, 77, 8, True)])
 def test_attention(nat, B, L, heads, causal):
     torch.manual_seed(L)
     d = heads * 64
@@ -253,4 +256,4 @@ def test_error_paths(nat):
     with pytest.raises(nat.NativeError):
         nat.linear(torch.zeros(4, 12, device=DEV).half(), torch.zeros(4, 12, device=DEV).half())  # K % 8 != 0
     with pytest.raises(nat.NativeError):
-        nat.attention(torch.zeros(600 * 1, 192, device=DEV).half(), 1, 600, 1, False)  # L > 512
+        nat.attention(torch.zeros(5000, 192, device=DEV).half(), 1, 5000, 1, False)  # L > 4096
