@@ -181,27 +181,35 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   if (warp == TMA_WARP) {
     // ---------------------------------------------------------------------------------- TMA producer
-    if (lane == 0) {
-      uint32_t u = 0;              // K/V units loaded so far (slot = u & 1)
-      uint32_t q_cnt[2] = {0, 0};  // Q tiles loaded per WG
-      const uint32_t kv_box_bytes = static_cast<uint32_t>(p.kb) * 128;
-      for (int g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
-        const Job j0 = job_of(p, g, 0), j1 = job_of(p, g, 1);
-        for (int jb = 0; jb < p.n_kvb; ++jb, ++u) {
-          const int slot = u & 1;
-          uint8_t* kbuf = smem + p.off_kv + slot * 2 * p.kreg_bytes;
-          uint8_t* vbuf = kbuf + p.kreg_bytes;
-          mbar_wait(&bars->kv_free[slot], ((u >> 1) & 1) ^ 1);
+    // The whole warp walks the loops (warp-uniform values stay in uniform registers); one elected lane issues.
+    uint32_t u = 0;              // K/V units loaded so far (slot = u & 1)
+    uint32_t q_cnt0 = 0, q_cnt1 = 0;  // Q tiles loaded per WG
+    const uint32_t kv_box_bytes = static_cast<uint32_t>(p.kb) * 128;
+    for (int g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
+      const Job j0 = job_of(p, g, 0), j1 = job_of(p, g, 1);
+      for (int jb = 0; jb < p.n_kvb; ++jb, ++u) {
+        const int slot = u & 1;
+        uint8_t* kbuf = smem + p.off_kv + slot * 2 * p.kreg_bytes;
+        uint8_t* vbuf = kbuf + p.kreg_bytes;
+        mbar_wait(&bars->kv_free[slot], ((u >> 1) & 1) ^ 1);
+        if (jb == 0) {
+          if (j0.active) mbar_wait(&bars->q_free[0], (q_cnt0 & 1) ^ 1);
+          if (j1.active) mbar_wait(&bars->q_free[1], (q_cnt1 & 1) ^ 1);
+        }
+        if (elect_one()) {
           if (p.split) {
             mbar_arrive_expect_tx(&bars->kv_full[slot], 2 * kv_box_bytes * ((j0.active ? 1 : 0) + (j1.active ? 1 : 0)));
-#pragma unroll
-            for (int w = 0; w < 2; ++w) {
-              const Job& j = w ? j1 : j0;
-              if (!j.active) continue;
-              const int b = j.item / p.heads, h = j.item % p.heads;
+            if (j0.active) {
+              const int b = j0.item / p.heads, h = j0.item % p.heads;
               const int row = b * p.L + jb * p.kb;
-              tma_load_2d(kbuf + w * p.sub_bytes, &tmKV, &bars->kv_full[slot], p.d + h * HEAD_DIM, row);
-              tma_load_2d(vbuf + w * p.sub_bytes, &tmKV, &bars->kv_full[slot], 2 * p.d + h * HEAD_DIM, row);
+              tma_load_2d(kbuf, &tmKV, &bars->kv_full[slot], p.d + h * HEAD_DIM, row);
+              tma_load_2d(vbuf, &tmKV, &bars->kv_full[slot], 2 * p.d + h * HEAD_DIM, row);
+            }
+            if (j1.active) {
+              const int b = j1.item / p.heads, h = j1.item % p.heads;
+              const int row = b * p.L + jb * p.kb;
+              tma_load_2d(kbuf + p.sub_bytes, &tmKV, &bars->kv_full[slot], p.d + h * HEAD_DIM, row);
+              tma_load_2d(vbuf + p.sub_bytes, &tmKV, &bars->kv_full[slot], 2 * p.d + h * HEAD_DIM, row);
             }
           } else {
             const int b = j0.item / p.heads, h = j0.item % p.heads;
@@ -211,69 +219,79 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             tma_load_2d(vbuf, &tmKV, &bars->kv_full[slot], 2 * p.d + h * HEAD_DIM, row);
           }
           if (jb == 0) {
-#pragma unroll
-            for (int w = 0; w < 2; ++w) {
-              const Job& j = w ? j1 : j0;
-              if (!j.active) continue;
-              const int b = j.item / p.heads, h = j.item % p.heads;
-              mbar_wait(&bars->q_free[w], (q_cnt[w] & 1) ^ 1);
-              mbar_arrive_expect_tx(&bars->q_full[w], Q_BYTES);
-              tma_load_2d(smem + w * Q_BYTES, &tmQ, &bars->q_full[w], h * HEAD_DIM, b * p.L + j.tile * 128);
-              ++q_cnt[w];
+            if (j0.active) {
+              const int b = j0.item / p.heads, h = j0.item % p.heads;
+              mbar_arrive_expect_tx(&bars->q_full[0], Q_BYTES);
+              tma_load_2d(smem, &tmQ, &bars->q_full[0], h * HEAD_DIM, b * p.L + j0.tile * 128);
+            }
+            if (j1.active) {
+              const int b = j1.item / p.heads, h = j1.item % p.heads;
+              mbar_arrive_expect_tx(&bars->q_full[1], Q_BYTES);
+              tma_load_2d(smem + Q_BYTES, &tmQ, &bars->q_full[1], h * HEAD_DIM, b * p.L + j1.tile * 128);
             }
           }
+        }
+        __syncwarp();
+        if (jb == 0) {
+          q_cnt0 += j0.active ? 1 : 0;
+          q_cnt1 += j1.active ? 1 : 0;
         }
       }
     }
   } else if (warp >= MMA_WARP0) {
     // ---------------------------------------------------------------------------------- MMA issuer of WG w
-    if (lane == 0) {
-      const int w = warp - MMA_WARP0;
-      const uint32_t region = tmem + w * 256;
-      const uint32_t q_addr = smem_u32(smem + w * Q_BYTES);
-      const uint32_t idesc_o = umma_idesc_f16(128, HEAD_DIM, 0, 1);
-      uint32_t u = 0, q_cnt = 0, st_cnt = 0;
-      for (int g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
-        const Job j = job_of(p, g, w);
-        for (int jb = 0; jb < p.n_kvb; ++jb, ++u) {
-          const int slot = u & 1;
-          mbar_wait(&bars->kv_full[slot], (u >> 1) & 1);
-          if (!j.active) {  // this WG sits the unit out: release its share of the slot
-            mbar_arrive(&bars->kv_free[slot]);
-            continue;
-          }
-          if (jb == 0) {
-            mbar_wait(&bars->q_full[w], q_cnt & 1);
-            mbar_wait(&bars->o_free[w], (q_cnt & 1) ^ 1);
-          }
-          tc_fence_after();
-          const uint32_t k_addr =
-              smem_u32(smem + p.off_kv + slot * 2 * p.kreg_bytes + (p.split ? w * p.sub_bytes : 0));
-          const uint32_t v_addr = k_addr + p.kreg_bytes;
-          const int n_cols = min(p.kb, p.lp16 - jb * p.kb);
-          // S[128, n_cols] = Q K^T
+    // (whole warp in the loops, one elected lane issues: see the producer)
+    const int w = warp - MMA_WARP0;
+    const uint32_t region = tmem + w * 256;
+    const uint32_t q_addr = smem_u32(smem + w * Q_BYTES);
+    const uint64_t q_desc = umma_desc_kmajor_sw128(q_addr);
+    const uint32_t idesc_o = umma_idesc_f16(128, HEAD_DIM, 0, 1);
+    uint32_t u = 0, q_cnt = 0, st_cnt = 0;
+    for (int g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
+      const Job j = job_of(p, g, w);
+      for (int jb = 0; jb < p.n_kvb; ++jb, ++u) {
+        const int slot = u & 1;
+        mbar_wait(&bars->kv_full[slot], (u >> 1) & 1);
+        if (!j.active) {  // this WG sits the unit out: release its share of the slot
+          if (lane == 0) mbar_arrive(&bars->kv_free[slot]);
+          __syncwarp();
+          continue;
+        }
+        if (jb == 0) {
+          mbar_wait(&bars->q_full[w], q_cnt & 1);
+          mbar_wait(&bars->o_free[w], (q_cnt & 1) ^ 1);
+        }
+        tc_fence_after();
+        const uint32_t k_addr =
+            smem_u32(smem + p.off_kv + slot * 2 * p.kreg_bytes + (p.split ? w * p.sub_bytes : 0));
+        const uint32_t v_addr = k_addr + p.kreg_bytes;
+        const int n_cols = min(p.kb, p.lp16 - jb * p.kb);
+        if (elect_one()) {
+          // S[128, n_cols] = Q K^T   (+2 in the descriptor's address field = 32 B = 16 fp16 along K)
           const uint32_t idesc_s = umma_idesc_f16(128, n_cols, 0, 0);
+          const uint64_t k_desc = umma_desc_kmajor_sw128(k_addr);
 #pragma unroll
-          for (int k = 0; k < HEAD_DIM / 16; ++k) {
-            umma_f16_ss(region, umma_desc_kmajor_sw128(q_addr + k * 32), umma_desc_kmajor_sw128(k_addr + k * 32),
-                        idesc_s, k != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < HEAD_DIM / 16; ++k) umma_f16_ss(region, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
           umma_commit(&bars->s_full[w]);
           if (jb == p.n_kvb - 1) umma_commit(&bars->q_free[w]);
-          // O[128, 64] (+)= P V : P from TMEM (8 columns per 16 keys), V MN-major (16 key rows per K step)
-          mbar_wait(&bars->p_full[w], st_cnt & 1);
-          tc_fence_after();
+        }
+        __syncwarp();
+        // O[128, 64] (+)= P V : P from TMEM (8 columns per 16 keys), V MN-major (16 key rows = 2048 B per K step)
+        mbar_wait(&bars->p_full[w], st_cnt & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t v_desc = umma_desc_mnmajor_sw128(v_addr, 1024);
           const int k_steps = n_cols >> 4;
-          for (int kk = 0; kk < k_steps; ++kk) {
-            umma_f16_ts(region + p.o_col, region + 8 * kk, umma_desc_mnmajor_sw128(v_addr + kk * 2048, 1024), idesc_o,
-                        (jb | kk) != 0 ? 1u : 0u);
-          }
+          umma_f16_ts(region + p.o_col, region, v_desc, idesc_o, jb != 0 ? 1u : 0u);
+          for (int kk = 1; kk < k_steps; ++kk)
+            umma_f16_ts(region + p.o_col, region + 8 * kk, v_desc + 128 * kk, idesc_o, 1u);
           umma_commit(&bars->kv_free[slot]);
           if (jb == p.n_kvb - 1) umma_commit(&bars->o_full[w]);
-          ++st_cnt;
         }
-        if (j.active) ++q_cnt;
+        __syncwarp();
+        ++st_cnt;
       }
+      if (j.active) ++q_cnt;
     }
   } else {
     // ---------------------------------------------------------------------------------- softmax WG w

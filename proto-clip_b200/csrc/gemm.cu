@@ -155,7 +155,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == TMA_WARP) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // The whole warp walks the loop (warp-uniform control flow keeps coordinates and barrier addresses in
+    // uniform registers); one elected lane issues. A single-lane `if (lane == 0)` region would make ptxas
+    // wrap every UTMALDG / UTCHMMA in a value-uniformity waterfall (ELECT / R2UR / BRA.U.ANY).
+    {
       int stage = 0;
       uint32_t phase = 0;
       int tidx = 0;
@@ -164,34 +167,39 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int n0 = (tile % n_blks) * BN + rank * 128;
         long long w_empty = 0;
         for (int kb = 0; kb < k_blks; ++kb) {
-          const long long tw = clock64();
+          const long long tw = (g.debug & 8) ? clock64() : 0;
           mbar_wait(&bars->empty[stage], phase ^ 1);
-          w_empty += clock64() - tw;
+          if (g.debug & 8) w_empty += clock64() - tw;
           uint8_t* sA = smem + stage * Smem::STAGE_BYTES;
           uint8_t* sB = sA + Smem::A_BYTES;
-          if (g.debug & 2) {
-            if (leader) mbar_arrive(&bars->full[stage]);
-          } else if (PAIR) {
-            if (leader) mbar_arrive_expect_tx(&bars->full[stage], TX_BYTES);
-            tma_load_2d_pair(sA, &tmA, &bars->full[stage], kb * BK, m0, kEvictNormal);
-            tma_load_2d_pair(sB, &tmW, &bars->full[stage], kb * BK, n0, kEvictLast);
-          } else {
-            mbar_arrive_expect_tx(&bars->full[stage], TX_BYTES);
-            tma_load_2d_hint(sA, &tmA, &bars->full[stage], kb * BK, m0, kEvictNormal);
-            tma_load_2d_hint(sB, &tmW, &bars->full[stage], kb * BK, n0, kEvictLast);
+          if (elect_one()) {
+            if (g.debug & 2) {
+              if (leader) mbar_arrive(&bars->full[stage]);
+            } else if (PAIR) {
+              if (leader) mbar_arrive_expect_tx(&bars->full[stage], TX_BYTES);
+              tma_load_2d_pair(sA, &tmA, &bars->full[stage], kb * BK, m0, kEvictNormal);
+              tma_load_2d_pair(sB, &tmW, &bars->full[stage], kb * BK, n0, kEvictLast);
+            } else {
+              mbar_arrive_expect_tx(&bars->full[stage], TX_BYTES);
+              tma_load_2d_hint(sA, &tmA, &bars->full[stage], kb * BK, m0, kEvictNormal);
+              tma_load_2d_hint(sB, &tmW, &bars->full[stage], kb * BK, n0, kEvictLast);
+            }
           }
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        TRACE(7, w_empty);
-        TRACE(8, clock64());
+        if (lane == 0) {
+          TRACE(7, w_empty);
+          TRACE(8, clock64());
+        }
       }
     }
   } else if (warp == MMA_WARP) {
     // ------------------------------------------------------------ MMA issuer (PAIR: leader CTA only)
-    if (leader && lane == 0) {
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_f16(TILE_M, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -199,43 +207,53 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t aphase = 0;
       int tidx = 0;
       for (int tile = worker; tile < num_tiles; tile += num_workers, ++tidx) {
-        TRACE(0, clock64());
-        TRACE(9, static_cast<long long>(globaltimer_ns()));
+        if (lane == 0) {
+          TRACE(0, clock64());
+          TRACE(9, static_cast<long long>(globaltimer_ns()));
+        }
         mbar_wait(&bars->tmem_empty[as], aphase ^ 1);
         tc_fence_after();
-        TRACE(1, clock64());
+        if (lane == 0) TRACE(1, clock64());
         long long w_full = 0;
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = 0; kb < k_blks; ++kb) {
-          const long long tw = clock64();
+          const long long tw = (g.debug & 8) ? clock64() : 0;
           mbar_wait(&bars->full[stage], phase);
-          w_full += clock64() - tw;
+          if (g.debug & 8) w_full += clock64() - tw;
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * Smem::STAGE_BYTES);
           const uint32_t b_addr = a_addr + Smem::A_BYTES;
-          if (!(g.debug & 4)) {
+          if (elect_one()) {
+            if (!(g.debug & 4)) {
+              const uint64_t da = umma_desc_kmajor_sw128(a_addr);
+              const uint64_t db = umma_desc_kmajor_sw128(b_addr);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              const uint64_t da = umma_desc_kmajor_sw128(a_addr + k * 32);
-              const uint64_t db = umma_desc_kmajor_sw128(b_addr + k * 32);
-              if (PAIR) umma_f16_ss_pair(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-              else umma_f16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < BK / 16; ++k) {
+                // advancing 16 fp16 along K inside the 128-byte swizzle row = +32 B = +2 in the address field
+                if (PAIR) umma_f16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                else umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              }
+            }
+            // frees this smem stage (in both CTAs) once the MMAs above retire
+            if (PAIR) umma_commit_pair(&bars->empty[stage], 0x3);
+            else umma_commit(&bars->empty[stage]);
+            // accumulator complete -> epilogue warps (of both CTAs)
+            if (kb == k_blks - 1) {
+              if (PAIR) umma_commit_pair(&bars->tmem_full[as], 0x3);
+              else umma_commit(&bars->tmem_full[as]);
             }
           }
-          // frees this smem stage (in both CTAs) once the MMAs above retire
-          if (PAIR) umma_commit_pair(&bars->empty[stage], 0x3);
-          else umma_commit(&bars->empty[stage]);
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        // accumulator complete -> epilogue warps (of both CTAs)
-        if (PAIR) umma_commit_pair(&bars->tmem_full[as], 0x3);
-        else umma_commit(&bars->tmem_full[as]);
-        TRACE(2, w_full);
-        TRACE(3, clock64());
-        TRACE(10, static_cast<long long>(globaltimer_ns()));
+        if (lane == 0) {
+          TRACE(2, w_full);
+          TRACE(3, clock64());
+          TRACE(10, static_cast<long long>(globaltimer_ns()));
+        }
         if (++as == 2) {
           as = 0;
           aphase ^= 1;
@@ -259,7 +277,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (worker < num_tiles) {
       const int c = (worker % n_blks) * BN + ep_tid;
       if (ep_tid < BN && g.bias != nullptr && c < g.N) bias_cur = __half2float(g.bias[c]);
-      if (EPI == EPI_BIAS_RES && lane == 0) {  // residual block of the very first staging block
+      if (EPI == EPI_BIAS_RES && elect_one()) {  // residual block of the very first staging block
         mbar_arrive_expect_tx(&res_bar[0], STG_BYTES);
         tma_load_2d(stg0, &tmR, &res_bar[0], (worker % n_blks) * BN + col_off,
                     (worker / n_blks) * TILE_M + row_off);
@@ -303,8 +321,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             else mbar_arrive(&bars->tmem_empty[as]);
           }
         }
-        // ---- staging buffer management (lane 0 owns this warp's bulk groups)
-        if (lane == 0) {
+        // ---- staging buffer management. The elected lane owns this warp's bulk groups (elect.sync picks the
+        // same lane for the same member mask every time); an elect-guarded region lets ptxas feed UTMALDG /
+        // UTMASTG from uniform registers without a per-value waterfall loop.
+        if (elect_one()) {
           if (EPI == EPI_BIAS_RES) {
             tma_store_wait_read<0>();  // every earlier store has drained its buffer: the other buffer is free
             // residual block of the NEXT staging block (possibly the first block of the next tile)
@@ -370,7 +390,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         fence_async_smem();  // generic-proxy writes -> visible to the TMA store
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one()) {
           if (!(g.debug & 1) && gcol0 < g.N && m0 + row_off < g.M) tma_store_2d(&tmC, stg, gcol0, m0 + row_off);
           tma_store_commit();
         }
@@ -381,7 +401,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         aphase ^= 1;
       }
     }
-    if (lane == 0) tma_store_wait_all<0>();  // results written before the CTA (and its shared memory) goes away
+    if (elect_one()) tma_store_wait_all<0>();  // results written before the CTA (and its shared memory) goes away
   }
 
   tc_fence_before();
