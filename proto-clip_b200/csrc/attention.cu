@@ -54,8 +54,16 @@ struct AttnParams {
   int sub_bytes;   // split: byte offset of WG 1's K (V) inside a slot's K (V) region
   int kreg_bytes;  // bytes of a slot's K region; the V region follows
   int off_kv;      // smem offset of slot 0 (slot 1 follows at + 2 * kreg_bytes)
+  int off_stage;   // 8 x 4 KB output staging blocks (one per softmax warp: 32 rows x 128 B, 128B-swizzled)
   int off_bars;
+  int dbg;           // bring-up only (env PC_ATTN_DEBUG): 1 = WG 1 idle, 2 = skip pass 1, 4 = skip pass 2 math
+  long long* trace;  // bring-up only (env PC_ATTN_TRACE=1): [group iteration][WG][8] clock64 samples of CTA 0
 };
+
+#define ATRACE(slot, cond)                                                                              \
+  do {                                                                                                  \
+    if (p.trace != nullptr && blockIdx.x == 0 && (cond) && git < 32) p.trace[(git * 2 + w) * 8 + (slot)] = clock64(); \
+  } while (0)
 
 struct AttnBars {
   uint64_t kv_full[2];  // per slot: TMA bytes landed
@@ -86,6 +94,7 @@ __device__ __forceinline__ Job job_of(const AttnParams& p, int g, int w) {
     j.tile = 2 * (g % p.ppi) + w;
     j.active = j.tile < p.m_tiles;
   }
+  if ((p.dbg & 1) && w == 1) j.active = false;
   return j;
 }
 
@@ -96,39 +105,44 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 // ---- softmax chunk helpers: 32 S columns [c0, c0+32) of this thread's row, already in registers ----------
-// Row maximum. ncv = number of valid key columns in this block (warp-uniform), cmax = last valid column of
-// THIS row (causal rows differ).
-template <bool MASK>
+// ncv = number of valid key columns in this block (warp-uniform), cmax = last valid column of THIS row (causal
+// rows differ). FULL chunks (every column valid for every row) take the branch-free path.
+template <bool FULL>
 __device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], int c0, int ncv, int cmax, float mx) {
+  float m1 = -INFINITY;
 #pragma unroll
   for (int q8 = 0; q8 < 4; ++q8) {
-    if (c0 + 8 * q8 < ncv) {
+    if (FULL || c0 + 8 * q8 < ncv) {
 #pragma unroll
-      for (int j = 0; j < 8; j += 2) {
+      for (int j = 0; j < 8; j += 4) {
         float a = __uint_as_float(v[8 * q8 + j]), b = __uint_as_float(v[8 * q8 + j + 1]);
-        if (MASK) {
+        float c = __uint_as_float(v[8 * q8 + j + 2]), d = __uint_as_float(v[8 * q8 + j + 3]);
+        if (!FULL) {
           a = (c0 + 8 * q8 + j <= cmax) ? a : -INFINITY;
           b = (c0 + 8 * q8 + j + 1 <= cmax) ? b : -INFINITY;
+          c = (c0 + 8 * q8 + j + 2 <= cmax) ? c : -INFINITY;
+          d = (c0 + 8 * q8 + j + 3 <= cmax) ? d : -INFINITY;
         }
         mx = fmaxf(mx, fmaxf(a, b));
+        m1 = fmaxf(m1, fmaxf(c, d));
       }
     }
   }
-  return mx;
+  return fmaxf(mx, m1);
 }
 // p = exp2(s * sc - mxs) -> packed fp16 pairs; returns the fp32 sum of the (unrounded) p.
-template <bool MASK>
+template <bool FULL>
 __device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], uint32_t (&pk)[16], int c0, int ncv, int cmax,
                                            float sc, float mxs) {
   float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
   for (int q8 = 0; q8 < 4; ++q8) {
-    if (c0 + 8 * q8 < ncv) {
+    if (FULL || c0 + 8 * q8 < ncv) {
 #pragma unroll
       for (int j = 0; j < 8; j += 2) {
         float e0 = ex2_approx(fmaf(__uint_as_float(v[8 * q8 + j]), sc, -mxs));
         float e1 = ex2_approx(fmaf(__uint_as_float(v[8 * q8 + j + 1]), sc, -mxs));
-        if (MASK) {
+        if (!FULL) {
           e0 = (c0 + 8 * q8 + j <= cmax) ? e0 : 0.0f;
           e1 = (c0 + 8 * q8 + j + 1 <= cmax) ? e1 : 0.0f;
         }
@@ -146,7 +160,7 @@ __device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], uint32_t (&p
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                 const AttnParams p) {
+                 const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem =
       reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -158,6 +172,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     if (lane == 0) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmKV);
+      tma_prefetch_desc(&tmO);
       for (int i = 0; i < 2; ++i) {
         mbar_init(&bars->kv_full[i], 1);
         mbar_init(&bars->kv_free[i], 2);
@@ -174,10 +189,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tmem_alloc(&bars->tmem_base, 512);
     tmem_relinquish();
   }
+  griddep_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
+  griddep_wait();  // qkv is the previous kernel's output
 
   if (warp == TMA_WARP) {
     // ---------------------------------------------------------------------------------- TMA producer
@@ -238,7 +255,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
     }
-  } else if (warp >= MMA_WARP0) {
+  } else if (warp == MMA_WARP0 || warp == MMA_WARP0 + 1) {
     // ---------------------------------------------------------------------------------- MMA issuer of WG w
     // (whole warp in the loops, one elected lane issues: see the producer)
     const int w = warp - MMA_WARP0;
@@ -261,6 +278,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           mbar_wait(&bars->q_full[w], q_cnt & 1);
           mbar_wait(&bars->o_free[w], (q_cnt & 1) ^ 1);
         }
+        // Stagger the warpgroups by half a period: WG 1 starts its first tile when WG 0 has finished its first
+        // softmax, so from then on one WG computes exponentials while the other waits on the tensor core.
+        if (w == 1 && u == 0) mbar_wait(&bars->p_full[0], 0);
         tc_fence_after();
         const uint32_t k_addr =
             smem_u32(smem + p.off_kv + slot * 2 * p.kreg_bytes + (p.split ? w * p.sub_bytes : 0));
@@ -293,7 +313,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       if (j.active) ++q_cnt;
     }
-  } else {
+  } else if (warp < MMA_WARP0) {
     // ---------------------------------------------------------------------------------- softmax WG w
     const int w = warp >> 2;
     const int quarter = warp & 3;
@@ -301,7 +321,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t t_row = tmem + w * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
     const float sc = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
     uint32_t st_cnt = 0, o_cnt = 0;
+    int git = -1;
     for (int g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
+      ++git;
       const Job j = job_of(p, g, w);
       if (!j.active) continue;
       const int i = j.tile * 128 + r;  // query index inside the sequence
@@ -313,25 +335,29 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const int ncv = min(n_cols, p.L - jb * p.kb);  // valid key columns of this block
         const int cmax = jmax - jb * p.kb;             // last valid column of this row (may be < 0)
         const int n_chunks = (ncv + 31) >> 5;
+        ATRACE(0, quarter == 0 && lane == 0 && jb == 0);
         mbar_wait(&bars->s_full[w], st_cnt & 1);
         tc_fence_after();
+        ATRACE(1, quarter == 0 && lane == 0 && jb == 0);
         if (warp_live) {
+          // ---- pass 1: row maximum of the block (next 32-column chunk in flight during the reduction)
           uint32_t va[32], vb[32];
-          // ---- pass 1: row maximum of the block
           float mx = -INFINITY;
           tmem_ld_32x32(t_row, va);
-          for (int c = 0; c < n_chunks; c += 2) {
+          for (int c = (p.dbg & 2) ? n_chunks : 0; c < n_chunks; c += 2) {
             tmem_wait_ld();
             if (c + 1 < n_chunks) tmem_ld_32x32(t_row + (c + 1) * 32, vb);
-            if (p.causal || (c + 1) * 32 > ncv) mx = chunk_max<true>(va, c * 32, ncv, cmax, mx);
-            else mx = chunk_max<false>(va, c * 32, ncv, cmax, mx);
+            if (p.causal || (c + 1) * 32 > ncv) mx = chunk_max<false>(va, c * 32, ncv, cmax, mx);
+            else mx = chunk_max<true>(va, c * 32, ncv, cmax, mx);
             if (c + 1 < n_chunks) {
               tmem_wait_ld();
               if (c + 2 < n_chunks) tmem_ld_32x32(t_row + (c + 2) * 32, va);
-              if (p.causal || (c + 2) * 32 > ncv) mx = chunk_max<true>(vb, (c + 1) * 32, ncv, cmax, mx);
-              else mx = chunk_max<false>(vb, (c + 1) * 32, ncv, cmax, mx);
+              if (p.causal || (c + 2) * 32 > ncv) mx = chunk_max<false>(vb, (c + 1) * 32, ncv, cmax, mx);
+              else mx = chunk_max<true>(vb, (c + 1) * 32, ncv, cmax, mx);
             }
           }
+          ATRACE(2, quarter == 0 && lane == 0 && jb == 0);
+          if (p.dbg & 2) { tmem_wait_ld(); mx = 4.0f; }
           const float m_new = fmaxf(m_run, mx);
           if (jb > 0) {
             // online softmax: bring O and the running sum to the new maximum. s_full(jb) implies that
@@ -357,32 +383,35 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const float mxs = m_new * sc;
           uint32_t pk[16];
           tmem_ld_32x32(t_row, va);
-          for (int c = 0; c < n_chunks; c += 2) {
+          for (int c = (p.dbg & 4) ? n_chunks : 0; c < n_chunks; c += 2) {
             tmem_wait_ld();
             if (c + 1 < n_chunks) tmem_ld_32x32(t_row + (c + 1) * 32, vb);
-            if (p.causal || (c + 1) * 32 > ncv) sum += chunk_exp<true>(va, pk, c * 32, ncv, cmax, sc, mxs);
-            else sum += chunk_exp<false>(va, pk, c * 32, ncv, cmax, sc, mxs);
+            if (p.causal || (c + 1) * 32 > ncv) sum += chunk_exp<false>(va, pk, c * 32, ncv, cmax, sc, mxs);
+            else sum += chunk_exp<true>(va, pk, c * 32, ncv, cmax, sc, mxs);
             tmem_st_32x16(t_row + c * 16, pk);
             if (c + 1 < n_chunks) {
               tmem_wait_ld();
               if (c + 2 < n_chunks) tmem_ld_32x32(t_row + (c + 2) * 32, va);
-              if (p.causal || (c + 2) * 32 > ncv) sum += chunk_exp<true>(vb, pk, (c + 1) * 32, ncv, cmax, sc, mxs);
-              else sum += chunk_exp<false>(vb, pk, (c + 1) * 32, ncv, cmax, sc, mxs);
+              if (p.causal || (c + 2) * 32 > ncv) sum += chunk_exp<false>(vb, pk, (c + 1) * 32, ncv, cmax, sc, mxs);
+              else sum += chunk_exp<true>(vb, pk, (c + 1) * 32, ncv, cmax, sc, mxs);
               tmem_st_32x16(t_row + (c + 1) * 16, pk);
             }
           }
           // P columns of the MMA's K extent that no chunk covered (n_cols rounds ncv up to 16 only, a chunk
           // covers 32: nothing is left) -- all of [0, n_cols / 2) is written at this point.
+          if (p.dbg & 4) tmem_wait_ld();
           tmem_wait_st();
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->p_full[w]);
+        ATRACE(3, quarter == 0 && lane == 0 && jb == 0);
       }
       // ---- O / sum -> fp16 -> out[row0 + i, h*64 .. h*64+63]
       mbar_wait(&bars->o_full[w], o_cnt & 1);
       ++o_cnt;
       tc_fence_after();
+      ATRACE(4, quarter == 0 && lane == 0);
       uint32_t oa[32], ob[32];
       if (warp_live) {
         tmem_ld_32x32(t_row + p.o_col, oa);
@@ -392,10 +421,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->o_free[w]);
-      if (warp_live && i < p.L) {
-        const int b = j.item / p.heads, h = j.item % p.heads;
+      if (warp_live) {
+        // fp16 rows into this warp's swizzled staging block (16-byte chunk c of row r at chunk c ^ (r & 7)), then
+        // one TMA store of the 32 x 64 block through the [B][L][d] map: rows past the sequence end are clipped.
+        uint8_t* stg = smem + p.off_stage + warp * 4096;
+        if (elect_one()) tma_store_wait_read<0>();  // the previous group's store has drained this block
+        __syncwarp();
         const float inv = __fdividef(1.0f, sum);
-        __half* dst = p.out + (static_cast<size_t>(b) * p.L + i) * p.d + h * HEAD_DIM;
+        uint8_t* my_row = stg + lane * 128;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           uint4 x;
@@ -403,7 +436,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           x.y = pack_half2(__uint_as_float(oa[8 * e + 2]) * inv, __uint_as_float(oa[8 * e + 3]) * inv);
           x.z = pack_half2(__uint_as_float(oa[8 * e + 4]) * inv, __uint_as_float(oa[8 * e + 5]) * inv);
           x.w = pack_half2(__uint_as_float(oa[8 * e + 6]) * inv, __uint_as_float(oa[8 * e + 7]) * inv);
-          *reinterpret_cast<uint4*>(dst + 8 * e) = x;
+          *reinterpret_cast<uint4*>(my_row + ((e ^ (lane & 7)) << 4)) = x;
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -412,10 +445,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           x.y = pack_half2(__uint_as_float(ob[8 * e + 2]) * inv, __uint_as_float(ob[8 * e + 3]) * inv);
           x.z = pack_half2(__uint_as_float(ob[8 * e + 4]) * inv, __uint_as_float(ob[8 * e + 5]) * inv);
           x.w = pack_half2(__uint_as_float(ob[8 * e + 6]) * inv, __uint_as_float(ob[8 * e + 7]) * inv);
-          *reinterpret_cast<uint4*>(dst + 32 + 8 * e) = x;
+          *reinterpret_cast<uint4*>(my_row + (((4 + e) ^ (lane & 7)) << 4)) = x;
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (elect_one()) {
+          const int b = j.item / p.heads, h = j.item % p.heads;
+          tma_store_3d(&tmO, stg, h * HEAD_DIM, j.tile * 128 + quarter * 32, b);
+          tma_store_commit();
         }
       }
+      ATRACE(5, quarter == 0 && lane == 0);
     }
+    if (elect_one()) tma_store_wait_all<0>();  // output written before the CTA (and its staging smem) goes away
   }
 
   tc_fence_before();
@@ -457,7 +499,8 @@ int launch_attention(const __half* qkv, __half* out, int B, int L, int heads, in
   p.sub_bytes = p.kb * 128;
   p.kreg_bytes = (p.split ? 2 : 1) * p.kb * 128;  // kb % 8 == 0 -> 1024-byte multiples (swizzle atoms)
   p.off_kv = 2 * Q_BYTES;
-  p.off_bars = p.off_kv + 4 * p.kreg_bytes;
+  p.off_stage = p.off_kv + 4 * p.kreg_bytes;
+  p.off_bars = p.off_stage + 8 * 4096;
   int smem_bytes = p.off_bars + static_cast<int>(sizeof(AttnBars)) + 1024;
   // one CTA per SM by construction (each CTA owns all 512 TMEM columns): ask for more than half the SM's smem
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
@@ -469,14 +512,47 @@ int launch_attention(const __half* qkv, __half* out, int B, int L, int heads, in
         cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured_bytes = smem_bytes;
   }
-  CUtensorMap tmQ, tmKV;
+  CUtensorMap tmQ, tmKV, tmO;
   const uint64_t rows = static_cast<uint64_t>(B) * L;
   PC_TRY(make_tmap_f16_2d(&tmQ, qkv, 3 * d, rows, static_cast<uint64_t>(3 * d) * 2, 64, 128));
   PC_TRY(make_tmap_f16_2d(&tmKV, qkv, 3 * d, rows, static_cast<uint64_t>(3 * d) * 2, 64, p.kb));
+  PC_TRY(make_tmap_f16_3d(&tmO, out, d, L, B, static_cast<uint64_t>(d) * 2, static_cast<uint64_t>(L) * d * 2, 32));
   const int sms = device_sm_count();
   const int grid = p.n_groups < sms ? p.n_groups : sms;
-  attention_kernel<<<grid, ATT_THREADS, smem_bytes, stream>>>(tmQ, tmKV, p);
-  PC_CHECK_CUDA(cudaGetLastError());
+  static int tracing = -1;
+  static long long* trace = nullptr;
+  static int dbg = 0;
+  if (tracing < 0) {
+    const char* e = getenv("PC_ATTN_TRACE");
+    tracing = (e && e[0] == '1') ? 1 : 0;
+    const char* f = getenv("PC_ATTN_DEBUG");
+    dbg = f ? atoi(f) : 0;
+  }
+  p.dbg = dbg;
+  if (tracing) {
+    if (!trace) PC_CHECK_CUDA(cudaMalloc(&trace, 32 * 2 * 8 * sizeof(long long)));
+    PC_CHECK_CUDA(cudaMemsetAsync(trace, 0, 32 * 2 * 8 * sizeof(long long), stream));
+    p.trace = trace;
+  }
+  PC_CHECK_CUDA(launch_pdl(attention_kernel, dim3(grid), dim3(ATT_THREADS), smem_bytes, stream, 1, tmQ, tmKV, tmO, p));
+  if (tracing) {
+    static int printed = 0;
+    long long h[32 * 2 * 8];
+    PC_CHECK_CUDA(cudaStreamSynchronize(stream));
+    PC_CHECK_CUDA(cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost));
+    if (printed++ == 3) {
+      const long long t0 = h[0] ? h[0] : h[8];
+      fprintf(stderr, "[attn trace] B*heads=%d L=%d (cycles since first sample, CTA 0)\n", p.items, L);
+      fprintf(stderr, "group WG  wait_s   s_full  pass1_end  p_arrive   o_full  stored\n");
+      for (int g = 0; g < 32; ++g)
+        for (int w = 0; w < 2; ++w) {
+          const long long* r = h + (g * 2 + w) * 8;
+          if (!r[1]) continue;
+          fprintf(stderr, "%4d  %d %8lld %8lld %9lld %9lld %8lld %8lld\n", g, w, r[0] - t0, r[1] - t0, r[2] - t0, r[3] - t0,
+                  r[4] - t0, r[5] - t0);
+        }
+    }
+  }
   return PC_OK;
 }
 

@@ -49,6 +49,46 @@ int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_
 int make_tmap_2d(CUtensorMap* out, const void* base, uint32_t elem_bytes, uint64_t inner, uint64_t rows,
                  uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows);
 
+// 3-D fp16 map [dim2][dim1][inner], box {64, box_rows, 1}, 128B swizzle (per-sequence tiles: OOB rows of a
+// sequence are clipped on store / zero-filled on load).
+int make_tmap_f16_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t dim1, uint64_t dim2,
+                     uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box_rows);
+
 int device_sm_count();
+
+// Programmatic dependent launch (PDL): kernels launched through launch_pdl() may be scheduled while the previous
+// kernel of the stream is still draining; they run their prologue (barrier init, TMEM allocation, descriptor
+// prefetch) and then block in griddep_wait() until the predecessor has completed and flushed its writes. Every
+// kernel launched this way MUST call griddep_wait() before its first global-memory access, and calls
+// griddep_launch_dependents() at its start so that its own successor can be scheduled early.
+// PC_NO_PDL=1 in the environment turns the launch attribute off (plain stream order) for A/B timing.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
+                       Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 }  // namespace pc

@@ -147,11 +147,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tmem_relinquish();
     }
   }
+  griddep_launch_dependents();  // the next kernel of the stream may start its own prologue from here on
   tc_fence_before();
   if (PAIR) cluster_sync_all();  // barriers of BOTH CTAs initialised before any remote arrive / multicast commit
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  griddep_wait();  // operands (and the residual / output buffers) belong to the previous kernel until here
 
   if (warp == TMA_WARP) {
     // ------------------------------------------------------------ TMA producer
@@ -463,25 +465,14 @@ int launch_impl(const GemmArgs& a0, cudaStream_t stream) {
   const int tiles = m_blks * n_blks;
   const int max_workers = PAIR ? device_sm_count() / 2 : device_sm_count();
   const int workers = tiles < max_workers ? tiles : max_workers;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(PAIR ? 2 * workers : workers);
-  cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = Smem::TOTAL;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
   static long long* trace = nullptr;
   if (a.debug & 8) {
     if (!trace) PC_CHECK_CUDA(cudaMalloc(&trace, 64 * 16 * sizeof(long long)));
     PC_CHECK_CUDA(cudaMemsetAsync(trace, 0, 64 * 16 * sizeof(long long), stream));
     a.trace = trace;
   }
-  PC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmW, tmC, tmR, a));
+  PC_CHECK_CUDA(launch_pdl(kern, dim3(PAIR ? 2 * workers : workers), dim3(GEMM_THREADS), Smem::TOTAL, stream, PAIR ? 2 : 1,
+                           tmA, tmW, tmC, tmR, a));
   if (a.debug & 8) {
     static int printed = 0;
     long long h[64 * 16];

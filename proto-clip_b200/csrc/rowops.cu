@@ -83,19 +83,96 @@ __device__ __forceinline__ void ln_store(RowF<NV>& r, int d, int lane, const flo
   }
 }
 
+// Persistent LayerNorm: each warp walks rows with a grid stride, keeps its gamma / beta slice in registers and
+// has the next row's 16-byte vectors in flight while it reduces and stores the current one (the activations are
+// L2-resident between two GEMMs, so the kernel is bound by load latency, not bandwidth).
 template <int NV>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ gamma,
                  const float* __restrict__ beta, const int* __restrict__ rows_idx, int rows, int d,
                  int row_stride_rows) {
-  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
-  if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  const size_t src = rows_idx ? static_cast<size_t>(rows_idx[row]) : static_cast<size_t>(row) * row_stride_rows;
-  RowF<NV> r;
-  int nvec;
-  load_row_f16(x + src * d, d, lane, r, nvec);
-  ln_store(r, d, lane, gamma, beta, y + static_cast<size_t>(row) * d);
+  const int vecs = d >> 3;
+  const int nwarps = gridDim.x * ROW_WARPS;
+  int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  griddep_launch_dependents();
+  // gamma | beta (weights, not produced by a kernel of this stream) staged once per CTA in shared memory
+  extern __shared__ float4 ln_params4[];
+  float* sg = reinterpret_cast<float*>(ln_params4);
+  float* sb = sg + d;
+  for (int i = threadIdx.x; i < (d >> 2); i += blockDim.x) {
+    reinterpret_cast<float4*>(sg)[i] = reinterpret_cast<const float4*>(gamma)[i];
+    reinterpret_cast<float4*>(sb)[i] = reinterpret_cast<const float4*>(beta)[i];
+  }
+  __syncthreads();
+  griddep_wait();  // x is the previous kernel's output
+  if (row >= rows) return;
+  uint4 cur[NV], nxt[NV];
+  auto src_of = [&](int r) -> const __half* {
+    const size_t src = rows_idx ? static_cast<size_t>(rows_idx[r]) : static_cast<size_t>(r) * row_stride_rows;
+    return x + src * d;
+  };
+  {
+    const __half* xr = src_of(row);
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+      if (lane + k * 32 < vecs) cur[k] = *reinterpret_cast<const uint4*>(xr + (lane + k * 32) * 8);
+  }
+  const float inv_d = 1.0f / static_cast<float>(d);
+  while (row < rows) {
+    const int next = row + nwarps;
+    if (next < rows) {
+      const __half* xr = src_of(next);
+#pragma unroll
+      for (int k = 0; k < NV; ++k)
+        if (lane + k * 32 < vecs) nxt[k] = *reinterpret_cast<const uint4*>(xr + (lane + k * 32) * 8);
+    }
+    float v[NV][8];
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+      if (lane + k * 32 < vecs) {
+        const __half2* h2 = reinterpret_cast<const __half2*>(&cur[k]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h2[e]);
+          v[k][2 * e] = f.x;
+          v[k][2 * e + 1] = f.y;
+          s += f.x + f.y;
+        }
+      }
+    const float mean = warp_sum(s) * inv_d;
+    float q = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+      if (lane + k * 32 < vecs)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          v[k][e] -= mean;
+          q += v[k][e] * v[k][e];
+        }
+    const float rstd = rsqrtf(warp_sum(q) * inv_d + 1e-5f);
+    __half* out = y + static_cast<size_t>(row) * d;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int vi = lane + k * 32;
+      if (vi < vecs) {
+        uint32_t pk[4];
+        float gm[8], bt[8];
+        *reinterpret_cast<float4*>(gm) = *reinterpret_cast<const float4*>(sg + vi * 8);
+        *reinterpret_cast<float4*>(gm + 4) = *reinterpret_cast<const float4*>(sg + vi * 8 + 4);
+        *reinterpret_cast<float4*>(bt) = *reinterpret_cast<const float4*>(sb + vi * 8);
+        *reinterpret_cast<float4*>(bt + 4) = *reinterpret_cast<const float4*>(sb + vi * 8 + 4);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          pk[e] = pack_half2(v[k][2 * e] * rstd * gm[2 * e] + bt[2 * e], v[k][2 * e + 1] * rstd * gm[2 * e + 1] + bt[2 * e + 1]);
+        *reinterpret_cast<uint4*>(out + vi * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) cur[k] = nxt[k];
+    row = next;
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -249,11 +326,19 @@ int grid_1d(size_t work, int block) {
 
 }  // namespace
 
+// persistent grid: up to 4 CTAs (32 warps) per SM, fewer when there are not enough rows
+static int ln_grid(int rows) {
+  const int want = (rows + ROW_WARPS - 1) / ROW_WARPS;
+  const int cap = device_sm_count() * 4;
+  return want < cap ? want : cap;
+}
+
 int launch_layernorm(const __half* x, __half* y, const float* gamma, const float* beta, int rows, int d,
                      int row_stride_rows, cudaStream_t stream) {
   PC_TRY(check_row_dims("layernorm", rows, d));
-#define CALL(NV) layernorm_kernel<NV><<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, stream>>>( \
-      x, y, gamma, beta, nullptr, rows, d, row_stride_rows)
+  const int grid = ln_grid(rows);
+#define CALL(NV) PC_CHECK_CUDA(launch_pdl(layernorm_kernel<NV>, dim3(grid), dim3(ROW_WARPS * 32), 2 * d * sizeof(float), stream, 1, \
+                                          x, y, gamma, beta, static_cast<const int*>(nullptr), rows, d, row_stride_rows))
   PC_DISPATCH_NV(d, CALL);
 #undef CALL
   PC_CHECK_CUDA(cudaGetLastError());
@@ -263,8 +348,9 @@ int launch_layernorm(const __half* x, __half* y, const float* gamma, const float
 int launch_layernorm_gather(const __half* x, const int* rows_idx, __half* y, const float* gamma,
                             const float* beta, int n, int d, cudaStream_t stream) {
   PC_TRY(check_row_dims("layernorm_gather", n, d));
-#define CALL(NV) layernorm_kernel<NV><<<(n + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, stream>>>( \
-      x, y, gamma, beta, rows_idx, n, d, 1)
+  const int grid = ln_grid(n);
+#define CALL(NV) PC_CHECK_CUDA(launch_pdl(layernorm_kernel<NV>, dim3(grid), dim3(ROW_WARPS * 32), 2 * d * sizeof(float), stream, 1, \
+                                          x, y, gamma, beta, rows_idx, n, d, 1))
   PC_DISPATCH_NV(d, CALL);
 #undef CALL
   PC_CHECK_CUDA(cudaGetLastError());
