@@ -2,24 +2,27 @@
 // (reference clip/model.py:173,183-185 -> nn.MultiheadAttention -> scaled_dot_product_attention; the text
 // tower's additive mask clip/model.py:326-332 is exactly "j > i -> -inf", i.e. the causal flag here).
 //
-// Persistent kernel, one CTA per SM, two independent softmax warpgroups ("WG", 128 threads = 128 query rows
-// = 128 TMEM lanes each) that ping-pong on the tensor core:
-//   warps 0-3 / 4-7   softmax WG 0 / 1, one query row per thread. S = Q K^T is read from TMEM twice (row max,
-//                     then exp2 / row sum); P is written back IN PLACE over S as packed fp16 (tcgen05.st) and
-//                     consumed by the PV MMA straight from TMEM (A operand in TMEM, tcgen05.mma "ts" form):
-//                     no shared-memory round trip and no proxy fence for P.
-//   warp 8 / 9        MMA issuer of WG 0 / 1 (one lane): S = Q K^T (Q, K from 128B-swizzled smem), then
-//                     O (+)= P V (V as the MN-major B operand). Two issuing threads, so the tensor pipe
-//                     always has the other WG's MMAs to run while one WG is inside its softmax.
-//   warp 10           TMA producer: Q tiles (one buffer per WG) and K/V blocks (two slots, shared by the WGs)
-//                     cut straight out of the packed qkv activation [B*L, 3d].
+// Persistent kernel, one CTA per SM (it owns all 512 TMEM columns), 19 warps:
+//   warps 0-15   softmax: two PAIRS of warpgroups (pair = one 256-column TMEM region = one 128-row query tile in
+//                flight). Inside a pair the two warpgroups split the KEY axis: thread (row r, half h) owns row r of
+//                the tile (TMEM lane r) and the S columns of half h. S = Q K^T is read from TMEM twice (row max,
+//                then exp2 / row sum; the two halves exchange max and sum through shared memory and a 64-thread
+//                named barrier); P is written back IN PLACE over the thread's own S columns as packed fp16
+//                (tcgen05.st) and consumed by the PV MMA straight from TMEM (A operand in TMEM, "ts" form): no
+//                shared-memory round trip and no proxy fence for P. Four softmax warps per scheduler keep the MUFU
+//                pipe busy across the TMEM-load latencies; the two pairs run half a period apart so one is in its
+//                exponentials while the other waits on the tensor core.
+//   warp 16 / 17 MMA issuer of pair 0 / 1: S = Q K^T (Q, K from 128B-swizzled smem), then O (+)= P V (V as the
+//                MN-major B operand). Whole warp in the loop, one elected lane issues.
+//   warp 18      TMA producer: Q tiles (one buffer per pair) and K/V blocks (two slots, shared by the pairs) cut
+//                straight out of the packed qkv activation [B*L, 3d].
 // Work decomposition: a GROUP is one K/V stream plus the (up to) two 128-row query tiles that use it:
-//   L <= 128   ("split")  the two WGs take two different (image, head) items; a K/V slot holds both items' K/V
-//   L  > 128              the two WGs take tiles 2t, 2t+1 of the same item and share its K/V
+//   L <= 128   ("split")  the two pairs take two different (image, head) items; a K/V slot holds both items' K/V
+//   L  > 128              the two pairs take tiles 2t, 2t+1 of the same item and share its K/V
 // Keys are processed in blocks of `kb` columns: the whole row in one block when L <= 256 (no rescaling at all:
 // 50 / 77 / 197 tokens), 192-key blocks with an online-softmax rescale of O in TMEM otherwise (257 / 577).
-// TMEM (512 columns) = one 256-column region per WG: S [0, kb), P [0, kb/2) over it, O at column 128 (single
-// block; S is dead by then) or 192 (multi block).
+// TMEM region of a pair (256 columns): S [0, n), P of half 0 at [0, cs/2), P of half 1 at [cs, cs + (n-cs)/2)
+// (cs = the column where half 1 starts), O at [192, 256) (over dead S columns when n > 192).
 #include <stdlib.h>
 
 #include "kernels.cuh"
@@ -30,9 +33,10 @@ namespace pc {
 namespace {
 
 constexpr int HEAD_DIM = 64;
-constexpr int MMA_WARP0 = 8;   // warps 0..7 are the two softmax warpgroups
-constexpr int TMA_WARP = 10;
-constexpr int ATT_THREADS = 11 * 32;
+constexpr int MMA_WARP0 = 16;  // warps 0..15: softmax, [pair][key half][lane quarter]
+constexpr int TMA_WARP = 18;
+constexpr int ATT_THREADS = 19 * 32;
+constexpr int O_COL = 192;     // O accumulator columns inside a pair's TMEM region
 constexpr int Q_BYTES = 128 * 128;  // one query tile: 128 rows x 64 fp16
 constexpr int KB_MULTI = 192;       // keys per block when the row does not fit one TMEM region
 
@@ -50,11 +54,11 @@ struct AttnParams {
   int n_groups;
   int n_kvb;       // key blocks per row
   int kb;          // keys per block (multiple of 16)
-  int o_col;       // column of O inside a WG's TMEM region
   int sub_bytes;   // split: byte offset of WG 1's K (V) inside a slot's K (V) region
   int kreg_bytes;  // bytes of a slot's K region; the V region follows
   int off_kv;      // smem offset of slot 0 (slot 1 follows at + 2 * kreg_bytes)
-  int off_stage;   // 8 x 4 KB output staging blocks (one per softmax warp: 32 rows x 128 B, 128B-swizzled)
+  int off_stage;   // 8 x 4 KB output staging blocks (one per pair x lane quarter: 32 rows x 128 B, 128B-swizzled)
+  int off_xch;     // max (x2, by block parity) / sum exchange between the two key halves: 3 x [pair][half][128] floats
   int off_bars;
   int dbg;           // bring-up only (env PC_ATTN_DEBUG): 1 = WG 1 idle, 2 = skip pass 1, 4 = skip pass 2 math
   long long* trace;  // bring-up only (env PC_ATTN_TRACE=1): [group iteration][WG][8] clock64 samples of CTA 0
@@ -71,9 +75,9 @@ struct AttnBars {
   uint64_t q_full[2];   // per WG
   uint64_t q_free[2];   // per WG: last S MMA of the group retired
   uint64_t s_full[2];   // per WG: S block in TMEM
-  uint64_t p_full[2];   // per WG: P block in TMEM (4 warp arrivals)
+  uint64_t p_full[2];   // per pair: P block in TMEM (8 warp arrivals)
   uint64_t o_full[2];   // per WG: last PV MMA of the group retired
-  uint64_t o_free[2];   // per WG: O read out, region reusable (4 warp arrivals)
+  uint64_t o_free[2];   // per pair: O read out, region reusable (8 warp arrivals)
   uint32_t tmem_base;
 };
 
@@ -104,60 +108,65 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-// ---- softmax chunk helpers: 32 S columns [c0, c0+32) of this thread's row, already in registers ----------
-// ncv = number of valid key columns in this block (warp-uniform), cmax = last valid column of THIS row (causal
-// rows differ). FULL chunks (every column valid for every row) take the branch-free path.
+// ---- softmax chunk helpers: 16 S columns [c0, c0+16) of this thread's row, already in registers ----------
+// cmax = last valid column of THIS row (sequence end; causal rows differ). FULL chunks (every column valid for
+// every row of the warp) take the branch-free, mask-free path.
 template <bool FULL>
-__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], int c0, int ncv, int cmax, float mx) {
+__device__ __forceinline__ float chunk_max(const uint32_t (&v)[16], int c0, int cmax, float mx) {
   float m1 = -INFINITY;
 #pragma unroll
-  for (int q8 = 0; q8 < 4; ++q8) {
-    if (FULL || c0 + 8 * q8 < ncv) {
-#pragma unroll
-      for (int j = 0; j < 8; j += 4) {
-        float a = __uint_as_float(v[8 * q8 + j]), b = __uint_as_float(v[8 * q8 + j + 1]);
-        float c = __uint_as_float(v[8 * q8 + j + 2]), d = __uint_as_float(v[8 * q8 + j + 3]);
-        if (!FULL) {
-          a = (c0 + 8 * q8 + j <= cmax) ? a : -INFINITY;
-          b = (c0 + 8 * q8 + j + 1 <= cmax) ? b : -INFINITY;
-          c = (c0 + 8 * q8 + j + 2 <= cmax) ? c : -INFINITY;
-          d = (c0 + 8 * q8 + j + 3 <= cmax) ? d : -INFINITY;
-        }
-        mx = fmaxf(mx, fmaxf(a, b));
-        m1 = fmaxf(m1, fmaxf(c, d));
-      }
+  for (int j = 0; j < 16; j += 4) {
+    float a = __uint_as_float(v[j]), b = __uint_as_float(v[j + 1]);
+    float c = __uint_as_float(v[j + 2]), d = __uint_as_float(v[j + 3]);
+    if (!FULL) {
+      a = (c0 + j <= cmax) ? a : -INFINITY;
+      b = (c0 + j + 1 <= cmax) ? b : -INFINITY;
+      c = (c0 + j + 2 <= cmax) ? c : -INFINITY;
+      d = (c0 + j + 3 <= cmax) ? d : -INFINITY;
     }
+    mx = fmaxf(mx, fmaxf(a, b));
+    m1 = fmaxf(m1, fmaxf(c, d));
   }
   return fmaxf(mx, m1);
 }
-// p = exp2(s * sc - mxs) -> packed fp16 pairs; returns the fp32 sum of the (unrounded) p.
+// packed fp32 pair math (one issue slot for two elements)
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  return static_cast<uint64_t>(__float_as_uint(lo)) | (static_cast<uint64_t>(__float_as_uint(hi)) << 32);
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// p = exp2(s * sc - mxs) -> packed fp16 pairs; `acc` accumulates the fp32 (unrounded) p as an (even, odd) pair.
 template <bool FULL>
-__device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], uint32_t (&pk)[16], int c0, int ncv, int cmax,
-                                           float sc, float mxs) {
-  float s0 = 0.0f, s1 = 0.0f;
+__device__ __forceinline__ uint64_t chunk_exp(const uint32_t (&v)[16], uint32_t (&pk)[8], int c0, int cmax, uint64_t sc2,
+                                              uint64_t nmxs2, uint64_t acc) {
 #pragma unroll
-  for (int q8 = 0; q8 < 4; ++q8) {
-    if (FULL || c0 + 8 * q8 < ncv) {
-#pragma unroll
-      for (int j = 0; j < 8; j += 2) {
-        float e0 = ex2_approx(fmaf(__uint_as_float(v[8 * q8 + j]), sc, -mxs));
-        float e1 = ex2_approx(fmaf(__uint_as_float(v[8 * q8 + j + 1]), sc, -mxs));
-        if (!FULL) {
-          e0 = (c0 + 8 * q8 + j <= cmax) ? e0 : 0.0f;
-          e1 = (c0 + 8 * q8 + j + 1 <= cmax) ? e1 : 0.0f;
-        }
-        s0 += e0;
-        s1 += e1;
-        pk[4 * q8 + (j >> 1)] = pack_half2(e0, e1);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) pk[4 * q8 + j] = 0u;
+  for (int j = 0; j < 16; j += 2) {
+    const uint64_t t = fma_f32x2(static_cast<uint64_t>(v[j]) | (static_cast<uint64_t>(v[j + 1]) << 32), sc2, nmxs2);
+    float e0 = ex2_approx(__uint_as_float(static_cast<uint32_t>(t)));
+    float e1 = ex2_approx(__uint_as_float(static_cast<uint32_t>(t >> 32)));
+    if (!FULL) {
+      e0 = (c0 + j <= cmax) ? e0 : 0.0f;
+      e1 = (c0 + j + 1 <= cmax) ? e1 : 0.0f;
     }
+    acc = add_f32x2(acc, pack_f32x2(e0, e1));
+    pk[j >> 1] = pack_half2(e0, e1);
   }
-  return s0 + s1;
+  return acc;
 }
 
+// MULTI: more than one key block per row (L > 256): compiles the online-softmax rescale in.
+// NCH: upper bound on the 16-column chunks of one key half (the softmax loops are fully unrolled over it: a lone
+// warp issues ~0.2 instructions per clock through branchy loop code, so straight-line code is what makes the
+// passes short). CAUSAL: the text tower's mask (every chunk takes the masked path).
+template <bool MULTI, int NCH, bool CAUSAL>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                  const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
@@ -165,7 +174,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint8_t* smem =
       reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   AttnBars* bars = reinterpret_cast<AttnBars*>(smem + p.off_bars);
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform: keeps role-derived values in uniform registers
   const int lane = threadIdx.x & 31;
 
   if (warp == TMA_WARP) {
@@ -179,9 +188,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_init(&bars->q_full[i], 1);
         mbar_init(&bars->q_free[i], 1);
         mbar_init(&bars->s_full[i], 1);
-        mbar_init(&bars->p_full[i], 4);
+        mbar_init(&bars->p_full[i], 8);
         mbar_init(&bars->o_full[i], 1);
-        mbar_init(&bars->o_free[i], 4);
+        mbar_init(&bars->o_free[i], 8);
       }
       fence_mbar_init();
     }
@@ -302,9 +311,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (elect_one()) {
           const uint64_t v_desc = umma_desc_mnmajor_sw128(v_addr, 1024);
           const int k_steps = n_cols >> 4;
-          umma_f16_ts(region + p.o_col, region, v_desc, idesc_o, jb != 0 ? 1u : 0u);
-          for (int kk = 1; kk < k_steps; ++kk)
-            umma_f16_ts(region + p.o_col, region + 8 * kk, v_desc + 128 * kk, idesc_o, 1u);
+          const int k_half = (k_steps + 1) >> 1;  // k-steps whose P was written by key half 0 (at column 8 * kk)
+          umma_f16_ts(region + O_COL, region, v_desc, idesc_o, jb != 0 ? 1u : 0u);
+          for (int kk = 1; kk < k_steps; ++kk) {
+            const uint32_t a_col = kk < k_half ? 8 * kk : 16 * k_half + 8 * (kk - k_half);
+            umma_f16_ts(region + O_COL, region + a_col, v_desc + 128 * kk, idesc_o, 1u);
+          }
           umma_commit(&bars->kv_free[slot]);
           if (jb == p.n_kvb - 1) umma_commit(&bars->o_full[w]);
         }
@@ -314,11 +326,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (j.active) ++q_cnt;
     }
   } else if (warp < MMA_WARP0) {
-    // ---------------------------------------------------------------------------------- softmax WG w
-    const int w = warp >> 2;
+    // ---------------------------------------------------------------------------------- softmax, pair w / half hf
+    const int w = warp >> 3;
+    const int hf = (warp >> 2) & 1;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;  // row of the tile == TMEM lane
     const uint32_t t_row = tmem + w * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t pair_bar = 1 + w * 4 + quarter;  // named barrier of the two warps that share these 32 rows
+    float* xmax0 = reinterpret_cast<float*>(smem + p.off_xch);  // [2 (block parity)][pair][half][128]
+    float* xsum = xmax0 + 1024;
+    const int x_mine = (w * 2 + hf) * 128 + r, x_other = (w * 2 + (hf ^ 1)) * 128 + r;
     const float sc = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
     uint32_t st_cnt = 0, o_cnt = 0;
     int git = -1;
@@ -328,106 +345,116 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (!j.active) continue;
       const int i = j.tile * 128 + r;  // query index inside the sequence
       const bool warp_live = j.tile * 128 + quarter * 32 < p.L;  // some row of this warp is a real query
-      const int jmax = p.causal ? min(i, p.L - 1) : p.L - 1;
+      const int jmax = CAUSAL ? min(i, p.L - 1) : p.L - 1;
       float m_run = -INFINITY, sum = 0.0f;
       for (int jb = 0; jb < p.n_kvb; ++jb, ++st_cnt) {
         const int n_cols = min(p.kb, p.lp16 - jb * p.kb);
         const int ncv = min(n_cols, p.L - jb * p.kb);  // valid key columns of this block
         const int cmax = jmax - jb * p.kb;             // last valid column of this row (may be < 0)
-        const int n_chunks = (ncv + 31) >> 5;
-        ATRACE(0, quarter == 0 && lane == 0 && jb == 0);
+        const int cs = (((n_cols >> 4) + 1) >> 1) << 4;  // first column of key half 1
+        const int c_lo = hf ? cs : 0;                    // this thread's S columns: [c_lo, c_lo + 16 * n16)
+        const int n16 = ((hf ? n_cols : cs) - c_lo) >> 4;
+        ATRACE(0, hf == 0 && quarter == 0 && lane == 0 && jb == 0);
         mbar_wait(&bars->s_full[w], st_cnt & 1);
         tc_fence_after();
-        ATRACE(1, quarter == 0 && lane == 0 && jb == 0);
+        ATRACE(1, hf == 0 && quarter == 0 && lane == 0 && jb == 0);
         if (warp_live) {
-          // ---- pass 1: row maximum of the block (next 32-column chunk in flight during the reduction)
-          uint32_t va[32], vb[32];
+          const uint32_t t_s = t_row + c_lo;
+          // number of leading chunks of this half that need no masking (warp-uniform; 0 for causal rows)
+          const int n_full = CAUSAL ? 0 : min(n16, max(0, (ncv - c_lo) >> 4));
+          uint32_t R[2][16];
+          // ---- pass 1: row maximum over this half (next chunk's load in flight during the reduction)
           float mx = -INFINITY;
-          tmem_ld_32x32(t_row, va);
-          for (int c = (p.dbg & 2) ? n_chunks : 0; c < n_chunks; c += 2) {
-            tmem_wait_ld();
-            if (c + 1 < n_chunks) tmem_ld_32x32(t_row + (c + 1) * 32, vb);
-            if (p.causal || (c + 1) * 32 > ncv) mx = chunk_max<false>(va, c * 32, ncv, cmax, mx);
-            else mx = chunk_max<true>(va, c * 32, ncv, cmax, mx);
-            if (c + 1 < n_chunks) {
-              tmem_wait_ld();
-              if (c + 2 < n_chunks) tmem_ld_32x32(t_row + (c + 2) * 32, va);
-              if (p.causal || (c + 2) * 32 > ncv) mx = chunk_max<false>(vb, (c + 1) * 32, ncv, cmax, mx);
-              else mx = chunk_max<true>(vb, (c + 1) * 32, ncv, cmax, mx);
+          if (!(p.dbg & 2)) {
+            if (n16 > 0) tmem_ld_32x16(t_s, R[0]);
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+              if (k < n16) {
+                tmem_wait_ld();
+                if (k + 1 < NCH && k + 1 < n16) tmem_ld_32x16(t_s + (k + 1) * 16, R[(k + 1) & 1]);
+                if (k < n_full) mx = chunk_max<true>(R[k & 1], c_lo + k * 16, cmax, mx);
+                else mx = chunk_max<false>(R[k & 1], c_lo + k * 16, cmax, mx);
+              }
             }
+          } else {
+            mx = 4.0f;
           }
-          ATRACE(2, quarter == 0 && lane == 0 && jb == 0);
-          if (p.dbg & 2) { tmem_wait_ld(); mx = 4.0f; }
+          float* xmax = xmax0 + (st_cnt & 1) * 512;  // double-buffered: the partner may still read the previous block's
+          xmax[x_mine] = mx;
+          named_bar_sync(pair_bar, 64);
+          mx = fmaxf(mx, xmax[x_other]);
+          ATRACE(2, hf == 0 && quarter == 0 && lane == 0 && jb == 0);
           const float m_new = fmaxf(m_run, mx);
-          if (jb > 0) {
-            // online softmax: bring O and the running sum to the new maximum. s_full(jb) implies that
-            // the PV MMA of block jb-1 has retired (same issuing thread, in-order pipe), so O is stable.
+          if (MULTI && jb > 0) {
+            // online softmax: bring this thread's 32 O columns and its partial sum to the new maximum. s_full(jb)
+            // implies that the PV MMA of block jb-1 has retired (same issuing thread, in-order pipe): O is stable.
             const float alpha = ex2_approx((m_run - m_new) * sc);
             if (__any_sync(0xffffffffu, alpha != 1.0f)) {
-              const uint32_t t_o = t_row + p.o_col;
-              tmem_ld_32x32(t_o, va);
-              tmem_ld_32x32(t_o + 32, vb);
+              const uint32_t t_o = t_row + O_COL + 32 * hf;
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                tmem_ld_32x16(t_o + 16 * hh, R[hh]);
+              }
               tmem_wait_ld();
 #pragma unroll
-              for (int e = 0; e < 32; ++e) {
-                va[e] = __float_as_uint(__uint_as_float(va[e]) * alpha);
-                vb[e] = __float_as_uint(__uint_as_float(vb[e]) * alpha);
+              for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) R[hh][e] = __float_as_uint(__uint_as_float(R[hh][e]) * alpha);
+                tmem_st_32x16(t_o + 16 * hh, R[hh]);
               }
-              tmem_st_32x32(t_o, va);
-              tmem_st_32x32(t_o + 32, vb);
             }
             sum *= alpha;
           }
           m_run = m_new;
-          // ---- pass 2: p = exp2((s - m) / 8 * log2 e), fp16 P written over S, fp32 row sum
-          const float mxs = m_new * sc;
-          uint32_t pk[16];
-          tmem_ld_32x32(t_row, va);
-          for (int c = (p.dbg & 4) ? n_chunks : 0; c < n_chunks; c += 2) {
-            tmem_wait_ld();
-            if (c + 1 < n_chunks) tmem_ld_32x32(t_row + (c + 1) * 32, vb);
-            if (p.causal || (c + 1) * 32 > ncv) sum += chunk_exp<false>(va, pk, c * 32, ncv, cmax, sc, mxs);
-            else sum += chunk_exp<true>(va, pk, c * 32, ncv, cmax, sc, mxs);
-            tmem_st_32x16(t_row + c * 16, pk);
-            if (c + 1 < n_chunks) {
-              tmem_wait_ld();
-              if (c + 2 < n_chunks) tmem_ld_32x32(t_row + (c + 2) * 32, va);
-              if (p.causal || (c + 2) * 32 > ncv) sum += chunk_exp<false>(vb, pk, (c + 1) * 32, ncv, cmax, sc, mxs);
-              else sum += chunk_exp<true>(vb, pk, (c + 1) * 32, ncv, cmax, sc, mxs);
-              tmem_st_32x16(t_row + (c + 1) * 16, pk);
+          // ---- pass 2: p = exp2((s - m) / 8 * log2 e), fp16 P written over this thread's own S columns
+          if (!(p.dbg & 4)) {
+            const uint64_t sc2 = pack_f32x2(sc, sc), nmxs2 = pack_f32x2(-m_new * sc, -m_new * sc);
+            uint64_t acc2 = 0;  // (0.0f, 0.0f)
+            uint32_t pk[8];
+            if (n16 > 0) tmem_ld_32x16(t_s, R[0]);
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+              if (k < n16) {
+                tmem_wait_ld();
+                if (k + 1 < NCH && k + 1 < n16) tmem_ld_32x16(t_s + (k + 1) * 16, R[(k + 1) & 1]);
+                if (k < n_full) acc2 = chunk_exp<true>(R[k & 1], pk, c_lo + k * 16, cmax, sc2, nmxs2, acc2);
+                else acc2 = chunk_exp<false>(R[k & 1], pk, c_lo + k * 16, cmax, sc2, nmxs2, acc2);
+                tmem_st_32x8(t_s + k * 8, pk);
+              }
             }
+            sum += __uint_as_float(static_cast<uint32_t>(acc2)) + __uint_as_float(static_cast<uint32_t>(acc2 >> 32));
           }
-          // P columns of the MMA's K extent that no chunk covered (n_cols rounds ncv up to 16 only, a chunk
-          // covers 32: nothing is left) -- all of [0, n_cols / 2) is written at this point.
-          if (p.dbg & 4) tmem_wait_ld();
           tmem_wait_st();
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->p_full[w]);
-        ATRACE(3, quarter == 0 && lane == 0 && jb == 0);
+        ATRACE(3, hf == 0 && quarter == 0 && lane == 0 && jb == 0);
       }
-      // ---- O / sum -> fp16 -> out[row0 + i, h*64 .. h*64+63]
+      // ---- O / sum -> fp16 -> out[b, i, h*64 + 32*hf .. +31]
+      if (warp_live) xsum[x_mine] = sum;  // published before the barrier below
       mbar_wait(&bars->o_full[w], o_cnt & 1);
       ++o_cnt;
       tc_fence_after();
-      ATRACE(4, quarter == 0 && lane == 0);
-      uint32_t oa[32], ob[32];
+      ATRACE(4, hf == 0 && quarter == 0 && lane == 0);
+      uint32_t oa[32];
       if (warp_live) {
-        tmem_ld_32x32(t_row + p.o_col, oa);
-        tmem_ld_32x32(t_row + p.o_col + 32, ob);
+        tmem_ld_32x32(t_row + O_COL + 32 * hf, oa);
         tmem_wait_ld();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->o_free[w]);
       if (warp_live) {
-        // fp16 rows into this warp's swizzled staging block (16-byte chunk c of row r at chunk c ^ (r & 7)), then
-        // one TMA store of the 32 x 64 block through the [B][L][d] map: rows past the sequence end are clipped.
-        uint8_t* stg = smem + p.off_stage + warp * 4096;
-        if (elect_one()) tma_store_wait_read<0>();  // the previous group's store has drained this block
-        __syncwarp();
-        const float inv = __fdividef(1.0f, sum);
+        // fp16 half-rows into the swizzled staging block of this (pair, quarter) (16-byte chunk c of row r at
+        // chunk c ^ (r & 7)), then one TMA store of the 32 x 64 block through the [B][L][d] map (rows past the
+        // sequence end are clipped). The half-0 warp owns the block's bulk groups.
+        uint8_t* stg = smem + p.off_stage + (w * 4 + quarter) * 4096;
+        if (hf == 0) {
+          if (elect_one()) tma_store_wait_read<0>();  // the previous group's store has drained this block
+        }
+        named_bar_sync(pair_bar, 64);  // staging free; partner's partial sum visible
+        const float inv = __fdividef(1.0f, sum + xsum[x_other]);
         uint8_t* my_row = stg + lane * 128;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -436,28 +463,23 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           x.y = pack_half2(__uint_as_float(oa[8 * e + 2]) * inv, __uint_as_float(oa[8 * e + 3]) * inv);
           x.z = pack_half2(__uint_as_float(oa[8 * e + 4]) * inv, __uint_as_float(oa[8 * e + 5]) * inv);
           x.w = pack_half2(__uint_as_float(oa[8 * e + 6]) * inv, __uint_as_float(oa[8 * e + 7]) * inv);
-          *reinterpret_cast<uint4*>(my_row + ((e ^ (lane & 7)) << 4)) = x;
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          uint4 x;
-          x.x = pack_half2(__uint_as_float(ob[8 * e + 0]) * inv, __uint_as_float(ob[8 * e + 1]) * inv);
-          x.y = pack_half2(__uint_as_float(ob[8 * e + 2]) * inv, __uint_as_float(ob[8 * e + 3]) * inv);
-          x.z = pack_half2(__uint_as_float(ob[8 * e + 4]) * inv, __uint_as_float(ob[8 * e + 5]) * inv);
-          x.w = pack_half2(__uint_as_float(ob[8 * e + 6]) * inv, __uint_as_float(ob[8 * e + 7]) * inv);
-          *reinterpret_cast<uint4*>(my_row + (((4 + e) ^ (lane & 7)) << 4)) = x;
+          *reinterpret_cast<uint4*>(my_row + (((4 * hf + e) ^ (lane & 7)) << 4)) = x;
         }
         fence_async_smem();
-        __syncwarp();
-        if (elect_one()) {
-          const int b = j.item / p.heads, h = j.item % p.heads;
-          tma_store_3d(&tmO, stg, h * HEAD_DIM, j.tile * 128 + quarter * 32, b);
-          tma_store_commit();
+        named_bar_sync(pair_bar, 64);  // both halves of the block written
+        if (hf == 0) {
+          if (elect_one()) {
+            const int b = j.item / p.heads, h = j.item % p.heads;
+            tma_store_3d(&tmO, stg, h * HEAD_DIM, j.tile * 128 + quarter * 32, b);
+            tma_store_commit();
+          }
         }
       }
-      ATRACE(5, quarter == 0 && lane == 0);
+      ATRACE(5, hf == 0 && quarter == 0 && lane == 0);
     }
-    if (elect_one()) tma_store_wait_all<0>();  // output written before the CTA (and its staging smem) goes away
+    if (hf == 0) {
+      if (elect_one()) tma_store_wait_all<0>();  // output written before the CTA (and its staging smem) goes away
+    }
   }
 
   tc_fence_before();
@@ -466,6 +488,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
+}
+
+template <bool MULTI, int NCH, bool CAUSAL>
+int launch_variant(int grid, int smem_bytes, cudaStream_t stream, const CUtensorMap& tmQ, const CUtensorMap& tmKV,
+                   const CUtensorMap& tmO, const AttnParams& p) {
+  static int configured_bytes = 0;
+  auto kern = attention_kernel<MULTI, NCH, CAUSAL>;
+  if (smem_bytes > configured_bytes) {
+    PC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured_bytes = smem_bytes;
+  }
+  PC_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(ATT_THREADS), smem_bytes, stream, 1, tmQ, tmKV, tmO, p));
+  return PC_OK;
 }
 
 }  // namespace
@@ -490,28 +525,21 @@ int launch_attention(const __half* qkv, __half* out, int B, int L, int heads, in
   if (p.lp16 <= 256) {
     p.n_kvb = 1;
     p.kb = p.lp16;
-    p.o_col = 128;
   } else {
     p.kb = KB_MULTI;
     p.n_kvb = (p.lp16 + p.kb - 1) / p.kb;
-    p.o_col = 192;
   }
   p.sub_bytes = p.kb * 128;
   p.kreg_bytes = (p.split ? 2 : 1) * p.kb * 128;  // kb % 8 == 0 -> 1024-byte multiples (swizzle atoms)
   p.off_kv = 2 * Q_BYTES;
   p.off_stage = p.off_kv + 4 * p.kreg_bytes;
-  p.off_bars = p.off_stage + 8 * 4096;
+  p.off_xch = p.off_stage + 8 * 4096;
+  p.off_bars = p.off_xch + 3 * 512 * 4;
   int smem_bytes = p.off_bars + static_cast<int>(sizeof(AttnBars)) + 1024;
   // one CTA per SM by construction (each CTA owns all 512 TMEM columns): ask for more than half the SM's smem
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
   PC_REQUIRE(smem_bytes <= 227 * 1024, PC_ERR_ARG, "attention: L = %d needs %d B smem", L, smem_bytes);
 
-  static int configured_bytes = 0;
-  if (smem_bytes > configured_bytes) {
-    PC_CHECK_CUDA(
-        cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    configured_bytes = smem_bytes;
-  }
   CUtensorMap tmQ, tmKV, tmO;
   const uint64_t rows = static_cast<uint64_t>(B) * L;
   PC_TRY(make_tmap_f16_2d(&tmQ, qkv, 3 * d, rows, static_cast<uint64_t>(3 * d) * 2, 64, 128));
@@ -534,7 +562,23 @@ int launch_attention(const __half* qkv, __half* out, int B, int L, int heads, in
     PC_CHECK_CUDA(cudaMemsetAsync(trace, 0, 32 * 2 * 8 * sizeof(long long), stream));
     p.trace = trace;
   }
-  PC_CHECK_CUDA(launch_pdl(attention_kernel, dim3(grid), dim3(ATT_THREADS), smem_bytes, stream, 1, tmQ, tmKV, tmO, p));
+  // instantiation: smallest unrolled chunk count that covers one key half of a block
+  const int need = ((p.kb >> 4) + 1) >> 1;
+  int rc;
+  if (p.n_kvb > 1) {
+    rc = p.causal ? launch_variant<true, 6, true>(grid, smem_bytes, stream, tmQ, tmKV, tmO, p)
+                  : launch_variant<true, 6, false>(grid, smem_bytes, stream, tmQ, tmKV, tmO, p);
+  } else if (need <= 4) {
+    rc = p.causal ? launch_variant<false, 4, true>(grid, smem_bytes, stream, tmQ, tmKV, tmO, p)
+                  : launch_variant<false, 4, false>(grid, smem_bytes, stream, tmQ, tmKV, tmO, p);
+  } else if (need <= 7) {
+    rc = p.causal ? launch_variant<false, 7, true>(grid, smem_bytes, stream, tmQ, tmKV, tmO, p)
+                  : launch_variant<false, 7, false>(grid, smem_bytes, stream, tmQ, tmKV, tmO, p);
+  } else {
+    rc = p.causal ? launch_variant<false, 8, true>(grid, smem_bytes, stream, tmQ, tmKV, tmO, p)
+                  : launch_variant<false, 8, false>(grid, smem_bytes, stream, tmQ, tmKV, tmO, p);
+  }
+  PC_TRY(rc);
   if (tracing) {
     static int printed = 0;
     long long h[32 * 2 * 8];

@@ -105,7 +105,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   Bars* bars = reinterpret_cast<Bars*>(smem + Smem::OFF_BARS);
   float* sbias = reinterpret_cast<float*>(smem + Smem::OFF_BIAS);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform: keeps role-derived values in uniform registers
   const int lane = threadIdx.x & 31;
   const int rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
   const bool leader = rank == 0;

@@ -212,6 +212,12 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
 // ------------------------------------------------------------------ UMMA descriptors
 // Shared-memory matrix descriptor (64-bit), sm_100 "version 1":
 //   [0,14)  start address >> 4        [16,30) leading-dim byte offset >> 4
