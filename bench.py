@@ -232,6 +232,10 @@ def run_ours(args):
     if rank == 0:
         roof = gemm_roofline(nat, dev, (mb or 96) * (c["image_resolution"] // c["vision_patch_size"]) ** 2 + (mb or 96),
                              c["vision_width"])
+    attn = None
+    if rank == 0:
+        attn = attention_roofline(nat, dev, mb or 96, (c["image_resolution"] // c["vision_patch_size"]) ** 2 + 1,
+                                  c["vision_width"] // 64)
     cpu = None
     parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -259,7 +263,7 @@ def run_ours(args):
             "model_tflops": round(value * flops_img / 1e12, 1),
             "model_frac_of_sustained_peak": round(value / world * flops_img / 1e12 / sustained, 4),
             "accuracy_on_synthetic_queries": round(acc, 4),
-            "roofline": roof, "cpu_baseline": cpu, "parity": parity, "peaks": src,
+            "roofline": roof, "roofline_attention": attn, "cpu_baseline": cpu, "parity": parity, "peaks": src,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -298,10 +302,41 @@ def gemm_roofline(nat, dev, M, d):
     ms = e0.elapsed_time(e1) / iters
     flops = 24.0 * M * d * d
     achieved = flops / (ms / 1e3) / 1e12
+    # DRAM read + write bytes of the same four launches (QKV 68.0 MB, out-proj 60.4 MB, c_fc 95.3 MB, c_proj 164.7 MB),
+    # one `ncu --set full` capture with cold caches: profiles/r01_ncu_gemm_summary.txt. Only valid for that shape.
+    traffic = 388.4e6 if (M, d) == (18912, 768) else None
     return {"bound": "tensor", "achieved": round(achieved, 1), "peak": sustained, "unit": "TFLOP/s",
-            "frac": round(achieved / sustained, 4), "traffic": None,
-            "kernel": f"gemm_tn_kernel<256,*>: 4 Linear launches of one ResidualAttentionBlock, M={M}, d={d}",
+            "frac": round(achieved / sustained, 4), "traffic": traffic,
+            "kernel": f"gemm_tn_kernel<pair,*>: 4 Linear launches of one ResidualAttentionBlock, M={M}, d={d}",
             "flops_per_4_launches": flops, "ms_per_4_launches": round(ms, 4), "peak_kind": f"bf16 sustained ({src})"}
+
+
+def attention_roofline(nat, dev, B, L, heads):
+    """attention_kernel alone at the micro-batch's shape: algorithmic 4*B*heads*L^2*64 flop per launch (QK^T + PV)."""
+    sustained, burst, src = measured_peaks()
+    torch.manual_seed(1)
+    qkv = torch.randn(B * L, 3 * heads * 64, device=dev).half()
+    for _ in range(5):
+        nat.attention(qkv, B, L, heads, False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 100
+    e0.record()
+    for _ in range(iters):
+        nat.attention(qkv, B, L, heads, False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    flops = 4.0 * B * heads * L * L * 64
+    achieved = flops / (ms / 1e3) / 1e12
+    exps = float(B) * heads * L * L
+    return {"bound": "tensor", "achieved": round(achieved, 1), "peak": burst, "unit": "TFLOP/s",
+            "frac": round(achieved / burst, 4), "traffic": None,
+            "kernel": f"attention_kernel<false,7,false>: B={B}, L={L}, heads={heads}, head_dim=64",
+            "flops_per_launch": flops, "us_per_launch": round(ms * 1e3, 2), "peak_kind": f"bf16 burst ({src})",
+            "note": "softmax-bound at head_dim 64: one exp2 per 256 tensor flops; the MUFU pipe (16 exp2/clk/SM) "
+                    "caps this shape at about 0.55 of the tensor peak",
+            "gexp_per_s": round(exps / (ms / 1e3) / 1e9, 1)}
 
 
 def cpu_baseline_and_parity(sd, head, host_images, clf, dev_images, sample):

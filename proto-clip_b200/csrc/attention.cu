@@ -57,7 +57,7 @@ struct AttnParams {
   int sub_bytes;   // split: byte offset of WG 1's K (V) inside a slot's K (V) region
   int kreg_bytes;  // bytes of a slot's K region; the V region follows
   int off_kv;      // smem offset of slot 0 (slot 1 follows at + 2 * kreg_bytes)
-  int off_stage;   // 8 x 4 KB output staging blocks (one per pair x lane quarter: 32 rows x 128 B, 128B-swizzled)
+  int off_stage;   // 16 x 2 KB output staging blocks (one per softmax warp: 32 rows x 64 B, 64B-swizzled)
   int off_xch;     // max (x2, by block parity) / sum exchange between the two key halves: 3 x [pair][half][128] floats
   int off_bars;
   int dbg;           // bring-up only (env PC_ATTN_DEBUG): 1 = WG 1 idle, 2 = skip pass 1, 4 = skip pass 2 math
@@ -93,6 +93,10 @@ __device__ __forceinline__ Job job_of(const AttnParams& p, int g, int w) {
     j.item = 2 * g + w;
     j.tile = 0;
     j.active = j.item < p.items;
+  } else if (p.ppi == 1) {  // one tile pair per item (128 < L <= 256): no divisions on the per-group path
+    j.item = g;
+    j.tile = w;
+    j.active = w < p.m_tiles;
   } else {
     j.item = g / p.ppi;
     j.tile = 2 * (g % p.ppi) + w;
@@ -446,16 +450,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->o_free[w]);
       if (warp_live) {
-        // fp16 half-rows into the swizzled staging block of this (pair, quarter) (16-byte chunk c of row r at
-        // chunk c ^ (r & 7)), then one TMA store of the 32 x 64 block through the [B][L][d] map (rows past the
-        // sequence end are clipped). The half-0 warp owns the block's bulk groups.
-        uint8_t* stg = smem + p.off_stage + (w * 4 + quarter) * 4096;
-        if (hf == 0) {
-          if (elect_one()) tma_store_wait_read<0>();  // the previous group's store has drained this block
-        }
-        named_bar_sync(pair_bar, 64);  // staging free; partner's partial sum visible
+        // fp16 half-rows (32 columns = 64 bytes) into this warp's own staging block, 64B-swizzled (16-byte chunk c
+        // of row r at chunk c ^ ((r >> 1) & 3): conflict-free), then one TMA store of the 32 x 32 block through the
+        // [B][L][d] map -- rows past the sequence end are clipped. No cross-warp hand-off: each warp owns its
+        // staging block and its bulk groups.
+        uint8_t* stg = smem + p.off_stage + warp * 2048;
+        if (elect_one()) tma_store_wait_read<0>();  // this warp's previous store has drained the block
+        named_bar_sync(pair_bar, 64);               // partner's partial row sum visible (and the wait above done)
         const float inv = __fdividef(1.0f, sum + xsum[x_other]);
-        uint8_t* my_row = stg + lane * 128;
+        uint8_t* my_row = stg + lane * 64;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           uint4 x;
@@ -463,23 +466,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           x.y = pack_half2(__uint_as_float(oa[8 * e + 2]) * inv, __uint_as_float(oa[8 * e + 3]) * inv);
           x.z = pack_half2(__uint_as_float(oa[8 * e + 4]) * inv, __uint_as_float(oa[8 * e + 5]) * inv);
           x.w = pack_half2(__uint_as_float(oa[8 * e + 6]) * inv, __uint_as_float(oa[8 * e + 7]) * inv);
-          *reinterpret_cast<uint4*>(my_row + (((4 * hf + e) ^ (lane & 7)) << 4)) = x;
+          *reinterpret_cast<uint4*>(my_row + ((e ^ ((lane >> 1) & 3)) << 4)) = x;
         }
         fence_async_smem();
-        named_bar_sync(pair_bar, 64);  // both halves of the block written
-        if (hf == 0) {
-          if (elect_one()) {
-            const int b = j.item / p.heads, h = j.item % p.heads;
-            tma_store_3d(&tmO, stg, h * HEAD_DIM, j.tile * 128 + quarter * 32, b);
-            tma_store_commit();
-          }
+        __syncwarp();
+        if (elect_one()) {
+          const int b = j.item / p.heads, h = j.item % p.heads;
+          tma_store_3d(&tmO, stg, h * HEAD_DIM + 32 * hf, j.tile * 128 + quarter * 32, b);
+          tma_store_commit();
         }
       }
       ATRACE(5, hf == 0 && quarter == 0 && lane == 0);
     }
-    if (hf == 0) {
-      if (elect_one()) tma_store_wait_all<0>();  // output written before the CTA (and its staging smem) goes away
-    }
+    if (elect_one()) tma_store_wait_all<0>();  // output written before the CTA (and its staging smem) goes away
   }
 
   tc_fence_before();
@@ -544,7 +543,7 @@ int launch_attention(const __half* qkv, __half* out, int B, int L, int heads, in
   const uint64_t rows = static_cast<uint64_t>(B) * L;
   PC_TRY(make_tmap_f16_2d(&tmQ, qkv, 3 * d, rows, static_cast<uint64_t>(3 * d) * 2, 64, 128));
   PC_TRY(make_tmap_f16_2d(&tmKV, qkv, 3 * d, rows, static_cast<uint64_t>(3 * d) * 2, 64, p.kb));
-  PC_TRY(make_tmap_f16_3d(&tmO, out, d, L, B, static_cast<uint64_t>(d) * 2, static_cast<uint64_t>(L) * d * 2, 32));
+  PC_TRY(make_tmap_f16_3d(&tmO, out, d, L, B, static_cast<uint64_t>(d) * 2, static_cast<uint64_t>(L) * d * 2, 32, 32));
   const int sms = device_sm_count();
   const int grid = p.n_groups < sms ? p.n_groups : sms;
   static int tracing = -1;

@@ -94,20 +94,20 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint32_t elem_bytes, uint64
   return PC_OK;
 }
 
-// 3-D fp16 map [dim2][dim1][inner] with a {64, box_rows, 1} box and 128B swizzle: rows are clipped / zero-filled
+// 3-D fp16 map [dim2][dim1][inner] with a {box_inner, box_rows, 1} box (64 columns: 128B swizzle, 32: 64B swizzle): rows are clipped / zero-filled
 // per dim-2 slice (used for per-sequence tiles: dim1 = tokens of one sequence, dim2 = sequences).
 int make_tmap_f16_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t dim1, uint64_t dim2,
-                     uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box_rows) {
+                     uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box_inner, uint32_t box_rows) {
   struct Key3 {
     const void* base;
     uint64_t inner, dim1, dim2, s1, s2;
-    uint32_t box_rows;
+    uint32_t box_inner, box_rows;
   };
   static thread_local std::vector<std::pair<Key3, CUtensorMap>> cache;
   for (const auto& e : cache) {
     const Key3& k = e.first;
     if (k.base == base && k.inner == inner && k.dim1 == dim1 && k.dim2 == dim2 && k.s1 == stride1_bytes &&
-        k.s2 == stride2_bytes && k.box_rows == box_rows) {
+        k.s2 == stride2_bytes && k.box_inner == box_inner && k.box_rows == box_rows) {
       *out = e.second;
       return PC_OK;
     }
@@ -116,17 +116,18 @@ int make_tmap_f16_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_
   PC_REQUIRE(fn != nullptr, PC_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   PC_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (stride1_bytes & 15) == 0 && (stride2_bytes & 15) == 0,
              PC_ERR_ALIGN, "TMA 3-D map: base / strides must be multiples of 16 bytes");
-  PC_REQUIRE(box_rows >= 1 && box_rows <= 256, PC_ERR_ARG, "TMA box rows %u unsupported", box_rows);
+  PC_REQUIRE(box_rows >= 1 && box_rows <= 256 && (box_inner == 64 || box_inner == 32), PC_ERR_ARG,
+             "TMA box %ux%u unsupported", box_inner, box_rows);
   cuuint64_t dims[3] = {inner, dim1, dim2};
   cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
-  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t box[3] = {box_inner, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, box_inner == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PC_REQUIRE(r == CUDA_SUCCESS, PC_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r);
   if (cache.size() > 64) cache.clear();
-  cache.emplace_back(Key3{base, inner, dim1, dim2, stride1_bytes, stride2_bytes, box_rows}, *out);
+  cache.emplace_back(Key3{base, inner, dim1, dim2, stride1_bytes, stride2_bytes, box_inner, box_rows}, *out);
   return PC_OK;
 }
 

@@ -49,10 +49,10 @@ int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_
 int make_tmap_2d(CUtensorMap* out, const void* base, uint32_t elem_bytes, uint64_t inner, uint64_t rows,
                  uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows);
 
-// 3-D fp16 map [dim2][dim1][inner], box {64, box_rows, 1}, 128B swizzle (per-sequence tiles: OOB rows of a
-// sequence are clipped on store / zero-filled on load).
+// 3-D fp16 map [dim2][dim1][inner], box {box_inner, box_rows, 1}; box_inner = 64 -> 128B swizzle, 32 -> 64B swizzle
+// (per-sequence tiles: OOB rows of a sequence are clipped on store / zero-filled on load).
 int make_tmap_f16_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t dim1, uint64_t dim2,
-                     uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box_rows);
+                     uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box_inner, uint32_t box_rows);
 
 int device_sm_count();
 

@@ -168,5 +168,15 @@ def main(only=None):
         print(arch, "done")
 
 
+def main_336():
+    """ViT-L/14@336px (config C4: L = 577 tokens -> the attention kernel's multi-block path). fp32 reference only."""
+    fx = tower_fixture("ViT-L/14@336px", B=2, P=1, with_fp16=False, with_blocks=False)
+    torch.save(fx, os.path.join(OUT, "tower_ViT_L_14_336px.pt"))
+    print("ViT-L/14@336px done")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "336":
+        main_336()
+    else:
+        main()
