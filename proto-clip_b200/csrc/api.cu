@@ -1,6 +1,8 @@
 // C ABI of libprotoclip_b200 (include/protoclip_b200.h): context, weight binding and the orchestration of
 // the kernels in gemm.cu / attention.cu / rowops.cu / head.cu into the reference's hot-path functions
 // (encode_image, encode_text, ResidualAttentionBlock, Adapter*, prototypes, P).
+#include <stdlib.h>
+
 #include <new>
 #include <vector>
 
@@ -14,11 +16,21 @@ static_assert(int(PC_EPI_BIAS) == int(EPI_BIAS) && int(PC_EPI_BIAS_QUICKGELU) ==
 
 namespace {
 
+// LayerNorm folded into the Linear that consumes it (kernels.cuh: EPI_LN_*): per layer, for in_proj (ln_1) and
+// c_fc (ln_2), the gamma-scaled weight and the two per-column vectors. Owned by the tower, built at bind time.
+struct FoldedLn {
+  __half* w = nullptr;  // [N, K] f16(W * gamma)
+  float* s = nullptr;   // [N]
+  float* c = nullptr;   // [N]
+};
+
 struct Tower {
   bool bound = false;
   int width = 0, layers = 0, heads = 0, L = 0, embed = 0;
   std::vector<pc_resblock_weights> blocks;
-  __half* proj_t = nullptr;  // owned: [embed, width] (transposed projection -> TN GEMM)
+  std::vector<FoldedLn> qkv_ln, fc_ln;  // per layer
+  void* fold_pool = nullptr;            // owned: one allocation behind qkv_ln / fc_ln
+  __half* proj_t = nullptr;             // owned: [embed, width] (transposed projection -> TN GEMM)
 };
 
 constexpr int kDefaultMicroBatch = 96;  // 96 * 197 tokens = 148 row blocks of 128: one GEMM wave per n-block
@@ -123,23 +135,121 @@ int resblock(const Tower& t, int layer, __half* x, __half* h, __half* big, int B
   return PC_OK;
 }
 
+// PC_NO_FUSED_LN=1 keeps LayerNorm as its own kernel (A/B timing, bring-up).
+bool fused_ln_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PC_NO_FUSED_LN");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+void free_folds(Tower& t) {
+  if (t.fold_pool) cudaFree(t.fold_pool);
+  t.fold_pool = nullptr;
+  t.qkv_ln.clear();
+  t.fc_ln.clear();
+}
+
+// Build the LN-folded copies of in_proj (with ln_1) and c_fc (with ln_2) for every layer.
+int build_folds(Tower& t) {
+  free_folds(t);
+  const size_t d = t.width;
+  const size_t w_bytes = align_up((3 * d + 4 * d) * d * sizeof(__half), 256);
+  const size_t v_bytes = align_up((3 * d + 4 * d) * sizeof(float), 256);
+  const size_t per_layer = w_bytes + 2 * v_bytes;
+  PC_CHECK_CUDA(cudaMalloc(&t.fold_pool, per_layer * t.layers));
+  t.qkv_ln.resize(t.layers);
+  t.fc_ln.resize(t.layers);
+  for (int l = 0; l < t.layers; ++l) {
+    uint8_t* base = static_cast<uint8_t*>(t.fold_pool) + per_layer * l;
+    __half* w = reinterpret_cast<__half*>(base);
+    float* sv = reinterpret_cast<float*>(base + w_bytes);
+    float* cv = reinterpret_cast<float*>(base + w_bytes + v_bytes);
+    t.qkv_ln[l] = FoldedLn{w, sv, cv};
+    t.fc_ln[l] = FoldedLn{w + 3 * d * d, sv + 3 * d, cv + 3 * d};
+    const pc_resblock_weights& b = t.blocks[l];
+    PC_TRY(launch_fold_ln(static_cast<const __half*>(b.in_proj_weight), static_cast<const float*>(b.ln_1_weight),
+                          static_cast<const float*>(b.ln_1_bias), static_cast<const __half*>(b.in_proj_bias),
+                          t.qkv_ln[l].w, t.qkv_ln[l].s, t.qkv_ln[l].c, static_cast<int>(3 * d), static_cast<int>(d), 0));
+    PC_TRY(launch_fold_ln(static_cast<const __half*>(b.c_fc_weight), static_cast<const float*>(b.ln_2_weight),
+                          static_cast<const float*>(b.ln_2_bias), static_cast<const __half*>(b.c_fc_bias),
+                          t.fc_ln[l].w, t.fc_ln[l].s, t.fc_ln[l].c, static_cast<int>(4 * d), static_cast<int>(d), 0));
+  }
+  PC_CHECK_CUDA(cudaDeviceSynchronize());
+  return PC_OK;
+}
+
+// The same block with both LayerNorms folded into the GEMMs that consume them (no LayerNorm launches):
+//   in : s1 = `parts_in` partial (sum, sum^2) pairs for every row of x
+//   out: s1 = gemm_stats_parts(rows, d) partial pairs of the new x (ready for the next block's ln_1)
+// QKV reads x directly with the gamma-scaled in_proj; out_proj writes the statistics of the row segments it
+// produces into s2; c_fc reads them (ln_2); c_proj writes the new s1. No atomics: results are bit-reproducible.
+int resblock_fused(const Tower& t, int layer, __half* x, __half* h, __half* big, float* s1, int parts_in, float* s2,
+                   int B, int L, int causal, cudaStream_t s) {
+  const pc_resblock_weights& w = t.blocks[layer];
+  const int d = t.width, rows = B * L;
+  GemmArgs g{};
+  g.M = rows; g.N = 3 * d; g.K = d;
+  g.A = x; g.lda = d;
+  g.W = t.qkv_ln[layer].w; g.ldw = d;
+  g.C = big; g.ldc = 3 * d;
+  g.ln_stats = s1; g.ln_parts = parts_in; g.ln_s = t.qkv_ln[layer].s; g.ln_c = t.qkv_ln[layer].c;
+  PC_TRY(launch_gemm(g, EPI_LN_BIAS, s));
+  PC_TRY(launch_attention(big, h, B, L, t.heads, causal, s));
+  g = GemmArgs{};
+  g.M = rows; g.N = d; g.K = d;
+  g.A = h; g.lda = d;
+  g.W = static_cast<const __half*>(w.out_proj_weight); g.ldw = d;
+  g.C = x; g.ldc = d;
+  g.bias = static_cast<const __half*>(w.out_proj_bias);
+  g.residual = x; g.ldr = d;
+  g.stats_out = s2;
+  PC_TRY(launch_gemm(g, EPI_BIAS_RES, s));
+  g = GemmArgs{};
+  g.M = rows; g.N = 4 * d; g.K = d;
+  g.A = x; g.lda = d;
+  g.W = t.fc_ln[layer].w; g.ldw = d;
+  g.C = big; g.ldc = 4 * d;
+  g.ln_stats = s2; g.ln_parts = gemm_stats_parts(rows, d); g.ln_s = t.fc_ln[layer].s; g.ln_c = t.fc_ln[layer].c;
+  PC_TRY(launch_gemm(g, EPI_LN_QGELU, s));
+  g = GemmArgs{};
+  g.M = rows; g.N = d; g.K = 4 * d;
+  g.A = big; g.lda = 4 * d;
+  g.W = static_cast<const __half*>(w.c_proj_weight); g.ldw = 4 * d;
+  g.C = x; g.ldc = d;
+  g.bias = static_cast<const __half*>(w.c_proj_bias);
+  g.residual = x; g.ldr = d;
+  g.stats_out = s1;
+  PC_TRY(launch_gemm(g, EPI_BIAS_RES, s));
+  return PC_OK;
+}
+
 // workspace carve-up shared by both towers: x [rows,d] | h [rows,d] | big [rows,4d] | idx [mb] ints
 struct TowerWs {
   __half *x, *h, *big;
   int* idx;
+  float *s1, *s2;  // LayerNorm statistics [rows][parts][2] (ln_1 / ln_2 inputs)
 };
+// partial pairs per row: at most one per 64 output columns of a residual GEMM (gemm_stats_parts)
+size_t stats_bytes(int rows, int d) { return align_up(static_cast<size_t>(rows) * ((d + 63) / 64) * 8, 256); }
 size_t tower_ws_bytes(int rows, int d, int mb) {
   return align_up(static_cast<size_t>(rows) * d * 2, 256) * 2 + align_up(static_cast<size_t>(rows) * d * 8, 256) +
-         align_up(static_cast<size_t>(mb) * 4, 256);
+         align_up(static_cast<size_t>(mb) * 4, 256) + 2 * stats_bytes(rows, d);
 }
-TowerWs carve(void* ws, int rows, int d) {
+TowerWs carve(void* ws, int rows, int d, int mb) {
   TowerWs t;
   uint8_t* p = static_cast<uint8_t*>(ws);
   const size_t a = align_up(static_cast<size_t>(rows) * d * 2, 256);
   t.x = reinterpret_cast<__half*>(p);
   t.h = reinterpret_cast<__half*>(p + a);
   t.big = reinterpret_cast<__half*>(p + 2 * a);
-  t.idx = reinterpret_cast<int*>(p + 2 * a + align_up(static_cast<size_t>(rows) * d * 8, 256));
+  uint8_t* q = p + 2 * a + align_up(static_cast<size_t>(rows) * d * 8, 256);
+  t.idx = reinterpret_cast<int*>(q);
+  q += align_up(static_cast<size_t>(mb) * 4, 256);
+  t.s1 = reinterpret_cast<float*>(q);
+  t.s2 = reinterpret_cast<float*>(q + stats_bytes(rows, d));
   return t;
 }
 
@@ -176,6 +286,8 @@ void pc_ctx_destroy(pc_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->vis.proj_t) cudaFree(ctx->vis.proj_t);
   if (ctx->txt.proj_t) cudaFree(ctx->txt.proj_t);
+  free_folds(ctx->vis);
+  free_folds(ctx->txt);
   if (ctx->conv1_p) cudaFree(ctx->conv1_p);
   delete ctx;
 }
@@ -217,6 +329,7 @@ int pc_vit_bind_weights(pc_ctx* ctx, const pc_vit_weights* w) {
                              static_cast<size_t>(ctx->Kpatch) * 2, static_cast<size_t>(ctx->Kpatch) * 2, t.width,
                              cudaMemcpyDeviceToDevice));
   PC_TRY(make_transposed(w->proj, t.width, t.embed, &t.proj_t));
+  PC_TRY(build_folds(t));
   t.bound = true;
   return PC_OK;
 }
@@ -243,6 +356,7 @@ int pc_text_bind_weights(pc_ctx* ctx, const pc_text_weights* w) {
   ctx->ln_final_w = static_cast<const float*>(w->ln_final_weight);
   ctx->ln_final_b = static_cast<const float*>(w->ln_final_bias);
   PC_TRY(make_transposed(w->text_projection, t.width, t.embed, &t.proj_t));
+  PC_TRY(build_folds(t));
   t.bound = true;
   return PC_OK;
 }
@@ -267,7 +381,7 @@ int pc_encode_image(pc_ctx* ctx, const void* images, int img_dtype, int B, void*
   PC_REQUIRE(workspace_bytes >= tower_ws_bytes(mb * t.L, t.width, mb), PC_ERR_WORKSPACE,
              "pc_encode_image: workspace %zu < %zu", workspace_bytes, tower_ws_bytes(mb * t.L, t.width, mb));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const TowerWs ws = carve(workspace, mb * t.L, t.width);
+  const TowerWs ws = carve(workspace, mb * t.L, t.width, mb);
   const int d = t.width, g2 = ctx->grid * ctx->grid;
   const size_t img_elems = static_cast<size_t>(3) * ctx->res * ctx->res;
   const size_t img_bytes = img_elems * (img_dtype == PC_IMG_F16 ? 2 : 4);
@@ -284,7 +398,13 @@ int pc_encode_image(pc_ctx* ctx, const void* images, int img_dtype, int B, void*
     g.C = ws.h; g.ldc = d;
     PC_TRY(launch_gemm(g, EPI_BIAS, s));
     PC_TRY(launch_embed_ln_pre(ws.h, ctx->cls, ctx->vpos, ctx->ln_pre_w, ctx->ln_pre_b, ws.x, n, t.L, d, s));
-    for (int l = 0; l < t.layers; ++l) PC_TRY(resblock(t, l, ws.x, ws.h, ws.big, n, t.L, 0, s));
+    if (fused_ln_enabled()) {
+      PC_TRY(launch_row_stats(ws.x, ws.s1, n * t.L, d, s));
+      for (int l = 0; l < t.layers; ++l)
+        PC_TRY(resblock_fused(t, l, ws.x, ws.h, ws.big, ws.s1, l == 0 ? 1 : gemm_stats_parts(n * t.L, d), ws.s2, n, t.L, 0, s));
+    } else {
+      for (int l = 0; l < t.layers; ++l) PC_TRY(resblock(t, l, ws.x, ws.h, ws.big, n, t.L, 0, s));
+    }
     // ln_post on the CLS rows, then @ proj (clip/model.py:233-236)
     PC_TRY(launch_layernorm(ws.x, ws.h, ctx->ln_post_w, ctx->ln_post_b, n, d, t.L, s));
     g = GemmArgs{};
@@ -319,14 +439,20 @@ int pc_encode_text(pc_ctx* ctx, const int64_t* tokens, int P, void* out, int l2n
   PC_REQUIRE(workspace_bytes >= tower_ws_bytes(mb * t.L, t.width, mb), PC_ERR_WORKSPACE,
              "pc_encode_text: workspace %zu < %zu", workspace_bytes, tower_ws_bytes(mb * t.L, t.width, mb));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const TowerWs ws = carve(workspace, mb * t.L, t.width);
+  const TowerWs ws = carve(workspace, mb * t.L, t.width, mb);
   const int d = t.width;
   __half* o = static_cast<__half*>(out);
   for (int p0 = 0; p0 < P; p0 += mb) {
     const int n = (P - p0 < mb) ? (P - p0) : mb;
     const int64_t* tok = tokens + static_cast<size_t>(p0) * t.L;
     PC_TRY(launch_text_embed(tok, ctx->tok_emb, ctx->tpos, ws.x, n, t.L, d, ctx->vocab, s));
-    for (int l = 0; l < t.layers; ++l) PC_TRY(resblock(t, l, ws.x, ws.h, ws.big, n, t.L, 1, s));
+    if (fused_ln_enabled()) {
+      PC_TRY(launch_row_stats(ws.x, ws.s1, n * t.L, d, s));
+      for (int l = 0; l < t.layers; ++l)
+        PC_TRY(resblock_fused(t, l, ws.x, ws.h, ws.big, ws.s1, l == 0 ? 1 : gemm_stats_parts(n * t.L, d), ws.s2, n, t.L, 1, s));
+    } else {
+      for (int l = 0; l < t.layers; ++l) PC_TRY(resblock(t, l, ws.x, ws.h, ws.big, n, t.L, 1, s));
+    }
     // ln_final is row-wise, so LN(gather(x)) == gather(LN(x)) (clip/model.py:348-352)
     PC_TRY(launch_eot_index(tok, ws.idx, n, t.L, s));
     PC_TRY(launch_layernorm_gather(ws.x, ws.idx, ws.h, ctx->ln_final_w, ctx->ln_final_b, n, d, s));
@@ -363,9 +489,13 @@ int pc_resblock_forward(pc_ctx* ctx, int tower, int layer, void* x, int B, int L
              "pc_resblock_forward: workspace must be 256-byte aligned");
   PC_REQUIRE(workspace_bytes >= tower_ws_bytes(B * L, t.width, 1), PC_ERR_WORKSPACE,
              "pc_resblock_forward: workspace %zu < %zu", workspace_bytes, tower_ws_bytes(B * L, t.width, 1));
-  const TowerWs ws = carve(workspace, B * L, t.width);
-  return resblock(t, layer, static_cast<__half*>(x), ws.h, ws.big, B, L, causal,
-                  static_cast<cudaStream_t>(stream));
+  const TowerWs ws = carve(workspace, B * L, t.width, 1);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (fused_ln_enabled()) {
+    PC_TRY(launch_row_stats(static_cast<const __half*>(x), ws.s1, B * L, t.width, s));
+    return resblock_fused(t, layer, static_cast<__half*>(x), ws.h, ws.big, ws.s1, 1, ws.s2, B, L, causal, s);
+  }
+  return resblock(t, layer, static_cast<__half*>(x), ws.h, ws.big, B, L, causal, s);
 }
 
 int pc_linear_forward(const void* x, int ldx, const void* w, int ldw, const void* bias, const void* residual,

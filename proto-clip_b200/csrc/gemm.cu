@@ -49,8 +49,10 @@ struct Smem {
   static constexpr int OFF_STAGING = STAGES * STAGE_BYTES;
   static constexpr int STAGING_BYTES = EPI_WARPS * 2 * STG_BYTES;
   static constexpr int OFF_BIAS = OFF_STAGING + STAGING_BYTES;
-  static constexpr int OFF_BARS = OFF_BIAS + 256 * 4;
-  static constexpr int TOTAL = OFF_BARS + 512 + 1024;  // + barrier block + 1024 B alignment slack
+  static constexpr int OFF_SCALE = OFF_BIAS + 256 * 4;  // s_n of the LayerNorm-folded epilogues
+  static constexpr int OFF_BARS = OFF_SCALE + 256 * 4;
+  static constexpr int TOTAL = OFF_BARS + 256;  // + barrier block; the buffer is declared 1024-byte aligned
+  static_assert(TOTAL <= 227 * 1024, "GEMM shared memory exceeds the 227 KB a CTA may use");
 };
 
 struct Bars {
@@ -61,7 +63,7 @@ struct Bars {
   uint64_t res_full[EPI_WARPS][2];  // residual block landed in staging buffer [warp][buf]
   uint32_t tmem_base;
 };
-static_assert(sizeof(Bars) <= 512, "barrier block");
+static_assert(sizeof(Bars) <= 256, "barrier block");
 
 // QuickGELU x * sigmoid(1.702 x) (clip/model.py:164-166) on a packed half2, with
 // sigmoid(t) = 0.5 * tanh(t / 2) + 0.5 so one MUFU.TANH serves two elements. fp16 math throughout, as the
@@ -98,12 +100,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int GRP_COLS = (EPI == EPI_F32) ? 32 : 64;  // columns per 128-byte staging row
   constexpr int NG = (BN / 2) / GRP_COLS;               // staging blocks per epilogue warp per tile
   constexpr uint32_t TX_BYTES = (PAIR ? 2 : 1) * Smem::STAGE_BYTES;
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   // identical carve-up in both CTAs of a pair (UMMA / commit / TMA-barrier addressing relies on equal offsets)
-  uint8_t* smem =
-      reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw;  // 1024-byte aligned (128B-swizzle atoms)
   Bars* bars = reinterpret_cast<Bars*>(smem + Smem::OFF_BARS);
   float* sbias = reinterpret_cast<float*>(smem + Smem::OFF_BIAS);
+  float* sscale = reinterpret_cast<float*>(smem + Smem::OFF_SCALE);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform: keeps role-derived values in uniform registers
   const int lane = threadIdx.x & 31;
@@ -275,10 +277,25 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int as = 0;
     uint32_t aphase = 0;
 
-    float bias_cur = 0.0f;  // one bias column per epilogue thread (BN <= 256 = epilogue threads), a tile ahead
+    constexpr bool LN = (EPI == EPI_LN_BIAS || EPI == EPI_LN_QGELU);
+    const float inv_k = 1.0f / static_cast<float>(g.K);
+    // one bias (LN: c_n and s_n) column per epilogue thread (BN <= 256 = epilogue threads), fetched a tile ahead
+    float bias_cur = 0.0f, scale_cur = 0.0f;
+    auto fetch_cols = [&](int t) {
+      const int c = (t % n_blks) * BN + ep_tid;
+      bias_cur = 0.0f;
+      scale_cur = 0.0f;
+      if (t < num_tiles && ep_tid < BN && c < g.N) {
+        if (LN) {
+          bias_cur = g.ln_c[c];
+          scale_cur = g.ln_s[c];
+        } else if (g.bias != nullptr) {
+          bias_cur = __half2float(g.bias[c]);
+        }
+      }
+    };
     if (worker < num_tiles) {
-      const int c = (worker % n_blks) * BN + ep_tid;
-      if (ep_tid < BN && g.bias != nullptr && c < g.N) bias_cur = __half2float(g.bias[c]);
+      fetch_cols(worker);
       if (EPI == EPI_BIAS_RES && elect_one()) {  // residual block of the very first staging block
         mbar_arrive_expect_tx(&res_bar[0], STG_BYTES);
         tma_load_2d(stg0, &tmR, &res_bar[0], (worker % n_blks) * BN + col_off,
@@ -291,13 +308,29 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n0 = (tile % n_blks) * BN;
       const int tile_next = tile + num_workers;
       named_bar_sync(1, EPI_WARPS * 32);  // previous tile's bias fully consumed
-      if (ep_tid < BN) sbias[ep_tid] = bias_cur;
-      named_bar_sync(1, EPI_WARPS * 32);
-      {  // next tile's bias value for this thread: in flight while this tile is processed
-        const int c = (tile_next % n_blks) * BN + ep_tid;
-        bias_cur = (tile_next < num_tiles && ep_tid < BN && g.bias != nullptr && c < g.N) ? __half2float(g.bias[c])
-                                                                                          : 0.0f;
+      if (ep_tid < BN) {
+        sbias[ep_tid] = bias_cur;
+        if (LN) sscale[ep_tid] = scale_cur;
       }
+      named_bar_sync(1, EPI_WARPS * 32);
+      fetch_cols(tile_next);  // next tile's columns: in flight while this tile is processed
+      // LayerNorm folding: this thread's row statistics -> out = acc * ln_a + (s_n * ln_b + c_n)
+      float ln_a = 0.0f, ln_b = 0.0f;
+      const int my_row_idx = m0 + row_off + lane;
+      if (LN && my_row_idx < g.M) {
+        const float2* st = reinterpret_cast<const float2*>(g.ln_stats) + static_cast<size_t>(my_row_idx) * g.ln_parts;
+        float sx = 0.0f, sq = 0.0f;
+        for (int q = 0; q < g.ln_parts; ++q) {  // fixed order: bit-reproducible statistics
+          const float2 t = st[q];
+          sx += t.x;
+          sq += t.y;
+        }
+        const float mean = sx * inv_k;
+        const float var = fmaxf(sq * inv_k - mean * mean, 0.0f);
+        ln_a = rsqrtf(var + 1e-5f);
+        ln_b = -mean * ln_a;
+      }
+      float st_sum = 0.0f, st_sq = 0.0f;  // EPI_BIAS_RES + stats_out: statistics of the row segment written here
       if (threadIdx.x == 0) TRACE(4, clock64());
       mbar_wait(&bars->tmem_full[as], aphase);
       tc_fence_after();
@@ -368,11 +401,25 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const float4 b0 = *reinterpret_cast<const float4*>(bcol + 8 * j);
               const float4 b1 = *reinterpret_cast<const float4*>(bcol + 8 * j + 4);
               uint4 pk;
-              pk.x = pack_half2(__uint_as_float(vv[0]) + b0.x, __uint_as_float(vv[1]) + b0.y);
-              pk.y = pack_half2(__uint_as_float(vv[2]) + b0.z, __uint_as_float(vv[3]) + b0.w);
-              pk.z = pack_half2(__uint_as_float(vv[4]) + b1.x, __uint_as_float(vv[5]) + b1.y);
-              pk.w = pack_half2(__uint_as_float(vv[6]) + b1.z, __uint_as_float(vv[7]) + b1.w);
-              if (EPI == EPI_BIAS_QGELU) {
+              if (LN) {
+                const float* scol = sscale + col_off + grp * GRP_COLS;
+                const float4 s0 = *reinterpret_cast<const float4*>(scol + 8 * j);
+                const float4 s1 = *reinterpret_cast<const float4*>(scol + 8 * j + 4);
+                pk.x = pack_half2(fmaf(__uint_as_float(vv[0]), ln_a, fmaf(s0.x, ln_b, b0.x)),
+                                  fmaf(__uint_as_float(vv[1]), ln_a, fmaf(s0.y, ln_b, b0.y)));
+                pk.y = pack_half2(fmaf(__uint_as_float(vv[2]), ln_a, fmaf(s0.z, ln_b, b0.z)),
+                                  fmaf(__uint_as_float(vv[3]), ln_a, fmaf(s0.w, ln_b, b0.w)));
+                pk.z = pack_half2(fmaf(__uint_as_float(vv[4]), ln_a, fmaf(s1.x, ln_b, b1.x)),
+                                  fmaf(__uint_as_float(vv[5]), ln_a, fmaf(s1.y, ln_b, b1.y)));
+                pk.w = pack_half2(fmaf(__uint_as_float(vv[6]), ln_a, fmaf(s1.z, ln_b, b1.z)),
+                                  fmaf(__uint_as_float(vv[7]), ln_a, fmaf(s1.w, ln_b, b1.w)));
+              } else {
+                pk.x = pack_half2(__uint_as_float(vv[0]) + b0.x, __uint_as_float(vv[1]) + b0.y);
+                pk.y = pack_half2(__uint_as_float(vv[2]) + b0.z, __uint_as_float(vv[3]) + b0.w);
+                pk.z = pack_half2(__uint_as_float(vv[4]) + b1.x, __uint_as_float(vv[5]) + b1.y);
+                pk.w = pack_half2(__uint_as_float(vv[6]) + b1.z, __uint_as_float(vv[7]) + b1.w);
+              }
+              if (EPI == EPI_BIAS_QGELU || EPI == EPI_LN_QGELU) {
                 pk.x = quick_gelu_f16x2(pk.x);
                 pk.y = quick_gelu_f16x2(pk.y);
                 pk.z = quick_gelu_f16x2(pk.z);
@@ -385,6 +432,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 pk.y = hadd2_u32(r.y, pk.y);
                 pk.z = hadd2_u32(r.z, pk.z);
                 pk.w = hadd2_u32(r.w, pk.w);
+                if (g.stats_out != nullptr) {  // statistics of the fp16 values the next LayerNorm will see
+                  const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[e]));
+                    st_sum += f.x + f.y;
+                    st_sq = fmaf(f.x, f.x, fmaf(f.y, f.y, st_sq));
+                  }
+                }
               }
               *slot = pk;
             }
@@ -396,6 +452,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (!(g.debug & 1) && gcol0 < g.N && m0 + row_off < g.M) tma_store_2d(&tmC, stg, gcol0, m0 + row_off);
           tma_store_commit();
         }
+      }
+      if (EPI == EPI_BIAS_RES && g.stats_out != nullptr && my_row_idx < g.M) {
+        // this thread's column segment of the row: partial pair (tile column block, column half)
+        float2* dst = reinterpret_cast<float2*>(g.stats_out) + static_cast<size_t>(my_row_idx) * (2 * n_blks) +
+                      2 * (tile % n_blks) + chalf;
+        *dst = make_float2(st_sum, st_sq);
       }
       if (threadIdx.x == 0) TRACE(6, clock64());
       if (++as == 2) {
@@ -509,11 +571,20 @@ int dispatch_epi(const GemmArgs& a, int epi, cudaStream_t stream) {
     case EPI_BIAS_QGELU: return launch_impl<PAIR, EPI_BIAS_QGELU>(a, stream);
     case EPI_BIAS_RES: return launch_impl<PAIR, EPI_BIAS_RES>(a, stream);
     case EPI_F32: return launch_impl<PAIR, EPI_F32>(a, stream);
+    case EPI_LN_BIAS: return launch_impl<PAIR, EPI_LN_BIAS>(a, stream);
+    case EPI_LN_QGELU: return launch_impl<PAIR, EPI_LN_QGELU>(a, stream);
     default: set_error("unknown GEMM epilogue %d", epi); return PC_ERR_ARG;
   }
 }
 
 }  // namespace
+
+static bool use_pair(int M, int N) { return M >= 256 && N >= 256 && !force_single_cta(); }
+
+int gemm_stats_parts(int M, int N) {
+  const int bn = use_pair(M, N) ? 256 : 128;
+  return 2 * ((N + bn - 1) / bn);
+}
 
 int launch_gemm(const GemmArgs& a, int epilogue, cudaStream_t stream) {
   PC_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, PC_ERR_ARG, "gemm: empty problem %dx%dx%d", a.M, a.N, a.K);
@@ -529,7 +600,11 @@ int launch_gemm(const GemmArgs& a, int epilogue, cudaStream_t stream) {
                    (reinterpret_cast<uintptr_t>(a.residual) & 15) == 0,
                PC_ERR_ALIGN, "gemm: residual must be non-null, 16-byte aligned, ldr %% 8 == 0");
   }
-  if (a.M >= 256 && a.N >= 256 && !force_single_cta()) return dispatch_epi<true>(a, epilogue, stream);
+  if (epilogue == EPI_LN_BIAS || epilogue == EPI_LN_QGELU) {
+    PC_REQUIRE(a.ln_stats != nullptr && a.ln_s != nullptr && a.ln_c != nullptr && a.ln_parts >= 1, PC_ERR_ARG,
+               "gemm: the LayerNorm-folded epilogues need ln_stats (ln_parts >= 1), ln_s and ln_c");
+  }
+  if (use_pair(a.M, a.N)) return dispatch_epi<true>(a, epilogue, stream);
   return dispatch_epi<false>(a, epilogue, stream);
 }
 

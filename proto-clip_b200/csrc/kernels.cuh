@@ -12,7 +12,13 @@ enum GemmEpilogue : int {
   EPI_BIAS = 0,        // C = f16(acc + bias)
   EPI_BIAS_QGELU = 1,  // C = quickgelu(f16(acc + bias))        (clip/model.py:164-166)
   EPI_BIAS_RES = 2,    // C = f16(acc + bias) + residual        (clip/model.py:188-189)
-  EPI_F32 = 3          // C(fp32) = acc (+ bias)
+  EPI_F32 = 3,         // C(fp32) = acc (+ bias)
+  // LayerNorm folded into the Linear that consumes it (clip/model.py:188-189: attn(ln_1(x)), mlp(ln_2(x))):
+  //   LN(x) W^T + b = rstd_r * (x (W.gamma)^T)[r,n] - rstd_r * mean_r * s_n + c_n,
+  //   s_n = sum_k (W.gamma)[n,k],  c_n = sum_k beta_k W[n,k] + b_n.
+  // A is the un-normalised x, W the gamma-scaled weight; (sum x, sum x^2) per row come from `ln_stats`.
+  EPI_LN_BIAS = 4,     // C = f16(LN-folded acc)
+  EPI_LN_QGELU = 5     // C = quickgelu(f16(LN-folded acc))
 };
 struct GemmArgs {
   int M, N, K;
@@ -21,11 +27,21 @@ struct GemmArgs {
   void* C; int ldc;           // [M, N] fp16 (fp32 for EPI_F32)
   const __half* bias;         // [N] or nullptr
   const __half* residual; int ldr;  // [M, N] fp16 (EPI_BIAS_RES); may alias C
+  // LayerNorm folding (all fp32). Row statistics are (sum, sum of squares) pairs of the fp16 activations, kept as
+  // `parts` partial pairs per row that the consumer adds in a fixed order (deterministic: no atomics).
+  const float* ln_stats;      // [M][ln_parts][2] read by EPI_LN_*: statistics of A's rows (over K columns)
+  int ln_parts;               // partial pairs per row in ln_stats
+  const float* ln_s;          // [N] s_n (EPI_LN_*)
+  const float* ln_c;          // [N] c_n (EPI_LN_*)
+  float* stats_out;           // [M][gemm_stats_parts(M, N)][2] or nullptr: EPI_BIAS_RES writes the statistics of
+                              // the row segments it produces (one partial pair per 64- or 128-column segment)
   int debug;                  // bring-up only (env PC_GEMM_DEBUG): 1 = skip epilogue body, 2 = skip TMA, 4 = skip MMA,
                               // 8 = per-tile cycle trace of CTA 0 (printed to stderr after a device sync)
   long long* trace;           // [tiles][16] clock64 samples when debug & 8
 };
 int launch_gemm(const GemmArgs& a, int epilogue, cudaStream_t stream);
+// partial (sum, sum^2) pairs per row that an EPI_BIAS_RES launch of this shape writes into stats_out
+int gemm_stats_parts(int M, int N);
 
 // ---------------------------------------------------------------- attention.cu (tcgen05 + TMA)
 // qkv: [B*L, 3*d] fp16, columns [0,d) = q, [d,2d) = k, [2d,3d) = v, head h at h*64 (nn.MultiheadAttention
@@ -37,6 +53,12 @@ int launch_attention(const __half* qkv, __half* out, int B, int L, int heads, in
 // row_stride_rows = L), eps = 1e-5 (clip/model.py:155-161).
 int launch_layernorm(const __half* x, __half* y, const float* gamma, const float* beta, int rows, int d,
                      int row_stride_rows, cudaStream_t stream);
+// stats[r] = (sum x[r,:], sum x[r,:]^2), fp32: seeds the LayerNorm statistics of a block input (GemmArgs::ln_stats)
+int launch_row_stats(const __half* x, float* stats, int rows, int d, cudaStream_t stream);
+// bind-time folding of LayerNorm(gamma, beta) into the Linear (W [N,K], bias [N] or null) that consumes it:
+// Wf = f16(W * gamma), s[n] = sum_k Wf[n,k], c[n] = sum_k beta[k] W[n,k] + bias[n]
+int launch_fold_ln(const __half* W, const float* gamma, const float* beta, const __half* bias, __half* Wf, float* s,
+                   float* c, int N, int K, cudaStream_t stream);
 // images [B,3,R,R] (fp32 or fp16) -> patch rows [B*g*g, Kp] fp16, column = c*p*p + i*p + j (conv1 weight
 // flattening order), zero-padded to Kp.
 int launch_patchify(const void* images, int img_is_f16, __half* out, int B, int R, int p, int Kp,
