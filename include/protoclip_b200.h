@@ -173,6 +173,15 @@ int pc_proto_classify(const void* q, const void* z_img, const void* z_txt, const
                       const float* zt_n2, int Q, int N, int D, float alpha, float beta, float* p_out,
                       int64_t* argmax, float* pmax, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Fused (alpha, beta) grid search (main.py:187-199 and 419-430 call P() 319 x 3 times on identical matmuls):
+ * the similarities are computed once, then counts[a * n_beta + b] = #{rows : argmax_n P(alpha_a, beta_b)[row, n]
+ * == labels[row]} (lowest-index tie-break, like Tensor.max). alphas / betas: f32 DEVICE arrays; labels: int64 [Q];
+ * counts: int32 [n_alpha * n_beta], cleared by the call. Workspace: pc_proto_classify_workspace_bytes(Q, N). */
+int pc_proto_grid_search(const void* q, const void* z_img, const void* z_txt, const float* zi_n2,
+                         const float* zt_n2, const int64_t* labels, int Q, int N, int D, const float* alphas,
+                         int n_alpha, const float* betas, int n_beta, int* counts, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,7 +26,7 @@ SYMBOLS = [
     "pc_encode_text_workspace_bytes", "pc_encode_text", "pc_resblock_workspace_bytes", "pc_resblock_forward",
     "pc_linear_forward", "pc_layernorm_forward", "pc_attention_forward", "pc_l2_normalize",
     "pc_adapter_fc_workspace_bytes", "pc_adapter_fc_forward", "pc_adapter_conv_forward", "pc_build_prototypes",
-    "pc_proto_classify_workspace_bytes", "pc_proto_classify",
+    "pc_proto_classify_workspace_bytes", "pc_proto_classify", "pc_proto_grid_search",
 ]
 
 
@@ -106,6 +106,7 @@ def load_library() -> C.CDLL:
     lib.pc_proto_classify_workspace_bytes.argtypes = [i, i]
     lib.pc_proto_classify_workspace_bytes.restype = sz
     lib.pc_proto_classify.argtypes = [vp, vp, vp, vp, vp, i, i, i, f, f, vp, vp, vp, vp, sz, vp]
+    lib.pc_proto_grid_search.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, vp, i, vp, i, vp, vp, sz, vp]
     _lib = lib
     return lib
 
@@ -257,6 +258,34 @@ def proto_classify(q: torch.Tensor, z_img: torch.Tensor, z_txt: torch.Tensor, zi
                                     pm.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(q.device)),
               "pc_proto_classify")
     return p, am, pm
+
+
+def proto_grid_search(q: torch.Tensor, z_img: torch.Tensor, z_txt: torch.Tensor, zi_n2: torch.Tensor,
+                      zt_n2: torch.Tensor, labels: torch.Tensor, alphas, betas) -> torch.Tensor:
+    """Fused (alpha, beta) grid of P() + argmax + accuracy (main.py:187-199, 419-430). Returns the int32 matrix of
+    correct predictions, [len(alphas), len(betas)]."""
+    lib = load_library()
+    q = require_cuda(q, torch.float16, "q")
+    z_img = require_cuda(z_img, torch.float16, "z_img")
+    z_txt = require_cuda(z_txt, torch.float16, "z_txt")
+    zi_n2 = require_cuda(zi_n2, torch.float32, "zi_n2")
+    zt_n2 = require_cuda(zt_n2, torch.float32, "zt_n2")
+    labels = require_cuda(labels, torch.int64, "labels")
+    Q, D = q.shape
+    N = z_img.shape[0]
+    if labels.numel() != Q:
+        raise NativeError(f"proto_grid_search: {labels.numel()} labels for {Q} queries")
+    a = torch.as_tensor(alphas, dtype=torch.float32).to(q.device).contiguous()
+    b = torch.as_tensor(betas, dtype=torch.float32).to(q.device).contiguous()
+    counts = torch.empty((a.numel(), b.numel()), dtype=torch.int32, device=q.device)
+    nbytes = lib.pc_proto_classify_workspace_bytes(Q, N)
+    ws = workspace(q.device, "classify", nbytes)
+    with torch.cuda.device(q.device):
+        check(lib.pc_proto_grid_search(q.data_ptr(), z_img.data_ptr(), z_txt.data_ptr(), zi_n2.data_ptr(),
+                                       zt_n2.data_ptr(), labels.data_ptr(), Q, N, D, a.data_ptr(), a.numel(),
+                                       b.data_ptr(), b.numel(), counts.data_ptr(), ws.data_ptr(), ws.numel(),
+                                       stream_ptr(q.device)), "pc_proto_grid_search")
+    return counts
 
 
 # ----------------------------------------------------------------------------- context (one per device)

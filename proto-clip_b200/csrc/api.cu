@@ -639,5 +639,38 @@ int pc_proto_classify(const void* q, const void* z_img, const void* z_txt, const
   return PC_OK;
 }
 
+int pc_proto_grid_search(const void* q, const void* z_img, const void* z_txt, const float* zi_n2, const float* zt_n2,
+                         const int64_t* labels, int Q, int N, int D, const float* alphas, int n_alpha,
+                         const float* betas, int n_beta, int* counts, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  PC_REQUIRE(q && z_img && z_txt && zi_n2 && zt_n2 && labels && alphas && betas && counts && Q > 0 && N > 0 && D > 0 &&
+                 n_alpha > 0 && n_beta > 0,
+             PC_ERR_ARG, "pc_proto_grid_search: null buffer or empty problem");
+  PC_REQUIRE(D % 8 == 0, PC_ERR_ARG, "pc_proto_grid_search: D = %d must be a multiple of 8", D);
+  PC_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, PC_ERR_ALIGN,
+             "pc_proto_grid_search: workspace must be 256-byte aligned");
+  PC_REQUIRE(workspace_bytes >= pc_proto_classify_workspace_bytes(Q, N), PC_ERR_WORKSPACE,
+             "pc_proto_grid_search: workspace %zu < %zu", workspace_bytes, pc_proto_classify_workspace_bytes(Q, N));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PC_CHECK_CUDA(cudaMemsetAsync(counts, 0, static_cast<size_t>(n_alpha) * n_beta * sizeof(int), s));
+  const int Np = static_cast<int>(align_up(N, 4));
+  float* dots = static_cast<float*>(workspace);
+  const __half* qh = static_cast<const __half*>(q);
+  for (int q0 = 0; q0 < Q; q0 += kClassifyChunk) {
+    const int n = (Q - q0 < kClassifyChunk) ? (Q - q0) : kClassifyChunk;
+    for (int bank = 0; bank < 2; ++bank) {
+      GemmArgs g{};
+      g.M = n; g.N = N; g.K = D;
+      g.A = qh + static_cast<size_t>(q0) * D; g.lda = D;
+      g.W = static_cast<const __half*>(bank == 0 ? z_img : z_txt); g.ldw = D;
+      g.C = dots + bank * Np; g.ldc = 2 * Np;
+      PC_TRY(launch_gemm(g, EPI_F32, s));
+    }
+    PC_TRY(launch_proto_grid(dots, 2 * Np, qh + static_cast<size_t>(q0) * D, D, zi_n2, zt_n2, n, N, labels + q0, alphas,
+                             n_alpha, betas, n_beta, counts, s));
+  }
+  return PC_OK;
+}
+
 }  // extern "C"
 #pragma GCC visibility pop

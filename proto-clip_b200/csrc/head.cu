@@ -268,7 +268,123 @@ proto_softmax_kernel(const float* __restrict__ dots, int ld, const __half* __res
   }
 }
 
+// (alpha, beta) grid of P() + argmax + accuracy in one pass over the similarities (main.py:187-199, 419-430: the
+// reference recomputes the two cdist matmuls and both softmaxes 319 x 3 times). One CTA per query row: the squared
+// distances to both prototype banks stay in shared memory; per beta the two softmaxes are evaluated once, per alpha
+// only the blend + argmax. counts[a * n_beta + b] += (argmax == label). Same arithmetic as proto_softmax_kernel.
+__global__ void __launch_bounds__(256)
+proto_grid_kernel(const float* __restrict__ dots, int ld, const __half* __restrict__ q, int D,
+                  const float* __restrict__ zi_n2, const float* __restrict__ zt_n2, int N,
+                  const int64_t* __restrict__ labels, const float* __restrict__ alphas, int n_alpha,
+                  const float* __restrict__ betas, int n_beta, int* __restrict__ counts) {
+  extern __shared__ float gsm[];  // d_i [N] | d_t [N] | e_i [N] | e_t [N]
+  __shared__ float red[32];
+  __shared__ int red_i[32];
+  float* d_i = gsm;
+  float* d_t = gsm + N;
+  float* e_i = gsm + 2 * N;
+  float* e_t = gsm + 3 * N;
+  const size_t row = blockIdx.x;
+  const float* di = dots + row * ld;
+  const float* dt = di + (ld >> 1);
+  float s = 0.0f;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    const float x = __half2float(q[row * D + c]);
+    s += x * x;
+  }
+  const float qn2 = block_sum(s, red);
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    d_i[n] = fmaxf(qn2 + zi_n2[n] - 2.0f * di[n], 0.0f);
+    d_t[n] = fmaxf(qn2 + zt_n2[n] - 2.0f * dt[n], 0.0f);
+  }
+  __syncthreads();
+  const int label = static_cast<int>(labels[row]);
+  const int wi = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int b = 0; b < n_beta; ++b) {
+    const float beta = betas[b];
+    float mi = -INFINITY, mt = -INFINITY;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+      mi = fmaxf(mi, -beta * d_i[n]);
+      mt = fmaxf(mt, -beta * d_t[n]);
+    }
+    mi = block_max(mi, red);
+    mt = block_max(mt, red);
+    float si = 0.0f, st = 0.0f;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+      const float a = __expf(-beta * d_i[n] - mi), c = __expf(-beta * d_t[n] - mt);
+      e_i[n] = a;
+      e_t[n] = c;
+      si += a;
+      st += c;
+    }
+    si = block_sum(si, red);
+    st = block_sum(st, red);
+    for (int a = 0; a < n_alpha; ++a) {
+      const float alpha = alphas[a];
+      const float ci = alpha / si, ct = (1.0f - alpha) / st;
+      float best = -1.0f;
+      int arg = 0x7fffffff;
+      for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        const float pv = ci * e_i[n] + ct * e_t[n];
+        if (pv > best) {
+          best = pv;
+          arg = n;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (ob > best || (ob == best && oa < arg)) {
+          best = ob;
+          arg = oa;
+        }
+      }
+      __syncthreads();
+      if (l == 0) {
+        red[wi] = best;
+        red_i[wi] = arg;
+      }
+      __syncthreads();
+      if (wi == 0) {
+        best = (l < nw) ? red[l] : -1.0f;
+        arg = (l < nw) ? red_i[l] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+          if (ob > best || (ob == best && oa < arg)) {
+            best = ob;
+            arg = oa;
+          }
+        }
+        if (l == 0 && arg == label) atomicAdd(&counts[a * n_beta + b], 1);
+      }
+    }
+    __syncthreads();  // e_i / e_t are rewritten by the next beta
+  }
+}
+
 }  // namespace
+
+int launch_proto_grid(const float* dots, int ld, const __half* q, int D, const float* zi_n2, const float* zt_n2, int Q,
+                      int N, const int64_t* labels, const float* alphas, int n_alpha, const float* betas, int n_beta,
+                      int* counts, cudaStream_t stream) {
+  PC_REQUIRE(dots && q && zi_n2 && zt_n2 && labels && alphas && betas && counts && Q > 0 && N > 0 && n_alpha > 0 &&
+                 n_beta > 0,
+             PC_ERR_ARG, "proto_grid: bad args");
+  const int smem = 4 * N * static_cast<int>(sizeof(float));
+  PC_REQUIRE(smem <= 200 * 1024, PC_ERR_ARG, "proto_grid: N=%d needs %d B smem", N, smem);
+  static int configured = 0;
+  if (smem > configured && smem > 48 * 1024) {
+    PC_CHECK_CUDA(cudaFuncSetAttribute(proto_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  proto_grid_kernel<<<Q, 256, smem, stream>>>(dots, ld, q, D, zi_n2, zt_n2, N, labels, alphas, n_alpha, betas, n_beta,
+                                              counts);
+  PC_CHECK_CUDA(cudaGetLastError());
+  return PC_OK;
+}
 
 int launch_build_prototypes(const __half* V, int N, int K, int D, int per_shot_norm, __half* z, float* zn2,
                             cudaStream_t stream) {

@@ -98,4 +98,10 @@ int launch_proto_softmax(const float* dots, int ld, const __half* q, int D, cons
                          const float* zt_n2, int Q, int N, float alpha, float beta, float* p_out,
                          int64_t* argmax, float* pmax, cudaStream_t stream);
 
+// (alpha, beta) grid search over the same logits: counts[a * n_beta + b] += (argmax P(alpha_a, beta_b) == label)
+// (main.py:187-199, 419-430). alphas / betas are device arrays; counts must be zero on entry.
+int launch_proto_grid(const float* dots, int ld, const __half* q, int D, const float* zi_n2, const float* zt_n2, int Q,
+                      int N, const int64_t* labels, const float* alphas, int n_alpha, const float* betas, int n_beta,
+                      int* counts, cudaStream_t stream);
+
 }  // namespace pc

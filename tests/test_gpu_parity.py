@@ -275,6 +275,26 @@ def test_full_size_properties_vit_b16(nat):
     assert same > diff
 
 
+def test_grid_search_matches_per_point_classification(nat):
+    """The fused (alpha, beta) sweep (main.py:187-199) counts exactly what 33 separate P()+argmax calls count."""
+    torch.manual_seed(3)
+    Q, N, D = 700, 61, 512
+    z = torch.nn.functional.normalize(torch.randn(N, D, device=DEV), dim=-1)
+    zi = torch.nn.functional.normalize(z + 0.3 * torch.randn(N, D, device=DEV), dim=-1).half()
+    zt = torch.nn.functional.normalize(z + 0.3 * torch.randn(N, D, device=DEV), dim=-1).half()
+    labels = torch.randint(0, N, (Q,), device=DEV)
+    q = torch.nn.functional.normalize(z[labels] + 0.9 * torch.randn(Q, D, device=DEV), dim=-1).half()
+    zi2, zt2 = zi.float().pow(2).sum(-1), zt.float().pow(2).sum(-1)
+    alphas, betas = [0.0, 0.3, 1.0], [0.1, 0.5, 1.0, 2.0, 5.0, 7.0, 9.0, 12.0, 15.0, 17.0, 20.0]
+    counts = nat.proto_grid_search(q, zi, zt, zi2, zt2, labels, alphas, betas).cpu()
+    assert counts.shape == (3, 11)
+    for i, a in enumerate(alphas):
+        for j, b in enumerate(betas):
+            _, am, _ = nat.proto_classify(q, zi, zt, zi2, zt2, a, b, want_p=False)
+            assert int((am == labels).sum()) == int(counts[i, j]), (a, b)
+    assert 0 < int(counts.min()) and int(counts.max()) < Q  # a non-trivial problem
+
+
 def test_error_paths(nat):
     ctx = nat.Context(torch.device(DEV))
     with pytest.raises(nat.NativeError):
