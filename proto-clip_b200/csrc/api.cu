@@ -33,7 +33,14 @@ struct Tower {
   __half* proj_t = nullptr;             // owned: [embed, width] (transposed projection -> TN GEMM)
 };
 
-constexpr int kDefaultMicroBatch = 96;  // 96 * 197 tokens = 148 row blocks of 128: one GEMM wave per n-block
+// Default micro-batch: as many sequences as fill ONE row-block wave of the CTA-pair GEMM (sm_count / 2 pairs x 256
+// rows): ViT-B/16 (L = 197) -> 96 images = 18 912 rows = 73.9 of 74 row blocks; ViT-L/14 -> 73; @336px -> 32.
+// Keeps every Linear at an integer number of waves and the activations (x, h, qkv / MLP hidden) L2-resident.
+inline int default_micro_batch(int L) {
+  const int rows = (device_sm_count() / 2) * 256;
+  const int mb = rows / (L > 0 ? L : 1);
+  return mb > 0 ? mb : 1;
+}
 constexpr int kClassifyChunk = 8192;    // queries per P() pass: [8192, 2N] fp32 dots stay L2-resident
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -363,7 +370,7 @@ int pc_text_bind_weights(pc_ctx* ctx, const pc_text_weights* w) {
 
 size_t pc_encode_image_workspace_bytes(const pc_ctx* ctx, int micro_batch) {
   if (!ctx || !ctx->vis.bound) return 0;
-  const int mb = micro_batch > 0 ? micro_batch : kDefaultMicroBatch;
+  const int mb = micro_batch > 0 ? micro_batch : default_micro_batch(ctx->vis.L);
   return tower_ws_bytes(mb * ctx->vis.L, ctx->vis.width, mb);
 }
 
@@ -375,7 +382,7 @@ int pc_encode_image(pc_ctx* ctx, const void* images, int img_dtype, int B, void*
   PC_REQUIRE(img_dtype == PC_IMG_F32 || img_dtype == PC_IMG_F16, PC_ERR_ARG, "pc_encode_image: image dtype %d",
              img_dtype);
   const Tower& t = ctx->vis;
-  const int mb = micro_batch > 0 ? micro_batch : kDefaultMicroBatch;
+  const int mb = micro_batch > 0 ? micro_batch : default_micro_batch(t.L);
   PC_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, PC_ERR_ALIGN,
              "pc_encode_image: workspace must be 256-byte aligned");
   PC_REQUIRE(workspace_bytes >= tower_ws_bytes(mb * t.L, t.width, mb), PC_ERR_WORKSPACE,
@@ -423,7 +430,7 @@ int pc_encode_image(pc_ctx* ctx, const void* images, int img_dtype, int B, void*
 
 size_t pc_encode_text_workspace_bytes(const pc_ctx* ctx, int micro_batch) {
   if (!ctx || !ctx->txt.bound) return 0;
-  const int mb = micro_batch > 0 ? micro_batch : 2 * kDefaultMicroBatch;
+  const int mb = micro_batch > 0 ? micro_batch : default_micro_batch(ctx->txt.L);
   return tower_ws_bytes(mb * ctx->txt.L, ctx->txt.width, mb);
 }
 
@@ -433,7 +440,7 @@ int pc_encode_text(pc_ctx* ctx, const int64_t* tokens, int P, void* out, int l2n
   PC_REQUIRE(ctx->txt.bound, PC_ERR_STATE, "pc_encode_text: text weights are not bound");
   PC_REQUIRE(tokens && out && P > 0, PC_ERR_ARG, "pc_encode_text: null buffer or empty batch");
   const Tower& t = ctx->txt;
-  const int mb = micro_batch > 0 ? micro_batch : 2 * kDefaultMicroBatch;
+  const int mb = micro_batch > 0 ? micro_batch : default_micro_batch(t.L);
   PC_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, PC_ERR_ALIGN,
              "pc_encode_text: workspace must be 256-byte aligned");
   PC_REQUIRE(workspace_bytes >= tower_ws_bytes(mb * t.L, t.width, mb), PC_ERR_WORKSPACE,

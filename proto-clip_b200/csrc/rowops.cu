@@ -229,35 +229,38 @@ fold_ln_kernel(const __half* __restrict__ W, const float* __restrict__ gamma, co
   }
 }
 
+// One thread per (image, channel, patch row i, patch gy, patch gx): p contiguous input pixels -> p contiguous fp16
+// values of patch row (b, gy, gx) at column c*p*p + i*p. Consecutive lanes take consecutive gx, so a warp reads one
+// contiguous stretch of an image row (coalesced) and writes p*2-byte segments. Zero-padding columns [K, Kp) are
+// written by the threads of the last patch row of the last channel.
 __global__ void __launch_bounds__(256)
 patchify_kernel(const void* __restrict__ images, int img_is_f16, __half* __restrict__ out, int B, int R, int p,
                 int g, int K, int Kp) {
-  const int pairs_per_row = Kp >> 1;
-  const size_t total = static_cast<size_t>(B) * g * g * pairs_per_row;
+  const size_t total = static_cast<size_t>(B) * 3 * p * g * g;
   for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
        t += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int col = static_cast<int>(t % pairs_per_row) * 2;
-    const size_t prow = t / pairs_per_row;
-    float v0 = 0.0f, v1 = 0.0f;
-    if (col < K) {
-      const int gx = static_cast<int>(prow % g);
-      const int gy = static_cast<int>((prow / g) % g);
-      const int b = static_cast<int>(prow / (static_cast<size_t>(g) * g));
-      const int c = col / (p * p);
-      const int rem = col % (p * p);
-      const int i = rem / p, j = rem % p;  // j even, p even -> (j, j+1) stay in one patch row
-      const size_t off = ((static_cast<size_t>(b) * 3 + c) * R + (gy * p + i)) * R + gx * p + j;
-      if (img_is_f16) {
-        const __half2 h = *reinterpret_cast<const __half2*>(static_cast<const __half*>(images) + off);
-        v0 = __low2float(h);
-        v1 = __high2float(h);
-      } else {
-        const float2 f = *reinterpret_cast<const float2*>(static_cast<const float*>(images) + off);
-        v0 = f.x;
-        v1 = f.y;
+    const int gx = static_cast<int>(t % g);
+    size_t r = t / g;
+    const int i = static_cast<int>(r % p);
+    r /= p;
+    const int gy = static_cast<int>(r % g);
+    r /= g;
+    const int c = static_cast<int>(r % 3);
+    const int b = static_cast<int>(r / 3);
+    const size_t src = ((static_cast<size_t>(b) * 3 + c) * R + (gy * p + i)) * R + gx * p;
+    __half* dst = out + (static_cast<size_t>(b) * g * g + gy * g + gx) * Kp + (c * p + i) * p;
+    if (img_is_f16) {
+      const __half2* in2 = reinterpret_cast<const __half2*>(static_cast<const __half*>(images) + src);
+      for (int j = 0; j < (p >> 1); ++j) reinterpret_cast<__half2*>(dst)[j] = in2[j];
+    } else {
+      const float2* in2 = reinterpret_cast<const float2*>(static_cast<const float*>(images) + src);
+      for (int j = 0; j < (p >> 1); ++j) {
+        const float2 f = in2[j];
+        reinterpret_cast<__half2*>(dst)[j] = __floats2half2_rn(f.x, f.y);
       }
     }
-    *reinterpret_cast<__half2*>(out + prow * Kp + col) = __floats2half2_rn(v0, v1);
+    if (c == 2 && i == p - 1)
+      for (int k = K; k < Kp; ++k) out[(static_cast<size_t>(b) * g * g + gy * g + gx) * Kp + k] = __float2half_rn(0.0f);
   }
 }
 
@@ -441,7 +444,7 @@ int launch_patchify(const void* images, int img_is_f16, __half* out, int B, int 
   const int g = R / p;
   const int K = 3 * p * p;
   PC_REQUIRE(Kp >= K && Kp % 8 == 0, PC_ERR_ARG, "patchify: padded K %d < %d or not a multiple of 8", Kp, K);
-  const size_t total = static_cast<size_t>(B) * g * g * (Kp / 2);
+  const size_t total = static_cast<size_t>(B) * 3 * p * g * g;
   patchify_kernel<<<grid_1d(total, 256), 256, 0, stream>>>(images, img_is_f16, out, B, R, p, g, K, Kp);
   PC_CHECK_CUDA(cudaGetLastError());
   return PC_OK;
