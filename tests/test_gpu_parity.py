@@ -251,6 +251,73 @@ def test_query_path_argmax_identical_to_oracle(nat, arch, adapter):
     assert torch.equal(am.cpu(), pred_o), "top-1 predictions must be identical to the reference algorithm"
 
 
+# ----------------------------------------------------------------------------- drop-in shells (reference names)
+def test_drop_in_shells_reproduce_the_reference_flow(nat, tmp_path, monkeypatch):
+    """clip.load(<state-dict path>) -> build_cache_model -> clip_classifier -> pre_load_features -> prototypes -> P,
+    i.e. main.py:495-544 + 399-409 + 436-438 through the shells that keep the reference's names, against the oracle."""
+    from proto_clip_b200 import clip, utils
+    arch, N, K, Q = "small", 6, 3, 30
+    c = synthetic.arch_config(arch)
+    sd = synthetic.make_state_dict(arch, 0)
+    path = tmp_path / "small_clip.pt"
+    torch.save(sd, path)
+    model, _ = clip.load(str(path))                                     # clip/clip.py:117-139 state-dict branch
+    assert model.visual.input_resolution == c["image_resolution"] and model.dtype == torch.float16
+    cfg = {"cache_dir": str(tmp_path / "cache"), "backbone": "small-synthetic", "shots": K, "augment_epoch": 1}
+    bases = synthetic.class_bases(N, c["image_resolution"], seed=1)
+    perm = torch.randperm(N * K, generator=torch.Generator().manual_seed(0))
+    sup_labels = torch.arange(N).repeat_interleave(K)[perm]              # a shuffled loader, as in the reference
+    support = synthetic.class_structured_images(bases, sup_labels, seed=2)
+    loader = [(support[i:i + 5], sup_labels[i:i + 5]) for i in range(0, N * K, 5)]
+    keys, values = utils.build_cache_model(cfg, model, loader)           # utils.py:284-332
+    assert keys.shape == (c["embed_dim"], N * K) and keys.dtype == torch.float16 and values.shape == (N * K, N)
+    order = torch.argsort(sup_labels, stable=True)
+    keys_o = O.l2_normalize(O.encode_image(sd, support, "fp32"))[order].t()
+    assert torch.equal(values.cpu().argmax(1), sup_labels[order])
+    # torch.argsort is not stable (neither here nor in the reference, utils.py:325): columns are sorted by class, the
+    # order of the K shots inside a class is unspecified -> match the columns of each class as a set
+    kc, scale = keys.float().cpu(), keys_o.abs().max()
+    for n in range(N):
+        ours, ref = kc[:, n * K:(n + 1) * K], keys_o[:, n * K:(n + 1) * K]
+        dist = (ours.t().unsqueeze(1) - ref.t().unsqueeze(0)).abs().amax(dim=2) / scale      # [K ours, K ref]
+        match = dist.argmin(dim=1)
+        assert sorted(match.tolist()) == list(range(K)) and dist.min(dim=1).values.max().item() < TOWER_TOL
+        keys_o[:, n * K:(n + 1) * K] = ref[:, match]                                          # same order as ours
+    # second call hits the cache files (same layout as the reference's visual_mb_{keys,values}_aug_*.pt)
+    k2, v2 = utils.build_cache_model(cfg, model, loader)
+    assert torch.equal(k2.cpu(), keys.cpu()) and torch.equal(v2.cpu(), values.cpu())
+    # textual memory: tokenisation is host-side BPE (needs the CLIP vocabulary file); prompt-shaped synthetic token
+    # rows stand in for it so that the encoder / mean / renormalise part of clip_classifier is what is compared
+    T = 2
+    tok = torch.zeros(N * T, c["context_length"], dtype=torch.int64)
+    gen = torch.Generator().manual_seed(5)
+    for i in range(N * T):
+        n = int(torch.randint(3, 9, (1,), generator=gen))
+        tok[i, 0], tok[i, 1 + n] = c["vocab_size"] - 2, c["vocab_size"] - 1
+        tok[i, 1:1 + n] = torch.randint(1, c["vocab_size"] - 2, (n,), generator=gen)
+    monkeypatch.setattr(utils.clip, "tokenize", lambda prompts: tok)
+    _, text_bank = utils.clip_classifier([f"class_{i}" for i in range(N)], ["a photo of a {}.", "a {}."], model)
+    assert text_bank.shape == (c["embed_dim"], N)
+    te = O.l2_normalize(O.encode_text(sd, tok, "fp32")).view(N, T, -1).mean(1)
+    assert rel_err(text_bank, O.l2_normalize(te).t()) < TOWER_TOL
+    # query features + prototypes + P
+    q_labels = torch.arange(Q) % N
+    queries = synthetic.class_structured_images(bases, q_labels, seed=3)
+    feats, labels = utils.pre_load_features(cfg, "test", model, [(queries[:16], q_labels[:16]), (queries[16:], q_labels[16:])])
+    assert feats.shape == (Q, c["embed_dim"]) and torch.equal(labels.cpu(), q_labels)
+    f_o = O.l2_normalize(O.encode_image(sd, queries, "fp32"))
+    assert rel_err(feats, f_o) < TOWER_TOL
+    T_al = synthetic.aligned_text_memory(keys_o.t().contiguous(), N, K, seed=6)   # class-aligned text memory
+    zi, zt = utils.build_prototypes(keys.t().contiguous().view(N, K, -1), T_al.to(DEV), K)   # main.py:399-405
+    zi_o, zt_o = O.build_prototypes(keys_o.t().contiguous(), N, K, True), O.text_prototypes(T_al)
+    p = utils.P(feats, zi, zt, 0.5, 12.0)                                 # utils.py:225-244
+    p_o = O.P(f_o, zi_o, zt_o, 0.5, 12.0)
+    assert p.dtype == torch.float32 and (p.cpu() - p_o).abs().max().item() < 2e-2
+    assert torch.equal(p.max(1)[1].cpu(), p_o.max(1)[1])                  # main.py:438
+    assert torch.equal(utils.predict(feats, zi, zt, 0.5, 12.0).cpu(), p_o.max(1)[1])
+    assert (p_o.max(1)[1] == q_labels).float().mean().item() > 0.9
+
+
 # ----------------------------------------------------------------------------- properties at full size
 def test_full_size_properties_vit_b16(nat):
     """ViT-B/16 at the benchmark's size: per-image results do not depend on batch position, batch size or
