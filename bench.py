@@ -244,7 +244,10 @@ def run_ours(args):
     if rank == 0:
         layers = c["vision_layers"]
         n_mb = math.ceil(B / (mb or 96))
-        launches = args.steps * (n_mb * (3 + 7 * layers + 2 + 1) + 8)
+        # per micro-batch: patchify, conv1 GEMM, embed+ln_pre, row_stats; per block 4 GEMMs (LayerNorm folded into two
+        # of them) + attention; ln_post, proj GEMM, l2norm. Per step: adapter (2 GEMMs, 2 LN kernels), l2norm,
+        # 2 similarity GEMMs + softmax/argmax.
+        launches = args.steps * (n_mb * (4 + 5 * layers + 3) + 8)
         sustained, burst, src = measured_peaks()
         flops_img = synthetic.vit_flops_per_image(ARCH) + 4.0 * N_CLASSES * D + 2.0 * D * D / 4 * 2
         line = {
