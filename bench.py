@@ -118,30 +118,36 @@ def run_ours(args):
     bases = synthetic.class_bases(N_CLASSES, R, seed=1, device=dev)           # same on every rank (same seed)
     numel = pipeline.HeadState.packed_numel(N_CLASSES, D, "fc")
     flat = None
-    if rank == 0 and args.lite:
-        # profiling mode (ncu launch lists): random prototypes, no support / text encoding, same query path
-        g = torch.Generator(device=dev).manual_seed(9)
-        V = nat.l2_normalize(torch.randn(N_CLASSES * K_SHOTS, D, generator=g, device=dev).half())
-        T = nat.l2_normalize(torch.randn(N_CLASSES, D, generator=g, device=dev).half())
-        adapter = synthetic.make_adapter_state_dict("fc", D, seed=4, out_gain=synthetic.trained_like_gain(D))
-        flat = pipeline.build_head_state(V, T, N_CLASSES, K_SHOTS, "fc", adapter, ALPHA, BETA).pack()
-    elif rank == 0:
+    if args.lite:
+        if rank == 0:
+            # profiling mode (ncu launch lists): random prototypes, no support / text encoding, same query path
+            g = torch.Generator(device=dev).manual_seed(9)
+            V = nat.l2_normalize(torch.randn(N_CLASSES * K_SHOTS, D, generator=g, device=dev).half())
+            T = nat.l2_normalize(torch.randn(N_CLASSES, D, generator=g, device=dev).half())
+            adapter = synthetic.make_adapter_state_dict("fc", D, seed=4, out_gain=synthetic.trained_like_gain(D))
+            flat = pipeline.build_head_state(V, T, N_CLASSES, K_SHOTS, "fc", adapter, ALPHA, BETA).pack()
+    else:
+        # one-off memory-bank build (utils.py:284-332, 256-273), sharded over the ranks with one all-gather per bank
+        # (SURVEY f2): 16 000 support images (augment_epoch 1) and N x 7 prompts. A random-init text tower is not
+        # class-aligned, so its output is timed / exercised only: the classifier's textual memory is the aligned
+        # synthetic bank below.
+        sup_lo, sup_hi = pdist.shard_bounds(N_CLASSES * K_SHOTS, rank, world)
         feats = []
-        for n0 in range(0, N_CLASSES, 64):  # 64 classes x 16 shots = 1024 support images per pass
-            labels = torch.arange(n0, min(n0 + 64, N_CLASSES), device=dev).repeat_interleave(K_SHOTS)
+        for n0 in range(sup_lo, sup_hi, 1024):
+            labels = torch.arange(n0, min(n0 + 1024, sup_hi), device=dev) // K_SHOTS
             imgs = synthetic.class_structured_images(bases, labels, seed=2 + n0)
-            feats.append(ctx.encode_image(imgs, l2norm=True, micro_batch=mb))   # utils.py:310,319 (augment_epoch 1)
-        V = torch.cat(feats)
-        # one-off text tower pass over N x 7 prompts (utils.py:256-273), timed for the record only: a random-init
-        # text tower is not class-aligned, so the classifier's textual memory is the aligned synthetic bank below
-        tokens = synthetic_tokens(N_CLASSES * N_TEMPLATES, c["context_length"], c["vocab_size"], 5).to(dev)
-        te = ctx.encode_text(tokens, l2norm=True).view(N_CLASSES, N_TEMPLATES, D)  # utils.py:266-267
-        _ = nat.l2_normalize(te.float().mean(dim=1).half())                       # utils.py:268-269
-        T = synthetic.aligned_text_memory(V, N_CLASSES, K_SHOTS, seed=6)
-        adapter = synthetic.make_adapter_state_dict("fc", D, seed=4, out_gain=synthetic.trained_like_gain(D))
-        head0 = pipeline.build_head_state(V, T, N_CLASSES, K_SHOTS, "fc", adapter, ALPHA, BETA)
-        flat = head0.pack()
-        assert flat.numel() == numel
+            feats.append(ctx.encode_image(imgs, l2norm=True, micro_batch=mb))   # utils.py:310,319
+        V = pdist.all_gather_rows(torch.cat(feats), N_CLASSES * K_SHOTS)
+        tok_lo, tok_hi = pdist.shard_bounds(N_CLASSES * N_TEMPLATES, rank, world)
+        tokens = synthetic_tokens(N_CLASSES * N_TEMPLATES, c["context_length"], c["vocab_size"], 5)[tok_lo:tok_hi].to(dev)
+        te = pdist.all_gather_rows(ctx.encode_text(tokens, l2norm=True), N_CLASSES * N_TEMPLATES)  # utils.py:266-267
+        if rank == 0:
+            _ = nat.l2_normalize(te.view(N_CLASSES, N_TEMPLATES, D).float().mean(dim=1).half())   # utils.py:268-269
+            T = synthetic.aligned_text_memory(V, N_CLASSES, K_SHOTS, seed=6)
+            adapter = synthetic.make_adapter_state_dict("fc", D, seed=4, out_gain=synthetic.trained_like_gain(D))
+            head0 = pipeline.build_head_state(V, T, N_CLASSES, K_SHOTS, "fc", adapter, ALPHA, BETA)
+            flat = head0.pack()
+            assert flat.numel() == numel
     flat = pdist.broadcast_flat(flat, numel, torch.float16, dev, src=0)
     head = pipeline.HeadState.unpack(flat, N_CLASSES, D, "fc", ALPHA, BETA)
     clf = pipeline.FewShotClassifier(ctx, head, micro_batch=mb)
@@ -258,7 +264,7 @@ def run_ours(args):
                        "backbone": ARCH, "n_classes": N_CLASSES, "shots": K_SHOTS, "adapter": "fc", "alpha": ALPHA,
                        "beta": BETA, "batch_per_gpu": B, "micro_batch": mb or 96, "image": "3x224x224 fp32",
                        "l2": "inputs larger than L2 (616 MB per batch, 2 alternating batches)",
-                       "parallelism": f"dp{world} (query shards, 1 NCCL broadcast of the head state)"},
+                       "parallelism": f"dp{world} (query shards; one-off memory-bank build sharded with 2 all-gathers, then 1 NCCL broadcast of the head state; no collective in the timed step)"},
             "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": int(pool_host[0].numel() * 4),
                     "d2h_bytes_per_step": int(B * 8), "ms_per_step": round(ms_e2e / args.steps, 3)},
             "gpu_launches": launches,

@@ -75,6 +75,30 @@ def gather_predictions(local: torch.Tensor, num_queries: int) -> Optional[torch.
         [o[: shard_bounds(num_queries, r, world)[1] - shard_bounds(num_queries, r, world)[0]] for r, o in enumerate(out)])
 
 
+def all_gather_rows(local: torch.Tensor, total_rows: int) -> torch.Tensor:
+    """Every rank holds the rows [shard_bounds(total_rows, rank, world)) of a [total_rows, ...] tensor; returns the
+    full tensor on every rank in row order. ONE all-gather (rows padded to ceil(total / world) per rank). This is
+    the collective of the sharded memory-bank build: support images / prompts are independent."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        assert local.shape[0] == total_rows
+        return local
+    world, rank = dist.get_world_size(), dist.get_rank()
+    per = (total_rows + world - 1) // world
+    lo, hi = shard_bounds(total_rows, rank, world)
+    assert local.shape[0] == hi - lo, f"rank {rank} holds {local.shape[0]} rows, expected {hi - lo}"
+    padded = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    padded[: hi - lo] = local
+    out = torch.empty((world * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded.contiguous())
+    if per * world == total_rows:
+        return out
+    keep = []
+    for r in range(world):
+        a, b = shard_bounds(total_rows, r, world)
+        keep.append(out[r * per: r * per + (b - a)])
+    return torch.cat(keep)
+
+
 def max_over_ranks(value: float, device: torch.device) -> float:
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return value

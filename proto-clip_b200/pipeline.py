@@ -124,3 +124,30 @@ class FewShotClassifier:
         """images: [B,3,R,R] f32/f16 on the context's device. Returns (p or None, argmax int64 [B], pmax)."""
         feats = self.ctx.encode_image(images, l2norm=True, micro_batch=self.micro_batch)
         return self.classify_features(feats, want_p=want_p)
+
+
+def build_memory_sharded(ctx: "nat.Context", support_images: torch.Tensor, prompt_tokens: Optional[torch.Tensor],
+                         micro_batch: int = 0) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Memory-bank construction sharded across ranks (utils.py:284-332 and 256-273 run it on one
+    GPU): every rank encodes its contiguous slice of the label-sorted support images ([N*K, 3, R, R], same tensor on
+    every rank or at least the rank's own slice filled) and of the prompt rows ([N*T, ctx] int64), then ONE
+    all-gather per bank. Returns (V [N*K, D] f16 L2-normalised, text features [N*T, D] f16 L2-normalised or None),
+    identical on every rank and identical to the single-GPU result (per-row arithmetic does not depend on the shard).
+    """
+    from . import dist as pdist
+    rank, _, world = pdist.env_rank()
+    total = support_images.shape[0]
+    lo, hi = pdist.shard_bounds(total, rank, world)
+    dev = ctx.device
+    D = ctx.vis_desc["embed_dim"]
+    local = ctx.encode_image(support_images[lo:hi].to(dev), l2norm=True, micro_batch=micro_batch) if hi > lo else \
+        torch.empty((0, D), dtype=torch.float16, device=dev)
+    V = pdist.all_gather_rows(local, total)
+    T = None
+    if prompt_tokens is not None:
+        tp = prompt_tokens.shape[0]
+        lo, hi = pdist.shard_bounds(tp, rank, world)
+        local_t = ctx.encode_text(prompt_tokens[lo:hi].to(dev), l2norm=True) if hi > lo else \
+            torch.empty((0, D), dtype=torch.float16, device=dev)
+        T = pdist.all_gather_rows(local_t, tp)
+    return V, T

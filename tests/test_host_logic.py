@@ -160,6 +160,11 @@ lo, hi = pdist.shard_bounds(Q, rank, world)
 q = torch.randn(Q, D, generator=torch.Generator().manual_seed(1))
 local_pred = (q[lo:hi] @ head.z_img.float().t()).argmax(1)                        # stand-in for the GPU classify
 allp = pdist.gather_predictions(local_pred, Q)
+# sharded memory-bank build (SURVEY f2): every rank produces its slice of the rows, one all-gather restores the order
+rows = torch.arange(37 * 5, dtype=torch.float32).view(37, 5)
+a, b = pdist.shard_bounds(37, rank, world)
+full = pdist.all_gather_rows(rows[a:b].clone(), 37)
+assert torch.equal(full, rows), full
 t = pdist.max_over_ranks(float(rank + 1), torch.device("cpu"))
 pdist.barrier()
 if rank == 0:
