@@ -60,7 +60,6 @@ struct AttnParams {
   int off_stage;   // 16 x 2 KB output staging blocks (one per softmax warp: 32 rows x 64 B, 64B-swizzled)
   int off_xch;     // max (x2, by block parity) / sum exchange between the two key halves: 3 x [pair][half][128] floats
   int off_bars;
-  int dbg;           // bring-up only (env PC_ATTN_DEBUG): 1 = WG 1 idle, 2 = skip pass 1, 4 = skip pass 2 math
   long long* trace;  // bring-up only (env PC_ATTN_TRACE=1): [group iteration][WG][8] clock64 samples of CTA 0
 };
 
@@ -102,7 +101,6 @@ __device__ __forceinline__ Job job_of(const AttnParams& p, int g, int w) {
     j.tile = 2 * (g % p.ppi) + w;
     j.active = j.tile < p.m_tiles;
   }
-  if ((p.dbg & 1) && w == 1) j.active = false;
   return j;
 }
 
@@ -369,19 +367,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           uint32_t R[2][16];
           // ---- pass 1: row maximum over this half (next chunk's load in flight during the reduction)
           float mx = -INFINITY;
-          if (!(p.dbg & 2)) {
-            if (n16 > 0) tmem_ld_32x16(t_s, R[0]);
+          if (n16 > 0) tmem_ld_32x16(t_s, R[0]);
 #pragma unroll
-            for (int k = 0; k < NCH; ++k) {
-              if (k < n16) {
-                tmem_wait_ld();
-                if (k + 1 < NCH && k + 1 < n16) tmem_ld_32x16(t_s + (k + 1) * 16, R[(k + 1) & 1]);
-                if (k < n_full) mx = chunk_max<true>(R[k & 1], c_lo + k * 16, cmax, mx);
-                else mx = chunk_max<false>(R[k & 1], c_lo + k * 16, cmax, mx);
-              }
+          for (int k = 0; k < NCH; ++k) {
+            if (k < n16) {
+              tmem_wait_ld();
+              if (k + 1 < NCH && k + 1 < n16) tmem_ld_32x16(t_s + (k + 1) * 16, R[(k + 1) & 1]);
+              if (k < n_full) mx = chunk_max<true>(R[k & 1], c_lo + k * 16, cmax, mx);
+              else mx = chunk_max<false>(R[k & 1], c_lo + k * 16, cmax, mx);
             }
-          } else {
-            mx = 4.0f;
           }
           float* xmax = xmax0 + (st_cnt & 1) * 512;  // double-buffered: the partner may still read the previous block's
           xmax[x_mine] = mx;
@@ -411,7 +405,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           }
           m_run = m_new;
           // ---- pass 2: p = exp2((s - m) / 8 * log2 e), fp16 P written over this thread's own S columns
-          if (!(p.dbg & 4)) {
+          {
             const uint64_t sc2 = pack_f32x2(sc, sc), nmxs2 = pack_f32x2(-m_new * sc, -m_new * sc);
             uint64_t acc2 = 0;  // (0.0f, 0.0f)
             uint32_t pk[8];
@@ -548,14 +542,10 @@ int launch_attention(const __half* qkv, __half* out, int B, int L, int heads, in
   const int grid = p.n_groups < sms ? p.n_groups : sms;
   static int tracing = -1;
   static long long* trace = nullptr;
-  static int dbg = 0;
   if (tracing < 0) {
     const char* e = getenv("PC_ATTN_TRACE");
     tracing = (e && e[0] == '1') ? 1 : 0;
-    const char* f = getenv("PC_ATTN_DEBUG");
-    dbg = f ? atoi(f) : 0;
   }
-  p.dbg = dbg;
   if (tracing) {
     if (!trace) PC_CHECK_CUDA(cudaMalloc(&trace, 32 * 2 * 8 * sizeof(long long)));
     PC_CHECK_CUDA(cudaMemsetAsync(trace, 0, 32 * 2 * 8 * sizeof(long long), stream));

@@ -393,14 +393,6 @@ static int ln_grid(int rows) {
 int launch_layernorm(const __half* x, __half* y, const float* gamma, const float* beta, int rows, int d,
                      int row_stride_rows, cudaStream_t stream) {
   PC_TRY(check_row_dims("layernorm", rows, d));
-  {  // bring-up only: PC_SKIP_LN=1 drops the big LayerNorm launches to measure their share of the step
-    static int skip = -1;
-    if (skip < 0) {
-      const char* e = getenv("PC_SKIP_LN");
-      skip = (e && e[0] == '1') ? 1 : 0;
-    }
-    if (skip && rows > 4096) return PC_OK;
-  }
   const int grid = ln_grid(rows);
 #define CALL(NV) PC_CHECK_CUDA(launch_pdl(layernorm_kernel<NV>, dim3(grid), dim3(ROW_WARPS * 32), 2 * d * sizeof(float), stream, 1, \
                                           x, y, gamma, beta, static_cast<const int*>(nullptr), rows, d, row_stride_rows))
