@@ -60,6 +60,7 @@ struct AttnParams {
   int off_stage;   // 16 x 2 KB output staging blocks (one per softmax warp: 32 rows x 64 B, 64B-swizzled)
   int off_xch;     // max (x2, by block parity) / sum exchange between the two key halves: 3 x [pair][half][128] floats
   int off_bars;
+  int stagger;       // 1: pair 1 starts half a period after pair 0 (default); PC_ATTN_NO_STAGGER=1 clears it (A/B)
   long long* trace;  // bring-up only (env PC_ATTN_TRACE=1): [group iteration][WG][8] clock64 samples of CTA 0
 };
 
@@ -291,7 +292,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         // Stagger the warpgroups by half a period: WG 1 starts its first tile when WG 0 has finished its first
         // softmax, so from then on one WG computes exponentials while the other waits on the tensor core.
-        if (w == 1 && u == 0) mbar_wait(&bars->p_full[0], 0);
+        if (p.stagger && w == 1 && u == 0) mbar_wait(&bars->p_full[0], 0);
         tc_fence_after();
         const uint32_t k_addr =
             smem_u32(smem + p.off_kv + slot * 2 * p.kreg_bytes + (p.split ? w * p.sub_bytes : 0));
@@ -542,10 +543,14 @@ int launch_attention(const __half* qkv, __half* out, int B, int L, int heads, in
   const int grid = p.n_groups < sms ? p.n_groups : sms;
   static int tracing = -1;
   static long long* trace = nullptr;
+  static int stagger = 1;
   if (tracing < 0) {
     const char* e = getenv("PC_ATTN_TRACE");
     tracing = (e && e[0] == '1') ? 1 : 0;
+    const char* f = getenv("PC_ATTN_NO_STAGGER");
+    stagger = (f && f[0] == '1') ? 0 : 1;
   }
+  p.stagger = stagger;
   if (tracing) {
     if (!trace) PC_CHECK_CUDA(cudaMalloc(&trace, 32 * 2 * 8 * sizeof(long long)));
     PC_CHECK_CUDA(cudaMemsetAsync(trace, 0, 32 * 2 * 8 * sizeof(long long), stream));

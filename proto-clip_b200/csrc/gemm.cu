@@ -35,35 +35,42 @@ namespace {
 
 constexpr int BM = 128;  // accumulator rows per CTA (TMEM lanes)
 constexpr int BK = 64;   // 64 fp16 = 128 B = one swizzle row
-constexpr int STAGES = 5;
+constexpr int MAX_STAGES = 6;
 constexpr int EPI_WARPS = 8;
 constexpr int TMA_WARP = EPI_WARPS;
 constexpr int MMA_WARP = EPI_WARPS + 1;
 constexpr int GEMM_THREADS = (EPI_WARPS + 2) * 32;
 constexpr int STG_BYTES = 32 * 128;  // one staging block: 32 rows x 128 B, 16-byte chunks XOR-swizzled by (row & 7)
 
-struct Smem {
+// Shared-memory plan per epilogue kind. The residual epilogue needs two staging blocks per warp (the residual tile
+// of block i+1 is TMA-prefetched while block i is stored) and gets a 5-deep operand ring; every other epilogue
+// stores out of ONE staging block per warp, which buys a sixth ring stage (the ring is latency-bound: both the
+// producer and the MMA issuer wait on each other at 5 stages).
+template <int EPI>
+struct SmemT {
+  static constexpr int NSTG = (EPI == EPI_BIAS_RES) ? 2 : 1;  // staging blocks per epilogue warp
+  static constexpr int STAGES = (EPI == EPI_BIAS_RES) ? 5 : 6;
   static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
   static constexpr int B_BYTES = 128 * BK * 2;  // 16 KB: 128 W rows per CTA in both modes
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int OFF_STAGING = STAGES * STAGE_BYTES;
-  static constexpr int STAGING_BYTES = EPI_WARPS * 2 * STG_BYTES;
+  static constexpr int STAGING_BYTES = EPI_WARPS * NSTG * STG_BYTES;
   static constexpr int OFF_BIAS = OFF_STAGING + STAGING_BYTES;
   static constexpr int OFF_SCALE = OFF_BIAS + 256 * 4;  // s_n of the LayerNorm-folded epilogues
   static constexpr int OFF_BARS = OFF_SCALE + 256 * 4;
-  static constexpr int TOTAL = OFF_BARS + 256;  // + barrier block; the buffer is declared 1024-byte aligned
+  static constexpr int TOTAL = OFF_BARS + 512;  // + barrier block; the buffer is declared 1024-byte aligned
   static_assert(TOTAL <= 227 * 1024, "GEMM shared memory exceeds the 227 KB a CTA may use");
 };
 
 struct Bars {
-  uint64_t full[STAGES];            // PAIR: used in the leader only (TMA bytes of both CTAs)
-  uint64_t empty[STAGES];           // per CTA
+  uint64_t full[MAX_STAGES];        // PAIR: used in the leader only (TMA bytes of both CTAs)
+  uint64_t empty[MAX_STAGES];       // per CTA
   uint64_t tmem_full[2];            // per CTA
   uint64_t tmem_empty[2];           // PAIR: leader only, 16 arrivals; SINGLE: 8 arrivals
   uint64_t res_full[EPI_WARPS][2];  // residual block landed in staging buffer [warp][buf]
   uint32_t tmem_base;
 };
-static_assert(sizeof(Bars) <= 256, "barrier block");
+static_assert(sizeof(Bars) <= 512, "barrier block");
 
 // QuickGELU x * sigmoid(1.702 x) (clip/model.py:164-166) on a packed half2, with
 // sigmoid(t) = 0.5 * tanh(t / 2) + 0.5 so one MUFU.TANH serves two elements. fp16 math throughout, as the
@@ -95,6 +102,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                const GemmArgs g) {
+  using Smem = SmemT<EPI>;
+  constexpr int STAGES = Smem::STAGES;
+  constexpr int NSTG = Smem::NSTG;
   constexpr int BN = PAIR ? 256 : 128;                  // tile columns (TMEM columns per accumulator stage)
   constexpr int TILE_M = PAIR ? 256 : 128;              // tile rows (both CTAs of a pair)
   constexpr int GRP_COLS = (EPI == EPI_F32) ? 32 : 64;  // columns per 128-byte staging row
@@ -269,7 +279,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int quarter = warp & 3;  // TMEM lanes 32 * quarter .. + 31 (hardware: warp id % 4)
     const int chalf = warp >> 2;   // column half of the tile
     const int ep_tid = threadIdx.x;
-    uint8_t* stg0 = smem + Smem::OFF_STAGING + warp * 2 * STG_BYTES;
+    uint8_t* stg0 = smem + Smem::OFF_STAGING + warp * NSTG * STG_BYTES;
     uint64_t* res_bar = bars->res_full[warp];
     const int row_off = rank * BM + quarter * 32;  // first row of this warp inside the tile
     const int col_off = chalf * (BN / 2);          // first column of this warp inside the tile
@@ -338,7 +348,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + col_off;
 #pragma unroll 1
       for (int grp = 0; grp < NG; ++grp, ++sg) {
-        uint8_t* stg = stg0 + (sg & 1) * STG_BYTES;
+        uint8_t* stg = stg0 + (NSTG == 2 ? (sg & 1) : 0) * STG_BYTES;
         uint8_t* my_row = stg + lane * 128;
         const int gcol0 = n0 + col_off + grp * GRP_COLS;
         // ---- accumulator block -> registers
@@ -375,7 +385,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                           (nt % n_blks) * BN + col_off + ngrp * GRP_COLS, (nt / n_blks) * TILE_M + row_off);
             }
           } else {
-            tma_store_wait_read<1>();  // the store issued two blocks ago has drained this buffer
+            tma_store_wait_read<0>();  // single staging block: the previous store has drained it
           }
         }
         __syncwarp();
@@ -499,6 +509,7 @@ bool force_single_cta() {
 
 template <bool PAIR, int EPI>
 int launch_impl(const GemmArgs& a0, cudaStream_t stream) {
+  using Smem = SmemT<EPI>;
   constexpr int BN = PAIR ? 256 : 128;
   constexpr int TILE_M = PAIR ? 256 : 128;
   static bool configured = false;
