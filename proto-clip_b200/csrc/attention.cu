@@ -2,27 +2,26 @@
 // (reference clip/model.py:173,183-185 -> nn.MultiheadAttention -> scaled_dot_product_attention; the text
 // tower's additive mask clip/model.py:326-332 is exactly "j > i -> -inf", i.e. the causal flag here).
 //
-// Persistent kernel, one CTA per SM (it owns all 512 TMEM columns), 19 warps:
-//   warps 0-15   softmax: two PAIRS of warpgroups (pair = one 256-column TMEM region = one 128-row query tile in
-//                flight). Inside a pair the two warpgroups split the KEY axis: thread (row r, half h) owns row r of
-//                the tile (TMEM lane r) and the S columns of half h. S = Q K^T is read from TMEM twice (row max,
-//                then exp2 / row sum; the two halves exchange max and sum through shared memory and a 64-thread
-//                named barrier); P is written back IN PLACE over the thread's own S columns as packed fp16
-//                (tcgen05.st) and consumed by the PV MMA straight from TMEM (A operand in TMEM, "ts" form): no
-//                shared-memory round trip and no proxy fence for P. Four softmax warps per scheduler keep the MUFU
-//                pipe busy across the TMEM-load latencies; the two pairs run half a period apart so one is in its
-//                exponentials while the other waits on the tensor core.
-//   warp 16 / 17 MMA issuer of pair 0 / 1: S = Q K^T (Q, K from 128B-swizzled smem), then O (+)= P V (V as the
-//                MN-major B operand). Whole warp in the loop, one elected lane issues.
-//   warp 18      TMA producer: Q tiles (one buffer per pair) and K/V blocks (two slots, shared by the pairs) cut
-//                straight out of the packed qkv activation [B*L, 3d].
-// Work decomposition: a GROUP is one K/V stream plus the (up to) two 128-row query tiles that use it:
-//   L <= 128   ("split")  the two pairs take two different (image, head) items; a K/V slot holds both items' K/V
-//   L  > 128              the two pairs take tiles 2t, 2t+1 of the same item and share its K/V
-// Keys are processed in blocks of `kb` columns: the whole row in one block when L <= 256 (no rescaling at all:
-// 50 / 77 / 197 tokens), 192-key blocks with an online-softmax rescale of O in TMEM otherwise (257 / 577).
-// TMEM region of a pair (256 columns): S [0, n), P of half 0 at [0, cs/2), P of half 1 at [cs, cs + (n-cs)/2)
-// (cs = the column where half 1 starts), O at [192, 256) (over dead S columns when n > 192).
+// Persistent kernel, one CTA per SM (it owns all 512 TMEM columns), 12 warps:
+//   warps 0-3 / 4-7   softmax warpgroup ("WG") 0 / 1: one 128-row query tile in flight each, one query row per
+//                     thread (row == TMEM lane). The key axis is streamed in blocks of 64 keys through a two-slot
+//                     S ring in TMEM: while the threads run the softmax of block j, the tensor core already
+//                     computes S of block j+1 and the PV product of block j-1, so the softmax warps only ever wait
+//                     at tile boundaries. A block's 64 scores are read from TMEM once, kept in registers for the
+//                     max and the exp2 pass, and P goes back IN PLACE as packed fp16 (tcgen05.st) to be consumed
+//                     by the PV MMA straight from TMEM (A operand in TMEM, "ts" form): no shared-memory round trip
+//                     and no proxy fence for P. Online softmax with a LAZY reference: the running reference
+//                     maximum only moves (and O, accumulated in TMEM, is only rescaled) when a block's maximum
+//                     exceeds it by more than 8 in the exp2 domain, so P stays below 2^8 and rescales are rare.
+//   warp 8 / 9        MMA issuer of WG 0 / 1 (whole warp in the loop, one elected lane issues):
+//                     S_0, S_1, PV_0, S_2, PV_1, ... (S_j into ring slot j & 1: the in-order tensor pipe guarantees
+//                     that PV_{j-2} has consumed the slot). Q, K from 128B-swizzled smem, V as the MN-major B operand.
+//   warp 10 / 11      TMA producers: the K / V rows of an item (slots shared by the two WGs) and WG 0's query tiles /
+//                     WG 1's query tiles, cut straight out of the packed qkv activation [B*L, 3d].
+// Work decomposition: a GROUP is one K/V set plus the (up to) two 128-row query tiles that use it:
+//   L <= 128   ("split")  the two WGs take two different (image, head) items; a K/V slot holds both items' K/V
+//   L  > 128              the two WGs take tiles 2t, 2t+1 of the same item and share its K/V
+// TMEM region of a WG (256 columns): S / P ring slots at [0, 64) and [64, 128), O at [128, 192).
 #include <stdlib.h>
 
 #include "kernels.cuh"
@@ -33,34 +32,34 @@ namespace pc {
 namespace {
 
 constexpr int HEAD_DIM = 64;
-constexpr int MMA_WARP0 = 16;  // warps 0..15: softmax, [pair][key half][lane quarter]
-constexpr int TMA_WARP = 18;
-constexpr int ATT_THREADS = 19 * 32;
-constexpr int O_COL = 192;     // O accumulator columns inside a pair's TMEM region
+constexpr int KVB = 64;          // keys per block (one S ring slot)
+constexpr int MMA_WARP0 = 8;     // warps 0..7: the two softmax warpgroups
+constexpr int TMA_WARP = 10;     // K/V of every group + Q tiles of WG 0
+constexpr int TMA_WARP_Q1 = 11;  // Q tiles of WG 1 (its own warp: the two WGs' tile boundaries stay decoupled)
+constexpr int ATT_THREADS = 12 * 32;
 constexpr int Q_BYTES = 128 * 128;  // one query tile: 128 rows x 64 fp16
-constexpr int KB_MULTI = 192;       // keys per block when the row does not fit one TMEM region
+constexpr int O_COL = 128;          // O accumulator columns inside a WG's TMEM region
+constexpr float RESCALE_LOG2 = 8.0f;  // move the reference maximum only when it is exceeded by 2^8
 
 struct AttnParams {
-  __half* out;     // [B*L, d]
   int L;           // tokens per sequence
   int lp16;        // L rounded up to 16
   int heads;
   int d;           // heads * 64
-  int causal;
   int items;       // B * heads
   int m_tiles;     // ceil(L / 128)
   int split;       // 1: L <= 128, the WGs take different items
   int ppi;         // non-split: tile pairs per item = ceil(m_tiles / 2)
   int n_groups;
-  int n_kvb;       // key blocks per row
-  int kb;          // keys per block (multiple of 16)
+  int n_blk;       // key blocks per row = ceil(lp16 / 64)
+  int kv_rows;     // rows per K/V TMA box
+  int kv_boxes;    // boxes per K (V) load
+  int n_slots;     // K/V slots (2 when they fit, else 1)
   int sub_bytes;   // split: byte offset of WG 1's K (V) inside a slot's K (V) region
   int kreg_bytes;  // bytes of a slot's K region; the V region follows
-  int off_kv;      // smem offset of slot 0 (slot 1 follows at + 2 * kreg_bytes)
-  int off_stage;   // 16 x 2 KB output staging blocks (one per softmax warp: 32 rows x 64 B, 64B-swizzled)
-  int off_xch;     // max (x2, by block parity) / sum exchange between the two key halves: 3 x [pair][half][128] floats
+  int off_kv;      // smem offset of slot 0
+  int off_stage;   // 8 x 4 KB output staging blocks (one per softmax warp: 32 rows x 128 B, 128B-swizzled)
   int off_bars;
-  int stagger;       // 1: pair 1 starts half a period after pair 0 (default); PC_ATTN_NO_STAGGER=1 clears it (A/B)
   long long* trace;  // bring-up only (env PC_ATTN_TRACE=1): [group iteration][WG][8] clock64 samples of CTA 0
 };
 
@@ -70,14 +69,14 @@ struct AttnParams {
   } while (0)
 
 struct AttnBars {
-  uint64_t kv_full[2];  // per slot: TMA bytes landed
-  uint64_t kv_free[2];  // per slot: both WGs' PV MMAs retired (2 arrivals)
-  uint64_t q_full[2];   // per WG
-  uint64_t q_free[2];   // per WG: last S MMA of the group retired
-  uint64_t s_full[2];   // per WG: S block in TMEM
-  uint64_t p_full[2];   // per pair: P block in TMEM (8 warp arrivals)
-  uint64_t o_full[2];   // per WG: last PV MMA of the group retired
-  uint64_t o_free[2];   // per pair: O read out, region reusable (8 warp arrivals)
+  uint64_t kv_full[2];     // per K/V slot: TMA bytes landed
+  uint64_t kv_free[2];     // per K/V slot: both WGs' last PV MMA of the group retired (2 arrivals)
+  uint64_t q_full[2];      // per WG
+  uint64_t q_free[2];      // per WG: last S MMA of the tile retired
+  uint64_t s_full[2][2];   // [WG][ring slot]: S block in TMEM
+  uint64_t p_full[2][2];   // [WG][ring slot]: P block in TMEM (4 warp arrivals)
+  uint64_t pv_done[2][2];  // [WG][block parity]: the PV MMA of a block retired
+  uint64_t o_free[2];      // per WG: O read out, accumulator reusable (4 warp arrivals)
   uint32_t tmem_base;
 };
 
@@ -110,28 +109,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-
-// ---- softmax chunk helpers: 16 S columns [c0, c0+16) of this thread's row, already in registers ----------
-// cmax = last valid column of THIS row (sequence end; causal rows differ). FULL chunks (every column valid for
-// every row of the warp) take the branch-free, mask-free path.
-template <bool FULL>
-__device__ __forceinline__ float chunk_max(const uint32_t (&v)[16], int c0, int cmax, float mx) {
-  float m1 = -INFINITY;
-#pragma unroll
-  for (int j = 0; j < 16; j += 4) {
-    float a = __uint_as_float(v[j]), b = __uint_as_float(v[j + 1]);
-    float c = __uint_as_float(v[j + 2]), d = __uint_as_float(v[j + 3]);
-    if (!FULL) {
-      a = (c0 + j <= cmax) ? a : -INFINITY;
-      b = (c0 + j + 1 <= cmax) ? b : -INFINITY;
-      c = (c0 + j + 2 <= cmax) ? c : -INFINITY;
-      d = (c0 + j + 3 <= cmax) ? d : -INFINITY;
-    }
-    mx = fmaxf(mx, fmaxf(a, b));
-    m1 = fmaxf(m1, fmaxf(c, d));
-  }
-  return fmaxf(mx, m1);
-}
 // packed fp32 pair math (one issue slot for two elements)
 __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
   return static_cast<uint64_t>(__float_as_uint(lo)) | (static_cast<uint64_t>(__float_as_uint(hi)) << 32);
@@ -146,18 +123,40 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
-// p = exp2(s * sc - mxs) -> packed fp16 pairs; `acc` accumulates the fp32 (unrounded) p as an (even, odd) pair.
+
+// ---- softmax chunk helpers: 16 S columns of this thread's row, already in registers. kmax = last valid key of
+// THIS row relative to the chunk's first key (sequence end; causal rows differ). FULL chunks (every key valid for
+// every row of the warp) take the mask-free path.
 template <bool FULL>
-__device__ __forceinline__ uint64_t chunk_exp(const uint32_t (&v)[16], uint32_t (&pk)[8], int c0, int cmax, uint64_t sc2,
-                                              uint64_t nmxs2, uint64_t acc) {
+__device__ __forceinline__ float chunk_max(const uint32_t (&v)[16], int kmax, float mx) {
+  float m1 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) {
+    float a = __uint_as_float(v[j]), b = __uint_as_float(v[j + 1]);
+    float c = __uint_as_float(v[j + 2]), d = __uint_as_float(v[j + 3]);
+    if (!FULL) {
+      a = (j <= kmax) ? a : -INFINITY;
+      b = (j + 1 <= kmax) ? b : -INFINITY;
+      c = (j + 2 <= kmax) ? c : -INFINITY;
+      d = (j + 3 <= kmax) ? d : -INFINITY;
+    }
+    mx = fmaxf(mx, fmaxf(a, b));
+    m1 = fmaxf(m1, fmaxf(c, d));
+  }
+  return fmaxf(mx, m1);
+}
+// p = exp2(s * sc - ref) -> packed fp16 pairs; `acc` accumulates the fp32 (unrounded) p as an (even, odd) pair.
+template <bool FULL>
+__device__ __forceinline__ uint64_t chunk_exp(const uint32_t (&v)[16], uint32_t (&pk)[8], int kmax, uint64_t sc2,
+                                              uint64_t nref2, uint64_t acc) {
 #pragma unroll
   for (int j = 0; j < 16; j += 2) {
-    const uint64_t t = fma_f32x2(static_cast<uint64_t>(v[j]) | (static_cast<uint64_t>(v[j + 1]) << 32), sc2, nmxs2);
+    const uint64_t t = fma_f32x2(static_cast<uint64_t>(v[j]) | (static_cast<uint64_t>(v[j + 1]) << 32), sc2, nref2);
     float e0 = ex2_approx(__uint_as_float(static_cast<uint32_t>(t)));
     float e1 = ex2_approx(__uint_as_float(static_cast<uint32_t>(t >> 32)));
     if (!FULL) {
-      e0 = (c0 + j <= cmax) ? e0 : 0.0f;
-      e1 = (c0 + j + 1 <= cmax) ? e1 : 0.0f;
+      e0 = (j <= kmax) ? e0 : 0.0f;
+      e1 = (j + 1 <= kmax) ? e1 : 0.0f;
     }
     acc = add_f32x2(acc, pack_f32x2(e0, e1));
     pk[j >> 1] = pack_half2(e0, e1);
@@ -165,19 +164,13 @@ __device__ __forceinline__ uint64_t chunk_exp(const uint32_t (&v)[16], uint32_t 
   return acc;
 }
 
-// MULTI: more than one key block per row (L > 256): compiles the online-softmax rescale in.
-// NCH: upper bound on the 16-column chunks of one key half (the softmax loops are fully unrolled over it: a lone
-// warp issues ~0.2 instructions per clock through branchy loop code, so straight-line code is what makes the
-// passes short). CAUSAL: the text tower's mask (every chunk takes the masked path).
-template <bool MULTI, int NCH, bool CAUSAL>
+template <bool CAUSAL>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                  const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem =
-      reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
   AttnBars* bars = reinterpret_cast<AttnBars*>(smem + p.off_bars);
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform: keeps role-derived values in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform (uniform registers)
   const int lane = threadIdx.x & 31;
 
   if (warp == TMA_WARP) {
@@ -190,10 +183,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_init(&bars->kv_free[i], 2);
         mbar_init(&bars->q_full[i], 1);
         mbar_init(&bars->q_free[i], 1);
-        mbar_init(&bars->s_full[i], 1);
-        mbar_init(&bars->p_full[i], 8);
-        mbar_init(&bars->o_full[i], 1);
-        mbar_init(&bars->o_free[i], 8);
+        mbar_init(&bars->o_free[i], 4);
+        for (int s = 0; s < 2; ++s) {
+          mbar_init(&bars->s_full[i][s], 1);
+          mbar_init(&bars->p_full[i][s], 4);
+          mbar_init(&bars->pv_done[i][s], 1);
+        }
       }
       fence_mbar_init();
     }
@@ -211,136 +206,140 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == TMA_WARP) {
     // ---------------------------------------------------------------------------------- TMA producer
     // The whole warp walks the loops (warp-uniform values stay in uniform registers); one elected lane issues.
-    uint32_t u = 0;              // K/V units loaded so far (slot = u & 1)
-    uint32_t q_cnt0 = 0, q_cnt1 = 0;  // Q tiles loaded per WG
-    const uint32_t kv_box_bytes = static_cast<uint32_t>(p.kb) * 128;
-    for (int g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
+    uint32_t u = 0;                   // K/V units loaded so far
+    uint32_t q_cnt0 = 0;              // Q tiles of WG 0 loaded so far
+    const uint32_t kv_box_bytes = static_cast<uint32_t>(p.kv_rows) * 128;
+    const uint32_t kv_bytes = kv_box_bytes * p.kv_boxes;  // one K (or V) of one item
+    for (int g = blockIdx.x; g < p.n_groups; g += gridDim.x, ++u) {
       const Job j0 = job_of(p, g, 0), j1 = job_of(p, g, 1);
-      for (int jb = 0; jb < p.n_kvb; ++jb, ++u) {
-        const int slot = u & 1;
-        uint8_t* kbuf = smem + p.off_kv + slot * 2 * p.kreg_bytes;
-        uint8_t* vbuf = kbuf + p.kreg_bytes;
-        mbar_wait(&bars->kv_free[slot], ((u >> 1) & 1) ^ 1);
-        if (jb == 0) {
-          if (j0.active) mbar_wait(&bars->q_free[0], (q_cnt0 & 1) ^ 1);
-          if (j1.active) mbar_wait(&bars->q_free[1], (q_cnt1 & 1) ^ 1);
-        }
-        if (elect_one()) {
-          if (p.split) {
-            mbar_arrive_expect_tx(&bars->kv_full[slot], 2 * kv_box_bytes * ((j0.active ? 1 : 0) + (j1.active ? 1 : 0)));
-            if (j0.active) {
-              const int b = j0.item / p.heads, h = j0.item % p.heads;
-              const int row = b * p.L + jb * p.kb;
-              tma_load_2d(kbuf, &tmKV, &bars->kv_full[slot], p.d + h * HEAD_DIM, row);
-              tma_load_2d(vbuf, &tmKV, &bars->kv_full[slot], 2 * p.d + h * HEAD_DIM, row);
-            }
-            if (j1.active) {
-              const int b = j1.item / p.heads, h = j1.item % p.heads;
-              const int row = b * p.L + jb * p.kb;
-              tma_load_2d(kbuf + p.sub_bytes, &tmKV, &bars->kv_full[slot], p.d + h * HEAD_DIM, row);
-              tma_load_2d(vbuf + p.sub_bytes, &tmKV, &bars->kv_full[slot], 2 * p.d + h * HEAD_DIM, row);
-            }
-          } else {
-            const int b = j0.item / p.heads, h = j0.item % p.heads;
-            const int row = b * p.L + jb * p.kb;
-            mbar_arrive_expect_tx(&bars->kv_full[slot], 2 * kv_box_bytes);
-            tma_load_2d(kbuf, &tmKV, &bars->kv_full[slot], p.d + h * HEAD_DIM, row);
-            tma_load_2d(vbuf, &tmKV, &bars->kv_full[slot], 2 * p.d + h * HEAD_DIM, row);
+      const int slot = (p.n_slots == 2) ? (u & 1) : 0;
+      const uint32_t use = (p.n_slots == 2) ? (u >> 1) : u;  // how many times this slot was filled before
+      uint8_t* kbuf = smem + p.off_kv + slot * 2 * p.kreg_bytes;
+      uint8_t* vbuf = kbuf + p.kreg_bytes;
+      mbar_wait(&bars->kv_free[slot], (use & 1) ^ 1);
+      if (elect_one()) {
+        const int n_items = p.split ? ((j0.active ? 1 : 0) + (j1.active ? 1 : 0)) : 1;
+        mbar_arrive_expect_tx(&bars->kv_full[slot], 2 * kv_bytes * n_items);
+        for (int w = 0; w < 2; ++w) {
+          const Job& j = w ? j1 : j0;
+          if (p.split ? !j.active : (w == 1)) continue;  // shared K/V: loaded once (j0 is always active)
+          const int b = j.item / p.heads, h = j.item % p.heads;
+          uint8_t* kd = kbuf + (p.split ? w * p.sub_bytes : 0);
+          uint8_t* vd = vbuf + (p.split ? w * p.sub_bytes : 0);
+          for (int x = 0; x < p.kv_boxes; ++x) {
+            const int row = b * p.L + x * p.kv_rows;
+            tma_load_2d(kd + x * kv_box_bytes, &tmKV, &bars->kv_full[slot], p.d + h * HEAD_DIM, row);
+            tma_load_2d(vd + x * kv_box_bytes, &tmKV, &bars->kv_full[slot], 2 * p.d + h * HEAD_DIM, row);
           }
-          if (jb == 0) {
-            if (j0.active) {
-              const int b = j0.item / p.heads, h = j0.item % p.heads;
-              mbar_arrive_expect_tx(&bars->q_full[0], Q_BYTES);
-              tma_load_2d(smem, &tmQ, &bars->q_full[0], h * HEAD_DIM, b * p.L + j0.tile * 128);
-            }
-            if (j1.active) {
-              const int b = j1.item / p.heads, h = j1.item % p.heads;
-              mbar_arrive_expect_tx(&bars->q_full[1], Q_BYTES);
-              tma_load_2d(smem + Q_BYTES, &tmQ, &bars->q_full[1], h * HEAD_DIM, b * p.L + j1.tile * 128);
-            }
-          }
-        }
-        __syncwarp();
-        if (jb == 0) {
-          q_cnt0 += j0.active ? 1 : 0;
-          q_cnt1 += j1.active ? 1 : 0;
         }
       }
+      __syncwarp();
+      if (j0.active) {  // WG 0's query tile (after the K/V of the group is on its way)
+        mbar_wait(&bars->q_free[0], (q_cnt0 & 1) ^ 1);
+        if (elect_one()) {
+          const int b = j0.item / p.heads, h = j0.item % p.heads;
+          mbar_arrive_expect_tx(&bars->q_full[0], Q_BYTES);
+          tma_load_2d(smem, &tmQ, &bars->q_full[0], h * HEAD_DIM, b * p.L + j0.tile * 128);
+        }
+        __syncwarp();
+        ++q_cnt0;
+      }
+    }
+  } else if (warp == TMA_WARP_Q1) {
+    // ---------------------------------------------------------------------------------- Q producer of WG 1
+    uint32_t q_cnt1 = 0;
+    for (int g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
+      const Job j1 = job_of(p, g, 1);
+      if (!j1.active) continue;
+      mbar_wait(&bars->q_free[1], (q_cnt1 & 1) ^ 1);
+      if (elect_one()) {
+        const int b = j1.item / p.heads, h = j1.item % p.heads;
+        mbar_arrive_expect_tx(&bars->q_full[1], Q_BYTES);
+        tma_load_2d(smem + Q_BYTES, &tmQ, &bars->q_full[1], h * HEAD_DIM, b * p.L + j1.tile * 128);
+      }
+      __syncwarp();
+      ++q_cnt1;
     }
   } else if (warp == MMA_WARP0 || warp == MMA_WARP0 + 1) {
     // ---------------------------------------------------------------------------------- MMA issuer of WG w
-    // (whole warp in the loops, one elected lane issues: see the producer)
     const int w = warp - MMA_WARP0;
     const uint32_t region = tmem + w * 256;
-    const uint32_t q_addr = smem_u32(smem + w * Q_BYTES);
-    const uint64_t q_desc = umma_desc_kmajor_sw128(q_addr);
+    const uint64_t q_desc = umma_desc_kmajor_sw128(smem_u32(smem + w * Q_BYTES));
     const uint32_t idesc_o = umma_idesc_f16(128, HEAD_DIM, 0, 1);
-    uint32_t u = 0, q_cnt = 0, st_cnt = 0;
-    for (int g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
+    uint32_t u = 0, q_cnt = 0;
+    uint32_t pf_cnt0 = 0, pf_cnt1 = 0;  // p_full phases consumed per ring slot
+    for (int g = blockIdx.x; g < p.n_groups; g += gridDim.x, ++u) {
       const Job j = job_of(p, g, w);
-      for (int jb = 0; jb < p.n_kvb; ++jb, ++u) {
-        const int slot = u & 1;
-        mbar_wait(&bars->kv_full[slot], (u >> 1) & 1);
-        if (!j.active) {  // this WG sits the unit out: release its share of the slot
-          if (lane == 0) mbar_arrive(&bars->kv_free[slot]);
-          __syncwarp();
-          continue;
-        }
-        if (jb == 0) {
-          mbar_wait(&bars->q_full[w], q_cnt & 1);
-          mbar_wait(&bars->o_free[w], (q_cnt & 1) ^ 1);
-        }
-        // Stagger the warpgroups by half a period: WG 1 starts its first tile when WG 0 has finished its first
-        // softmax, so from then on one WG computes exponentials while the other waits on the tensor core.
-        if (p.stagger && w == 1 && u == 0) mbar_wait(&bars->p_full[0], 0);
-        tc_fence_after();
-        const uint32_t k_addr =
-            smem_u32(smem + p.off_kv + slot * 2 * p.kreg_bytes + (p.split ? w * p.sub_bytes : 0));
-        const uint32_t v_addr = k_addr + p.kreg_bytes;
-        const int n_cols = min(p.kb, p.lp16 - jb * p.kb);
-        if (elect_one()) {
-          // S[128, n_cols] = Q K^T   (+2 in the descriptor's address field = 32 B = 16 fp16 along K)
-          const uint32_t idesc_s = umma_idesc_f16(128, n_cols, 0, 0);
-          const uint64_t k_desc = umma_desc_kmajor_sw128(k_addr);
-#pragma unroll
-          for (int k = 0; k < HEAD_DIM / 16; ++k) umma_f16_ss(region, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-          umma_commit(&bars->s_full[w]);
-          if (jb == p.n_kvb - 1) umma_commit(&bars->q_free[w]);
-        }
+      const int slot = (p.n_slots == 2) ? (u & 1) : 0;
+      const uint32_t use = (p.n_slots == 2) ? (u >> 1) : u;
+      mbar_wait(&bars->kv_full[slot], use & 1);
+      if (!j.active) {  // this WG sits the group out: release its share of the slot
+        if (lane == 0) mbar_arrive(&bars->kv_free[slot]);
         __syncwarp();
-        // O[128, 64] (+)= P V : P from TMEM (8 columns per 16 keys), V MN-major (16 key rows = 2048 B per K step)
-        mbar_wait(&bars->p_full[w], st_cnt & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t v_desc = umma_desc_mnmajor_sw128(v_addr, 1024);
-          const int k_steps = n_cols >> 4;
-          const int k_half = (k_steps + 1) >> 1;  // k-steps whose P was written by key half 0 (at column 8 * kk)
-          umma_f16_ts(region + O_COL, region, v_desc, idesc_o, jb != 0 ? 1u : 0u);
-          for (int kk = 1; kk < k_steps; ++kk) {
-            const uint32_t a_col = kk < k_half ? 8 * kk : 16 * k_half + 8 * (kk - k_half);
-            umma_f16_ts(region + O_COL, region + a_col, v_desc + 128 * kk, idesc_o, 1u);
-          }
-          umma_commit(&bars->kv_free[slot]);
-          if (jb == p.n_kvb - 1) umma_commit(&bars->o_full[w]);
-        }
-        __syncwarp();
-        ++st_cnt;
+        continue;
       }
-      if (j.active) ++q_cnt;
+      mbar_wait(&bars->q_full[w], q_cnt & 1);
+      // Stagger the warpgroups: WG 1 starts its first tile when WG 0 has delivered its first P block, so that one WG
+      // tends to be in its exponentials while the other is in its max / hand-off phase.
+      if (w == 1 && q_cnt == 0) mbar_wait(&bars->p_full[0][0], 0);
+      tc_fence_after();
+      const uint32_t k_addr = smem_u32(smem + p.off_kv + slot * 2 * p.kreg_bytes + (p.split ? w * p.sub_bytes : 0));
+      const uint32_t v_addr = k_addr + p.kreg_bytes;
+      const uint64_t k_desc = umma_desc_kmajor_sw128(k_addr);
+      const uint64_t v_desc = umma_desc_mnmajor_sw128(v_addr, 1024);
+      // S_0; then for t = 1 .. n_blk: S_t (if any) followed by PV_{t-1}
+      for (int t = 0; t <= p.n_blk; ++t) {
+        if (t < p.n_blk) {
+          const int n_cols = min(KVB, p.lp16 - t * KVB);
+          if (elect_one()) {
+            // S_t[128, n_cols] = Q K_t^T into ring slot t & 1 (key row r of K at byte r * 128: >> 4 in the descriptor)
+            const uint32_t idesc_s = umma_idesc_f16(128, n_cols, 0, 0);
+            const uint64_t kd = k_desc + static_cast<uint64_t>(t) * (KVB * 128 / 16);
+#pragma unroll
+            for (int k = 0; k < HEAD_DIM / 16; ++k)
+              umma_f16_ss(region + (t & 1) * KVB, q_desc + 2 * k, kd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+            umma_commit(&bars->s_full[w][t & 1]);
+            if (t == p.n_blk - 1) umma_commit(&bars->q_free[w]);
+          }
+          __syncwarp();
+        }
+        if (t >= 1) {
+          const int jb = t - 1;
+          const int n_cols = min(KVB, p.lp16 - jb * KVB);
+          if (jb == 0) mbar_wait(&bars->o_free[w], (q_cnt & 1) ^ 1);  // the previous tile's O has been read out
+          if (jb & 1) {
+            mbar_wait(&bars->p_full[w][1], pf_cnt1 & 1);
+            ++pf_cnt1;
+          } else {
+            mbar_wait(&bars->p_full[w][0], pf_cnt0 & 1);
+            ++pf_cnt0;
+          }
+          tc_fence_after();
+          if (elect_one()) {
+            // O[128, 64] (+)= P_jb V_jb : P from TMEM (8 columns per 16 keys), V MN-major (16 key rows = 2048 B per step)
+            const uint64_t vd = v_desc + static_cast<uint64_t>(jb) * (KVB * 128 / 16);
+            const int k_steps = n_cols >> 4;
+            for (int kk = 0; kk < k_steps; ++kk)
+              umma_f16_ts(region + O_COL, region + (jb & 1) * KVB + 8 * kk, vd + 128 * kk, idesc_o, (jb | kk) != 0 ? 1u : 0u);
+            umma_commit(&bars->pv_done[w][jb & 1]);
+            if (jb == p.n_blk - 1) umma_commit(&bars->kv_free[slot]);
+          }
+          __syncwarp();
+        }
+      }
+      ++q_cnt;
     }
   } else if (warp < MMA_WARP0) {
-    // ---------------------------------------------------------------------------------- softmax, pair w / half hf
-    const int w = warp >> 3;
-    const int hf = (warp >> 2) & 1;
+    // ---------------------------------------------------------------------------------- softmax WG w
+    const int w = warp >> 2;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;  // row of the tile == TMEM lane
     const uint32_t t_row = tmem + w * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
-    const uint32_t pair_bar = 1 + w * 4 + quarter;  // named barrier of the two warps that share these 32 rows
-    float* xmax0 = reinterpret_cast<float*>(smem + p.off_xch);  // [2 (block parity)][pair][half][128]
-    float* xsum = xmax0 + 1024;
-    const int x_mine = (w * 2 + hf) * 128 + r, x_other = (w * 2 + (hf ^ 1)) * 128 + r;
     const float sc = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-    uint32_t st_cnt = 0, o_cnt = 0;
+    const uint64_t sc2 = pack_f32x2(sc, sc);
+    uint32_t sf_cnt0 = 0, sf_cnt1 = 0;  // s_full phases consumed per ring slot
+    uint32_t pv_obs0 = 0, pv_obs1 = 0;  // pv_done phases observed per block parity
+    uint32_t pv_exp0 = 0, pv_exp1 = 0;  // PV MMAs that follow the P blocks delivered so far, per block parity
     int git = -1;
     for (int g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
       ++git;
@@ -348,130 +347,168 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (!j.active) continue;
       const int i = j.tile * 128 + r;  // query index inside the sequence
       const bool warp_live = j.tile * 128 + quarter * 32 < p.L;  // some row of this warp is a real query
-      const int jmax = CAUSAL ? min(i, p.L - 1) : p.L - 1;
-      float m_run = -INFINITY, sum = 0.0f;
-      for (int jb = 0; jb < p.n_kvb; ++jb, ++st_cnt) {
-        const int n_cols = min(p.kb, p.lp16 - jb * p.kb);
-        const int ncv = min(n_cols, p.L - jb * p.kb);  // valid key columns of this block
-        const int cmax = jmax - jb * p.kb;             // last valid column of this row (may be < 0)
-        const int cs = (((n_cols >> 4) + 1) >> 1) << 4;  // first column of key half 1
-        const int c_lo = hf ? cs : 0;                    // this thread's S columns: [c_lo, c_lo + 16 * n16)
-        const int n16 = ((hf ? n_cols : cs) - c_lo) >> 4;
-        ATRACE(0, hf == 0 && quarter == 0 && lane == 0 && jb == 0);
-        mbar_wait(&bars->s_full[w], st_cnt & 1);
+      const int jmax = CAUSAL ? min(i, p.L - 1) : p.L - 1;       // last key this row attends to
+      float m_ref = -INFINITY;  // reference maximum of the row (raw score units)
+      uint64_t acc2 = 0;        // running (even, odd) sums of p
+      for (int jb = 0; jb < p.n_blk; ++jb) {
+        const int s = jb & 1;
+        const int n16 = min(KVB, p.lp16 - jb * KVB) >> 4;  // 16-key chunks of this block
+        const int kbase = jb * KVB;
+        if (jb == 0) ATRACE(0, quarter == 0 && lane == 0);
+        if (s) {
+          mbar_wait(&bars->s_full[w][1], sf_cnt1 & 1);
+          ++sf_cnt1;
+        } else {
+          mbar_wait(&bars->s_full[w][0], sf_cnt0 & 1);
+          ++sf_cnt0;
+        }
         tc_fence_after();
-        ATRACE(1, hf == 0 && quarter == 0 && lane == 0 && jb == 0);
+        if (jb == 0) ATRACE(1, quarter == 0 && lane == 0);
+        // S_jb complete => every PV of this parity delivered so far (PV_{jb-2}, ...) has retired, because it was issued
+        // before S_jb on the in-order pipe: keep the phase bookkeeping of that barrier in step (no real waiting)
+        if (s) {
+          while (pv_obs1 < pv_exp1) {
+            mbar_wait(&bars->pv_done[w][1], pv_obs1 & 1);
+            ++pv_obs1;
+          }
+        } else {
+          while (pv_obs0 < pv_exp0) {
+            mbar_wait(&bars->pv_done[w][0], pv_obs0 & 1);
+            ++pv_obs0;
+          }
+        }
         if (warp_live) {
-          const uint32_t t_s = t_row + c_lo;
-          // number of leading chunks of this half that need no masking (warp-uniform; 0 for causal rows)
-          const int n_full = CAUSAL ? 0 : min(n16, max(0, (ncv - c_lo) >> 4));
-          uint32_t R[2][16];
-          // ---- pass 1: row maximum over this half (next chunk's load in flight during the reduction)
+          const uint32_t t_s = t_row + s * KVB;
+          uint32_t R[4][16];
+          // all four chunks are loaded (columns past the block's end hold stale data that is never used): straight-
+          // line loads keep the 64 scores in registers
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tmem_ld_32x16(t_s + k * 16, R[k]);
+          tmem_wait_ld();
+          // blocks whose every key is valid for every row of the warp need no masking (never for causal rows)
+          const bool full = !CAUSAL && kbase + n16 * 16 <= p.L;
+          // ---- block maximum
           float mx = -INFINITY;
-          if (n16 > 0) tmem_ld_32x16(t_s, R[0]);
+          if (full) {
 #pragma unroll
-          for (int k = 0; k < NCH; ++k) {
-            if (k < n16) {
-              tmem_wait_ld();
-              if (k + 1 < NCH && k + 1 < n16) tmem_ld_32x16(t_s + (k + 1) * 16, R[(k + 1) & 1]);
-              if (k < n_full) mx = chunk_max<true>(R[k & 1], c_lo + k * 16, cmax, mx);
-              else mx = chunk_max<false>(R[k & 1], c_lo + k * 16, cmax, mx);
-            }
+            for (int k = 0; k < 4; ++k)
+              if (k < n16) mx = chunk_max<true>(R[k], 0, mx);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < n16) mx = chunk_max<false>(R[k], jmax - kbase - k * 16, mx);
           }
-          float* xmax = xmax0 + (st_cnt & 1) * 512;  // double-buffered: the partner may still read the previous block's
-          xmax[x_mine] = mx;
-          named_bar_sync(pair_bar, 64);
-          mx = fmaxf(mx, xmax[x_other]);
-          ATRACE(2, hf == 0 && quarter == 0 && lane == 0 && jb == 0);
-          const float m_new = fmaxf(m_run, mx);
-          if (MULTI && jb > 0) {
-            // online softmax: bring this thread's 32 O columns and its partial sum to the new maximum. s_full(jb)
-            // implies that the PV MMA of block jb-1 has retired (same issuing thread, in-order pipe): O is stable.
-            const float alpha = ex2_approx((m_run - m_new) * sc);
-            if (__any_sync(0xffffffffu, alpha != 1.0f)) {
-              const uint32_t t_o = t_row + O_COL + 32 * hf;
-#pragma unroll
-              for (int hh = 0; hh < 2; ++hh) {
-                tmem_ld_32x16(t_o + 16 * hh, R[hh]);
+          // ---- lazy reference update: only when the block exceeds the reference by more than 2^8
+          if (jb == 0) {
+            m_ref = mx;
+          } else {
+            const bool grow = (mx - m_ref) * sc > RESCALE_LOG2;  // false for NaN / (-inf) - (-inf)
+            if (__any_sync(0xffffffffu, grow)) {
+              // O and the running sums follow the new reference. PV_{jb-1} (other parity) must have retired first.
+              if (s) {
+                while (pv_obs0 < pv_exp0) {
+                  mbar_wait(&bars->pv_done[w][0], pv_obs0 & 1);
+                  ++pv_obs0;
+                }
+              } else {
+                while (pv_obs1 < pv_exp1) {
+                  mbar_wait(&bars->pv_done[w][1], pv_obs1 & 1);
+                  ++pv_obs1;
+                }
               }
-              tmem_wait_ld();
+              tc_fence_after();
+              const float alpha = grow ? ex2_approx((m_ref - mx) * sc) : 1.0f;  // m_ref = -inf -> 0
+              if (grow) m_ref = mx;
+              uint32_t o[16];
 #pragma unroll
-              for (int hh = 0; hh < 2; ++hh) {
-#pragma unroll
-                for (int e = 0; e < 16; ++e) R[hh][e] = __float_as_uint(__uint_as_float(R[hh][e]) * alpha);
-                tmem_st_32x16(t_o + 16 * hh, R[hh]);
-              }
-            }
-            sum *= alpha;
-          }
-          m_run = m_new;
-          // ---- pass 2: p = exp2((s - m) / 8 * log2 e), fp16 P written over this thread's own S columns
-          {
-            const uint64_t sc2 = pack_f32x2(sc, sc), nmxs2 = pack_f32x2(-m_new * sc, -m_new * sc);
-            uint64_t acc2 = 0;  // (0.0f, 0.0f)
-            uint32_t pk[8];
-            if (n16 > 0) tmem_ld_32x16(t_s, R[0]);
-#pragma unroll
-            for (int k = 0; k < NCH; ++k) {
-              if (k < n16) {
+              for (int hh = 0; hh < 4; ++hh) {
+                tmem_ld_32x16(t_row + O_COL + 16 * hh, o);
                 tmem_wait_ld();
-                if (k + 1 < NCH && k + 1 < n16) tmem_ld_32x16(t_s + (k + 1) * 16, R[(k + 1) & 1]);
-                if (k < n_full) acc2 = chunk_exp<true>(R[k & 1], pk, c_lo + k * 16, cmax, sc2, nmxs2, acc2);
-                else acc2 = chunk_exp<false>(R[k & 1], pk, c_lo + k * 16, cmax, sc2, nmxs2, acc2);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+                tmem_st_32x16(t_row + O_COL + 16 * hh, o);
+              }
+              acc2 = fma_f32x2(acc2, pack_f32x2(alpha, alpha), 0);
+            }
+          }
+          // ---- p = exp2((s - ref) / 8 * log2 e), fp16 P written over the slot's own S columns
+          const float nref = (m_ref == -INFINITY) ? 0.0f : -m_ref * sc;
+          const uint64_t nref2 = pack_f32x2(nref, nref);
+          uint32_t pk[8];
+          if (full) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < n16) {
+                acc2 = chunk_exp<true>(R[k], pk, 0, sc2, nref2, acc2);
                 tmem_st_32x8(t_s + k * 8, pk);
               }
-            }
-            sum += __uint_as_float(static_cast<uint32_t>(acc2)) + __uint_as_float(static_cast<uint32_t>(acc2 >> 32));
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < n16) {
+                acc2 = chunk_exp<false>(R[k], pk, jmax - kbase - k * 16, sc2, nref2, acc2);
+                tmem_st_32x8(t_s + k * 8, pk);
+              }
           }
           tmem_wait_st();
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->p_full[w]);
-        ATRACE(3, hf == 0 && quarter == 0 && lane == 0 && jb == 0);
+        if (lane == 0) mbar_arrive(&bars->p_full[w][s]);
+        if (s) ++pv_exp1;  // the issuer follows this arrival with PV_jb
+        else ++pv_exp0;
       }
-      // ---- O / sum -> fp16 -> out[b, i, h*64 + 32*hf .. +31]
-      if (warp_live) xsum[x_mine] = sum;  // published before the barrier below
-      mbar_wait(&bars->o_full[w], o_cnt & 1);
-      ++o_cnt;
+      ATRACE(3, quarter == 0 && lane == 0);
+      // ---- all PV MMAs of the tile retired -> O / sum -> fp16 -> out[b, i, h*64 .. h*64+63]
+      while (pv_obs0 < pv_exp0) {
+        mbar_wait(&bars->pv_done[w][0], pv_obs0 & 1);
+        ++pv_obs0;
+      }
+      while (pv_obs1 < pv_exp1) {
+        mbar_wait(&bars->pv_done[w][1], pv_obs1 & 1);
+        ++pv_obs1;
+      }
       tc_fence_after();
-      ATRACE(4, hf == 0 && quarter == 0 && lane == 0);
-      uint32_t oa[32];
+      ATRACE(4, quarter == 0 && lane == 0);
+      uint32_t O4[4][16];
       if (warp_live) {
-        tmem_ld_32x32(t_row + O_COL + 32 * hf, oa);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tmem_ld_32x16(t_row + O_COL + 16 * k, O4[k]);
         tmem_wait_ld();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->o_free[w]);
       if (warp_live) {
-        // fp16 half-rows (32 columns = 64 bytes) into this warp's own staging block, 64B-swizzled (16-byte chunk c
-        // of row r at chunk c ^ ((r >> 1) & 3): conflict-free), then one TMA store of the 32 x 32 block through the
-        // [B][L][d] map -- rows past the sequence end are clipped. No cross-warp hand-off: each warp owns its
-        // staging block and its bulk groups.
-        uint8_t* stg = smem + p.off_stage + warp * 2048;
-        if (elect_one()) tma_store_wait_read<0>();  // this warp's previous store has drained the block
-        named_bar_sync(pair_bar, 64);               // partner's partial row sum visible (and the wait above done)
-        const float inv = __fdividef(1.0f, sum + xsum[x_other]);
-        uint8_t* my_row = stg + lane * 64;
+        // fp16 rows into this warp's swizzled staging block (16-byte chunk c of row r at chunk c ^ (r & 7)), then
+        // one TMA store of the 32 x 64 block through the [B][L][d] map: rows past the sequence end are clipped.
+        uint8_t* stg = smem + p.off_stage + warp * 4096;
+        if (elect_one()) tma_store_wait_read<0>();  // the previous tile's store has drained this block
+        __syncwarp();
+        const float sum = __uint_as_float(static_cast<uint32_t>(acc2)) + __uint_as_float(static_cast<uint32_t>(acc2 >> 32));
+        const float inv = __fdividef(1.0f, sum);
+        uint8_t* my_row = stg + lane * 128;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          uint4 x;
-          x.x = pack_half2(__uint_as_float(oa[8 * e + 0]) * inv, __uint_as_float(oa[8 * e + 1]) * inv);
-          x.y = pack_half2(__uint_as_float(oa[8 * e + 2]) * inv, __uint_as_float(oa[8 * e + 3]) * inv);
-          x.z = pack_half2(__uint_as_float(oa[8 * e + 4]) * inv, __uint_as_float(oa[8 * e + 5]) * inv);
-          x.w = pack_half2(__uint_as_float(oa[8 * e + 6]) * inv, __uint_as_float(oa[8 * e + 7]) * inv);
-          *reinterpret_cast<uint4*>(my_row + ((e ^ ((lane >> 1) & 3)) << 4)) = x;
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            uint4 x;
+            x.x = pack_half2(__uint_as_float(O4[k][8 * e + 0]) * inv, __uint_as_float(O4[k][8 * e + 1]) * inv);
+            x.y = pack_half2(__uint_as_float(O4[k][8 * e + 2]) * inv, __uint_as_float(O4[k][8 * e + 3]) * inv);
+            x.z = pack_half2(__uint_as_float(O4[k][8 * e + 4]) * inv, __uint_as_float(O4[k][8 * e + 5]) * inv);
+            x.w = pack_half2(__uint_as_float(O4[k][8 * e + 6]) * inv, __uint_as_float(O4[k][8 * e + 7]) * inv);
+            *reinterpret_cast<uint4*>(my_row + (((2 * k + e) ^ (lane & 7)) << 4)) = x;
+          }
         }
         fence_async_smem();
         __syncwarp();
         if (elect_one()) {
           const int b = j.item / p.heads, h = j.item % p.heads;
-          tma_store_3d(&tmO, stg, h * HEAD_DIM + 32 * hf, j.tile * 128 + quarter * 32, b);
+          tma_store_3d(&tmO, stg, h * HEAD_DIM, j.tile * 128 + quarter * 32, b);
           tma_store_commit();
         }
       }
-      ATRACE(5, hf == 0 && quarter == 0 && lane == 0);
+      ATRACE(5, quarter == 0 && lane == 0);
     }
     if (elect_one()) tma_store_wait_all<0>();  // output written before the CTA (and its staging smem) goes away
   }
@@ -484,11 +521,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
 }
 
-template <bool MULTI, int NCH, bool CAUSAL>
+template <bool CAUSAL>
 int launch_variant(int grid, int smem_bytes, cudaStream_t stream, const CUtensorMap& tmQ, const CUtensorMap& tmKV,
                    const CUtensorMap& tmO, const AttnParams& p) {
   static int configured_bytes = 0;
-  auto kern = attention_kernel<MULTI, NCH, CAUSAL>;
+  auto kern = attention_kernel<CAUSAL>;
   if (smem_bytes > configured_bytes) {
     PC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured_bytes = smem_bytes;
@@ -502,77 +539,55 @@ int launch_variant(int grid, int smem_bytes, cudaStream_t stream, const CUtensor
 int launch_attention(const __half* qkv, __half* out, int B, int L, int heads, int causal,
                      cudaStream_t stream) {
   PC_REQUIRE(qkv && out && B > 0 && L > 0 && heads > 0, PC_ERR_ARG, "attention: bad arguments");
-  PC_REQUIRE(L <= 4096, PC_ERR_ARG, "attention: L = %d is beyond the supported sequence length (4096)", L);
   const int d = heads * HEAD_DIM;
   AttnParams p{};
-  p.out = out;
   p.L = L;
   p.lp16 = (L + 15) / 16 * 16;
   p.heads = heads;
   p.d = d;
-  p.causal = causal ? 1 : 0;
   p.items = B * heads;
   p.m_tiles = (L + 127) / 128;
   p.split = p.m_tiles == 1 ? 1 : 0;
   p.ppi = (p.m_tiles + 1) / 2;
   p.n_groups = p.split ? (p.items + 1) / 2 : p.items * p.ppi;
-  if (p.lp16 <= 256) {
-    p.n_kvb = 1;
-    p.kb = p.lp16;
-  } else {
-    p.kb = KB_MULTI;
-    p.n_kvb = (p.lp16 + p.kb - 1) / p.kb;
-  }
-  p.sub_bytes = p.kb * 128;
-  p.kreg_bytes = (p.split ? 2 : 1) * p.kb * 128;  // kb % 8 == 0 -> 1024-byte multiples (swizzle atoms)
+  p.n_blk = (p.lp16 + KVB - 1) / KVB;
+  // K / V of one item: lp16 rows of 128 bytes, fetched in boxes of at most 256 rows
+  p.kv_boxes = (p.lp16 + 255) / 256;
+  p.kv_rows = ((p.lp16 + p.kv_boxes - 1) / p.kv_boxes + 7) / 8 * 8;
+  const int item_bytes = p.kv_rows * p.kv_boxes * 128;  // multiple of 1024 (swizzle atoms)
+  p.sub_bytes = item_bytes;
+  p.kreg_bytes = (p.split ? 2 : 1) * item_bytes;
   p.off_kv = 2 * Q_BYTES;
-  p.off_stage = p.off_kv + 4 * p.kreg_bytes;
-  p.off_xch = p.off_stage + 8 * 4096;
-  p.off_bars = p.off_xch + 3 * 512 * 4;
-  int smem_bytes = p.off_bars + static_cast<int>(sizeof(AttnBars)) + 1024;
+  const int fixed = 2 * Q_BYTES + 8 * 4096 + static_cast<int>(sizeof(AttnBars)) + 256;
+  p.n_slots = (fixed + 4 * p.kreg_bytes <= 227 * 1024) ? 2 : 1;
+  p.off_stage = p.off_kv + p.n_slots * 2 * p.kreg_bytes;
+  p.off_bars = p.off_stage + 8 * 4096;
+  int smem_bytes = p.off_bars + static_cast<int>(sizeof(AttnBars));
+  PC_REQUIRE(smem_bytes <= 227 * 1024, PC_ERR_ARG,
+             "attention: L = %d needs %d B of shared memory for one item's K and V (limit 227 KB)", L, smem_bytes);
   // one CTA per SM by construction (each CTA owns all 512 TMEM columns): ask for more than half the SM's smem
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
-  PC_REQUIRE(smem_bytes <= 227 * 1024, PC_ERR_ARG, "attention: L = %d needs %d B smem", L, smem_bytes);
 
   CUtensorMap tmQ, tmKV, tmO;
   const uint64_t rows = static_cast<uint64_t>(B) * L;
   PC_TRY(make_tmap_f16_2d(&tmQ, qkv, 3 * d, rows, static_cast<uint64_t>(3 * d) * 2, 64, 128));
-  PC_TRY(make_tmap_f16_2d(&tmKV, qkv, 3 * d, rows, static_cast<uint64_t>(3 * d) * 2, 64, p.kb));
-  PC_TRY(make_tmap_f16_3d(&tmO, out, d, L, B, static_cast<uint64_t>(d) * 2, static_cast<uint64_t>(L) * d * 2, 32, 32));
+  PC_TRY(make_tmap_f16_2d(&tmKV, qkv, 3 * d, rows, static_cast<uint64_t>(3 * d) * 2, 64, p.kv_rows));
+  PC_TRY(make_tmap_f16_3d(&tmO, out, d, L, B, static_cast<uint64_t>(d) * 2, static_cast<uint64_t>(L) * d * 2, 64, 32));
   const int sms = device_sm_count();
   const int grid = p.n_groups < sms ? p.n_groups : sms;
   static int tracing = -1;
   static long long* trace = nullptr;
-  static int stagger = 1;
   if (tracing < 0) {
     const char* e = getenv("PC_ATTN_TRACE");
     tracing = (e && e[0] == '1') ? 1 : 0;
-    const char* f = getenv("PC_ATTN_NO_STAGGER");
-    stagger = (f && f[0] == '1') ? 0 : 1;
   }
-  p.stagger = stagger;
   if (tracing) {
     if (!trace) PC_CHECK_CUDA(cudaMalloc(&trace, 32 * 2 * 8 * sizeof(long long)));
     PC_CHECK_CUDA(cudaMemsetAsync(trace, 0, 32 * 2 * 8 * sizeof(long long), stream));
     p.trace = trace;
   }
-  // instantiation: smallest unrolled chunk count that covers one key half of a block
-  const int need = ((p.kb >> 4) + 1) >> 1;
-  int rc;
-  if (p.n_kvb > 1) {
-    rc = p.causal ? launch_variant<true, 6, true>(grid, smem_bytes, stream, tmQ, tmKV, tmO, p)
-                  : launch_variant<true, 6, false>(grid, smem_bytes, stream, tmQ, tmKV, tmO, p);
-  } else if (need <= 4) {
-    rc = p.causal ? launch_variant<false, 4, true>(grid, smem_bytes, stream, tmQ, tmKV, tmO, p)
-                  : launch_variant<false, 4, false>(grid, smem_bytes, stream, tmQ, tmKV, tmO, p);
-  } else if (need <= 7) {
-    rc = p.causal ? launch_variant<false, 7, true>(grid, smem_bytes, stream, tmQ, tmKV, tmO, p)
-                  : launch_variant<false, 7, false>(grid, smem_bytes, stream, tmQ, tmKV, tmO, p);
-  } else {
-    rc = p.causal ? launch_variant<false, 8, true>(grid, smem_bytes, stream, tmQ, tmKV, tmO, p)
-                  : launch_variant<false, 8, false>(grid, smem_bytes, stream, tmQ, tmKV, tmO, p);
-  }
-  PC_TRY(rc);
+  PC_TRY(causal ? launch_variant<true>(grid, smem_bytes, stream, tmQ, tmKV, tmO, p)
+                : launch_variant<false>(grid, smem_bytes, stream, tmQ, tmKV, tmO, p));
   if (tracing) {
     static int printed = 0;
     long long h[32 * 2 * 8];
@@ -581,13 +596,13 @@ int launch_attention(const __half* qkv, __half* out, int B, int L, int heads, in
     if (printed++ == 3) {
       const long long t0 = h[0] ? h[0] : h[8];
       fprintf(stderr, "[attn trace] B*heads=%d L=%d (cycles since first sample, CTA 0)\n", p.items, L);
-      fprintf(stderr, "group WG  wait_s   s_full  pass1_end  p_arrive   o_full  stored\n");
+      fprintf(stderr, "group WG  wait_s0  s0_full  last_p_arrive  pv_all_done  stored\n");
       for (int g = 0; g < 32; ++g)
         for (int w = 0; w < 2; ++w) {
           const long long* r = h + (g * 2 + w) * 8;
           if (!r[1]) continue;
-          fprintf(stderr, "%4d  %d %8lld %8lld %9lld %9lld %8lld %8lld\n", g, w, r[0] - t0, r[1] - t0, r[2] - t0, r[3] - t0,
-                  r[4] - t0, r[5] - t0);
+          fprintf(stderr, "%4d  %d %8lld %8lld %14lld %12lld %7lld\n", g, w, r[0] - t0, r[1] - t0, r[3] - t0, r[4] - t0,
+                  r[5] - t0);
         }
     }
   }
