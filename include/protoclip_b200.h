@@ -97,12 +97,48 @@ typedef struct {
   const pc_resblock_weights* blocks; /* HOST array */
 } pc_text_weights;
 
+/* ModifiedResNet (clip/model.py:95-152; RN50 / RN101 / RN50x4 / RN50x16 / RN50x64 visual towers, config C5).
+ * One bias-free Conv2d + eval-mode BatchNorm2d pair in the reference's state-dict layout and dtypes after
+ * convert_weights (conv fp16, BatchNorm fp32; clip/model.py:17-26, 109-114, 373-394). */
+typedef struct {
+  const void* conv_weight;      /* f16 [Cout, Cin, k, k], k = 1 or 3 */
+  const void* bn_weight;        /* f32 [Cout] */
+  const void* bn_bias;          /* f32 [Cout] */
+  const void* bn_running_mean;  /* f32 [Cout] */
+  const void* bn_running_var;   /* f32 [Cout] */
+} pc_conv_bn_weights;
+
+/* Bottleneck (clip/model.py:10-53): conv1 1x1 inplanes->planes, conv2 3x3, avgpool(stride), conv3 1x1 planes->4*planes,
+ * downsample = avgpool(stride) + 1x1 conv + BN when stride > 1 or inplanes != 4*planes. */
+typedef struct {
+  int inplanes, planes, stride;
+  pc_conv_bn_weights conv1, conv2, conv3;
+  pc_conv_bn_weights downsample; /* `downsample.0.weight` / `downsample.1.*`; conv_weight == NULL: no such branch */
+} pc_bottleneck_weights;
+
+typedef struct {
+  int image_resolution, width, output_dim, heads; /* heads = width * 32 / 64 (clip/model.py:260) */
+  int layers[4];                                  /* bottlenecks in layer1..layer4 */
+  pc_conv_bn_weights stem[3];                     /* conv1/bn1 (3x3 stride 2), conv2/bn2, conv3/bn3 */
+  const pc_bottleneck_weights* blocks;            /* HOST array, layer1 blocks first (device pointers inside) */
+  const void* attnpool_positional_embedding;      /* f32 [(res/32)^2 + 1, 32*width] */
+  const void *q_proj_weight, *q_proj_bias;        /* f16 [E, E], [E], E = 32*width (AttentionPool2d, :56-92) */
+  const void *k_proj_weight, *k_proj_bias;
+  const void *v_proj_weight, *v_proj_bias;
+  const void *c_proj_weight, *c_proj_bias;        /* f16 [output_dim, E], [output_dim] */
+} pc_rn_weights;
+
+/* Bind a ModifiedResNet as the context's visual tower (replaces a bound ViT and vice versa). BatchNorm is folded
+ * into re-laid-out fp16 weight copies + fp32 shifts owned by the context; pc_encode_image then runs this tower. */
+int pc_rn_bind_weights(pc_ctx* ctx, const pc_rn_weights* w);
+
 /* Bind tower weights (views; the tensors must outlive the context). Stands in for build_model +
  * load_state_dict (clip/model.py:397-434). Synchronous; may allocate (bind time only). */
 int pc_vit_bind_weights(pc_ctx* ctx, const pc_vit_weights* w);
 int pc_text_bind_weights(pc_ctx* ctx, const pc_text_weights* w);
 
-/* CLIP.encode_image (clip/model.py:338-339 -> 221-238) [+ the `/= norm` of utils.py:352 when l2norm != 0].
+/* CLIP.encode_image (clip/model.py:338-339 -> 221-238 for a ViT, -> 137-152 for a ModifiedResNet)
+ * [+ the `/= norm` of utils.py:352 when l2norm != 0].
  * images: [B, 3, res, res] f32 or f16 (NCHW, already normalised); feat_out: f16 [B, embed_dim].
  * The batch is walked in micro-batches of `micro_batch` images (0 = library default) so activations stay
  * L2-resident; workspace must hold pc_encode_image_workspace_bytes(ctx, micro_batch). */
@@ -127,6 +163,13 @@ int pc_resblock_forward(pc_ctx* ctx, int tower, int layer, void* x, int B, int L
  * nn.Linear / F.linear: out[M,N] = x[M,K] @ w[N,K]^T (+ bias) with the epilogues above. */
 int pc_linear_forward(const void* x, int ldx, const void* w, int ldw, const void* bias, const void* residual,
                       int ldr, void* out, int ldo, int M, int N, int K, int epilogue, void* stream);
+/* 1x1 Conv2d + eval BatchNorm2d [+ identity] [+ ReLU] of a Bottleneck (clip/model.py:43-52) on NHWC pixels, i.e.
+ * pc_linear_forward with an fp32 per-channel shift (the folded BatchNorm bias, nullable) and an optional ReLU applied
+ * to the fp16 result (after the fp16 residual add for PC_EPI_BIAS_RESIDUAL). epilogue: PC_EPI_BIAS or
+ * PC_EPI_BIAS_RESIDUAL. */
+int pc_linear_shift_relu_forward(const void* x, int ldx, const void* w, int ldw, const float* shift,
+                                 const void* residual, int ldr, void* out, int ldo, int M, int N, int K, int epilogue,
+                                 int relu, void* stream);
 /* clip.model.LayerNorm.forward (clip/model.py:155-161): f16 in/out, f32 gamma/beta, eps 1e-5. */
 int pc_layernorm_forward(const void* x, void* y, const void* gamma, const void* beta, int rows, int d,
                          void* stream);

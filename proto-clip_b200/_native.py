@@ -22,7 +22,7 @@ EPI_BIAS, EPI_BIAS_QUICKGELU, EPI_BIAS_RESIDUAL, EPI_F32 = 0, 1, 2, 3
 # every symbol include/protoclip_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "pc_version", "pc_last_error", "pc_ctx_create", "pc_ctx_destroy", "pc_vit_bind_weights",
-    "pc_text_bind_weights", "pc_encode_image_workspace_bytes", "pc_encode_image",
+    "pc_text_bind_weights", "pc_rn_bind_weights", "pc_linear_shift_relu_forward", "pc_encode_image_workspace_bytes", "pc_encode_image",
     "pc_encode_text_workspace_bytes", "pc_encode_text", "pc_resblock_workspace_bytes", "pc_resblock_forward",
     "pc_linear_forward", "pc_layernorm_forward", "pc_attention_forward", "pc_l2_normalize",
     "pc_adapter_fc_workspace_bytes", "pc_adapter_fc_forward", "pc_adapter_conv_forward", "pc_build_prototypes",
@@ -52,6 +52,23 @@ class TextWeights(C.Structure):
                [(n, C.c_void_p) for n in ("token_embedding", "positional_embedding", "ln_final_weight",
                                           "ln_final_bias", "text_projection")] + \
                [("blocks", C.POINTER(ResblockWeights))]
+
+
+class ConvBnWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("conv_weight", "bn_weight", "bn_bias", "bn_running_mean", "bn_running_var")]
+
+
+class BottleneckWeights(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("inplanes", "planes", "stride")] + \
+               [(n, ConvBnWeights) for n in ("conv1", "conv2", "conv3", "downsample")]
+
+
+class RnWeights(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("image_resolution", "width", "output_dim", "heads")] + \
+               [("layers", C.c_int * 4), ("stem", ConvBnWeights * 3), ("blocks", C.POINTER(BottleneckWeights))] + \
+               [(n, C.c_void_p) for n in ("attnpool_positional_embedding", "q_proj_weight", "q_proj_bias",
+                                          "k_proj_weight", "k_proj_bias", "v_proj_weight", "v_proj_bias",
+                                          "c_proj_weight", "c_proj_bias")]
 
 
 class AdapterFCWeights(C.Structure):
@@ -85,6 +102,7 @@ def load_library() -> C.CDLL:
     lib.pc_ctx_destroy.restype = None
     lib.pc_vit_bind_weights.argtypes = [vp, C.POINTER(VitWeights)]
     lib.pc_text_bind_weights.argtypes = [vp, C.POINTER(TextWeights)]
+    lib.pc_rn_bind_weights.argtypes = [vp, C.POINTER(RnWeights)]
     lib.pc_encode_image_workspace_bytes.argtypes = [vp, i]
     lib.pc_encode_image_workspace_bytes.restype = sz
     lib.pc_encode_image.argtypes = [vp, vp, i, i, vp, i, i, vp, sz, vp]
@@ -95,6 +113,7 @@ def load_library() -> C.CDLL:
     lib.pc_resblock_workspace_bytes.restype = sz
     lib.pc_resblock_forward.argtypes = [vp, i, i, vp, i, i, i, vp, sz, vp]
     lib.pc_linear_forward.argtypes = [vp, i, vp, i, vp, vp, i, vp, i, i, i, i, i, vp]
+    lib.pc_linear_shift_relu_forward.argtypes = [vp, i, vp, i, vp, vp, i, vp, i, i, i, i, i, i, vp]
     lib.pc_layernorm_forward.argtypes = [vp, vp, vp, vp, i, i, vp]
     lib.pc_attention_forward.argtypes = [vp, vp, i, i, i, i, vp]
     lib.pc_l2_normalize.argtypes = [vp, vp, i, i, vp]
@@ -158,9 +177,11 @@ def workspace(device: torch.device, tag: str, nbytes: int) -> torch.Tensor:
 
 # ----------------------------------------------------------------------------- primitive ops
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, epilogue: int = EPI_BIAS,
-           residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+           residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+           bias_f32: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
     """F.linear on the tcgen05 GEMM: x [M,K] f16, w [N,K] f16 -> [M,N] f16 (f32 for EPI_F32).
-    `out`, if given, must be a contiguous [M, ldo >= N] tensor of the output dtype (ldo a multiple of 8, 4 for f32)."""
+    `out`, if given, must be a contiguous [M, ldo >= N] tensor of the output dtype (ldo a multiple of 8, 4 for f32).
+    bias_f32 / relu select the conv + folded-BatchNorm (+ identity) + ReLU form (pc_linear_shift_relu_forward)."""
     lib = load_library()
     x = require_cuda(x, torch.float16, "x")
     w = require_cuda(w, torch.float16, "w")
@@ -180,6 +201,17 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         bias = require_cuda(bias, torch.float16, "bias")
     if residual is not None:
         residual = require_cuda(residual, torch.float16, "residual")
+    if bias_f32 is not None or relu:
+        if bias is not None:
+            raise ValueError("pass either bias (f16) or bias_f32, not both")
+        if bias_f32 is not None:
+            bias_f32 = require_cuda(bias_f32, torch.float32, "bias_f32")
+        with torch.cuda.device(x.device):
+            check(lib.pc_linear_shift_relu_forward(
+                x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), ptr(bias_f32), ptr(residual),
+                residual.stride(0) if residual is not None else 0, out.data_ptr(), ldo, M, N, K, epilogue, int(relu),
+                stream_ptr(x.device)), "pc_linear_shift_relu_forward")
+        return out[:, :N] if out.shape[1] != N else out
     with torch.cuda.device(x.device):
         check(lib.pc_linear_forward(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), ptr(bias), ptr(residual),
                                     residual.stride(0) if residual is not None else 0, out.data_ptr(), ldo, M, N, K,
@@ -338,9 +370,57 @@ class Context:
         self._keep.append(t)
         return t
 
+    def _conv_bn(self, dst: ConvBnWeights, sd: dict, conv_key: str, bn_prefix: str) -> None:
+        dst.conv_weight = self._dev(sd[conv_key], torch.float16).data_ptr()
+        dst.bn_weight = self._dev(sd[bn_prefix + "weight"], torch.float32).data_ptr()
+        dst.bn_bias = self._dev(sd[bn_prefix + "bias"], torch.float32).data_ptr()
+        dst.bn_running_mean = self._dev(sd[bn_prefix + "running_mean"], torch.float32).data_ptr()
+        dst.bn_running_var = self._dev(sd[bn_prefix + "running_var"], torch.float32).data_ptr()
+
+    def bind_visual_rn(self, sd: dict) -> dict:
+        """ModifiedResNet state dict (clip/model.py:95-152 key names; architecture inferred like build_model,
+        clip/model.py:407-414). Conv / attention-pool Linear tensors -> f16, BatchNorm and pos-emb stay f32."""
+        counts = [len(set(k.split(".")[2] for k in sd if k.startswith(f"visual.layer{b}."))) for b in (1, 2, 3, 4)]
+        width = sd["visual.layer1.0.conv1.weight"].shape[0]
+        grid = round((sd["visual.attnpool.positional_embedding"].shape[0] - 1) ** 0.5)
+        out_dim = sd["visual.attnpool.c_proj.weight"].shape[0]
+        w = RnWeights()
+        w.image_resolution, w.width, w.output_dim, w.heads = grid * 32, width, out_dim, width * 32 // 64
+        for i in range(4):
+            w.layers[i] = counts[i]
+        for i in range(3):
+            self._conv_bn(w.stem[i], sd, f"visual.conv{i + 1}.weight", f"visual.bn{i + 1}.")
+        blocks = (BottleneckWeights * sum(counts))()
+        inpl, nb = width, 0
+        for li in range(4):
+            planes = width * (2 ** li)
+            for b in range(counts[li]):
+                p = f"visual.layer{li + 1}.{b}."
+                blk = blocks[nb]
+                blk.inplanes, blk.planes, blk.stride = inpl, planes, (2 if (li > 0 and b == 0) else 1)
+                for j in (1, 2, 3):
+                    self._conv_bn(getattr(blk, f"conv{j}"), sd, f"{p}conv{j}.weight", f"{p}bn{j}.")
+                if p + "downsample.0.weight" in sd:
+                    self._conv_bn(blk.downsample, sd, p + "downsample.0.weight", p + "downsample.1.")
+                inpl, nb = planes * 4, nb + 1
+        w.blocks = C.cast(blocks, C.POINTER(BottleneckWeights))
+        pre = "visual.attnpool."
+        w.attnpool_positional_embedding = self._dev(sd[pre + "positional_embedding"], torch.float32).data_ptr()
+        for nm in ("q", "k", "v", "c"):
+            setattr(w, f"{nm}_proj_weight", self._dev(sd[f"{pre}{nm}_proj.weight"], torch.float16).data_ptr())
+            setattr(w, f"{nm}_proj_bias", self._dev(sd[f"{pre}{nm}_proj.bias"], torch.float16).data_ptr())
+        with torch.cuda.device(self.device):
+            check(self.lib.pc_rn_bind_weights(self.handle, C.byref(w)), "pc_rn_bind_weights")
+        self.vis_desc = dict(image_resolution=grid * 32, patch_size=None, width=width, layers=tuple(counts),
+                             heads=width * 32 // 64, embed_dim=out_dim, L=grid * grid + 1)
+        return self.vis_desc
+
     def bind_visual(self, sd: dict) -> dict:
         """sd: OpenAI-CLIP state dict (clip/model.py:397-434 key names). fp16 conversion follows
-        convert_weights (clip/model.py:373-394): Linear/conv/MHA/proj -> f16, LayerNorm/embeddings stay f32."""
+        convert_weights (clip/model.py:373-394): Linear/conv/MHA/proj -> f16, LayerNorm/embeddings stay f32.
+        State dicts without `visual.proj` hold a ModifiedResNet (clip/model.py:398) -> bind_visual_rn."""
+        if "visual.proj" not in sd:
+            return self.bind_visual_rn(sd)
         width = sd["visual.conv1.weight"].shape[0]
         patch = sd["visual.conv1.weight"].shape[-1]
         layers = len([k for k in sd if k.startswith("visual.") and k.endswith(".attn.in_proj_weight")])

@@ -5,7 +5,8 @@ encoder on a CPU copy raises.
 
 build_model / convert_weights keep the reference's semantics (clip/model.py:373-434): architecture inferred from
 tensor shapes, Linear / conv / MHA / projection tensors converted to fp16, LayerNorm and embeddings kept fp32.
-ModifiedResNet towers (clip/model.py:10-152) are not built yet.
+ModifiedResNet checkpoints (no `visual.proj` key, clip/model.py:398) bind the RN tower of the library
+(pc_rn_bind_weights: NHWC activations, eval BatchNorm folded into tcgen05 GEMM operands).
 """
 from __future__ import annotations
 
@@ -20,11 +21,15 @@ from .. import _native as nat
 _FP16_SUFFIXES = ("attn.in_proj_weight", "attn.in_proj_bias", "attn.out_proj.weight", "attn.out_proj.bias",
                   "mlp.c_fc.weight", "mlp.c_fc.bias", "mlp.c_proj.weight", "mlp.c_proj.bias")
 _FP16_KEYS = ("visual.conv1.weight", "visual.proj", "text_projection")
+_RN_FP16_MARKERS = (".conv1.weight", ".conv2.weight", ".conv3.weight", ".downsample.0.weight", "_proj.weight", "_proj.bias")
 _META_KEYS = ("input_resolution", "context_length", "vocab_size")
 
 
 def _is_fp16_key(key: str) -> bool:
-    return key in _FP16_KEYS or key.endswith(_FP16_SUFFIXES)
+    if key in _FP16_KEYS or key.endswith(_FP16_SUFFIXES):
+        return True
+    # ModifiedResNet: every nn.Conv2d and the attention pool's nn.Linear modules (clip/model.py:377-380)
+    return key.startswith("visual.") and key.endswith(_RN_FP16_MARKERS)
 
 
 def convert_weights(state_dict: Dict[str, torch.Tensor]) -> "OrderedDict[str, torch.Tensor]":
@@ -32,6 +37,9 @@ def convert_weights(state_dict: Dict[str, torch.Tensor]) -> "OrderedDict[str, to
     out: "OrderedDict[str, torch.Tensor]" = OrderedDict()
     for k, v in state_dict.items():
         if k in _META_KEYS:
+            continue
+        if k.endswith("num_batches_tracked"):
+            out[k] = v.detach().clone()  # BatchNorm's int64 counter keeps its dtype
             continue
         out[k] = v.detach().half() if _is_fp16_key(k) else v.detach().float()
     return out
@@ -49,18 +57,22 @@ class _VisualInfo(nn.Module):
 class CLIP(nn.Module):
     def __init__(self, state_dict: Dict[str, torch.Tensor]):
         super().__init__()
-        if "visual.proj" not in state_dict:
-            raise NotImplementedError(
-                "ModifiedResNet (RN50/RN101/RN50x4/RN50x16) towers are not built in this round; ViT checkpoints only")
         sd = convert_weights(state_dict)
         self._keys = list(sd.keys())
         for k, v in sd.items():
             self.register_buffer(k.replace(".", "__"), v, persistent=False)
-        width = sd["visual.conv1.weight"].shape[0]
-        patch = sd["visual.conv1.weight"].shape[-1]
-        grid = round((sd["visual.positional_embedding"].shape[0] - 1) ** 0.5)
-        layers = len([k for k in sd if k.startswith("visual.") and k.endswith(".attn.in_proj_weight")])
-        self.visual = _VisualInfo(grid * patch, sd["visual.proj"].shape[1], patch, width, layers)
+        if "visual.proj" in sd:  # clip/model.py:398-405
+            width = sd["visual.conv1.weight"].shape[0]
+            patch = sd["visual.conv1.weight"].shape[-1]
+            grid = round((sd["visual.positional_embedding"].shape[0] - 1) ** 0.5)
+            layers = len([k for k in sd if k.startswith("visual.") and k.endswith(".attn.in_proj_weight")])
+            self.visual = _VisualInfo(grid * patch, sd["visual.proj"].shape[1], patch, width, layers)
+        else:  # ModifiedResNet, clip/model.py:406-414
+            layers = tuple(len(set(k.split(".")[2] for k in sd if k.startswith(f"visual.layer{b}."))) for b in (1, 2, 3, 4))
+            width = sd["visual.layer1.0.conv1.weight"].shape[0]
+            grid = round((sd["visual.attnpool.positional_embedding"].shape[0] - 1) ** 0.5)
+            assert grid ** 2 + 1 == sd["visual.attnpool.positional_embedding"].shape[0]
+            self.visual = _VisualInfo(grid * 32, sd["visual.attnpool.c_proj.weight"].shape[0], None, width, layers)
         self.context_length = sd["positional_embedding"].shape[0]
         self.vocab_size = sd["token_embedding.weight"].shape[0]
         self._ctx: Optional["nat.Context"] = None

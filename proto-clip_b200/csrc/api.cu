@@ -33,6 +33,31 @@ struct Tower {
   __half* proj_t = nullptr;             // owned: [embed, width] (transposed projection -> TN GEMM)
 };
 
+// ModifiedResNet (clip/model.py:95-152): every conv + eval BatchNorm pair folded at bind time into a TN GEMM operand.
+struct ConvBn {
+  __half* w = nullptr;     // owned: [cout, Kp], column = tap * cin + ci, BatchNorm scale folded in
+  float* shift = nullptr;  // owned: [cout] fp32
+  int cout = 0, cin = 0, k = 0, Kp = 0;
+};
+struct RnBlock {
+  ConvBn c1, c2, c3, down;
+  bool has_down = false;
+  int inplanes = 0, planes = 0, stride = 1;
+};
+struct RnTower {
+  bool bound = false;
+  int res = 0, width = 0, heads = 0, embed = 0, out_dim = 0, tokens = 0;
+  ConvBn stem[3];
+  std::vector<RnBlock> blocks;
+  __half* qkv_w = nullptr;  // owned: [3E, E] = [q_proj; k_proj; v_proj] (packed in-proj order of the attention kernel)
+  __half* qkv_b = nullptr;  // owned: [3E]
+  const float* pos = nullptr;
+  const __half *c_w = nullptr, *c_b = nullptr;
+  std::vector<void*> owned;
+  size_t max_act = 0, max_col = 0;  // per image, in fp16 elements: largest activation / im2col operand
+};
+constexpr int kRnMicroBatch = 32;
+
 // Default micro-batch: as many sequences as fill ONE row-block wave of the CTA-pair GEMM (sm_count / 2 pairs x 256
 // rows): ViT-B/16 (L = 197) -> 96 images = 18 912 rows = 73.9 of 74 row blocks; ViT-L/14 -> 73; @336px -> 32.
 // Keeps every Linear at an integer number of waves and the activations (x, h, qkv / MLP hidden) L2-resident.
@@ -50,6 +75,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 struct pc_ctx {
   int device = 0;
   Tower vis, txt;
+  RnTower rn;  // bound instead of `vis` for ModifiedResNet checkpoints
   // visual stem
   int res = 0, patch = 0, grid = 0, Kpatch = 0, Kp = 0;
   __half* conv1_p = nullptr;  // owned: [width, Kp] zero-padded flattening of conv1.weight
@@ -260,6 +286,145 @@ TowerWs carve(void* ws, int rows, int d, int mb) {
   return t;
 }
 
+
+// ------------------------------------------------------------------------------------------ ModifiedResNet
+void free_rn(RnTower& t) {
+  for (void* p : t.owned) cudaFree(p);
+  t = RnTower{};
+}
+
+int fold_one(RnTower& t, const pc_conv_bn_weights& src, int cout, int cin, int k, ConvBn* out) {
+  PC_REQUIRE(src.conv_weight && src.bn_weight && src.bn_bias && src.bn_running_mean && src.bn_running_var, PC_ERR_ARG,
+             "pc_rn_bind_weights: null conv / BatchNorm tensor (Cout %d, Cin %d, k %d)", cout, cin, k);
+  PC_REQUIRE(cout % 8 == 0 && (k == 3 || cin % 8 == 0), PC_ERR_ARG,
+             "pc_rn_bind_weights: channel counts must be multiples of 8 (Cout %d, Cin %d)", cout, cin);
+  out->cout = cout; out->cin = cin; out->k = k;
+  out->Kp = static_cast<int>(align_up(static_cast<size_t>(cin) * k * k, 8));
+  PC_CHECK_CUDA(cudaMalloc(&out->w, static_cast<size_t>(cout) * out->Kp * sizeof(__half)));
+  t.owned.push_back(out->w);
+  PC_CHECK_CUDA(cudaMalloc(&out->shift, static_cast<size_t>(cout) * sizeof(float)));
+  t.owned.push_back(out->shift);
+  return launch_fold_conv_bn(static_cast<const __half*>(src.conv_weight), static_cast<const float*>(src.bn_weight),
+                             static_cast<const float*>(src.bn_bias), static_cast<const float*>(src.bn_running_mean),
+                             static_cast<const float*>(src.bn_running_var), out->w, out->shift, cout, cin, k, out->Kp, 0);
+}
+
+// conv (+ folded BN) [+ identity] [+ ReLU] of `rows` pixels: a [rows, c.Kp] x c.w [cout, Kp]^T -> out [rows, cout]
+int conv_gemm(const ConvBn& c, const __half* a, __half* out, int rows, const __half* identity, int relu, cudaStream_t s) {
+  GemmArgs g{};
+  g.M = rows; g.N = c.cout; g.K = c.Kp;
+  g.A = a; g.lda = c.Kp;
+  g.W = c.w; g.ldw = c.Kp;
+  g.C = out; g.ldc = c.cout;
+  g.bias_f32 = c.shift;
+  g.relu = relu;
+  if (identity) {
+    g.residual = identity; g.ldr = c.cout;
+    return launch_gemm(g, EPI_BIAS_RES, s);
+  }
+  return launch_gemm(g, EPI_BIAS, s);
+}
+
+struct RnWs {
+  __half* buf[5];  // activation buffers of max_act * mb elements each
+  __half* col;     // im2col operand, max_col * mb elements
+};
+size_t rn_ws_bytes(const RnTower& t, int mb) {
+  return 5 * align_up(t.max_act * mb * 2, 256) + align_up(t.max_col * mb * 2, 256);
+}
+RnWs rn_carve(const RnTower& t, void* ws, int mb) {
+  RnWs r;
+  uint8_t* p = static_cast<uint8_t*>(ws);
+  const size_t a = align_up(t.max_act * mb * 2, 256);
+  for (int i = 0; i < 5; ++i) r.buf[i] = reinterpret_cast<__half*>(p + i * a);
+  r.col = reinterpret_cast<__half*>(p + 5 * a);
+  return r;
+}
+
+// largest activation / im2col operand per image along the forward below
+void rn_plan(RnTower& t) {
+  size_t act = 0, col = 0;
+  auto A = [&](size_t v) { if (v > act) act = v; };
+  auto C = [&](size_t v) { if (v > col) col = v; };
+  size_t h = t.res / 2;
+  C(h * h * 32); A(h * h * t.stem[0].cout);
+  C(h * h * t.stem[1].Kp); A(h * h * t.stem[1].cout);
+  C(h * h * t.stem[2].Kp); A(h * h * t.stem[2].cout);
+  h /= 2;
+  for (const RnBlock& b : t.blocks) {
+    A(h * h * b.planes);
+    C(h * h * b.c2.Kp);
+    const size_t ho = h / b.stride;
+    A(ho * ho * b.planes * 4);
+    A(ho * ho * b.inplanes);
+    h = ho;
+  }
+  A(static_cast<size_t>(t.tokens) * 3 * t.embed);
+  t.max_act = act;
+  t.max_col = col;
+}
+
+// ModifiedResNet.forward (clip/model.py:137-152) on n images -> feat [n, out_dim]
+int rn_forward(const RnTower& t, const void* img, int img_is_f16, int n, __half* feat, const RnWs& ws, cudaStream_t s) {
+  __half *x = ws.buf[0], *y = ws.buf[1], *t1 = ws.buf[2], *t2 = ws.buf[3], *t3 = ws.buf[4];
+  int h = t.res / 2;
+  // stem (:139-141): three conv + BN + ReLU, then avgpool(2)
+  PC_TRY(launch_stem_im2col(img, img_is_f16, ws.col, n, t.res, s));
+  PC_TRY(conv_gemm(t.stem[0], ws.col, t1, n * h * h, nullptr, 1, s));
+  PC_TRY(launch_im2col3x3(t1, ws.col, n, h, h, t.stem[1].cin, s));
+  PC_TRY(conv_gemm(t.stem[1], ws.col, t2, n * h * h, nullptr, 1, s));
+  PC_TRY(launch_im2col3x3(t2, ws.col, n, h, h, t.stem[2].cin, s));
+  PC_TRY(conv_gemm(t.stem[2], ws.col, t1, n * h * h, nullptr, 1, s));
+  PC_TRY(launch_avgpool_nhwc(t1, x, n, h, h, t.stem[2].cout, 2, s));
+  h /= 2;
+  // layer1..layer4 (:146-149), Bottleneck.forward (:40-53)
+  for (const RnBlock& b : t.blocks) {
+    const int rows = n * h * h;
+    PC_TRY(conv_gemm(b.c1, x, t1, rows, nullptr, 1, s));
+    PC_TRY(launch_im2col3x3(t1, ws.col, n, h, h, b.planes, s));
+    PC_TRY(conv_gemm(b.c2, ws.col, t2, rows, nullptr, 1, s));
+    const __half* main = t2;
+    const __half* identity = x;
+    const int ho = h / b.stride;
+    if (b.stride > 1) {
+      PC_TRY(launch_avgpool_nhwc(t2, t1, n, h, h, b.planes, b.stride, s));
+      main = t1;
+    }
+    if (b.has_down) {
+      const __half* src = x;
+      __half* idb = t3;
+      if (b.stride > 1) {
+        PC_TRY(launch_avgpool_nhwc(x, t3, n, h, h, b.inplanes, b.stride, s));
+        src = t3;
+        idb = t2;  // free: the pooled main branch lives in t1
+      }
+      PC_TRY(conv_gemm(b.down, src, idb, n * ho * ho, nullptr, 0, s));
+      identity = idb;
+    }
+    PC_TRY(conv_gemm(b.c3, main, y, n * ho * ho, identity, 1, s));
+    __half* sw = x; x = y; y = sw;
+    h = ho;
+  }
+  // AttentionPool2d (:67-92): tokens, packed q/k/v projection, attention, c_proj of the mean token's row
+  const int E = t.embed, L = t.tokens;
+  PC_TRY(launch_attnpool_tokens(x, t.pos, t1, n, h * h, E, s));
+  GemmArgs g{};
+  g.M = n * L; g.N = 3 * E; g.K = E;
+  g.A = t1; g.lda = E;
+  g.W = t.qkv_w; g.ldw = E;
+  g.C = t2; g.ldc = 3 * E;
+  g.bias = t.qkv_b;
+  PC_TRY(launch_gemm(g, EPI_BIAS, s));
+  PC_TRY(launch_attention(t2, t3, n, L, t.heads, 0, s));
+  g = GemmArgs{};
+  g.M = n; g.N = t.out_dim; g.K = E;
+  g.A = t3; g.lda = L * E;  // row 0 of every image
+  g.W = t.c_w; g.ldw = E;
+  g.C = feat; g.ldc = t.out_dim;
+  g.bias = t.c_b;
+  return launch_gemm(g, EPI_BIAS, s);
+}
+
 }  // namespace
 
 #pragma GCC visibility push(default)
@@ -296,6 +461,7 @@ void pc_ctx_destroy(pc_ctx* ctx) {
   free_folds(ctx->vis);
   free_folds(ctx->txt);
   if (ctx->conv1_p) cudaFree(ctx->conv1_p);
+  free_rn(ctx->rn);
   delete ctx;
 }
 
@@ -313,6 +479,7 @@ int pc_vit_bind_weights(pc_ctx* ctx, const pc_vit_weights* w) {
              PC_ERR_ARG, "pc_vit_bind_weights: null stem tensor");
   PC_TRY(check_blocks(w->blocks, w->layers));
   ctx->vis.bound = false;
+  free_rn(ctx->rn);
   ctx->res = w->image_resolution;
   ctx->patch = w->patch_size;
   ctx->grid = ctx->res / ctx->patch;
@@ -337,6 +504,82 @@ int pc_vit_bind_weights(pc_ctx* ctx, const pc_vit_weights* w) {
                              cudaMemcpyDeviceToDevice));
   PC_TRY(make_transposed(w->proj, t.width, t.embed, &t.proj_t));
   PC_TRY(build_folds(t));
+  t.bound = true;
+  return PC_OK;
+}
+
+int pc_rn_bind_weights(pc_ctx* ctx, const pc_rn_weights* w) {
+  PC_TRY(use_device(ctx));
+  PC_REQUIRE(w != nullptr && w->blocks != nullptr, PC_ERR_ARG, "pc_rn_bind_weights: weights are null");
+  PC_REQUIRE(w->width >= 16 && w->width % 16 == 0 && w->heads * 64 == w->width * 32, PC_ERR_ARG,
+             "pc_rn_bind_weights: width %d / heads %d (width must be a multiple of 16, head_dim 64)", w->width, w->heads);
+  PC_REQUIRE(w->image_resolution > 0 && w->image_resolution % 32 == 0 && w->output_dim > 0 && w->output_dim % 8 == 0,
+             PC_ERR_ARG, "pc_rn_bind_weights: resolution %d / output_dim %d", w->image_resolution, w->output_dim);
+  PC_REQUIRE(w->attnpool_positional_embedding && w->q_proj_weight && w->q_proj_bias && w->k_proj_weight &&
+                 w->k_proj_bias && w->v_proj_weight && w->v_proj_bias && w->c_proj_weight && w->c_proj_bias,
+             PC_ERR_ARG, "pc_rn_bind_weights: null attention-pool tensor");
+  free_rn(ctx->rn);
+  ctx->vis.bound = false;
+  RnTower& t = ctx->rn;
+  t.res = w->image_resolution; t.width = w->width; t.heads = w->heads; t.embed = w->width * 32;
+  t.out_dim = w->output_dim;
+  const int g = t.res / 32;
+  t.tokens = g * g + 1;
+  const int half_w = w->width / 2;
+  int rc = fold_one(t, w->stem[0], half_w, 3, 3, &t.stem[0]);
+  if (rc == PC_OK) rc = fold_one(t, w->stem[1], half_w, half_w, 3, &t.stem[1]);
+  if (rc == PC_OK) rc = fold_one(t, w->stem[2], w->width, half_w, 3, &t.stem[2]);
+  // the stem im2col writes 32 columns (27 taps x channels + padding)
+  if (rc == PC_OK && t.stem[0].Kp != 32) { set_error("pc_rn_bind_weights: stem K %d", t.stem[0].Kp); rc = PC_ERR_ARG; }
+  int inpl = w->width, nb = 0;
+  for (int li = 0; li < 4 && rc == PC_OK; ++li) {
+    if (w->layers[li] <= 0) { set_error("pc_rn_bind_weights: layer%d has %d blocks", li + 1, w->layers[li]); rc = PC_ERR_ARG; }
+    for (int b = 0; b < w->layers[li] && rc == PC_OK; ++b, ++nb) {
+      const pc_bottleneck_weights& src = w->blocks[nb];
+      const int planes = w->width << li, stride = (li > 0 && b == 0) ? 2 : 1;
+      if (src.inplanes != inpl || src.planes != planes || src.stride != stride) {
+        set_error("pc_rn_bind_weights: block %d is (%d, %d, stride %d), expected (%d, %d, stride %d)", nb, src.inplanes,
+                  src.planes, src.stride, inpl, planes, stride);
+        rc = PC_ERR_ARG;
+        break;
+      }
+      RnBlock blk;
+      blk.inplanes = inpl; blk.planes = planes; blk.stride = stride;
+      rc = fold_one(t, src.conv1, planes, inpl, 1, &blk.c1);
+      if (rc == PC_OK) rc = fold_one(t, src.conv2, planes, planes, 3, &blk.c2);
+      if (rc == PC_OK) rc = fold_one(t, src.conv3, planes * 4, planes, 1, &blk.c3);
+      blk.has_down = stride > 1 || inpl != planes * 4;
+      if (rc == PC_OK && blk.has_down) rc = fold_one(t, src.downsample, planes * 4, inpl, 1, &blk.down);
+      t.blocks.push_back(blk);
+      inpl = planes * 4;
+    }
+  }
+  if (rc == PC_OK && inpl != t.embed) { set_error("pc_rn_bind_weights: trunk width %d != 32 * width", inpl); rc = PC_ERR_ARG; }
+  if (rc == PC_OK) {
+    // packed [q; k; v] in-projection: the attention kernel's qkv column order
+    const size_t E = t.embed, wb = E * E * sizeof(__half), bb = E * sizeof(__half);
+    cudaError_t e = cudaMalloc(&t.qkv_w, 3 * wb);
+    if (e == cudaSuccess) { t.owned.push_back(t.qkv_w); e = cudaMalloc(&t.qkv_b, 3 * bb); }
+    if (e == cudaSuccess) {
+      t.owned.push_back(t.qkv_b);
+      const void* ws3[3] = {w->q_proj_weight, w->k_proj_weight, w->v_proj_weight};
+      const void* bs3[3] = {w->q_proj_bias, w->k_proj_bias, w->v_proj_bias};
+      for (int i = 0; i < 3 && e == cudaSuccess; ++i) {
+        e = cudaMemcpy(t.qkv_w + i * E * E, ws3[i], wb, cudaMemcpyDeviceToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(t.qkv_b + i * E, bs3[i], bb, cudaMemcpyDeviceToDevice);
+      }
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { set_error("pc_rn_bind_weights: %s", cudaGetErrorString(e)); rc = PC_ERR_CUDA; }
+  }
+  if (rc != PC_OK) {
+    free_rn(ctx->rn);
+    return rc;
+  }
+  t.pos = static_cast<const float*>(w->attnpool_positional_embedding);
+  t.c_w = static_cast<const __half*>(w->c_proj_weight);
+  t.c_b = static_cast<const __half*>(w->c_proj_bias);
+  rn_plan(t);
   t.bound = true;
   return PC_OK;
 }
@@ -369,6 +612,7 @@ int pc_text_bind_weights(pc_ctx* ctx, const pc_text_weights* w) {
 }
 
 size_t pc_encode_image_workspace_bytes(const pc_ctx* ctx, int micro_batch) {
+  if (ctx && ctx->rn.bound) return rn_ws_bytes(ctx->rn, micro_batch > 0 ? micro_batch : kRnMicroBatch);
   if (!ctx || !ctx->vis.bound) return 0;
   const int mb = micro_batch > 0 ? micro_batch : default_micro_batch(ctx->vis.L);
   return tower_ws_bytes(mb * ctx->vis.L, ctx->vis.width, mb);
@@ -377,10 +621,30 @@ size_t pc_encode_image_workspace_bytes(const pc_ctx* ctx, int micro_batch) {
 int pc_encode_image(pc_ctx* ctx, const void* images, int img_dtype, int B, void* feat_out, int l2norm,
                     int micro_batch, void* workspace, size_t workspace_bytes, void* stream) {
   PC_TRY(use_device(ctx));
-  PC_REQUIRE(ctx->vis.bound, PC_ERR_STATE, "pc_encode_image: visual weights are not bound");
+  PC_REQUIRE(ctx->vis.bound || ctx->rn.bound, PC_ERR_STATE, "pc_encode_image: visual weights are not bound");
   PC_REQUIRE(images && feat_out && B > 0, PC_ERR_ARG, "pc_encode_image: null buffer or empty batch");
   PC_REQUIRE(img_dtype == PC_IMG_F32 || img_dtype == PC_IMG_F16, PC_ERR_ARG, "pc_encode_image: image dtype %d",
              img_dtype);
+  if (ctx->rn.bound) {  // ModifiedResNet tower (clip/model.py:137-152)
+    const RnTower& r = ctx->rn;
+    const int rmb = micro_batch > 0 ? micro_batch : kRnMicroBatch;
+    PC_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, PC_ERR_ALIGN,
+               "pc_encode_image: workspace must be 256-byte aligned");
+    PC_REQUIRE(workspace_bytes >= rn_ws_bytes(r, rmb), PC_ERR_WORKSPACE, "pc_encode_image: workspace %zu < %zu",
+               workspace_bytes, rn_ws_bytes(r, rmb));
+    cudaStream_t rs = static_cast<cudaStream_t>(stream);
+    const RnWs rws = rn_carve(r, workspace, rmb);
+    const size_t ib = static_cast<size_t>(3) * r.res * r.res * (img_dtype == PC_IMG_F16 ? 2 : 4);
+    __half* rf = static_cast<__half*>(feat_out);
+    for (int b0 = 0; b0 < B; b0 += rmb) {
+      const int n = (B - b0 < rmb) ? (B - b0) : rmb;
+      __half* f = rf + static_cast<size_t>(b0) * r.out_dim;
+      PC_TRY(rn_forward(r, static_cast<const uint8_t*>(images) + static_cast<size_t>(b0) * ib,
+                        img_dtype == PC_IMG_F16, n, f, rws, rs));
+      if (l2norm) PC_TRY(launch_l2norm(f, f, n, r.out_dim, rs));
+    }
+    return PC_OK;
+  }
   const Tower& t = ctx->vis;
   const int mb = micro_batch > 0 ? micro_batch : default_micro_batch(t.L);
   PC_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, PC_ERR_ALIGN,
@@ -513,6 +777,22 @@ int pc_linear_forward(const void* x, int ldx, const void* w, int ldw, const void
   g.W = static_cast<const __half*>(w); g.ldw = ldw;
   g.C = out; g.ldc = ldo;
   g.bias = static_cast<const __half*>(bias);
+  g.residual = static_cast<const __half*>(residual); g.ldr = ldr;
+  return launch_gemm(g, epilogue, static_cast<cudaStream_t>(stream));
+}
+
+int pc_linear_shift_relu_forward(const void* x, int ldx, const void* w, int ldw, const float* shift,
+                                 const void* residual, int ldr, void* out, int ldo, int M, int N, int K, int epilogue,
+                                 int relu, void* stream) {
+  PC_REQUIRE(epilogue == EPI_BIAS || epilogue == EPI_BIAS_RES, PC_ERR_ARG,
+             "pc_linear_shift_relu_forward: epilogue %d (PC_EPI_BIAS or PC_EPI_BIAS_RESIDUAL)", epilogue);
+  GemmArgs g{};
+  g.M = M; g.N = N; g.K = K;
+  g.A = static_cast<const __half*>(x); g.lda = ldx;
+  g.W = static_cast<const __half*>(w); g.ldw = ldw;
+  g.C = out; g.ldc = ldo;
+  g.bias_f32 = shift;
+  g.relu = relu ? 1 : 0;
   g.residual = static_cast<const __half*>(residual); g.ldr = ldr;
   return launch_gemm(g, epilogue, static_cast<cudaStream_t>(stream));
 }

@@ -1,0 +1,225 @@
+// ModifiedResNet support kernels (reference clip/model.py:10-152). Activations are NHWC fp16, i.e. pixel-major
+// [B*H*W, C] matrices, so that every 1x1 convolution IS a TN GEMM on gemm.cu's tcgen05 kernel and every 3x3
+// convolution is one after a vectorised im2col gather; eval-mode BatchNorm is folded into the fp16 weights and an
+// fp32 per-channel shift at bind time, ReLU and the identity add run in the GEMM epilogue. What is left for this
+// file is HBM-bound data movement: 16-byte vector loads / stores, one 8-channel vector per thread, grid-stride.
+#include "kernels.cuh"
+
+namespace pc {
+namespace {
+
+constexpr int CT = 256;  // threads per block
+
+inline int grid_for(size_t work) {
+  const size_t blocks = (work + CT - 1) / CT;
+  const size_t cap = static_cast<size_t>(device_sm_count()) * 16;
+  return static_cast<int>(blocks < cap ? (blocks ? blocks : 1) : cap);
+}
+
+// w [Cout, Cin, k, k] fp16 (nn.Conv2d layout) + BatchNorm2d(weight, bias, running_mean, running_var; eps 1e-5) ->
+// wf [Cout, Kp] fp16 with column = (ky * k + kx) * Cin + ci (the im2col order below), zero-padded to Kp, scaled by
+// gamma / sqrt(var + eps); shift[co] = beta - mean * scale (fp32).
+__global__ void fold_conv_bn_kernel(const __half* __restrict__ w, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, const float* __restrict__ mean,
+                                    const float* __restrict__ var, __half* __restrict__ wf, float* __restrict__ shift,
+                                    int Cout, int Cin, int k, int Kp) {
+  const size_t total = static_cast<size_t>(Cout) * Kp;
+  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int col = static_cast<int>(t % Kp);
+    const int co = static_cast<int>(t / Kp);
+    const float scale = gamma[co] * rsqrtf(var[co] + 1e-5f);
+    float v = 0.0f;
+    if (col < Cin * k * k) {
+      const int ci = col % Cin, tap = col / Cin;
+      v = __half2float(w[(static_cast<size_t>(co) * Cin + ci) * k * k + tap]) * scale;
+    }
+    wf[t] = __float2half_rn(v);
+    if (col == 0) shift[co] = beta[co] - mean[co] * scale;
+  }
+}
+
+// Stem conv1 (3 -> w/2, 3x3, stride 2, padding 1; clip/model.py:109) as a GEMM operand: images [B,3,R,R] (fp32 or
+// fp16, NCHW) -> rows [B*Ho*Wo, 32] fp16, column = (ky*3 + kx)*3 + c, columns 27..31 zero. One thread per output
+// pixel; neighbouring threads read neighbouring input columns.
+__global__ void __launch_bounds__(CT)
+stem_im2col_kernel(const void* __restrict__ images, int img_is_f16, __half* __restrict__ out, int B, int R, int Ho) {
+  const size_t total = static_cast<size_t>(B) * Ho * Ho;
+  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ox = static_cast<int>(t % Ho);
+    const int oy = static_cast<int>((t / Ho) % Ho);
+    const int b = static_cast<int>(t / (static_cast<size_t>(Ho) * Ho));
+    __align__(16) __half v[32];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int iy = 2 * oy + ky - 1, ix = 2 * ox + kx - 1;
+        const bool in = iy >= 0 && iy < R && ix >= 0 && ix < R;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float f = 0.0f;
+          if (in) {
+            const size_t src = ((static_cast<size_t>(b) * 3 + c) * R + iy) * R + ix;
+            f = img_is_f16 ? __half2float(static_cast<const __half*>(images)[src]) : static_cast<const float*>(images)[src];
+          }
+          v[(ky * 3 + kx) * 3 + c] = __float2half_rn(f);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 27; c < 32; ++c) v[c] = __float2half_rn(0.0f);
+    uint4* dst = reinterpret_cast<uint4*>(out + t * 32);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[q] = reinterpret_cast<const uint4*>(v)[q];
+  }
+}
+
+// 3x3, stride 1, padding 1 im2col on NHWC: x [B,H,W,C] -> col [B*H*W, 9*C], column = tap*C + c. One thread per
+// (pixel, tap, 8-channel vector); consecutive threads write consecutive 16-byte vectors of the output row.
+__global__ void __launch_bounds__(CT)
+im2col3x3_kernel(const __half* __restrict__ x, __half* __restrict__ col, int B, int H, int W, int C) {
+  const int cv = C >> 3;
+  const size_t per_pixel = static_cast<size_t>(9) * cv;
+  const size_t total = static_cast<size_t>(B) * H * W * per_pixel;
+  const uint4* xs = reinterpret_cast<const uint4*>(x);
+  uint4* cd = reinterpret_cast<uint4*>(col);
+  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int e = static_cast<int>(t % per_pixel);
+    const size_t pix = t / per_pixel;
+    const int tap = e / cv, v = e % cv;
+    const int px = static_cast<int>(pix % W);
+    const int py = static_cast<int>((pix / W) % H);
+    const size_t b = pix / (static_cast<size_t>(W) * H);
+    const int iy = py + tap / 3 - 1, ix = px + tap % 3 - 1;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) val = xs[((b * H + iy) * W + ix) * cv + v];
+    cd[t] = val;
+  }
+}
+
+// nn.AvgPool2d(s) on NHWC fp16 (clip/model.py:23,35,115): fp32 accumulation, one rounding.
+__global__ void __launch_bounds__(CT)
+avgpool_nhwc_kernel(const __half* __restrict__ x, __half* __restrict__ y, int B, int H, int W, int C, int s) {
+  const int cv = C >> 3, Ho = H / s, Wo = W / s;
+  const size_t total = static_cast<size_t>(B) * Ho * Wo * cv;
+  const uint4* xs = reinterpret_cast<const uint4*>(x);
+  const float inv = 1.0f / static_cast<float>(s * s);
+  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(t % cv);
+    size_t r = t / cv;
+    const int ox = static_cast<int>(r % Wo);
+    r /= Wo;
+    const int oy = static_cast<int>(r % Ho);
+    const size_t b = r / Ho;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int dy = 0; dy < s; ++dy)
+      for (int dx = 0; dx < s; ++dx) {
+        const uint4 q = xs[((b * H + oy * s + dy) * W + ox * s + dx) * cv + v];
+        const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h[e]);
+          acc[2 * e] += f.x;
+          acc[2 * e + 1] += f.y;
+        }
+      }
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(acc[2 * e] * inv, acc[2 * e + 1] * inv);
+    reinterpret_cast<uint4*>(y)[t] = o;
+  }
+}
+
+// AttentionPool2d token assembly (clip/model.py:68-70): tok[b,0,:] = f16(mean_p x[b,p,:]) + f16(pos[0]),
+// tok[b,1+p,:] = x[b,p,:] + f16(pos[1+p]) (fp16 adds). One thread per (image, 8-channel vector): the column walk
+// over the HW pixels is coalesced across the threads of a warp.
+__global__ void __launch_bounds__(CT)
+attnpool_tokens_kernel(const __half* __restrict__ x, const float* __restrict__ pos, __half* __restrict__ tok, int B,
+                       int HW, int C) {
+  const int cv = C >> 3;
+  const size_t total = static_cast<size_t>(B) * cv;
+  const uint4* xs = reinterpret_cast<const uint4*>(x);
+  uint4* ts = reinterpret_cast<uint4*>(tok);
+  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(t % cv);
+    const size_t b = t / cv;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int p = 0; p <= HW; ++p) {
+      // p == HW handles the mean token (row 0) once every pixel has been accumulated
+      const float* pr = pos + static_cast<size_t>(p == HW ? 0 : p + 1) * C + v * 8;
+      const float4 p0 = *reinterpret_cast<const float4*>(pr), p1 = *reinterpret_cast<const float4*>(pr + 4);
+      const float pf[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+      uint4 q;
+      __half2* h = reinterpret_cast<__half2*>(&q);
+      if (p < HW) {
+        q = xs[(b * HW + p) * cv + v];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h[e]);
+          acc[2 * e] += f.x;
+          acc[2 * e + 1] += f.y;
+        }
+      } else {
+        const float inv = 1.0f / static_cast<float>(HW);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(acc[2 * e] * inv, acc[2 * e + 1] * inv);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) h[e] = __hadd2(h[e], __floats2half2_rn(pf[2 * e], pf[2 * e + 1]));
+      ts[(b * (HW + 1) + (p == HW ? 0 : p + 1)) * cv + v] = q;
+    }
+  }
+}
+
+}  // namespace
+
+int launch_fold_conv_bn(const __half* w, const float* gamma, const float* beta, const float* mean, const float* var,
+                        __half* wf, float* shift, int Cout, int Cin, int k, int Kp, cudaStream_t stream) {
+  PC_REQUIRE(w && gamma && beta && mean && var && wf && shift, PC_ERR_ARG, "fold_conv_bn: null tensor");
+  PC_REQUIRE(Cout > 0 && Cin > 0 && (k == 1 || k == 3) && Kp >= Cin * k * k && Kp % 8 == 0, PC_ERR_ARG,
+             "fold_conv_bn: Cout=%d Cin=%d k=%d Kp=%d", Cout, Cin, k, Kp);
+  fold_conv_bn_kernel<<<grid_for(static_cast<size_t>(Cout) * Kp), CT, 0, stream>>>(w, gamma, beta, mean, var, wf, shift,
+                                                                                   Cout, Cin, k, Kp);
+  PC_CHECK_CUDA(cudaGetLastError());
+  return PC_OK;
+}
+
+int launch_stem_im2col(const void* images, int img_is_f16, __half* out, int B, int R, cudaStream_t stream) {
+  PC_REQUIRE(images && out && B > 0 && R > 0 && R % 2 == 0, PC_ERR_ARG, "stem_im2col: B=%d R=%d", B, R);
+  stem_im2col_kernel<<<grid_for(static_cast<size_t>(B) * (R / 2) * (R / 2)), CT, 0, stream>>>(images, img_is_f16, out, B,
+                                                                                              R, R / 2);
+  PC_CHECK_CUDA(cudaGetLastError());
+  return PC_OK;
+}
+
+int launch_im2col3x3(const __half* x, __half* col, int B, int H, int W, int C, cudaStream_t stream) {
+  PC_REQUIRE(x && col && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, PC_ERR_ARG,
+             "im2col3x3: B=%d H=%d W=%d C=%d (C must be a multiple of 8)", B, H, W, C);
+  im2col3x3_kernel<<<grid_for(static_cast<size_t>(B) * H * W * 9 * (C / 8)), CT, 0, stream>>>(x, col, B, H, W, C);
+  PC_CHECK_CUDA(cudaGetLastError());
+  return PC_OK;
+}
+
+int launch_avgpool_nhwc(const __half* x, __half* y, int B, int H, int W, int C, int s, cudaStream_t stream) {
+  PC_REQUIRE(x && y && B > 0 && s > 0 && H % s == 0 && W % s == 0 && C % 8 == 0, PC_ERR_ARG,
+             "avgpool: B=%d H=%d W=%d C=%d s=%d", B, H, W, C, s);
+  avgpool_nhwc_kernel<<<grid_for(static_cast<size_t>(B) * (H / s) * (W / s) * (C / 8)), CT, 0, stream>>>(x, y, B, H, W,
+                                                                                                         C, s);
+  PC_CHECK_CUDA(cudaGetLastError());
+  return PC_OK;
+}
+
+int launch_attnpool_tokens(const __half* x, const float* pos, __half* tok, int B, int HW, int C, cudaStream_t stream) {
+  PC_REQUIRE(x && pos && tok && B > 0 && HW > 0 && C % 8 == 0, PC_ERR_ARG, "attnpool_tokens: B=%d HW=%d C=%d", B, HW, C);
+  attnpool_tokens_kernel<<<grid_for(static_cast<size_t>(B) * (C / 8)), CT, 0, stream>>>(x, pos, tok, B, HW, C);
+  PC_CHECK_CUDA(cudaGetLastError());
+  return PC_OK;
+}
+
+}  // namespace pc

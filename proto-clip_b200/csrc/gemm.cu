@@ -92,6 +92,13 @@ __device__ __forceinline__ uint32_t hadd2_u32(uint32_t a, uint32_t b) {
   return *reinterpret_cast<const uint32_t*>(&r);
 }
 
+// nn.ReLU on a packed fp16 pair (NaN propagates like torch.relu: max.NaN)
+__device__ __forceinline__ uint32_t relu_f16x2(uint32_t a) {
+  uint32_t r;
+  asm("max.NaN.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(0u));
+  return r;
+}
+
 #define TRACE(slot, val)                                                                   \
   do {                                                                                     \
     if ((g.debug & 8) && blockIdx.x == 0 && tidx < 64) g.trace[tidx * 16 + (slot)] = (val); \
@@ -299,6 +306,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (LN) {
           bias_cur = g.ln_c[c];
           scale_cur = g.ln_s[c];
+        } else if (g.bias_f32 != nullptr) {
+          bias_cur = g.bias_f32[c];
         } else if (g.bias != nullptr) {
           bias_cur = __half2float(g.bias[c]);
         }
@@ -451,6 +460,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     st_sq = fmaf(f.x, f.x, fmaf(f.y, f.y, st_sq));
                   }
                 }
+              }
+              if ((EPI == EPI_BIAS || EPI == EPI_BIAS_RES) && g.relu) {
+                pk.x = relu_f16x2(pk.x);
+                pk.y = relu_f16x2(pk.y);
+                pk.z = relu_f16x2(pk.z);
+                pk.w = relu_f16x2(pk.w);
               }
               *slot = pk;
             }

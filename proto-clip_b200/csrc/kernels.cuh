@@ -26,6 +26,9 @@ struct GemmArgs {
   const __half* W; int ldw;   // [N, K] row-major
   void* C; int ldc;           // [M, N] fp16 (fp32 for EPI_F32)
   const __half* bias;         // [N] or nullptr
+  const float* bias_f32;      // [N] fp32 bias used instead of `bias` when non-null (folded BatchNorm shift)
+  int relu;                   // 1: ReLU on the fp16 result (after the residual add for EPI_BIAS_RES): the conv + BN
+                              // (+ identity) + ReLU of a Bottleneck (clip/model.py:43-52); EPI_BIAS / EPI_BIAS_RES only
   const __half* residual; int ldr;  // [M, N] fp16 (EPI_BIAS_RES); may alias C
   // LayerNorm folding (all fp32). Row statistics are (sum, sum of squares) pairs of the fp16 activations, kept as
   // `parts` partial pairs per row that the consumer adds in a fixed order (deterministic: no atomics).
@@ -76,6 +79,21 @@ int launch_layernorm_gather(const __half* x, const int* rows, __half* y, const f
                             int n, int d, cudaStream_t stream);
 // in-place or out-of-place row L2 normalisation in fp16 storage / fp32 math: y = x / ||x||
 int launch_l2norm(const __half* x, __half* y, int rows, int d, cudaStream_t stream);
+
+// ---------------------------------------------------------------- convnet.cu (ModifiedResNet, clip/model.py:10-152)
+// Activations are NHWC fp16 = pixel-major [B*H*W, C] GEMM operands.
+// bind time: conv [Cout,Cin,k,k] fp16 + eval BatchNorm (eps 1e-5) -> wf [Cout,Kp] (column = tap*Cin + ci, scaled,
+// zero-padded) and shift [Cout] fp32
+int launch_fold_conv_bn(const __half* w, const float* gamma, const float* beta, const float* mean, const float* var,
+                        __half* wf, float* shift, int Cout, int Cin, int k, int Kp, cudaStream_t stream);
+// stem conv1 operand: images [B,3,R,R] -> [B*(R/2)^2, 32] (3x3, stride 2, pad 1; column = tap*3 + c, 27..31 zero)
+int launch_stem_im2col(const void* images, int img_is_f16, __half* out, int B, int R, cudaStream_t stream);
+// 3x3 / stride 1 / pad 1 operand: x [B,H,W,C] -> [B*H*W, 9*C] (column = tap*C + c)
+int launch_im2col3x3(const __half* x, __half* col, int B, int H, int W, int C, cudaStream_t stream);
+// nn.AvgPool2d(s): [B,H,W,C] -> [B,H/s,W/s,C]
+int launch_avgpool_nhwc(const __half* x, __half* y, int B, int H, int W, int C, int s, cudaStream_t stream);
+// AttentionPool2d tokens: [B,HW,C] -> [B,HW+1,C] = [mean; pixels] + pos (clip/model.py:68-70)
+int launch_attnpool_tokens(const __half* x, const float* pos, __half* tok, int B, int HW, int C, cudaStream_t stream);
 
 // ---------------------------------------------------------------- head.cu
 int launch_build_prototypes(const __half* V, int N, int K, int D, int per_shot_norm, __half* z, float* zn2,

@@ -24,6 +24,12 @@ ARCHS: Dict[str, Tuple[int, ...]] = {
     # small towers for fast CPU oracles / golden fixtures (head_dim stays 64)
     "tiny": (64, 32, 2, 128, 8, 77, 512, 64, 1, 2),
     "small": (128, 64, 3, 256, 16, 77, 1024, 128, 2, 2),
+    # ModifiedResNet towers (clip/model.py:95-152): vision_layers is the 4-tuple of bottleneck counts, vision_width
+    # the stem width (embed_dim of the attention pool = 32 * width, heads = width / 2), no patch size
+    "RN50": (1024, 224, (3, 4, 6, 3), 64, None, 77, 49408, 512, 8, 12),
+    "RN50x16": (768, 384, (6, 8, 18, 8), 96, None, 77, 49408, 768, 12, 12),
+    "rn_tiny": (64, 64, (1, 1, 1, 1), 16, None, 77, 512, 64, 1, 2),
+    "rn_small": (128, 96, (2, 1, 2, 1), 32, None, 77, 1024, 128, 2, 2),
 }
 
 
@@ -66,26 +72,103 @@ def _blocks(sd, prefix: str, width: int, layers: int, gen: torch.Generator):
         sd[p + "ln_2.bias"] = n(width, std=0.05)
 
 
+def rn_flops_per_image(name: str) -> float:
+    """2*MAC count of one ModifiedResNet encode_image (convs + attention pool as the reference computes it)."""
+    c = arch_config(name)
+    w, r = c["vision_width"], c["image_resolution"]
+    f = 0.0
+    h = r // 2
+    f += 2.0 * h * h * (27 * (w // 2) + 9 * (w // 2) * (w // 2) + 9 * (w // 2) * w)
+    h //= 2
+    inpl = w
+    for li, nb in enumerate(c["vision_layers"]):
+        planes = w * (2 ** li)
+        for b in range(nb):
+            stride = 2 if (li > 0 and b == 0) else 1
+            f += 2.0 * h * h * (inpl * planes + 9 * planes * planes)
+            ho = h // stride
+            f += 2.0 * ho * ho * planes * planes * 4
+            if stride > 1 or inpl != planes * 4:
+                f += 2.0 * ho * ho * inpl * planes * 4
+            h, inpl = ho, planes * 4
+    L, E = h * h + 1, w * 32
+    f += 2.0 * L * 3 * E * E + 4.0 * L * L * E + 2.0 * L * E * c["embed_dim"]
+    return f
+
+
+def _conv_bn(sd, prefix: str, idx: str, cout: int, cin: int, k: int, gen: torch.Generator, bn_name: str = None):
+    """conv{idx}.weight fp16 + bn{idx}.{weight,bias,running_mean,running_var,num_batches_tracked} fp32 (eval BN)."""
+    def n(*shape, std=1.0):
+        return torch.randn(*shape, generator=gen) * std
+
+    cname = f"{prefix}conv{idx}.weight" if bn_name is None else f"{prefix}0.weight"
+    bname = f"{prefix}bn{idx}." if bn_name is None else f"{prefix}{bn_name}."
+    sd[cname] = n(cout, cin, k, k, std=(2.0 / (cin * k * k)) ** 0.5).half()
+    sd[bname + "weight"] = 1.0 + n(cout, std=0.1)
+    sd[bname + "bias"] = n(cout, std=0.1)
+    sd[bname + "running_mean"] = n(cout, std=0.1)
+    sd[bname + "running_var"] = 1.0 + 0.2 * torch.rand(cout, generator=gen)
+    sd[bname + "num_batches_tracked"] = torch.tensor(0, dtype=torch.int64)
+
+
+def _make_rn_visual(sd, c: dict, gen: torch.Generator):
+    """ModifiedResNet parameters with the reference's key names (clip/model.py:10-152). BN statistics are random
+    (not the identity) so that the eval-mode BatchNorm folding is exercised; bn3 gains are damped so that the
+    residual stream keeps a stable magnitude over up to 40 bottlenecks."""
+    def n(*shape, std=1.0):
+        return torch.randn(*shape, generator=gen) * std
+
+    w = c["vision_width"]
+    _conv_bn(sd, "visual.", "1", w // 2, 3, 3, gen)
+    _conv_bn(sd, "visual.", "2", w // 2, w // 2, 3, gen)
+    _conv_bn(sd, "visual.", "3", w, w // 2, 3, gen)
+    inpl = w
+    for li, nb in enumerate(c["vision_layers"]):
+        planes = w * (2 ** li)
+        for b in range(nb):
+            stride = 2 if (li > 0 and b == 0) else 1
+            p = f"visual.layer{li + 1}.{b}."
+            _conv_bn(sd, p, "1", planes, inpl, 1, gen)
+            _conv_bn(sd, p, "2", planes, planes, 3, gen)
+            _conv_bn(sd, p, "3", planes * 4, planes, 1, gen)
+            sd[p + "bn3.weight"] = sd[p + "bn3.weight"] * 0.3
+            if stride > 1 or inpl != planes * 4:
+                _conv_bn(sd, p + "downsample.", "", planes * 4, inpl, 1, gen, bn_name="1")
+            inpl = planes * 4
+    E = w * 32
+    g = c["image_resolution"] // 32
+    std = E ** -0.5
+    sd["visual.attnpool.positional_embedding"] = n(g * g + 1, E, std=std)
+    for nm in ("k_proj", "q_proj", "v_proj"):
+        sd[f"visual.attnpool.{nm}.weight"] = n(E, E, std=std).half()
+        sd[f"visual.attnpool.{nm}.bias"] = n(E, std=0.02).half()
+    sd["visual.attnpool.c_proj.weight"] = n(c["embed_dim"], E, std=std).half()
+    sd["visual.attnpool.c_proj.bias"] = n(c["embed_dim"], std=0.02).half()
+
+
 def make_state_dict(name: str, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
     c = arch_config(name)
     gen = torch.Generator().manual_seed(1_000_003 * seed + 17)
     sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
     vw, p, e = c["vision_width"], c["vision_patch_size"], c["embed_dim"]
-    g = c["image_resolution"] // p
-    scale = vw ** -0.5
 
     def n(*shape, std=1.0):
         return torch.randn(*shape, generator=gen) * std
 
-    sd["visual.class_embedding"] = n(vw, std=scale)
-    sd["visual.positional_embedding"] = n(g * g + 1, vw, std=scale)
-    sd["visual.proj"] = n(vw, e, std=scale).half()
-    sd["visual.conv1.weight"] = n(vw, 3, p, p, std=(3 * p * p) ** -0.5).half()
-    sd["visual.ln_pre.weight"] = 1.0 + n(vw, std=0.05)
-    sd["visual.ln_pre.bias"] = n(vw, std=0.05)
-    _blocks(sd, "visual.transformer.resblocks.", vw, c["vision_layers"], gen)
-    sd["visual.ln_post.weight"] = 1.0 + n(vw, std=0.05)
-    sd["visual.ln_post.bias"] = n(vw, std=0.05)
+    if isinstance(c["vision_layers"], tuple):
+        _make_rn_visual(sd, c, gen)
+    else:
+        g = c["image_resolution"] // p
+        scale = vw ** -0.5
+        sd["visual.class_embedding"] = n(vw, std=scale)
+        sd["visual.positional_embedding"] = n(g * g + 1, vw, std=scale)
+        sd["visual.proj"] = n(vw, e, std=scale).half()
+        sd["visual.conv1.weight"] = n(vw, 3, p, p, std=(3 * p * p) ** -0.5).half()
+        sd["visual.ln_pre.weight"] = 1.0 + n(vw, std=0.05)
+        sd["visual.ln_pre.bias"] = n(vw, std=0.05)
+        _blocks(sd, "visual.transformer.resblocks.", vw, c["vision_layers"], gen)
+        sd["visual.ln_post.weight"] = 1.0 + n(vw, std=0.05)
+        sd["visual.ln_post.bias"] = n(vw, std=0.05)
     tw = c["transformer_width"]
     sd["positional_embedding"] = n(c["context_length"], tw, std=0.01)
     sd["text_projection"] = n(tw, e, std=tw ** -0.5).half()

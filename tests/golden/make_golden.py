@@ -168,6 +168,22 @@ def main(only=None):
         print(arch, "done")
 
 
+def rn_fixture(arch: str, B: int, with_fp16: bool):
+    """ModifiedResNet towers (clip/model.py:95-152, config C5): reference image features on seeded images."""
+    out = {"arch": arch, "seed": 0, "B": B, "image_seed": 7}
+    images = images_for(arch, B, 7)
+    for mode in (["fp32", "fp16"] if with_fp16 else ["fp32"]):
+        model, _ = build_ref_clip(arch, 0, fp32=(mode == "fp32"))
+        out[f"image_features_{mode}"] = model.encode_image(images).float().clone()   # clip/model.py:338 -> :137-152
+    return out
+
+
+def main_rn():
+    for arch, B, h in (("rn_tiny", 4, True), ("rn_small", 3, True), ("RN50", 2, False), ("RN50x16", 1, False)):
+        torch.save(rn_fixture(arch, B, h), os.path.join(OUT, f"tower_{arch}.pt"))
+        print(arch, "done")
+
+
 def main_336():
     """ViT-L/14@336px (config C4: L = 577 tokens -> the attention kernel's multi-block path). fp32 reference only."""
     fx = tower_fixture("ViT-L/14@336px", B=2, P=1, with_fp16=False, with_blocks=False)
@@ -178,5 +194,7 @@ def main_336():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "336":
         main_336()
+    elif len(sys.argv) > 1 and sys.argv[1] == "rn":
+        main_rn()
     else:
         main()

@@ -41,6 +41,11 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(nat.TextWeights) == 6 * 4 + 6 * 8
     assert ctypes.sizeof(nat.AdapterFCWeights) == 6 * 8 + 8  # int + padding
     assert ctypes.sizeof(nat.AdapterConvWeights) == 9 * 8
+    # ModifiedResNet: conv+bn = 5 pointers; bottleneck = 3 ints (+ pad) + 4 conv+bn; rn = 4 + 4 ints, 3 stem conv+bn,
+    # blocks pointer, 9 attention-pool pointers
+    assert ctypes.sizeof(nat.ConvBnWeights) == 5 * 8
+    assert ctypes.sizeof(nat.BottleneckWeights) == 16 + 4 * 40
+    assert ctypes.sizeof(nat.RnWeights) == 8 * 4 + 3 * 40 + 8 + 9 * 8
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

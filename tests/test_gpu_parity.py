@@ -148,6 +148,67 @@ def test_towers_match_reference_goldens(nat, name):
     assert torch.equal(ctx.encode_image(images.half()), f)
 
 
+@pytest.mark.parametrize("name", ["rn_tiny", "rn_small", "RN50", "RN50x16"])
+def test_resnet_towers_match_reference_goldens(nat, name):
+    """ModifiedResNet (clip/model.py:95-152, config C5's backbone family): stem, bottlenecks with folded eval
+    BatchNorm, anti-aliased downsampling, attention pool — against the reference's own outputs."""
+    fx = load_golden(f"tower_{name}.pt")
+    sd = synthetic.make_state_dict(fx["arch"], fx["seed"])
+    ctx = nat.Context(torch.device(DEV))
+    ctx.bind_visual(sd)
+    images = golden_images(fx).to(DEV)
+    f = ctx.encode_image(images)
+    e_img = rel_err(f, fx["image_features_fp32"])
+    gap = rel_err(fx["image_features_fp16"], fx["image_features_fp32"]) if "image_features_fp16" in fx else float("nan")
+    print(f"{name}: image rel err {e_img:.2e} (reference fp16-vs-fp32 {gap:.2e})")
+    assert torch.isfinite(f.float()).all()
+    assert e_img < TOWER_TOL
+    cos = torch.nn.functional.cosine_similarity(f.float().cpu(), fx["image_features_fp32"], dim=-1).min().item()
+    assert cos > 0.99999
+    assert torch.equal(ctx.encode_image(images.half()), f)
+
+
+def test_resnet_tower_properties_and_rebinding(nat):
+    """Per-image results of the RN tower do not depend on batch position or micro-batching (bit-exact); binding a ViT
+    afterwards replaces the RN tower (and back)."""
+    sd = synthetic.make_state_dict("rn_small", 0)
+    ctx = nat.Context(torch.device(DEV))
+    ctx.bind_visual(sd)
+    B = 70
+    bases = synthetic.class_bases(7, 96, seed=1, device=DEV)
+    images = synthetic.class_structured_images(bases, torch.arange(B, device=DEV) % 7, seed=3)
+    f = ctx.encode_image(images, l2norm=True)
+    assert (f.float().norm(dim=-1) - 1).abs().max().item() < 2e-3
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(0)).to(DEV)
+    assert torch.equal(ctx.encode_image(images[perm], l2norm=True), f[perm])
+    assert torch.equal(ctx.encode_image(images, l2norm=True, micro_batch=9), f)
+    ref = O.l2_normalize(O.encode_image(sd, images[:6].cpu(), "fp32"))
+    assert rel_err(f[:6], ref) < TOWER_TOL
+    vit = synthetic.make_state_dict("tiny", 0)
+    ctx.bind_visual(vit)
+    assert ctx.vis_desc["patch_size"] == 8
+    fx = load_golden("tower_tiny.pt")
+    assert rel_err(ctx.encode_image(golden_images(fx).to(DEV)), fx["image_features_fp32"]) < TOWER_TOL
+    ctx.bind_visual(sd)
+    assert torch.equal(ctx.encode_image(images[:9], l2norm=True), f[:9])
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 48, 32), (1000, 96, 432), (513, 384, 96), (77, 3072, 768)])
+def test_linear_relu_epilogues(nat, M, N, K):
+    """conv + folded-BN (+ identity) + ReLU epilogues of the Bottleneck GEMMs (clip/model.py:43-52): fp32 shift,
+    ReLU after the fp16 residual add."""
+    torch.manual_seed(M + N)
+    x = (torch.randn(M, K, device=DEV) * 0.5).half()
+    w = (torch.randn(N, K, device=DEV) * 0.1).half()
+    shift = torch.randn(N, device=DEV)
+    r = torch.randn(M, N, device=DEV).half()
+    acc = x.float() @ w.float().t() + shift
+    got = nat.linear(x, w, None, nat.EPI_BIAS, bias_f32=shift, relu=True)
+    assert rel_err(got, torch.relu(acc)) < 2e-3 and (got >= 0).all()
+    got = nat.linear(x, w, None, nat.EPI_BIAS_RESIDUAL, residual=r, bias_f32=shift, relu=True)
+    assert rel_err(got, torch.relu((acc.half() + r).float())) < 2e-3 and (got >= 0).all()
+
+
 @pytest.mark.parametrize("name", ["tiny", "small"])
 def test_resblock_matches_reference_goldens(nat, name):
     fx = load_golden(f"tower_{name}.pt")

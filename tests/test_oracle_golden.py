@@ -27,6 +27,17 @@ def test_towers_match_reference_goldens(name):
         assert rel_err(O.encode_text(sd, fx["tokens"], "fp16"), fx["text_features_fp16"]) < FP16_TOL
 
 
+@pytest.mark.parametrize("name", ["rn_tiny", "rn_small", "RN50"])
+def test_resnet_towers_match_reference_goldens(name):
+    """ModifiedResNet / Bottleneck / AttentionPool2d (clip/model.py:10-152) restatement vs the reference's outputs."""
+    fx = load_golden(f"tower_{name}.pt")
+    sd = synthetic.make_state_dict(fx["arch"], fx["seed"])
+    images = golden_images(fx)
+    assert rel_err(O.encode_image(sd, images, "fp32"), fx["image_features_fp32"]) < FP32_TOL
+    if "image_features_fp16" in fx:
+        assert rel_err(O.encode_image(sd, images, "fp16"), fx["image_features_fp16"]) < FP16_TOL
+
+
 @pytest.mark.parametrize("name", ["tiny", "small"])
 def test_resblock_matches_reference_goldens(name):
     fx = load_golden(f"tower_{name}.pt")
