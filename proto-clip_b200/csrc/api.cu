@@ -56,7 +56,7 @@ struct RnTower {
   std::vector<void*> owned;
   size_t max_act = 0, max_col = 0;  // per image, in fp16 elements: largest activation / im2col operand
 };
-constexpr int kRnMicroBatch = 32;
+constexpr int kRnMicroBatch = 64;
 
 // Default micro-batch: as many sequences as fill ONE row-block wave of the CTA-pair GEMM (sm_count / 2 pairs x 256
 // rows): ViT-B/16 (L = 197) -> 96 images = 18 912 rows = 73.9 of 74 row blocks; ViT-L/14 -> 73; @336px -> 32.
@@ -327,7 +327,7 @@ int conv_gemm(const ConvBn& c, const __half* a, __half* out, int rows, const __h
 
 struct RnWs {
   __half* buf[5];  // activation buffers of max_act * mb elements each
-  __half* col;     // im2col operand, max_col * mb elements
+  __half* col;     // stem im2col operand / bordered 3x3 input, max_col * mb elements
 };
 size_t rn_ws_bytes(const RnTower& t, int mb) {
   return 5 * align_up(t.max_act * mb * 2, 256) + align_up(t.max_col * mb * 2, 256);
@@ -341,19 +341,34 @@ RnWs rn_carve(const RnTower& t, void* ws, int mb) {
   return r;
 }
 
-// largest activation / im2col operand per image along the forward below
+// 3x3 / pad 1 conv (+ folded BN + ReLU) as an implicit GEMM: xp and out are bordered [n, h+2, w+2, C] tensors
+int conv3x3_gemm(const ConvBn& c, const __half* xp, __half* out, int n, int h, cudaStream_t s) {
+  GemmArgs g{};
+  g.M = n * (h + 2) * (h + 2); g.N = c.cout; g.K = c.cin;
+  g.A = xp; g.lda = c.cin;
+  g.W = c.w; g.ldw = c.Kp;
+  g.C = out; g.ldc = c.cout;
+  g.bias_f32 = c.shift;
+  g.relu = 1;
+  g.conv_taps = 9;
+  g.conv_pitch = h + 2;
+  return launch_gemm(g, EPI_BIAS, s);
+}
+
+// largest activation / staging operand per image along the forward below
 void rn_plan(RnTower& t) {
   size_t act = 0, col = 0;
   auto A = [&](size_t v) { if (v > act) act = v; };
   auto C = [&](size_t v) { if (v > col) col = v; };
   size_t h = t.res / 2;
   C(h * h * 32); A(h * h * t.stem[0].cout);
-  C(h * h * t.stem[1].Kp); A(h * h * t.stem[1].cout);
-  C(h * h * t.stem[2].Kp); A(h * h * t.stem[2].cout);
+  C((h + 2) * (h + 2) * t.stem[1].cin); A((h + 2) * (h + 2) * t.stem[1].cout);
+  A((h + 2) * (h + 2) * t.stem[2].cout);
   h /= 2;
   for (const RnBlock& b : t.blocks) {
     A(h * h * b.planes);
-    C(h * h * b.c2.Kp);
+    C((h + 2) * (h + 2) * b.planes);
+    A((h + 2) * (h + 2) * b.planes);
     const size_t ho = h / b.stride;
     A(ho * ho * b.planes * 4);
     A(ho * ho * b.inplanes);
@@ -368,40 +383,36 @@ void rn_plan(RnTower& t) {
 int rn_forward(const RnTower& t, const void* img, int img_is_f16, int n, __half* feat, const RnWs& ws, cudaStream_t s) {
   __half *x = ws.buf[0], *y = ws.buf[1], *t1 = ws.buf[2], *t2 = ws.buf[3], *t3 = ws.buf[4];
   int h = t.res / 2;
-  // stem (:139-141): three conv + BN + ReLU, then avgpool(2)
+  // stem (:139-141): three conv + BN + ReLU, then avgpool(2). conv1 (3 channels, stride 2) goes through a 32-column
+  // im2col; conv2 / conv3 are implicit GEMMs chained in the bordered layout (frame re-zeroed in between)
   PC_TRY(launch_stem_im2col(img, img_is_f16, ws.col, n, t.res, s));
   PC_TRY(conv_gemm(t.stem[0], ws.col, t1, n * h * h, nullptr, 1, s));
-  PC_TRY(launch_im2col3x3(t1, ws.col, n, h, h, t.stem[1].cin, s));
-  PC_TRY(conv_gemm(t.stem[1], ws.col, t2, n * h * h, nullptr, 1, s));
-  PC_TRY(launch_im2col3x3(t2, ws.col, n, h, h, t.stem[2].cin, s));
-  PC_TRY(conv_gemm(t.stem[2], ws.col, t1, n * h * h, nullptr, 1, s));
-  PC_TRY(launch_avgpool_nhwc(t1, x, n, h, h, t.stem[2].cout, 2, s));
+  PC_TRY(launch_pad_nhwc(t1, ws.col, n, h, h, t.stem[1].cin, s));
+  PC_TRY(conv3x3_gemm(t.stem[1], ws.col, t2, n, h, s));
+  PC_TRY(launch_zero_border(t2, n, h, h, t.stem[2].cin, s));
+  PC_TRY(conv3x3_gemm(t.stem[2], t2, t1, n, h, s));
+  PC_TRY(launch_avgpool_nhwc(t1, x, n, h, h, t.stem[2].cout, 2, 1, s));
   h /= 2;
   // layer1..layer4 (:146-149), Bottleneck.forward (:40-53)
   for (const RnBlock& b : t.blocks) {
-    const int rows = n * h * h;
-    PC_TRY(conv_gemm(b.c1, x, t1, rows, nullptr, 1, s));
-    PC_TRY(launch_im2col3x3(t1, ws.col, n, h, h, b.planes, s));
-    PC_TRY(conv_gemm(b.c2, ws.col, t2, rows, nullptr, 1, s));
-    const __half* main = t2;
-    const __half* identity = x;
     const int ho = h / b.stride;
-    if (b.stride > 1) {
-      PC_TRY(launch_avgpool_nhwc(t2, t1, n, h, h, b.planes, b.stride, s));
-      main = t1;
-    }
-    if (b.has_down) {
+    PC_TRY(conv_gemm(b.c1, x, t1, n * h * h, nullptr, 1, s));
+    PC_TRY(launch_pad_nhwc(t1, ws.col, n, h, h, b.planes, s));
+    PC_TRY(conv3x3_gemm(b.c2, ws.col, t2, n, h, s));
+    // interior of the bordered conv2 output -> t1, through the anti-aliasing avgpool when the block strides (:45)
+    if (b.stride > 1) PC_TRY(launch_avgpool_nhwc(t2, t1, n, h, h, b.planes, b.stride, 1, s));
+    else PC_TRY(launch_unpad_nhwc(t2, t1, n, h, h, b.planes, s));
+    const __half* identity = x;
+    if (b.has_down) {  // :34-38, :48-49
       const __half* src = x;
-      __half* idb = t3;
       if (b.stride > 1) {
-        PC_TRY(launch_avgpool_nhwc(x, t3, n, h, h, b.inplanes, b.stride, s));
+        PC_TRY(launch_avgpool_nhwc(x, t3, n, h, h, b.inplanes, b.stride, 0, s));
         src = t3;
-        idb = t2;  // free: the pooled main branch lives in t1
       }
-      PC_TRY(conv_gemm(b.down, src, idb, n * ho * ho, nullptr, 0, s));
-      identity = idb;
+      PC_TRY(conv_gemm(b.down, src, t2, n * ho * ho, nullptr, 0, s));
+      identity = t2;
     }
-    PC_TRY(conv_gemm(b.c3, main, y, n * ho * ho, identity, 1, s));
+    PC_TRY(conv_gemm(b.c3, t1, y, n * ho * ho, identity, 1, s));
     __half* sw = x; x = y; y = sw;
     h = ho;
   }

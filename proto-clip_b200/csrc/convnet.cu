@@ -1,6 +1,7 @@
 // ModifiedResNet support kernels (reference clip/model.py:10-152). Activations are NHWC fp16, i.e. pixel-major
 // [B*H*W, C] matrices, so that every 1x1 convolution IS a TN GEMM on gemm.cu's tcgen05 kernel and every 3x3
-// convolution is one after a vectorised im2col gather; eval-mode BatchNorm is folded into the fp16 weights and an
+// convolution is an implicit GEMM over a zero-bordered copy (GemmArgs::conv_taps: nine row-shifted TMA views of the
+// same tensor, no im2col matrix); eval-mode BatchNorm is folded into the fp16 weights and an
 // fp32 per-channel shift at bind time, ReLU and the identity add run in the GEMM epilogue. What is left for this
 // file is HBM-bound data movement: 16-byte vector loads / stores, one 8-channel vector per thread, grid-stride.
 #include "kernels.cuh"
@@ -76,34 +77,75 @@ stem_im2col_kernel(const void* __restrict__ images, int img_is_f16, __half* __re
   }
 }
 
-// 3x3, stride 1, padding 1 im2col on NHWC: x [B,H,W,C] -> col [B*H*W, 9*C], column = tap*C + c. One thread per
-// (pixel, tap, 8-channel vector); consecutive threads write consecutive 16-byte vectors of the output row.
+// Zero-bordered copy for the implicit 3x3 convolution (GemmArgs::conv_taps): x [B,H,W,C] -> xp [B,H+2,W+2,C] with
+// a one-pixel zero frame (the padding = 1 of nn.Conv2d, clip/model.py:20,111-113). One thread per 8-channel vector.
 __global__ void __launch_bounds__(CT)
-im2col3x3_kernel(const __half* __restrict__ x, __half* __restrict__ col, int B, int H, int W, int C) {
-  const int cv = C >> 3;
-  const size_t per_pixel = static_cast<size_t>(9) * cv;
-  const size_t total = static_cast<size_t>(B) * H * W * per_pixel;
+pad_nhwc_kernel(const __half* __restrict__ x, __half* __restrict__ xp, int B, int H, int W, int C) {
+  const int cv = C >> 3, Hp = H + 2, Wp = W + 2;
+  const size_t total = static_cast<size_t>(B) * Hp * Wp * cv;
   const uint4* xs = reinterpret_cast<const uint4*>(x);
-  uint4* cd = reinterpret_cast<uint4*>(col);
+  uint4* xd = reinterpret_cast<uint4*>(xp);
   for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
        t += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int e = static_cast<int>(t % per_pixel);
-    const size_t pix = t / per_pixel;
-    const int tap = e / cv, v = e % cv;
-    const int px = static_cast<int>(pix % W);
-    const int py = static_cast<int>((pix / W) % H);
-    const size_t b = pix / (static_cast<size_t>(W) * H);
-    const int iy = py + tap / 3 - 1, ix = px + tap % 3 - 1;
+    const int v = static_cast<int>(t % cv);
+    size_t r = t / cv;
+    const int px = static_cast<int>(r % Wp) - 1;
+    r /= Wp;
+    const int py = static_cast<int>(r % Hp) - 1;
+    const size_t b = r / Hp;
     uint4 val = make_uint4(0u, 0u, 0u, 0u);
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W) val = xs[((b * H + iy) * W + ix) * cv + v];
-    cd[t] = val;
+    if (py >= 0 && py < H && px >= 0 && px < W) val = xs[((b * H + py) * W + px) * cv + v];
+    xd[t] = val;
   }
 }
 
-// nn.AvgPool2d(s) on NHWC fp16 (clip/model.py:23,35,115): fp32 accumulation, one rounding.
+// Inverse: the interior of a bordered tensor xp [B,H+2,W+2,C] -> x [B,H,W,C] (drops the garbage frame rows the
+// implicit convolution produces).
 __global__ void __launch_bounds__(CT)
-avgpool_nhwc_kernel(const __half* __restrict__ x, __half* __restrict__ y, int B, int H, int W, int C, int s) {
+unpad_nhwc_kernel(const __half* __restrict__ xp, __half* __restrict__ x, int B, int H, int W, int C) {
+  const int cv = C >> 3, Hp = H + 2, Wp = W + 2;
+  const size_t total = static_cast<size_t>(B) * H * W * cv;
+  const uint4* xs = reinterpret_cast<const uint4*>(xp);
+  uint4* xd = reinterpret_cast<uint4*>(x);
+  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(t % cv);
+    size_t r = t / cv;
+    const int px = static_cast<int>(r % W);
+    r /= W;
+    const int py = static_cast<int>(r % H);
+    const size_t b = r / H;
+    xd[t] = xs[((b * Hp + py + 1) * Wp + px + 1) * cv + v];
+  }
+}
+
+// Re-zero the frame of a bordered tensor in place (between two chained implicit convolutions of the stem).
+__global__ void __launch_bounds__(CT)
+zero_border_kernel(__half* __restrict__ xp, int B, int H, int W, int C) {
+  const int cv = C >> 3, Hp = H + 2, Wp = W + 2;
+  const int frame = 2 * Wp + 2 * H;  // frame pixels per image: top + bottom rows, left + right columns of the rest
+  const size_t total = static_cast<size_t>(B) * frame * cv;
+  uint4* xd = reinterpret_cast<uint4*>(xp);
+  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(t % cv);
+    size_t r = t / cv;
+    const int f = static_cast<int>(r % frame);
+    const size_t b = r / frame;
+    int py, px;
+    if (f < Wp) { py = 0; px = f; }
+    else if (f < 2 * Wp) { py = Hp - 1; px = f - Wp; }
+    else { const int e = f - 2 * Wp; py = 1 + (e >> 1); px = (e & 1) ? Wp - 1 : 0; }
+    xd[((b * Hp + py) * Wp + px) * cv + v] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+// nn.AvgPool2d(s) on NHWC fp16 (clip/model.py:23,35,115): fp32 accumulation, one rounding. pad = 1: the input is a
+// bordered tensor [B,H+2,W+2,C] (output of an implicit convolution) whose interior is pooled.
+__global__ void __launch_bounds__(CT)
+avgpool_nhwc_kernel(const __half* __restrict__ x, __half* __restrict__ y, int B, int H, int W, int C, int s, int pad) {
   const int cv = C >> 3, Ho = H / s, Wo = W / s;
+  const int Hi = H + 2 * pad, Wi = W + 2 * pad;
   const size_t total = static_cast<size_t>(B) * Ho * Wo * cv;
   const uint4* xs = reinterpret_cast<const uint4*>(x);
   const float inv = 1.0f / static_cast<float>(s * s);
@@ -118,7 +160,7 @@ avgpool_nhwc_kernel(const __half* __restrict__ x, __half* __restrict__ y, int B,
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int dy = 0; dy < s; ++dy)
       for (int dx = 0; dx < s; ++dx) {
-        const uint4 q = xs[((b * H + oy * s + dy) * W + ox * s + dx) * cv + v];
+        const uint4 q = xs[((b * Hi + oy * s + dy + pad) * Wi + ox * s + dx + pad) * cv + v];
         const __half2* h = reinterpret_cast<const __half2*>(&q);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -198,19 +240,35 @@ int launch_stem_im2col(const void* images, int img_is_f16, __half* out, int B, i
   return PC_OK;
 }
 
-int launch_im2col3x3(const __half* x, __half* col, int B, int H, int W, int C, cudaStream_t stream) {
-  PC_REQUIRE(x && col && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, PC_ERR_ARG,
-             "im2col3x3: B=%d H=%d W=%d C=%d (C must be a multiple of 8)", B, H, W, C);
-  im2col3x3_kernel<<<grid_for(static_cast<size_t>(B) * H * W * 9 * (C / 8)), CT, 0, stream>>>(x, col, B, H, W, C);
+int launch_pad_nhwc(const __half* x, __half* xp, int B, int H, int W, int C, cudaStream_t stream) {
+  PC_REQUIRE(x && xp && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, PC_ERR_ARG,
+             "pad_nhwc: B=%d H=%d W=%d C=%d (C must be a multiple of 8)", B, H, W, C);
+  pad_nhwc_kernel<<<grid_for(static_cast<size_t>(B) * (H + 2) * (W + 2) * (C / 8)), CT, 0, stream>>>(x, xp, B, H, W, C);
   PC_CHECK_CUDA(cudaGetLastError());
   return PC_OK;
 }
 
-int launch_avgpool_nhwc(const __half* x, __half* y, int B, int H, int W, int C, int s, cudaStream_t stream) {
+int launch_unpad_nhwc(const __half* xp, __half* x, int B, int H, int W, int C, cudaStream_t stream) {
+  PC_REQUIRE(x && xp && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, PC_ERR_ARG,
+             "unpad_nhwc: B=%d H=%d W=%d C=%d (C must be a multiple of 8)", B, H, W, C);
+  unpad_nhwc_kernel<<<grid_for(static_cast<size_t>(B) * H * W * (C / 8)), CT, 0, stream>>>(xp, x, B, H, W, C);
+  PC_CHECK_CUDA(cudaGetLastError());
+  return PC_OK;
+}
+
+int launch_zero_border(__half* xp, int B, int H, int W, int C, cudaStream_t stream) {
+  PC_REQUIRE(xp && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, PC_ERR_ARG, "zero_border: B=%d H=%d W=%d C=%d", B, H, W, C);
+  zero_border_kernel<<<grid_for(static_cast<size_t>(B) * (2 * (W + 2) + 2 * H) * (C / 8)), CT, 0, stream>>>(xp, B, H, W, C);
+  PC_CHECK_CUDA(cudaGetLastError());
+  return PC_OK;
+}
+
+int launch_avgpool_nhwc(const __half* x, __half* y, int B, int H, int W, int C, int s, int in_bordered,
+                        cudaStream_t stream) {
   PC_REQUIRE(x && y && B > 0 && s > 0 && H % s == 0 && W % s == 0 && C % 8 == 0, PC_ERR_ARG,
              "avgpool: B=%d H=%d W=%d C=%d s=%d", B, H, W, C, s);
-  avgpool_nhwc_kernel<<<grid_for(static_cast<size_t>(B) * (H / s) * (W / s) * (C / 8)), CT, 0, stream>>>(x, y, B, H, W,
-                                                                                                         C, s);
+  avgpool_nhwc_kernel<<<grid_for(static_cast<size_t>(B) * (H / s) * (W / s) * (C / 8)), CT, 0, stream>>>(
+      x, y, B, H, W, C, s, in_bordered ? 1 : 0);
   PC_CHECK_CUDA(cudaGetLastError());
   return PC_OK;
 }

@@ -132,7 +132,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_workers = PAIR ? (gridDim.x >> 1) : gridDim.x;
   const int m_blks = (g.M + TILE_M - 1) / TILE_M;
   const int n_blks = (g.N + BN - 1) / BN;
-  const int k_blks = (g.K + BK - 1) / BK;
+  const int kb_per_tap = (g.K + BK - 1) / BK;
+  const int k_blks = (g.conv_taps > 0 ? g.conv_taps : 1) * kb_per_tap;
   const int num_tiles = m_blks * n_blks;
 
   if (warp == TMA_WARP && lane == 0) {
@@ -193,17 +194,24 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (g.debug & 8) w_empty += clock64() - tw;
           uint8_t* sA = smem + stage * Smem::STAGE_BYTES;
           uint8_t* sB = sA + Smem::A_BYTES;
+          int a_col = kb * BK, a_row = m0, w_col = kb * BK;
+          if (g.conv_taps > 0) {  // implicit 3x3 convolution: k-block = (tap, channel block), A rows shifted per tap
+            const int tap = kb / kb_per_tap, kc = (kb - tap * kb_per_tap) * BK;
+            a_col = kc;
+            w_col = tap * g.K + kc;
+            a_row = m0 + (tap / 3 - 1) * g.conv_pitch + (tap % 3 - 1);
+          }
           if (elect_one()) {
             if (g.debug & 2) {
               if (leader) mbar_arrive(&bars->full[stage]);
             } else if (PAIR) {
               if (leader) mbar_arrive_expect_tx(&bars->full[stage], TX_BYTES);
-              tma_load_2d_pair(sA, &tmA, &bars->full[stage], kb * BK, m0, kEvictNormal);
-              tma_load_2d_pair(sB, &tmW, &bars->full[stage], kb * BK, n0, kEvictLast);
+              tma_load_2d_pair(sA, &tmA, &bars->full[stage], a_col, a_row, kEvictNormal);
+              tma_load_2d_pair(sB, &tmW, &bars->full[stage], w_col, n0, kEvictLast);
             } else {
               mbar_arrive_expect_tx(&bars->full[stage], TX_BYTES);
-              tma_load_2d_hint(sA, &tmA, &bars->full[stage], kb * BK, m0, kEvictNormal);
-              tma_load_2d_hint(sB, &tmW, &bars->full[stage], kb * BK, n0, kEvictLast);
+              tma_load_2d_hint(sA, &tmA, &bars->full[stage], a_col, a_row, kEvictNormal);
+              tma_load_2d_hint(sB, &tmW, &bars->full[stage], w_col, n0, kEvictLast);
             }
           }
           __syncwarp();
@@ -537,7 +545,8 @@ int launch_impl(const GemmArgs& a0, cudaStream_t stream) {
   a.debug = debug_flags();
   CUtensorMap tmA, tmW, tmC, tmR;
   PC_TRY(make_tmap_2d(&tmA, a.A, 2, a.K, a.M, static_cast<uint64_t>(a.lda) * 2, BK, BM));
-  PC_TRY(make_tmap_2d(&tmW, a.W, 2, a.K, a.N, static_cast<uint64_t>(a.ldw) * 2, BK, 128));
+  PC_TRY(make_tmap_2d(&tmW, a.W, 2, a.conv_taps > 0 ? a.conv_taps * a.K : a.K, a.N, static_cast<uint64_t>(a.ldw) * 2, BK,
+                      128));
   if (EPI == EPI_F32) {
     PC_TRY(make_tmap_2d(&tmC, a.C, 4, a.N, a.M, static_cast<uint64_t>(a.ldc) * 4, 32, 32));
   } else {
@@ -630,6 +639,9 @@ int launch_gemm(const GemmArgs& a, int epilogue, cudaStream_t stream) {
     PC_REQUIRE(a.ln_stats != nullptr && a.ln_s != nullptr && a.ln_c != nullptr && a.ln_parts >= 1, PC_ERR_ARG,
                "gemm: the LayerNorm-folded epilogues need ln_stats (ln_parts >= 1), ln_s and ln_c");
   }
+  PC_REQUIRE(a.conv_taps == 0 || (a.conv_taps == 9 && a.conv_pitch >= 3 && a.ldw >= 9 * a.K), PC_ERR_ARG,
+             "gemm: implicit convolution needs 9 taps, a row pitch and W [N, 9*K] (taps %d, pitch %d, ldw %d)",
+             a.conv_taps, a.conv_pitch, a.ldw);
   if (use_pair(a.M, a.N)) return dispatch_epi<true>(a, epilogue, stream);
   return dispatch_epi<false>(a, epilogue, stream);
 }

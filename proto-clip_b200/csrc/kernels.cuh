@@ -27,6 +27,12 @@ struct GemmArgs {
   void* C; int ldc;           // [M, N] fp16 (fp32 for EPI_F32)
   const __half* bias;         // [N] or nullptr
   const float* bias_f32;      // [N] fp32 bias used instead of `bias` when non-null (folded BatchNorm shift)
+  // 3x3 / stride 1 / padding 1 convolution as an implicit GEMM over a ZERO-BORDERED NHWC activation
+  // A = [B*(H+2)*(W+2), K = C] (conv_taps = 9, conv_pitch = W + 2): k-block (tap, c0) reads A rows shifted by
+  // (tap/3 - 1) * conv_pitch + (tap%3 - 1) (TMA zero-fills rows outside the tensor) against W columns
+  // [tap*C + c0, +64) of W [N, 9*C]; output rows are in the same bordered layout (border rows hold garbage).
+  int conv_taps;              // 0 = plain GEMM, 9 = 3x3 taps
+  int conv_pitch;             // W + 2
   int relu;                   // 1: ReLU on the fp16 result (after the residual add for EPI_BIAS_RES): the conv + BN
                               // (+ identity) + ReLU of a Bottleneck (clip/model.py:43-52); EPI_BIAS / EPI_BIAS_RES only
   const __half* residual; int ldr;  // [M, N] fp16 (EPI_BIAS_RES); may alias C
@@ -88,10 +94,15 @@ int launch_fold_conv_bn(const __half* w, const float* gamma, const float* beta, 
                         __half* wf, float* shift, int Cout, int Cin, int k, int Kp, cudaStream_t stream);
 // stem conv1 operand: images [B,3,R,R] -> [B*(R/2)^2, 32] (3x3, stride 2, pad 1; column = tap*3 + c, 27..31 zero)
 int launch_stem_im2col(const void* images, int img_is_f16, __half* out, int B, int R, cudaStream_t stream);
-// 3x3 / stride 1 / pad 1 operand: x [B,H,W,C] -> [B*H*W, 9*C] (column = tap*C + c)
-int launch_im2col3x3(const __half* x, __half* col, int B, int H, int W, int C, cudaStream_t stream);
-// nn.AvgPool2d(s): [B,H,W,C] -> [B,H/s,W/s,C]
-int launch_avgpool_nhwc(const __half* x, __half* y, int B, int H, int W, int C, int s, cudaStream_t stream);
+// operand of the implicit 3x3 convolution (GemmArgs::conv_taps): x [B,H,W,C] -> xp [B,H+2,W+2,C], zero frame
+int launch_pad_nhwc(const __half* x, __half* xp, int B, int H, int W, int C, cudaStream_t stream);
+// interior of a bordered tensor: xp [B,H+2,W+2,C] -> x [B,H,W,C]
+int launch_unpad_nhwc(const __half* xp, __half* x, int B, int H, int W, int C, cudaStream_t stream);
+// zero the frame of a bordered tensor in place
+int launch_zero_border(__half* xp, int B, int H, int W, int C, cudaStream_t stream);
+// nn.AvgPool2d(s): [B,H,W,C] -> [B,H/s,W/s,C]; in_bordered: the input is [B,H+2,W+2,C], its interior is pooled
+int launch_avgpool_nhwc(const __half* x, __half* y, int B, int H, int W, int C, int s, int in_bordered,
+                        cudaStream_t stream);
 // AttentionPool2d tokens: [B,HW,C] -> [B,HW+1,C] = [mean; pixels] + pos (clip/model.py:68-70)
 int launch_attnpool_tokens(const __half* x, const float* pos, __half* tok, int B, int HW, int C, cudaStream_t stream);
 

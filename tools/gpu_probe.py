@@ -153,7 +153,38 @@ def case_cublas():
         timed_loop(lambda: torch.matmul(x, w.t(), out=out), 2.0 * M * N * K, f"cublas {M}x{N}x{K}")
 
 
+def case_tower(arch, B, micro_batch=0):
+    """encode_image throughput of a whole visual tower (resident images), against the tower's 2*MAC count."""
+    import torch
+    from proto_clip_b200 import _native as nat
+    from proto_clip_b200 import synthetic
+    c = synthetic.arch_config(arch)
+    sd = synthetic.make_state_dict(arch, 0)
+    ctx = nat.Context(torch.device("cuda:0"))
+    ctx.bind_visual(sd)
+    R = c["image_resolution"]
+    images = torch.randn(B, 3, R, R, device="cuda")
+    out = torch.empty(B, c["embed_dim"], device="cuda", dtype=torch.float16)
+    flops = (synthetic.rn_flops_per_image(arch) if isinstance(c["vision_layers"], tuple)
+             else synthetic.vit_flops_per_image(arch)) * B
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    for _ in range(2):
+        ctx.encode_image(images, l2norm=True, micro_batch=micro_batch, out=out)
+    t0.record()
+    n = 3
+    for _ in range(n):
+        ctx.encode_image(images, l2norm=True, micro_batch=micro_batch, out=out)
+    t1.record(); torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / n
+    print(f"[tower {arch} B{B} mb{micro_batch}] {ms:.2f} ms  {B / ms * 1e3:.0f} img/s  {flops / ms / 1e9:.0f} TFLOP/s", flush=True)
+
+
 CASES = {
+    "tower_rn50x16": lambda: case_tower("RN50x16", 128),
+    "tower_rn50x16_mb16": lambda: case_tower("RN50x16", 128, 16),
+    "tower_rn50x16_mb64": lambda: case_tower("RN50x16", 128, 64),
+    "tower_rn50": lambda: case_tower("RN50", 512),
+    "tower_vitb16": lambda: case_tower("ViT-B/16", 960),
     "gemm_small": lambda: case_gemm(128, 256, 64),
     "gemm_k": lambda: case_gemm(128, 256, 768),
     "gemm_n128": lambda: case_gemm(300, 128, 512),
