@@ -93,9 +93,16 @@ def make_adapter(cfg, ndim):
     raise NameError(f"unknown adapter alias {cfg['adapter']!r}: expected 'conv-3x', 'conv-2x' or 'fc'")
 
 
+# "main" = the reference's main.py, "qt" = its main.qt.py (the Q^T training variant; on the inference path it differs
+# only in the un-rounded alpha grid, main.qt.py:109-111, and in the checkpoint directory name, main.qt.py:327).
+VARIANT = "main"
+
+
 def alpha_beta_lists():
-    """main.py:142-146: 11 alphas x 29 betas."""
-    alpha_list = np.arange(0, 1.1, 0.1).round(1)
+    """main.py:142-146 / main.qt.py:109-113: 11 alphas x 29 betas."""
+    alpha_list = np.arange(0, 1.1, 0.1)
+    if VARIANT == "main":
+        alpha_list = alpha_list.round(1)
     beta_list = np.concatenate((np.arange(0.1, 1, 0.1), np.arange(1, 21, 1.0)))
     return alpha_list, beta_list
 
@@ -167,7 +174,8 @@ def run_proto_clip(cfg, visual_memory_keys, visual_memory_values, val_features, 
     # ---- testing a trained Proto-CLIP-F (main.py:383-455)
     with torch.no_grad():
         print("Testing...")
-        model_dir = f"{model_dir_root}/alpha-beta/{best_alpha}-{best_beta}"
+        ab_dir = "alpha-beta" if VARIANT == "main" else "best-alpha-beta"  # main.py:385 / main.qt.py:327
+        model_dir = f"{model_dir_root}/{ab_dir}/{best_alpha}-{best_beta}"
         model_prefix = f"best_lr_{cfg['lr']}_aug_{cfg['augment_epoch']}_epochs_{cfg['train_epoch']}"
         pv, pt, pa = (os.path.join(model_dir, f"{model_prefix}_{s}.pt") for s in ("v", "t", "a"))
         try:
