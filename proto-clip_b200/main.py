@@ -236,6 +236,7 @@ def main(argv=None):
 
     print("Preparing dataset.")
     from proto_clip_b200 import datasets
+    datasets.configure(clip_model.visual.input_resolution)
     if cfg["dataset"] == "imagenet":
         dataset = datasets.ImageNet(cfg["root_path"], cfg["shots"], preprocess)
         train_loader_cache = torch.utils.data.DataLoader(dataset.train, batch_size=train_bs, num_workers=n_workers,

@@ -6,6 +6,8 @@ Tolerances: the reference's own fp16-vs-fp32 deviation on these fixtures is ~1.3
 (see make_golden.py outputs); the CUDA path computes in fp16 storage / fp32 accumulation like the reference's
 GPU path, so it must stay within TOWER_TOL = 4e-3 of the fp32 reference. Argmax predictions must be identical.
 """
+import os
+
 import pytest
 import torch
 
@@ -433,3 +435,105 @@ def test_error_paths(nat):
         nat.linear(torch.zeros(4, 12, device=DEV).half(), torch.zeros(4, 12, device=DEV).half())  # K % 8 != 0
     with pytest.raises(nat.NativeError):
         nat.attention(torch.zeros(5000, 192, device=DEV).half(), 1, 5000, 1, False)  # L > 4096
+
+
+# ----------------------------------------------------------------------------- main.py CLI end to end
+@pytest.mark.parametrize("backbone,adapter", [("synthetic:small", "fc"), ("synthetic:rn_small", "conv-2x")])
+def test_main_cli_end_to_end_on_synthetic_dataset(nat, tmp_path, monkeypatch, backbone, adapter):
+    """`main.py --config ... --dataset synthetic:N:Q --backbone synthetic:<arch>`: clip.load, memory banks, cached
+    features, the fused (alpha, beta) grid, then `--only_test` with trained-model files laid out as the reference saves
+    them (main.py:352-369) — everything on the CUDA library, checked against the oracle's accuracy on the same data."""
+    import yaml
+    from proto_clip_b200 import main as M
+    from proto_clip_b200 import utils
+    monkeypatch.chdir(tmp_path)                       # ./caches/<dataset>/... like the reference
+    arch = backbone.split(":")[1]
+    c = synthetic.arch_config(arch)
+    N, K, Q = 6, 2, 48
+    cfg = {"root_path": "DATA", "shots": K, "backbone": backbone, "dataset": f"synthetic:{N}:{Q}", "only_test": False,
+           "lr": 0.0001, "augment_epoch": 1, "train_epoch": 1, "alpha": 0.5, "beta": 12, "adapter": adapter,
+           "train_vis_mem_only": False, "losses": ["L1"]}
+    (tmp_path / "cfg.yml").write_text(yaml.safe_dump(cfg))
+    tok = torch.zeros(N, c["context_length"], dtype=torch.int64)
+    gen = torch.Generator().manual_seed(5)
+    for i in range(N):
+        n = int(torch.randint(3, 9, (1,), generator=gen))
+        tok[i, 0], tok[i, 1 + n] = c["vocab_size"] - 2, c["vocab_size"] - 1
+        tok[i, 1:1 + n] = torch.randint(1, c["vocab_size"] - 2, (n,), generator=gen)
+    monkeypatch.setattr(utils.clip, "tokenize", lambda prompts: tok)   # BPE vocabulary file is not shipped
+    argv = ["--config", "cfg.yml", "--dataset", cfg["dataset"]]
+    out = M.main(argv)
+    assert 0.0 <= out["zero_shot_val_acc"] <= 1.0
+    root = utils.get_model_dir_root({**cfg, "cache_dir": os.path.join("./caches", cfg["dataset"])})
+    val_pkl = utils.load(f"{root}/zero_shot_hp_search_val_{utils.beautify(backbone)}_K_{K}.pkl", "grid")
+    assert val_pkl.shape == (319, 3) and val_pkl.dtype.name == "float64"
+    keys = torch.load(f"{root}/aug/visual_mb_keys_aug_1_{K}_shots.pt")
+    feats, labels = torch.load(f"{root}/test_features.pt"), torch.load(f"{root}/test_labels.pt")
+    assert keys.shape == (c["embed_dim"], N * K) and feats.shape == (Q, c["embed_dim"]) and labels.shape == (Q,)
+    # a "trained" Proto-CLIP-F whose memories are the training-free ones, saved where main.py looks for them
+    D = c["embed_dim"]
+    asd = synthetic.make_adapter_state_dict(adapter, D, seed=4, out_gain=synthetic.trained_like_gain(D))
+    T = synthetic.aligned_text_memory(keys.t().contiguous(), N, K, seed=6)
+    mdir = f"{root}/alpha-beta/0.5-12"
+    os.makedirs(mdir, exist_ok=True)
+    prefix = f"{mdir}/best_lr_0.0001_aug_1_epochs_1"
+    torch.save(torch.nn.Parameter(keys.t().contiguous().clone()), prefix + "_v.pt")
+    torch.save(torch.nn.Parameter(T.cuda()), prefix + "_t.pt")
+    torch.save({k: v.cuda() for k, v in asd.items()}, prefix + "_a.pt")
+    res = M.main(argv + ["--only_test"])
+    # oracle on the same cached features
+    zi, zt = O.build_prototypes(keys.t().float().cpu(), N, K, True), O.text_prototypes(T.float().cpu())
+    f = feats.float().cpu()
+    q = O.adapter_fc(asd, f) if adapter == "fc" else O.adapter_conv(asd, f, adapter)
+    pred = O.predict(O.P(O.l2_normalize(q), zi, zt, 0.5, 12.0))
+    acc_o = (pred == labels.cpu()).float().mean().item()
+    print(f"{backbone}/{adapter}: CLI test accuracy {res['test_acc']:.4f}, oracle {acc_o:.4f}")
+    # same accuracy as the reference algorithm on the same features; well above chance (1 / N) even for the random-init
+    # ResNet, whose features keep less of the synthetic class structure than the ViT's
+    assert abs(res["test_acc"] - acc_o) < 1e-6 and acc_o > (0.9 if adapter == "fc" else 2.0 / N)
+
+
+def test_toolkit_callers_top_k_and_ood(nat, tmp_path, monkeypatch):
+    """ProtoClipClassifier.classify_objects (top-k names / probabilities) and test_ood_performance through the toolkit
+    shells, on a trained-model file set in the reference's formats, against the oracle."""
+    import json
+    import types
+    import yaml
+    from proto_clip_b200 import toolkit
+    monkeypatch.chdir(tmp_path)
+    arch, N, K, Q = "small", 8, 2, 24
+    c = synthetic.arch_config(arch)
+    D = c["embed_dim"]
+    sd = synthetic.make_state_dict(arch, 0)
+    bases = synthetic.class_bases(N, c["image_resolution"], seed=1)
+    support = synthetic.class_structured_images(bases, torch.arange(N).repeat_interleave(K), seed=2)
+    labels = torch.arange(Q) % N
+    queries = synthetic.class_structured_images(bases, labels, seed=3)
+    V = O.l2_normalize(O.encode_image(sd, support, "fp32")).half()
+    T = synthetic.aligned_text_memory(V, N, K, seed=6)
+    asd = synthetic.make_adapter_state_dict("fc", D, seed=4, out_gain=synthetic.trained_like_gain(D))
+    torch.save(torch.nn.Parameter(V.clone(), requires_grad=False), "mb_v.pt")
+    torch.save(torch.nn.Parameter(T.clone(), requires_grad=False), "mb_t.pt")
+    torch.save(asd, "adapter.pt")
+    cfg = {"backbone": f"synthetic:{arch}", "shots": K, "alpha": 0.5, "beta": 12.0, "adapter": "fc", "top_k": 3,
+           "cache_dir": str(tmp_path / "cache")}
+    (tmp_path / "cfg.yml").write_text(yaml.safe_dump(cfg))
+    (tmp_path / "split.json").write_text(json.dumps({"train": [[f"img_{i}.jpg", i, f"object_{i}"] for i in range(N)]}))
+    args = types.SimpleNamespace(config="cfg.yml", splits_path="split.json", adapter=None, memory_bank_v_path="mb_v.pt",
+                                 memory_bank_t_path="mb_t.pt", adapter_weights_path="adapter.pt")
+    clf = toolkit.ProtoClipClassifier(args)
+    names, probs = clf.classify_objects(queries.to(DEV))
+    # oracle
+    zi, zt = O.build_prototypes(V.float(), N, K, True), O.text_prototypes(T.float())
+    p_o, pred_o, _ = O.classify_queries(sd, asd, "fc", queries, zi, zt, 0.5, 12.0, "fp32")
+    top_p, top_i = p_o.topk(3, dim=1)
+    assert probs.shape == (Q, 3) and (probs.cpu() - top_p).abs().max().item() < 2e-2
+    assert [row[0] for row in names] == [f"object {i}" for i in pred_o.tolist()]
+    assert all(len(row) == 3 for row in names)
+    loader = [(queries[i:i + 10], labels[i:i + 10]) for i in range(0, Q, 10)]
+    acc = toolkit.test_ood_performance(cfg, "synthetic", 0, 10, memory_bank_v_path="mb_v.pt", memory_bank_t_path="mb_t.pt",
+                                       adapter_type="fc", adapter_weights_path="adapter.pt", test_loader=loader)
+    assert abs(acc - 100.0 * (pred_o == labels).float().mean().item()) < 1e-4
+    with pytest.raises(FileNotFoundError):
+        toolkit.load_pretrained_mb_and_adapters(memory_bank_v_path="nope_v.pt", memory_bank_t_path="nope_t.pt",
+                                                adapter_type="fc", adapter_weights_path="adapter.pt")

@@ -186,3 +186,24 @@ def test_gloo_broadcast_shard_gather(world, tmp_path):
                        env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     assert f"OK {world}" in r.stdout
+
+
+def test_datasets_front_door_and_qt_variant(monkeypatch):
+    """datasets alias dispatch (synthetic built in, reference aliases delegated or refused loudly) and the main.qt.py
+    variant switches (un-rounded alpha grid, best-alpha-beta checkpoint directory)."""
+    from proto_clip_b200 import datasets
+    ds = datasets.build_dataset("synthetic:6:40", "DATA", 3)
+    assert len(ds.classnames) == 6 and len(ds.train_x) == 18 and len(ds.test) == 40 and len(ds.val) == 40
+    assert ds.train_x.labels.tolist() == [c for c in range(6) for _ in range(3)]
+    assert len(datasets.build_data_loader(data_source=ds.test, batch_size=16, is_train=False)) == 3
+    monkeypatch.delenv("PROTOCLIP_REFERENCE_ROOT", raising=False)
+    monkeypatch.setattr(datasets, "_ref_pkg", None)
+    with pytest.raises(RuntimeError, match="PROTOCLIP_REFERENCE_ROOT"):
+        datasets.build_dataset("dtd", "DATA", 1)
+    main = load_main()
+    import numpy as np
+    a_main, _ = main.alpha_beta_lists()
+    monkeypatch.setattr(main, "VARIANT", "qt")
+    a_qt, b_qt = main.alpha_beta_lists()
+    assert len(a_qt) == 11 and len(b_qt) == 29 and np.allclose(a_qt, a_main) and a_qt[3] != a_main[3]  # 0.30000000000000004
+    assert os.path.isfile(os.path.join(PKG, "main.qt.py"))
