@@ -341,7 +341,7 @@ def attention_roofline(nat, dev, B, L, heads):
     exps = float(B) * heads * L * L
     return {"bound": "tensor", "achieved": round(achieved, 1), "peak": burst, "unit": "TFLOP/s",
             "frac": round(achieved / burst, 4), "traffic": None,
-            "kernel": f"attention_kernel<false,7,false>: B={B}, L={L}, heads={heads}, head_dim=64",
+            "kernel": f"{'attention5_kernel' if L <= 256 else 'attention_kernel'}<causal=false>: B={B}, L={L}, heads={heads}, head_dim=64",
             "flops_per_launch": flops, "us_per_launch": round(ms * 1e3, 2), "peak_kind": f"bf16 burst ({src})",
             "note": "softmax-bound at head_dim 64: one exp2 per 256 tensor flops; the MUFU pipe (16 exp2/clk/SM) "
                     "caps this shape at about 0.55 of the tensor peak",
