@@ -207,3 +207,41 @@ def test_datasets_front_door_and_qt_variant(monkeypatch):
     a_qt, b_qt = main.alpha_beta_lists()
     assert len(a_qt) == 11 and len(b_qt) == 29 and np.allclose(a_qt, a_main) and a_qt[3] != a_main[3]  # 0.30000000000000004
     assert os.path.isfile(os.path.join(PKG, "main.qt.py"))
+
+
+def test_resnet_state_dict_surface():
+    """build_model on a ModifiedResNet state dict (clip/model.py:406-414): architecture inferred from tensor shapes,
+    convert_weights dtypes (conv / attention-pool Linear fp16, BatchNorm + pos-emb fp32, counters int64), and the
+    CPU copy refuses to run (no fallback)."""
+    from proto_clip_b200 import _native as nat
+    from proto_clip_b200.clip import model as M
+    sd = synthetic.make_state_dict("rn_small", 0)
+    m = M.build_model({k: v.float() if v.is_floating_point() else v for k, v in sd.items()})  # an fp32 checkpoint
+    assert m.visual.input_resolution == 96 and m.visual.layers == (2, 1, 2, 1) and m.visual.output_dim == 128
+    out = m.state_dict()
+    assert list(out.keys()) == list(sd.keys())
+    for k, v in out.items():
+        if k.endswith("num_batches_tracked"):
+            assert v.dtype == torch.int64
+        elif k.startswith("visual.") and (".conv" in k or "downsample.0" in k or "_proj." in k):
+            assert v.dtype == torch.float16, k
+        elif k.startswith("visual."):
+            assert v.dtype == torch.float32, k
+    with pytest.raises(nat.NativeError):
+        m.encode_image(torch.zeros(1, 3, 96, 96))
+    # the flop model used by tools/gpu_probe.py matches SURVEY.md's table (RN50x16: ~149.4 GFLOP / image)
+    assert abs(synthetic.rn_flops_per_image("RN50x16") / 1e9 - 149.4) < 0.1
+
+
+def test_abi_argument_errors_without_gpu():
+    """Entry points validate their arguments before touching the device: bad calls return a negative PC_ERR_* code and
+    set pc_last_error(), with or without a GPU."""
+    import ctypes
+    from proto_clip_b200 import _native as nat
+    lib = nat.load_library()
+    rc = lib.pc_linear_shift_relu_forward(None, 8, None, 8, None, None, 0, None, 8, 4, 8, 8, nat.EPI_BIAS_QUICKGELU, 1, None)
+    assert rc == -1 and b"epilogue" in lib.pc_last_error()
+    assert lib.pc_rn_bind_weights(None, None) < 0 and len(lib.pc_last_error()) > 0
+    assert lib.pc_encode_image_workspace_bytes(None, 0) == 0
+    w = nat.AdapterConvWeights()
+    assert lib.pc_adapter_conv_forward(ctypes.byref(w), 5, None, None, 1, 512, None) < 0
