@@ -146,6 +146,16 @@ size_t pc_encode_image_workspace_bytes(const pc_ctx* ctx, int micro_batch);
 int pc_encode_image(pc_ctx* ctx, const void* images, int img_dtype, int B, void* feat_out, int l2norm,
                     int micro_batch, void* workspace, size_t workspace_bytes, void* stream);
 
+/* `_transform(n_px)` of clip/clip.py:77-84 for ONE image: Resize(n_px, BICUBIC) -> CenterCrop(n_px) -> ToTensor ->
+ * Normalize(CLIP mean / std). rgb: uint8 [H, W, 3] in DEVICE memory (what `image.convert("RGB")` holds); out: [3, n_px,
+ * n_px] f32 or f16 (out_dtype = PC_IMG_F32 / PC_IMG_F16), e.g. one slot of the batch handed to pc_encode_image. Byte-
+ * exact with Pillow's 8-bit antialiased resampler and torchvision's size / crop arithmetic (the third-party code the
+ * reference calls); fp32 results identical to ToTensor + Normalize. The only host work is building the filter tables
+ * (double precision) and one small host-to-device copy of them on `stream`. */
+size_t pc_preprocess_workspace_bytes(int H, int W, int n_px);
+int pc_preprocess_image(const uint8_t* rgb, int H, int W, int n_px, void* out, int out_dtype, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 /* CLIP.encode_text (clip/model.py:341-354). tokens: int64 [P, context_length] (clip.tokenize output,
  * clip/clip.py:194-230); out: f16 [P, embed_dim]. */
 size_t pc_encode_text_workspace_bytes(const pc_ctx* ctx, int micro_batch);

@@ -42,6 +42,30 @@ def _transform(n_px: int):
     ])
 
 
+class GPUTransform:
+    """The same `_transform(n_px)` on the GPU (pc_preprocess_image): PIL image or HxWx3 uint8 array -> CUDA tensor
+    [3, n_px, n_px], bit-identical to the host pipeline above (Pillow's 8-bit bicubic resampler restated in integer
+    arithmetic). For callers that already hold decoded pixels (the toolkit's cropped objects, video frames): the
+    DataLoader workers of main.py keep the host transform, because JPEG decoding lives there anyway."""
+
+    def __init__(self, n_px: int, device: Union[str, torch.device] = "cuda", dtype: torch.dtype = torch.float32):
+        self.n_px, self.device, self.dtype = n_px, torch.device(device), dtype
+
+    def __call__(self, image, out: torch.Tensor = None) -> torch.Tensor:
+        import numpy as np
+        from .. import _native as nat
+        if isinstance(image, torch.Tensor):
+            rgb = image
+        else:
+            if hasattr(image, "convert"):  # PIL.Image
+                image = image.convert("RGB")
+            arr = np.ascontiguousarray(np.asarray(image))
+            if arr.ndim == 2:
+                arr = np.repeat(arr[:, :, None], 3, axis=2)
+            rgb = torch.from_numpy(arr[:, :, :3].copy())
+        return nat.preprocess_image(rgb.to(self.device, non_blocking=True), self.n_px, out=out, dtype=self.dtype)
+
+
 def _read_state_dict(path: str):
     try:
         return torch.jit.load(path, map_location="cpu").eval().state_dict()
@@ -69,6 +93,7 @@ def load(name: str, device: Union[str, torch.device] = "cuda", jit: bool = False
     else:
         raise RuntimeError(f"Model {name} not found; available models = {available_models()}")
     model = build_model(state_dict).to(device)
+    model.preprocess_gpu = GPUTransform(model.visual.input_resolution, device)  # same arithmetic, on the device
     return model, _transform(model.visual.input_resolution)
 
 

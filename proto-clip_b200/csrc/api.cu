@@ -703,6 +703,17 @@ int pc_encode_image(pc_ctx* ctx, const void* images, int img_dtype, int B, void*
   return PC_OK;
 }
 
+size_t pc_preprocess_workspace_bytes(int H, int W, int n_px) { return preprocess_workspace_bytes(H, W, n_px); }
+
+int pc_preprocess_image(const uint8_t* rgb, int H, int W, int n_px, void* out, int out_dtype, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  PC_REQUIRE(out_dtype == PC_IMG_F32 || out_dtype == PC_IMG_F16, PC_ERR_ARG, "pc_preprocess_image: out dtype %d", out_dtype);
+  PC_REQUIRE(workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, PC_ERR_ALIGN,
+             "pc_preprocess_image: workspace must be 256-byte aligned");
+  return launch_preprocess(rgb, H, W, n_px, out, out_dtype == PC_IMG_F16, workspace, workspace_bytes,
+                           static_cast<cudaStream_t>(stream));
+}
+
 size_t pc_encode_text_workspace_bytes(const pc_ctx* ctx, int micro_batch) {
   if (!ctx || !ctx->txt.bound) return 0;
   const int mb = micro_batch > 0 ? micro_batch : default_micro_batch(ctx->txt.L);

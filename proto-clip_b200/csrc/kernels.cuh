@@ -110,6 +110,13 @@ int launch_avgpool_nhwc(const __half* x, __half* y, int B, int H, int W, int C, 
 // AttentionPool2d tokens: [B,HW,C] -> [B,HW+1,C] = [mean; pixels] + pos (clip/model.py:68-70)
 int launch_attnpool_tokens(const __half* x, const float* pos, __half* tok, int B, int HW, int C, cudaStream_t stream);
 
+// ---------------------------------------------------------------- preprocess.cu (clip/clip.py:77-84 `_transform`)
+// one RGB uint8 image [H, W, 3] (device) -> [3, n_px, n_px] fp32 / fp16: bicubic antialiased resize of the shorter side
+// to n_px (byte-exact with Pillow), centre crop, /255, CLIP mean / std
+size_t preprocess_workspace_bytes(int H, int W, int n_px);
+int launch_preprocess(const uint8_t* rgb, int H, int W, int n_px, void* out, int out_f16, void* workspace,
+                      size_t workspace_bytes, cudaStream_t stream);
+
 // ---------------------------------------------------------------- head.cu
 int launch_build_prototypes(const __half* V, int N, int K, int D, int per_shot_norm, __half* z, float* zn2,
                             cudaStream_t stream);

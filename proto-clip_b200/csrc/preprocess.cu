@@ -1,0 +1,222 @@
+// CLIP image preprocessing (reference clip/clip.py:77-84):
+//   Resize(n_px, BICUBIC) -> CenterCrop(n_px) -> convert("RGB") -> ToTensor() -> Normalize(mean, std)
+// for one RGB uint8 image [H, W, 3] already in device memory, byte-exact with what the reference runs on the host:
+// Pillow's 8-bit antialiased resampler (src/libImaging/Resample.c: separable, fixed-point weights with 22 fractional
+// bits, a uint8 intermediate image between the horizontal and the vertical pass) and torchvision's size / crop
+// arithmetic. Only the n_px x n_px window that survives the centre crop is computed.
+//
+// Integer / byte work, HBM-bound and tiny: the weight tables are built on the host in double precision with the exact
+// expression order of precompute_coeffs / normalize_coeffs_8bpc and travel to the device with one small H2D copy; two
+// kernels (horizontal taps -> uint8 rows; vertical taps -> byte -> /255, -mean, /std with correctly rounded fp32 ops,
+// no FMA contraction) write the [3, n_px, n_px] tensor the encoders consume.
+#include <math.h>
+
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace pc {
+namespace {
+
+constexpr int PRECISION_BITS = 32 - 8 - 2;  // Resample.c
+
+double bicubic_filter(double x) {  // Resample.c bicubic_filter, a = -0.5
+  const double a = -0.5;
+  if (x < 0.0) x = -x;
+  if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+  if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+  return 0.0;
+}
+
+// precompute_coeffs + normalize_coeffs_8bpc for output indices [o0, o0 + n) of a resize in_size -> out_size.
+// bounds[i] = (first source index, tap count), kk[i * ksize + t] = fixed-point weight. Returns ksize.
+int coeffs(int in_size, int out_size, int o0, int n, std::vector<int>* bounds, std::vector<int>* kk) {
+  const double scale = static_cast<double>(in_size) / out_size;
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = 2.0 * filterscale;
+  const int ksize = static_cast<int>(ceil(support)) * 2 + 1;
+  bounds->assign(static_cast<size_t>(n) * 2, 0);
+  kk->assign(static_cast<size_t>(n) * ksize, 0);
+  if (in_size == out_size) {  // Pillow skips the pass: identity taps reproduce the bytes exactly
+    for (int i = 0; i < n; ++i) {
+      (*bounds)[2 * i] = o0 + i;
+      (*bounds)[2 * i + 1] = 1;
+      (*kk)[static_cast<size_t>(i) * ksize] = 1 << PRECISION_BITS;
+    }
+    return ksize;
+  }
+  const double ss = 1.0 / filterscale;
+  std::vector<double> w(ksize);
+  for (int i = 0; i < n; ++i) {
+    const int xx = o0 + i;
+    const double center = 0.0 + (xx + 0.5) * scale;
+    int xmin = static_cast<int>(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = static_cast<int>(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    double ww = 0.0;
+    for (int x = 0; x < xmax; ++x) {
+      w[x] = bicubic_filter((x + xmin - center + 0.5) * ss);
+      ww += w[x];
+    }
+    for (int x = 0; x < xmax; ++x) {
+      const double v = ww != 0.0 ? w[x] / ww : w[x];
+      (*kk)[static_cast<size_t>(i) * ksize + x] =
+          v < 0 ? static_cast<int>(-0.5 + v * (1 << PRECISION_BITS)) : static_cast<int>(0.5 + v * (1 << PRECISION_BITS));
+    }
+    (*bounds)[2 * i] = xmin;
+    (*bounds)[2 * i + 1] = xmax;
+  }
+  return ksize;
+}
+
+__device__ __forceinline__ int clip8(int acc) {  // Resample.c clip8
+  const int v = acc >> PRECISION_BITS;
+  return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+// horizontal pass: tmp[r][xx][c] for source rows y0 + r, r in [0, rows), and the n_px surviving output columns
+__global__ void __launch_bounds__(256)
+resample_h_kernel(const uint8_t* __restrict__ src, int W, int y0, int rows, int n_px, const int* __restrict__ bounds,
+                  const int* __restrict__ kk, int ksize, uint8_t* __restrict__ tmp) {
+  const int total = rows * n_px;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int xx = t % n_px, r = t / n_px;
+    const int xmin = bounds[2 * xx], n = bounds[2 * xx + 1];
+    const uint8_t* p = src + (static_cast<size_t>(y0 + r) * W + xmin) * 3;
+    const int* k = kk + xx * ksize;
+    int a0 = 1 << (PRECISION_BITS - 1), a1 = a0, a2 = a0;
+    for (int x = 0; x < n; ++x) {
+      const int kv = k[x];
+      a0 += p[3 * x] * kv;
+      a1 += p[3 * x + 1] * kv;
+      a2 += p[3 * x + 2] * kv;
+    }
+    uint8_t* o = tmp + static_cast<size_t>(t) * 3;
+    o[0] = static_cast<uint8_t>(clip8(a0));
+    o[1] = static_cast<uint8_t>(clip8(a1));
+    o[2] = static_cast<uint8_t>(clip8(a2));
+  }
+}
+
+// vertical pass + ToTensor + Normalize: out[c][yy][xx] = ((byte / 255) - mean_c) / std_c, every op rounded to fp32
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+resample_v_norm_kernel(const uint8_t* __restrict__ tmp, int y0, int n_px, const int* __restrict__ bounds,
+                       const int* __restrict__ kk, int ksize, OutT* __restrict__ out) {
+  const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};   // clip/clip.py:83
+  const float stdv[3] = {0.26862954f, 0.26130258f, 0.27577711f};
+  const int total = n_px * n_px;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int xx = t % n_px, yy = t / n_px;
+    const int ymin = bounds[2 * yy] - y0, n = bounds[2 * yy + 1];
+    const int* k = kk + yy * ksize;
+    int a[3] = {1 << (PRECISION_BITS - 1), 1 << (PRECISION_BITS - 1), 1 << (PRECISION_BITS - 1)};
+    for (int y = 0; y < n; ++y) {
+      const uint8_t* p = tmp + (static_cast<size_t>(ymin + y) * n_px + xx) * 3;
+      const int kv = k[y];
+      a[0] += p[0] * kv;
+      a[1] += p[1] * kv;
+      a[2] += p[2] * kv;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float x = __fdiv_rn(static_cast<float>(clip8(a[c])), 255.0f);         // ToTensor
+      const float v = __fdiv_rn(__fsub_rn(x, mean[c]), stdv[c]);                   // Normalize
+      out[static_cast<size_t>(c) * total + t] = static_cast<OutT>(v);
+    }
+  }
+}
+
+inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+struct Plan {
+  int new_h, new_w, top, left, y0, y1;
+  int ksize_h, ksize_v;
+  std::vector<int> bh, kh, bv, kv;
+};
+
+// Python's round(): half to even (torchvision F.center_crop: int(round((size - crop) / 2.0)))
+int round_half_even(double v) {
+  const double f = floor(v);
+  const double d = v - f;
+  if (d > 0.5) return static_cast<int>(f) + 1;
+  if (d < 0.5) return static_cast<int>(f);
+  return (static_cast<long long>(f) % 2 == 0) ? static_cast<int>(f) : static_cast<int>(f) + 1;
+}
+
+void make_plan(int H, int W, int n_px, Plan* p) {
+  // torchvision _compute_resized_output_size: shorter side -> n_px, longer side int(n_px * long / short)
+  const int shrt = W <= H ? W : H, lng = W <= H ? H : W;
+  const int new_long = static_cast<int>(static_cast<double>(n_px) * lng / shrt);
+  p->new_w = W <= H ? n_px : new_long;
+  p->new_h = W <= H ? new_long : n_px;
+  p->top = round_half_even((p->new_h - n_px) / 2.0);
+  p->left = round_half_even((p->new_w - n_px) / 2.0);
+  p->ksize_h = coeffs(W, p->new_w, p->left, n_px, &p->bh, &p->kh);
+  p->ksize_v = coeffs(H, p->new_h, p->top, n_px, &p->bv, &p->kv);
+  p->y0 = p->bv[0];
+  p->y1 = p->bv[2 * (n_px - 1)] + p->bv[2 * (n_px - 1) + 1];
+}
+
+size_t table_bytes(int n_px, int ksize_h, int ksize_v) {
+  return align256(static_cast<size_t>(n_px) * (4 + ksize_h + ksize_v) * sizeof(int));
+}
+
+int taps(int in_size, int out_size) {  // ksize of precompute_coeffs
+  const double scale = static_cast<double>(in_size) / out_size;
+  return static_cast<int>(ceil(2.0 * (scale < 1.0 ? 1.0 : scale))) * 2 + 1;
+}
+
+}  // namespace
+
+size_t preprocess_workspace_bytes(int H, int W, int n_px) {
+  if (H <= 0 || W <= 0 || n_px <= 0) return 0;
+  const int shrt = W <= H ? W : H, lng = W <= H ? H : W;
+  const int new_long = static_cast<int>(static_cast<double>(n_px) * lng / shrt);
+  // the intermediate image holds at most H source rows of the n_px surviving columns
+  return table_bytes(n_px, taps(W, W <= H ? n_px : new_long), taps(H, W <= H ? new_long : n_px)) +
+         align256(static_cast<size_t>(H) * n_px * 3);
+}
+
+int launch_preprocess(const uint8_t* rgb, int H, int W, int n_px, void* out, int out_f16, void* workspace,
+                      size_t workspace_bytes, cudaStream_t stream) {
+  PC_REQUIRE(rgb && out && workspace, PC_ERR_ARG, "preprocess: null buffer");
+  PC_REQUIRE(H > 0 && W > 0 && n_px > 0 && n_px <= 4096 && H <= 32768 && W <= 32768, PC_ERR_ARG,
+             "preprocess: image %dx%d -> %d px", H, W, n_px);
+  Plan p;
+  make_plan(H, W, n_px, &p);
+  PC_REQUIRE(p.new_h >= n_px && p.new_w >= n_px, PC_ERR_ARG, "preprocess: resized image %dx%d smaller than the crop %d",
+             p.new_h, p.new_w, n_px);
+  const int rows = p.y1 - p.y0;
+  const size_t tb = table_bytes(n_px, p.ksize_h, p.ksize_v);
+  PC_REQUIRE(workspace_bytes >= tb + align256(static_cast<size_t>(rows) * n_px * 3), PC_ERR_WORKSPACE,
+             "preprocess: workspace %zu < %zu", workspace_bytes, tb + align256(static_cast<size_t>(rows) * n_px * 3));
+  // one H2D copy of all four tables: [bh | bv | kh | kv]
+  std::vector<int> host;
+  host.reserve(static_cast<size_t>(n_px) * (4 + p.ksize_h + p.ksize_v));
+  host.insert(host.end(), p.bh.begin(), p.bh.end());
+  host.insert(host.end(), p.bv.begin(), p.bv.end());
+  host.insert(host.end(), p.kh.begin(), p.kh.end());
+  host.insert(host.end(), p.kv.begin(), p.kv.end());
+  int* d_bh = static_cast<int*>(workspace);
+  int* d_bv = d_bh + 2 * n_px;
+  int* d_kh = d_bv + 2 * n_px;
+  int* d_kv = d_kh + static_cast<size_t>(n_px) * p.ksize_h;
+  uint8_t* tmp = static_cast<uint8_t*>(workspace) + tb;
+  PC_CHECK_CUDA(cudaMemcpyAsync(d_bh, host.data(), host.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+  const int t1 = rows * n_px, t2 = n_px * n_px;
+  resample_h_kernel<<<(t1 + 255) / 256, 256, 0, stream>>>(rgb, W, p.y0, rows, n_px, d_bh, d_kh, p.ksize_h, tmp);
+  PC_CHECK_CUDA(cudaGetLastError());
+  if (out_f16)
+    resample_v_norm_kernel<__half><<<(t2 + 255) / 256, 256, 0, stream>>>(tmp, p.y0, n_px, d_bv, d_kv, p.ksize_v,
+                                                                          static_cast<__half*>(out));
+  else
+    resample_v_norm_kernel<float><<<(t2 + 255) / 256, 256, 0, stream>>>(tmp, p.y0, n_px, d_bv, d_kv, p.ksize_v,
+                                                                         static_cast<float*>(out));
+  PC_CHECK_CUDA(cudaGetLastError());
+  return PC_OK;
+}
+
+}  // namespace pc

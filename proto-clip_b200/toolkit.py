@@ -119,9 +119,13 @@ class ProtoClipClassifier:
     def _features(self, cropped_images) -> torch.Tensor:
         if isinstance(cropped_images, torch.Tensor):  # already preprocessed [B, 3, R, R]
             batches = [cropped_images[i:i + 64] for i in range(0, cropped_images.shape[0], 64)]
-        else:  # HxWx3 uint8 arrays, as the segmentation node hands them over (image_utils.py:8-25)
-            from PIL import Image
-            batches = [self.preprocess(Image.fromarray(im)).unsqueeze(0) for im in cropped_images]
+        else:  # HxWx3 uint8 arrays, as the segmentation node hands them over (image_utils.py:8-25): the reference
+            # runs Image.fromarray + the host transform per crop; the same arithmetic runs on the GPU here
+            n = self.clip_model.visual.input_resolution
+            batch = torch.empty(len(cropped_images), 3, n, n, device="cuda")
+            for i, im in enumerate(cropped_images):
+                self.clip_model.preprocess_gpu(im, out=batch[i])
+            batches = [batch[i:i + 64] for i in range(0, batch.shape[0], 64)]
         return pre_load_features_without_cache(self.clip_model, batches)
 
     def classify_objects(self, cropped_images, log=False, rgb_image=None):

@@ -184,6 +184,27 @@ def main_rn():
         print(arch, "done")
 
 
+def preprocess_fixture():
+    """The reference's `_transform(n_px)` (clip/clip.py:77-84: PIL bicubic resize, centre crop, ToTensor, Normalize) on
+    seeded RGB images of assorted sizes: inputs (uint8) and the reference's fp32 outputs."""
+    import numpy as np
+    from PIL import Image
+    tf = {n: ref.clip.clip._transform(n) for n in (32, 64, 96)}  # clip/clip.py:77-84, the real reference function
+    rng = np.random.default_rng(5)
+    cases = []
+    for (h, w, n) in ((37, 53, 32), (53, 37, 32), (64, 64, 64), (100, 80, 64), (45, 200, 32), (240, 320, 96), (300, 224, 96)):
+        base = rng.random((h // 4 + 2, w // 4 + 2, 3))
+        img = np.asarray(Image.fromarray((base * 255).astype(np.uint8)).resize((w, h), Image.BILINEAR))  # smooth content
+        img = np.clip(img.astype(np.int32) + rng.integers(-20, 21, img.shape), 0, 255).astype(np.uint8)  # + texture
+        cases.append({"image": torch.from_numpy(img.copy()), "n_px": n, "out": tf[n](Image.fromarray(img)).clone()})
+    return {"cases": cases, "pillow": __import__("PIL").__version__, "torchvision": __import__("torchvision").__version__}
+
+
+def main_preprocess():
+    torch.save(preprocess_fixture(), os.path.join(OUT, "preprocess.pt"))
+    print("preprocess done")
+
+
 def main_336():
     """ViT-L/14@336px (config C4: L = 577 tokens -> the attention kernel's multi-block path). fp32 reference only."""
     fx = tower_fixture("ViT-L/14@336px", B=2, P=1, with_fp16=False, with_blocks=False)
@@ -196,5 +217,7 @@ if __name__ == "__main__":
         main_336()
     elif len(sys.argv) > 1 and sys.argv[1] == "rn":
         main_rn()
+    elif len(sys.argv) > 1 and sys.argv[1] == "preprocess":
+        main_preprocess()
     else:
         main()

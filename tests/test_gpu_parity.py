@@ -530,6 +530,18 @@ def test_toolkit_callers_top_k_and_ood(nat, tmp_path, monkeypatch):
     assert probs.shape == (Q, 3) and (probs.cpu() - top_p).abs().max().item() < 2e-2
     assert [row[0] for row in names] == [f"object {i}" for i in pred_o.tolist()]
     assert all(len(row) == 3 for row in names)
+    # raw uint8 crops (what the robot's segmentation node hands over): preprocessed on the GPU, identical to the
+    # reference's host transform (PIL bicubic resize, centre crop, ToTensor, Normalize) followed by the same classifier
+    import numpy as np
+    from PIL import Image
+    rng = np.random.default_rng(3)
+    crops = [np.clip(np.kron(rng.random((h // 4 + 1, w // 4 + 1, 3)), np.ones((4, 4, 1)))[:h, :w] * 255, 0, 255).astype(np.uint8)
+             for (h, w) in ((90, 70), (64, 64), (50, 120), (130, 40), (33, 47))]
+    names_gpu, probs_gpu = clf.classify_objects(crops)
+    host = torch.stack([clf.preprocess(Image.fromarray(c)) for c in crops])
+    assert torch.equal(torch.stack([clf.clip_model.preprocess_gpu(c) for c in crops]).cpu(), host)
+    names_host, probs_host = clf.classify_objects(host.to(DEV))
+    assert names_gpu == names_host and torch.equal(probs_gpu, probs_host)
     loader = [(queries[i:i + 10], labels[i:i + 10]) for i in range(0, Q, 10)]
     acc = toolkit.test_ood_performance(cfg, "synthetic", 0, 10, memory_bank_v_path="mb_v.pt", memory_bank_t_path="mb_t.pt",
                                        adapter_type="fc", adapter_weights_path="adapter.pt", test_loader=loader)
