@@ -179,7 +179,40 @@ def case_tower(arch, B, micro_batch=0):
     print(f"[tower {arch} B{B} mb{micro_batch}] {ms:.2f} ms  {B / ms * 1e3:.0f} img/s  {flops / ms / 1e9:.0f} TFLOP/s", flush=True)
 
 
+def case_preprocess(h=480, w=640, n_px=224, count=256):
+    """pc_preprocess_image (the reference's `_transform`) per image, images resident on the device, next to the reference's
+    host pipeline (PIL + torchvision) on one core."""
+    import numpy as np
+    import torch
+    from proto_clip_b200 import _native as nat
+    from proto_clip_b200 import clip
+    rng = np.random.default_rng(0)
+    imgs = [torch.from_numpy((rng.random((h, w, 3)) * 255).astype(np.uint8)).cuda() for _ in range(8)]
+    batch = torch.empty(count, 3, n_px, n_px, device="cuda")
+    for i in range(8):
+        nat.preprocess_image(imgs[i % 8], n_px, out=batch[i])
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(count):
+        nat.preprocess_image(imgs[i % 8], n_px, out=batch[i])
+    t1.record(); torch.cuda.synchronize()
+    us = t0.elapsed_time(t1) * 1e3 / count
+    bytes_alg = h * w * 3 + 3 * n_px * n_px * 4
+    from PIL import Image
+    tf = clip.clip._transform(n_px)
+    pil = [Image.fromarray(im.cpu().numpy()) for im in imgs]
+    t = time.time()
+    for i in range(64):
+        tf(pil[i % 8])
+    cpu_us = (time.time() - t) * 1e6 / 64
+    print(f"[preprocess {h}x{w} -> {n_px}] GPU {us:.1f} us / image ({1e6 / us:.0f} img/s, {bytes_alg / us / 1e3:.1f} GB/s algorithmic)"
+          f"  |  host PIL + torchvision {cpu_us:.0f} us / image on one core ({1e6 / cpu_us:.0f} img/s)", flush=True)
+
+
 CASES = {
+    "preprocess_vga": lambda: case_preprocess(480, 640, 224),
+    "preprocess_small": lambda: case_preprocess(96, 120, 224),
+    "preprocess_hd": lambda: case_preprocess(1080, 1920, 336),
     "tower_rn50x16": lambda: case_tower("RN50x16", 128),
     "tower_rn50x16_mb16": lambda: case_tower("RN50x16", 128, 16),
     "tower_rn50x16_mb64": lambda: case_tower("RN50x16", 128, 64),
