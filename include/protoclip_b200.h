@@ -155,6 +155,11 @@ int pc_encode_image(pc_ctx* ctx, const void* images, int img_dtype, int B, void*
 size_t pc_preprocess_workspace_bytes(int H, int W, int n_px);
 int pc_preprocess_image(const uint8_t* rgb, int H, int W, int n_px, void* out, int out_dtype, void* workspace,
                         size_t workspace_bytes, void* stream);
+/* The same for B images of one size, rgb: uint8 [B, H, W, 3] -> out [B, 3, n_px, n_px], in two launches (what a
+ * DataLoader's default collate of decoded, same-size frames gives; the filter tables are built once per size). */
+size_t pc_preprocess_batch_workspace_bytes(int B, int H, int W, int n_px);
+int pc_preprocess_batch(const uint8_t* rgb, int B, int H, int W, int n_px, void* out, int out_dtype, void* workspace,
+                        size_t workspace_bytes, void* stream);
 
 /* CLIP.encode_text (clip/model.py:341-354). tokens: int64 [P, context_length] (clip.tokenize output,
  * clip/clip.py:194-230); out: f16 [P, embed_dim]. */

@@ -23,7 +23,7 @@ EPI_BIAS, EPI_BIAS_QUICKGELU, EPI_BIAS_RESIDUAL, EPI_F32 = 0, 1, 2, 3
 SYMBOLS = [
     "pc_version", "pc_last_error", "pc_ctx_create", "pc_ctx_destroy", "pc_vit_bind_weights",
     "pc_text_bind_weights", "pc_rn_bind_weights", "pc_linear_shift_relu_forward",
-    "pc_preprocess_workspace_bytes", "pc_preprocess_image", "pc_encode_image_workspace_bytes", "pc_encode_image",
+    "pc_preprocess_workspace_bytes", "pc_preprocess_image", "pc_preprocess_batch_workspace_bytes", "pc_preprocess_batch", "pc_encode_image_workspace_bytes", "pc_encode_image",
     "pc_encode_text_workspace_bytes", "pc_encode_text", "pc_resblock_workspace_bytes", "pc_resblock_forward",
     "pc_linear_forward", "pc_layernorm_forward", "pc_attention_forward", "pc_l2_normalize",
     "pc_adapter_fc_workspace_bytes", "pc_adapter_fc_forward", "pc_adapter_conv_forward", "pc_build_prototypes",
@@ -110,6 +110,9 @@ def load_library() -> C.CDLL:
     lib.pc_preprocess_workspace_bytes.argtypes = [i, i, i]
     lib.pc_preprocess_workspace_bytes.restype = sz
     lib.pc_preprocess_image.argtypes = [vp, i, i, i, vp, i, vp, sz, vp]
+    lib.pc_preprocess_batch_workspace_bytes.argtypes = [i, i, i, i]
+    lib.pc_preprocess_batch_workspace_bytes.restype = sz
+    lib.pc_preprocess_batch.argtypes = [vp, i, i, i, i, vp, i, vp, sz, vp]
     lib.pc_encode_text_workspace_bytes.argtypes = [vp, i]
     lib.pc_encode_text_workspace_bytes.restype = sz
     lib.pc_encode_text.argtypes = [vp, vp, i, vp, i, i, vp, sz, vp]
@@ -250,23 +253,27 @@ def attention(qkv: torch.Tensor, B: int, L: int, heads: int, causal: bool) -> to
 
 def preprocess_image(rgb: torch.Tensor, n_px: int, out: Optional[torch.Tensor] = None,
                      dtype: torch.dtype = torch.float32) -> torch.Tensor:
-    """`_transform(n_px)` (clip/clip.py:77-84) of one RGB uint8 image [H, W, 3] on the GPU -> [3, n_px, n_px]."""
+    """`_transform(n_px)` (clip/clip.py:77-84) on the GPU: one RGB uint8 image [H, W, 3] -> [3, n_px, n_px], or a batch of
+    same-size images [B, H, W, 3] -> [B, 3, n_px, n_px] (two launches for the whole batch)."""
     lib = load_library()
     if not rgb.is_cuda:
         raise NativeError("preprocess_image: the image must be a CUDA uint8 tensor; there is no CPU path")
-    if rgb.dtype != torch.uint8 or rgb.dim() != 3 or rgb.shape[2] != 3:
-        raise ValueError(f"preprocess_image: expected uint8 [H, W, 3], got {rgb.dtype} {tuple(rgb.shape)}")
+    if rgb.dtype != torch.uint8 or rgb.dim() not in (3, 4) or rgb.shape[-1] != 3:
+        raise ValueError(f"preprocess_image: expected uint8 [H, W, 3] or [B, H, W, 3], got {rgb.dtype} {tuple(rgb.shape)}")
     rgb = rgb.contiguous()
-    H, W = int(rgb.shape[0]), int(rgb.shape[1])
+    batched = rgb.dim() == 4
+    B = int(rgb.shape[0]) if batched else 1
+    H, W = int(rgb.shape[-3]), int(rgb.shape[-2])
+    shape = (B, 3, n_px, n_px) if batched else (3, n_px, n_px)
     if out is None:
-        out = torch.empty((3, n_px, n_px), dtype=dtype, device=rgb.device)
-    elif tuple(out.shape) != (3, n_px, n_px) or not out.is_contiguous() or out.dtype not in (torch.float32, torch.float16):
-        raise ValueError("preprocess_image: out must be a contiguous [3, n_px, n_px] f32 / f16 tensor")
-    ws = workspace(rgb.device, "preprocess", lib.pc_preprocess_workspace_bytes(H, W, n_px))
+        out = torch.empty(shape, dtype=dtype, device=rgb.device)
+    elif tuple(out.shape) != shape or not out.is_contiguous() or out.dtype not in (torch.float32, torch.float16):
+        raise ValueError(f"preprocess_image: out must be a contiguous {shape} f32 / f16 tensor")
+    ws = workspace(rgb.device, "preprocess", lib.pc_preprocess_batch_workspace_bytes(B, H, W, n_px))
     with torch.cuda.device(rgb.device):
-        check(lib.pc_preprocess_image(rgb.data_ptr(), H, W, n_px, out.data_ptr(),
+        check(lib.pc_preprocess_batch(rgb.data_ptr(), B, H, W, n_px, out.data_ptr(),
                                       PC_IMG_F16 if out.dtype == torch.float16 else PC_IMG_F32, ws.data_ptr(), ws.numel(),
-                                      stream_ptr(rgb.device)), "pc_preprocess_image")
+                                      stream_ptr(rgb.device)), "pc_preprocess_batch")
     return out
 
 

@@ -703,15 +703,21 @@ int pc_encode_image(pc_ctx* ctx, const void* images, int img_dtype, int B, void*
   return PC_OK;
 }
 
-size_t pc_preprocess_workspace_bytes(int H, int W, int n_px) { return preprocess_workspace_bytes(H, W, n_px); }
+size_t pc_preprocess_workspace_bytes(int H, int W, int n_px) { return preprocess_workspace_bytes(1, H, W, n_px); }
+size_t pc_preprocess_batch_workspace_bytes(int B, int H, int W, int n_px) { return preprocess_workspace_bytes(B, H, W, n_px); }
+
+int pc_preprocess_batch(const uint8_t* rgb, int B, int H, int W, int n_px, void* out, int out_dtype, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  PC_REQUIRE(out_dtype == PC_IMG_F32 || out_dtype == PC_IMG_F16, PC_ERR_ARG, "pc_preprocess_batch: out dtype %d", out_dtype);
+  PC_REQUIRE(workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, PC_ERR_ALIGN,
+             "pc_preprocess_batch: workspace must be 256-byte aligned");
+  return launch_preprocess(rgb, B, H, W, n_px, out, out_dtype == PC_IMG_F16, workspace, workspace_bytes,
+                           static_cast<cudaStream_t>(stream));
+}
 
 int pc_preprocess_image(const uint8_t* rgb, int H, int W, int n_px, void* out, int out_dtype, void* workspace,
                         size_t workspace_bytes, void* stream) {
-  PC_REQUIRE(out_dtype == PC_IMG_F32 || out_dtype == PC_IMG_F16, PC_ERR_ARG, "pc_preprocess_image: out dtype %d", out_dtype);
-  PC_REQUIRE(workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, PC_ERR_ALIGN,
-             "pc_preprocess_image: workspace must be 256-byte aligned");
-  return launch_preprocess(rgb, H, W, n_px, out, out_dtype == PC_IMG_F16, workspace, workspace_bytes,
-                           static_cast<cudaStream_t>(stream));
+  return pc_preprocess_batch(rgb, 1, H, W, n_px, out, out_dtype, workspace, workspace_bytes, stream);
 }
 
 size_t pc_encode_text_workspace_bytes(const pc_ctx* ctx, int micro_batch) {

@@ -111,10 +111,10 @@ int launch_avgpool_nhwc(const __half* x, __half* y, int B, int H, int W, int C, 
 int launch_attnpool_tokens(const __half* x, const float* pos, __half* tok, int B, int HW, int C, cudaStream_t stream);
 
 // ---------------------------------------------------------------- preprocess.cu (clip/clip.py:77-84 `_transform`)
-// one RGB uint8 image [H, W, 3] (device) -> [3, n_px, n_px] fp32 / fp16: bicubic antialiased resize of the shorter side
+// B same-size RGB uint8 images [B, H, W, 3] (device) -> [B, 3, n_px, n_px] fp32 / fp16: bicubic antialiased resize of the shorter side
 // to n_px (byte-exact with Pillow), centre crop, /255, CLIP mean / std
-size_t preprocess_workspace_bytes(int H, int W, int n_px);
-int launch_preprocess(const uint8_t* rgb, int H, int W, int n_px, void* out, int out_f16, void* workspace,
+size_t preprocess_workspace_bytes(int B, int H, int W, int n_px);
+int launch_preprocess(const uint8_t* rgb, int B, int H, int W, int n_px, void* out, int out_f16, void* workspace,
                       size_t workspace_bytes, cudaStream_t stream);
 
 // ---------------------------------------------------------------- head.cu

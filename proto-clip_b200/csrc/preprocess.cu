@@ -1,6 +1,6 @@
 // CLIP image preprocessing (reference clip/clip.py:77-84):
 //   Resize(n_px, BICUBIC) -> CenterCrop(n_px) -> convert("RGB") -> ToTensor() -> Normalize(mean, std)
-// for one RGB uint8 image [H, W, 3] already in device memory, byte-exact with what the reference runs on the host:
+// for a batch of same-size RGB uint8 images [B, H, W, 3] already in device memory, byte-exact with what the reference runs on the host:
 // Pillow's 8-bit antialiased resampler (src/libImaging/Resample.c: separable, fixed-point weights with 22 fractional
 // bits, a uint8 intermediate image between the horizontal and the vertical pass) and torchvision's size / crop
 // arithmetic. Only the n_px x n_px window that survives the centre crop is computed.
@@ -76,15 +76,19 @@ __device__ __forceinline__ int clip8(int acc) {  // Resample.c clip8
   return v < 0 ? 0 : (v > 255 ? 255 : v);
 }
 
-// horizontal pass: tmp[r][xx][c] for source rows y0 + r, r in [0, rows), and the n_px surviving output columns
+// horizontal pass: tmp[b][r][xx][c] for source rows y0 + r, r in [0, rows), and the n_px surviving output columns of
+// every image b of the batch (images [B, H, W, 3], same size)
 __global__ void __launch_bounds__(256)
-resample_h_kernel(const uint8_t* __restrict__ src, int W, int y0, int rows, int n_px, const int* __restrict__ bounds,
-                  const int* __restrict__ kk, int ksize, uint8_t* __restrict__ tmp) {
-  const int total = rows * n_px;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
-    const int xx = t % n_px, r = t / n_px;
+resample_h_kernel(const uint8_t* __restrict__ src, int B, int H, int W, int y0, int rows, int n_px,
+                  const int* __restrict__ bounds, const int* __restrict__ kk, int ksize, uint8_t* __restrict__ tmp) {
+  const size_t total = static_cast<size_t>(B) * rows * n_px;
+  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int xx = static_cast<int>(t % n_px);
+    const int r = static_cast<int>((t / n_px) % rows);
+    const size_t b = t / (static_cast<size_t>(n_px) * rows);
     const int xmin = bounds[2 * xx], n = bounds[2 * xx + 1];
-    const uint8_t* p = src + (static_cast<size_t>(y0 + r) * W + xmin) * 3;
+    const uint8_t* p = src + ((b * H + y0 + r) * W + xmin) * 3;
     const int* k = kk + xx * ksize;
     int a0 = 1 << (PRECISION_BITS - 1), a1 = a0, a2 = a0;
     for (int x = 0; x < n; ++x) {
@@ -103,18 +107,22 @@ resample_h_kernel(const uint8_t* __restrict__ src, int W, int y0, int rows, int 
 // vertical pass + ToTensor + Normalize: out[c][yy][xx] = ((byte / 255) - mean_c) / std_c, every op rounded to fp32
 template <typename OutT>
 __global__ void __launch_bounds__(256)
-resample_v_norm_kernel(const uint8_t* __restrict__ tmp, int y0, int n_px, const int* __restrict__ bounds,
+resample_v_norm_kernel(const uint8_t* __restrict__ tmp, int B, int rows, int y0, int n_px, const int* __restrict__ bounds,
                        const int* __restrict__ kk, int ksize, OutT* __restrict__ out) {
   const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};   // clip/clip.py:83
   const float stdv[3] = {0.26862954f, 0.26130258f, 0.27577711f};
-  const int total = n_px * n_px;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
-    const int xx = t % n_px, yy = t / n_px;
+  const int plane = n_px * n_px;
+  const size_t total = static_cast<size_t>(B) * plane;
+  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int pix = static_cast<int>(t % plane);
+    const size_t b = t / plane;
+    const int xx = pix % n_px, yy = pix / n_px;
     const int ymin = bounds[2 * yy] - y0, n = bounds[2 * yy + 1];
     const int* k = kk + yy * ksize;
     int a[3] = {1 << (PRECISION_BITS - 1), 1 << (PRECISION_BITS - 1), 1 << (PRECISION_BITS - 1)};
     for (int y = 0; y < n; ++y) {
-      const uint8_t* p = tmp + (static_cast<size_t>(ymin + y) * n_px + xx) * 3;
+      const uint8_t* p = tmp + ((b * rows + ymin + y) * n_px + xx) * 3;
       const int kv = k[y];
       a[0] += p[0] * kv;
       a[1] += p[1] * kv;
@@ -124,7 +132,7 @@ resample_v_norm_kernel(const uint8_t* __restrict__ tmp, int y0, int n_px, const 
     for (int c = 0; c < 3; ++c) {
       const float x = __fdiv_rn(static_cast<float>(clip8(a[c])), 255.0f);         // ToTensor
       const float v = __fdiv_rn(__fsub_rn(x, mean[c]), stdv[c]);                   // Normalize
-      out[static_cast<size_t>(c) * total + t] = static_cast<OutT>(v);
+      out[(b * 3 + c) * plane + pix] = static_cast<OutT>(v);
     }
   }
 }
@@ -171,28 +179,33 @@ int taps(int in_size, int out_size) {  // ksize of precompute_coeffs
 
 }  // namespace
 
-size_t preprocess_workspace_bytes(int H, int W, int n_px) {
-  if (H <= 0 || W <= 0 || n_px <= 0) return 0;
+size_t preprocess_workspace_bytes(int B, int H, int W, int n_px) {
+  if (B <= 0 || H <= 0 || W <= 0 || n_px <= 0) return 0;
   const int shrt = W <= H ? W : H, lng = W <= H ? H : W;
   const int new_long = static_cast<int>(static_cast<double>(n_px) * lng / shrt);
   // the intermediate image holds at most H source rows of the n_px surviving columns
   return table_bytes(n_px, taps(W, W <= H ? n_px : new_long), taps(H, W <= H ? new_long : n_px)) +
-         align256(static_cast<size_t>(H) * n_px * 3);
+         align256(static_cast<size_t>(B) * H * n_px * 3);
 }
 
-int launch_preprocess(const uint8_t* rgb, int H, int W, int n_px, void* out, int out_f16, void* workspace,
+int launch_preprocess(const uint8_t* rgb, int B, int H, int W, int n_px, void* out, int out_f16, void* workspace,
                       size_t workspace_bytes, cudaStream_t stream) {
   PC_REQUIRE(rgb && out && workspace, PC_ERR_ARG, "preprocess: null buffer");
-  PC_REQUIRE(H > 0 && W > 0 && n_px > 0 && n_px <= 4096 && H <= 32768 && W <= 32768, PC_ERR_ARG,
-             "preprocess: image %dx%d -> %d px", H, W, n_px);
-  Plan p;
-  make_plan(H, W, n_px, &p);
+  PC_REQUIRE(B > 0 && H > 0 && W > 0 && n_px > 0 && n_px <= 4096 && H <= 32768 && W <= 32768, PC_ERR_ARG,
+             "preprocess: %d images %dx%d -> %d px", B, H, W, n_px);
+  // the filter tables depend on (H, W, n_px) only: the last plan is kept (a loader's images mostly share one size)
+  static thread_local Plan p;
+  static thread_local int pH = 0, pW = 0, pN = 0;
+  if (pH != H || pW != W || pN != n_px) {
+    make_plan(H, W, n_px, &p);
+    pH = H; pW = W; pN = n_px;
+  }
   PC_REQUIRE(p.new_h >= n_px && p.new_w >= n_px, PC_ERR_ARG, "preprocess: resized image %dx%d smaller than the crop %d",
              p.new_h, p.new_w, n_px);
   const int rows = p.y1 - p.y0;
   const size_t tb = table_bytes(n_px, p.ksize_h, p.ksize_v);
-  PC_REQUIRE(workspace_bytes >= tb + align256(static_cast<size_t>(rows) * n_px * 3), PC_ERR_WORKSPACE,
-             "preprocess: workspace %zu < %zu", workspace_bytes, tb + align256(static_cast<size_t>(rows) * n_px * 3));
+  PC_REQUIRE(workspace_bytes >= tb + align256(static_cast<size_t>(B) * rows * n_px * 3), PC_ERR_WORKSPACE,
+             "preprocess: workspace %zu < %zu", workspace_bytes, tb + align256(static_cast<size_t>(B) * rows * n_px * 3));
   // one H2D copy of all four tables: [bh | bv | kh | kv]
   std::vector<int> host;
   host.reserve(static_cast<size_t>(n_px) * (4 + p.ksize_h + p.ksize_v));
@@ -206,15 +219,18 @@ int launch_preprocess(const uint8_t* rgb, int H, int W, int n_px, void* out, int
   int* d_kv = d_kh + static_cast<size_t>(n_px) * p.ksize_h;
   uint8_t* tmp = static_cast<uint8_t*>(workspace) + tb;
   PC_CHECK_CUDA(cudaMemcpyAsync(d_bh, host.data(), host.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
-  const int t1 = rows * n_px, t2 = n_px * n_px;
-  resample_h_kernel<<<(t1 + 255) / 256, 256, 0, stream>>>(rgb, W, p.y0, rows, n_px, d_bh, d_kh, p.ksize_h, tmp);
+  const size_t t1 = static_cast<size_t>(B) * rows * n_px, t2 = static_cast<size_t>(B) * n_px * n_px;
+  const size_t cap = static_cast<size_t>(device_sm_count()) * 32;  // grid-stride beyond 32 blocks per SM
+  const int g1 = static_cast<int>(((t1 + 255) / 256 < cap) ? (t1 + 255) / 256 : cap);
+  const int g2 = static_cast<int>(((t2 + 255) / 256 < cap) ? (t2 + 255) / 256 : cap);
+  resample_h_kernel<<<g1, 256, 0, stream>>>(rgb, B, H, W, p.y0, rows, n_px, d_bh, d_kh, p.ksize_h, tmp);
   PC_CHECK_CUDA(cudaGetLastError());
   if (out_f16)
-    resample_v_norm_kernel<__half><<<(t2 + 255) / 256, 256, 0, stream>>>(tmp, p.y0, n_px, d_bv, d_kv, p.ksize_v,
-                                                                          static_cast<__half*>(out));
+    resample_v_norm_kernel<__half><<<g2, 256, 0, stream>>>(tmp, B, rows, p.y0, n_px, d_bv, d_kv, p.ksize_v,
+                                                           static_cast<__half*>(out));
   else
-    resample_v_norm_kernel<float><<<(t2 + 255) / 256, 256, 0, stream>>>(tmp, p.y0, n_px, d_bv, d_kv, p.ksize_v,
-                                                                         static_cast<float*>(out));
+    resample_v_norm_kernel<float><<<g2, 256, 0, stream>>>(tmp, B, rows, p.y0, n_px, d_bv, d_kv, p.ksize_v,
+                                                          static_cast<float*>(out));
   PC_CHECK_CUDA(cudaGetLastError());
   return PC_OK;
 }

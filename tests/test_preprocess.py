@@ -74,6 +74,11 @@ def test_cuda_preprocess_fixture_and_errors():
     for i, case in enumerate(big):
         nat.preprocess_image(case["image"].cuda(), 96, out=batch[i])
         assert torch.equal(batch[i].cpu(), case["out"])
+    # a batch of same-size images in two launches = the images one by one
+    imgs = torch.stack([torch.from_numpy(random_image(120, 90, s)) for s in range(9)]).cuda()
+    one_by_one = torch.stack([nat.preprocess_image(im, 64) for im in imgs])
+    assert torch.equal(nat.preprocess_image(imgs, 64), one_by_one)
+    assert np.array_equal(one_by_one[4].cpu().numpy(), PO.clip_preprocess(imgs[4].cpu().numpy(), 64))
     with pytest.raises(nat.NativeError):
         nat.preprocess_image(torch.zeros(8, 8, 3, dtype=torch.uint8), 8)        # CPU tensor: no fallback
     with pytest.raises(ValueError):

@@ -198,6 +198,16 @@ def case_preprocess(h=480, w=640, n_px=224, count=256):
     t1.record(); torch.cuda.synchronize()
     us = t0.elapsed_time(t1) * 1e3 / count
     bytes_alg = h * w * 3 + 3 * n_px * n_px * 4
+    stack = torch.stack([imgs[i % 8] for i in range(count)])
+    for _ in range(3):
+        nat.preprocess_image(stack, n_px, out=batch)
+    t0.record()
+    for _ in range(10):
+        nat.preprocess_image(stack, n_px, out=batch)
+    t1.record(); torch.cuda.synchronize()
+    us_b = t0.elapsed_time(t1) * 1e3 / 10 / count
+    print(f"[preprocess {h}x{w} -> {n_px}] batched ({count} images / call): {us_b:.2f} us / image ({1e6 / us_b:.0f} img/s, "
+          f"{bytes_alg / us_b / 1e3:.0f} GB/s algorithmic)", flush=True)
     from PIL import Image
     tf = clip.clip._transform(n_px)
     pil = [Image.fromarray(im.cpu().numpy()) for im in imgs]
