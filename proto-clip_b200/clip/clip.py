@@ -58,7 +58,11 @@ class GPUTransform:
             rgb = image
         else:
             if hasattr(image, "convert"):  # PIL.Image
-                image = image.convert("RGB")
+                if image.mode not in ("RGB", "L"):
+                    # the reference resizes BEFORE convert("RGB"): Pillow resamples palette / bilevel images with NEAREST
+                    # and alpha images in premultiplied form, which this RGB kernel does not reproduce
+                    raise ValueError(f"GPUTransform handles RGB / L images; use the host `preprocess` for mode {image.mode!r}")
+                image = image.convert("RGB")  # for L: resize-then-replicate == replicate-then-resize, channel by channel
             arr = np.ascontiguousarray(np.asarray(image))
             if arr.ndim == 2:
                 arr = np.repeat(arr[:, :, None], 3, axis=2)

@@ -41,6 +41,26 @@ def test_oracle_matches_live_pil_and_torchvision(h, w, n):
     assert np.array_equal(PO.resize_bicubic_u8(img, nw, nh), pil)
 
 
+def test_gpu_transform_refuses_modes_it_cannot_reproduce():
+    """Palette / alpha images are resized differently by Pillow (NEAREST, premultiplied alpha) before convert("RGB"):
+    the device transform says so instead of silently diverging from the reference."""
+    Image = pytest.importorskip("PIL.Image")
+    from proto_clip_b200.clip.clip import GPUTransform
+    tf = GPUTransform(32)
+    for mode in ("P", "RGBA", "1"):
+        with pytest.raises(ValueError, match="host `preprocess`"):
+            tf(Image.new(mode, (40, 50)))
+
+
+def test_grayscale_resize_commutes_with_rgb_conversion():
+    """The reference converts to RGB after the resize; for mode L the GPU path converts first — same bytes."""
+    Image = pytest.importorskip("PIL.Image")
+    g = random_image(70, 45, 1)[:, :, 0].copy()
+    after = np.asarray(Image.fromarray(g).resize((32, 49), Image.BICUBIC).convert("RGB"))
+    before = PO.resize_bicubic_u8(np.repeat(g[:, :, None], 3, axis=2), 32, 49)
+    assert np.array_equal(after, before)
+
+
 def test_size_arithmetic():
     assert PO.resized_size(480, 640, 224) == (224, 298) and PO.resized_size(640, 480, 224) == (298, 224)
     assert PO.crop_offsets(224, 298, 224) == (0, 37) and PO.crop_offsets(225, 224, 224) == (0, 0)  # round half to even
