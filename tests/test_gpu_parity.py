@@ -195,6 +195,27 @@ def test_resnet_tower_properties_and_rebinding(nat):
     assert torch.equal(ctx.encode_image(images[:9], l2norm=True), f[:9])
 
 
+def test_full_size_properties_rn50x16(nat):
+    """RN50x16 at config C5's size (384 px, 40 bottlenecks, 145-token attention pool): per-image results do not depend on
+    batch position or micro-batching (bit-exact), the golden image keeps its reference features inside a larger batch."""
+    fx = load_golden("tower_RN50x16.pt")
+    sd = synthetic.make_state_dict("RN50x16", 0)
+    ctx = nat.Context(torch.device(DEV))
+    ctx.bind_visual(sd)
+    B = 11
+    bases = synthetic.class_bases(4, 384, seed=1, device=DEV)
+    images = synthetic.class_structured_images(bases, torch.arange(B, device=DEV) % 4, seed=3)
+    images[3] = golden_images(fx).to(DEV)[0]
+    f = ctx.encode_image(images)
+    assert torch.isfinite(f.float()).all()
+    assert rel_err(f[3:4], fx["image_features_fp32"]) < TOWER_TOL
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(0)).to(DEV)
+    assert torch.equal(ctx.encode_image(images[perm]), f[perm])
+    assert torch.equal(ctx.encode_image(images, micro_batch=4), f)
+    fn = ctx.encode_image(images, l2norm=True)
+    assert (fn.float().norm(dim=-1) - 1).abs().max().item() < 2e-3
+
+
 @pytest.mark.parametrize("M,N,K", [(300, 48, 32), (1000, 96, 432), (513, 384, 96), (77, 3072, 768)])
 def test_linear_relu_epilogues(nat, M, N, K):
     """conv + folded-BN (+ identity) + ReLU epilogues of the Bottleneck GEMMs (clip/model.py:43-52): fp32 shift,
