@@ -24,6 +24,7 @@
 // TMEM region of a WG (256 columns): S / P ring slots at [0, 64) and [64, 128), O at [128, 192).
 #include <stdlib.h>
 
+#include "attn_common.cuh"
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -102,66 +103,6 @@ __device__ __forceinline__ Job job_of(const AttnParams& p, int g, int w) {
     j.active = j.tile < p.m_tiles;
   }
   return j;
-}
-
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// packed fp32 pair math (one issue slot for two elements)
-__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
-  return static_cast<uint64_t>(__float_as_uint(lo)) | (static_cast<uint64_t>(__float_as_uint(hi)) << 32);
-}
-__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-
-// ---- softmax chunk helpers: 16 S columns of this thread's row, already in registers. kmax = last valid key of
-// THIS row relative to the chunk's first key (sequence end; causal rows differ). FULL chunks (every key valid for
-// every row of the warp) take the mask-free path.
-template <bool FULL>
-__device__ __forceinline__ float chunk_max(const uint32_t (&v)[16], int kmax, float mx) {
-  float m1 = -INFINITY;
-#pragma unroll
-  for (int j = 0; j < 16; j += 4) {
-    float a = __uint_as_float(v[j]), b = __uint_as_float(v[j + 1]);
-    float c = __uint_as_float(v[j + 2]), d = __uint_as_float(v[j + 3]);
-    if (!FULL) {
-      a = (j <= kmax) ? a : -INFINITY;
-      b = (j + 1 <= kmax) ? b : -INFINITY;
-      c = (j + 2 <= kmax) ? c : -INFINITY;
-      d = (j + 3 <= kmax) ? d : -INFINITY;
-    }
-    mx = fmaxf(mx, fmaxf(a, b));
-    m1 = fmaxf(m1, fmaxf(c, d));
-  }
-  return fmaxf(mx, m1);
-}
-// p = exp2(s * sc - ref) -> packed fp16 pairs; `acc` accumulates the fp32 (unrounded) p as an (even, odd) pair.
-template <bool FULL>
-__device__ __forceinline__ uint64_t chunk_exp(const uint32_t (&v)[16], uint32_t (&pk)[8], int kmax, uint64_t sc2,
-                                              uint64_t nref2, uint64_t acc) {
-#pragma unroll
-  for (int j = 0; j < 16; j += 2) {
-    const uint64_t t = fma_f32x2(static_cast<uint64_t>(v[j]) | (static_cast<uint64_t>(v[j + 1]) << 32), sc2, nref2);
-    float e0 = ex2_approx(__uint_as_float(static_cast<uint32_t>(t)));
-    float e1 = ex2_approx(__uint_as_float(static_cast<uint32_t>(t >> 32)));
-    if (!FULL) {
-      e0 = (j <= kmax) ? e0 : 0.0f;
-      e1 = (j + 1 <= kmax) ? e1 : 0.0f;
-    }
-    acc = add_f32x2(acc, pack_f32x2(e0, e1));
-    pk[j >> 1] = pack_half2(e0, e1);
-  }
-  return acc;
 }
 
 template <bool CAUSAL>
