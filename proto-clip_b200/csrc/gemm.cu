@@ -614,7 +614,16 @@ int dispatch_epi(const GemmArgs& a, int epi, cudaStream_t stream) {
 
 }  // namespace
 
-static bool use_pair(int M, int N) { return M >= 256 && N >= 256 && !force_single_cta(); }
+// Smallest N that goes to the CTA-pair (256 x 256 tile) kernel; PC_GEMM_PAIR_MIN_N overrides it (A/B timing).
+static int pair_min_n() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PC_GEMM_PAIR_MIN_N");
+    v = (e && atoi(e) > 0) ? atoi(e) : 192;  // 192: +6 % on the RN50x16 tower (planes = 192 layers), no ViT shape in [192, 256)
+  }
+  return v;
+}
+static bool use_pair(int M, int N) { return M >= 256 && N >= pair_min_n() && !force_single_cta(); }
 
 int gemm_stats_parts(int M, int N) {
   const int bn = use_pair(M, N) ? 256 : 128;
