@@ -480,7 +480,8 @@ int launch_variant(int grid, int smem_bytes, cudaStream_t stream, const CUtensor
 int launch_attention(const __half* qkv, __half* out, int B, int L, int heads, int causal,
                      cudaStream_t stream) {
   PC_REQUIRE(qkv && out && B > 0 && L > 0 && heads > 0, PC_ERR_ARG, "attention: bad arguments");
-  if (attention5_supports(L)) return launch_attention5(qkv, out, B, L, heads, causal, stream);  // four tiles in flight
+  if (attention6_supports(L)) return launch_attention6(qkv, out, B, L, heads, causal, stream);  // whole-row S in TMEM
+  if (attention5_supports(L)) return launch_attention5(qkv, out, B, L, heads, causal, stream);  // round-1 kernel (A/B)
   const int d = heads * HEAD_DIM;
   AttnParams p{};
   p.L = L;

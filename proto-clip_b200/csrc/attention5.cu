@@ -421,12 +421,12 @@ int launch_variant5(int grid, int smem_bytes, cudaStream_t stream, const CUtenso
 
 // L <= 256 and the two channels' K/V fit next to four query tiles
 bool attention5_supports(int L) {
-  static int off = -1;
-  if (off < 0) {
-    const char* e = getenv("PC_ATTN_TWO_TILES");  // A/B switch: keep every shape on attention.cu's kernel
-    off = (e && e[0] == '1') ? 1 : 0;
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("PC_ATTN_IMPL");  // A/B switch: 5 = this kernel, 2 = attention.cu for every shape
+    on = (e && atoi(e) == 5) ? 1 : 0;
   }
-  return !off && L <= 256;
+  return on && L <= 256;
 }
 
 int launch_attention5(const __half* qkv, __half* out, int B, int L, int heads, int causal, cudaStream_t stream) {

@@ -1,0 +1,647 @@
+// Multi-head self-attention core for sequences of at most 208 tokens (ViT-B/32, ViT-B/16, the text tower, the
+// ModifiedResNet attention pools): WHOLE-ROW scores in TMEM, exact (single-pass) softmax.
+// Same contract as attention.cu (reference clip/model.py:173,183-185; causal flag = the text mask of
+// clip/model.py:326-332).
+//
+// Why: the round-1 kernel (attention5.cu) streamed 64-key blocks through an online softmax. Per block it paid one
+// S commit -> mbarrier -> tcgen05.ld hop, one P -> mbarrier -> PV hop and a possible O rescale, and ncu showed it
+// bound by instruction issue (ALU pipe 40 %, MUFU 36 %, tensor 17 %), not by a pipe it could saturate. For L <= 208
+// the whole score row fits in TMEM, so a query tile costs TWO hops in total and a minimal instruction stream:
+//   S[128, lp16] = Q K^T          two UMMA batches (N = 128 and N = lp16 - 128), one commit
+//   row maximum over all keys     tcgen05.ld + 3-input max only, then p = exp2((s - max) * scale) written back
+//                                 IN PLACE as packed fp16: per pair of scores one FFMA2, two MUFU.EX2 (or the FMA-pipe
+//                                 polynomial), one FADD2 (row sum) and one F2FP -- no running maximum, no rescale of O
+//   O[128, 64] = P V              two UMMA batches with P as the TMEM A operand; the first starts while the
+//                                 exponentials of the other part are still running
+//
+// TMEM: 256 columns per query tile. S_a (keys [0,128)) at [0,128), S_b at [128, 128 + nb), nb <= 80; the O accumulator
+// at [192,256). Every softmax thread writes its fp16 P IN PLACE over score columns it has already read itself (so
+// there is no hazard between threads): P is not contiguous, each UMMA k-step of P V addresses its own 8 columns.
+// Part b (keys >= 128) is exponentiated FIRST: once it is done its last score chunk [192,208) is dead and P_b V_b
+// may start accumulating O while part a's exponentials are still running; S_a of the NEXT tile does not overlap O,
+// so it is issued right behind the tile's last P V MMA without waiting for the epilogue.
+//
+// Persistent kernel, one CTA per SM, 20 warps:
+//   warps 0-7 / 8-15  softmax warpgroup 0 / 1 (8 warps = one 128-row query tile): the two tiles of one (image, head)
+//                    item (128 < L <= 208) or two different items (L <= 128, "split"). TWO threads per query row
+//                    (row == TMEM lane; warps q and q + 4 of a group share lane quadrant q): thread 0 owns key chunks
+//                    [0, h0), thread 1 owns [h0, nch), h0 = ceil(nch / 2). Each takes the maximum of its own chunks,
+//                    the two meet through shared memory (one 64-thread named barrier), each exponentiates its own
+//                    chunks, the partial row sums meet the same way, and in the epilogue each thread scales and
+//                    stores 32 of the row's 64 output columns. Four softmax warps per scheduler keep the MUFU pipe fed
+//                    (a single warp reaches 75 % of it, profiles/r01_ubench2.log); NP of every 8 score pairs take
+//                    a cubic polynomial on the FMA pipe instead. The two warpgroups can hand the MUFU pipe to each
+//                    other through a pair of named barriers (ping-pong, PC_ATTN6_PINGPONG).
+//   warp 16 / 17     MMA issuer of WG 0 / 1 (whole warp in the loop, one elected lane issues)
+//   warp 18          TMA producer: a STAGE holds everything an item needs (Q tile 0, Q tile 1, K, V: 96 KB); two
+//                    stages, so the next item's operands land while the current one is computed
+//   warp 19          idle (warpgroup padding)
+#include <stdlib.h>
+
+#include "attn_common.cuh"
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace pc {
+namespace {
+
+constexpr int HEAD_DIM = 64;
+constexpr int MMA_WARP0 = 16;
+constexpr int TMA_WARP = 18;
+constexpr int THREADS6 = 20 * 32;
+constexpr int TILE_BYTES = 128 * 128;  // 128 rows x 64 fp16, 128B-swizzled
+constexpr int OFF_Q = 0;               // Q tile of WG 0, then of WG 1
+constexpr int OFF_K = 2 * TILE_BYTES;  // 256 key rows (split: 128 per WG)
+constexpr int OFF_V = 4 * TILE_BYTES;
+constexpr int STAGE_BYTES = 6 * TILE_BYTES;   // 96 KB
+constexpr int OFF_OUT = 2 * STAGE_BYTES;      // 16 x 2 KB output staging blocks (one per softmax warp: 32 rows x 64 B)
+constexpr int OFF_XCH = OFF_OUT + 16 * 2048;  // row maximum / partial row sum exchange [tile][thread of the row][row] fp32
+constexpr int OFF_BARS = OFF_XCH + 2 * 2 * 128 * 4;
+constexpr int O_COL = 192;   // O accumulator inside a tile's 256-column TMEM region
+constexpr int SB_COL = 128;  // S_b
+
+struct Params6 {
+  int L, lp16, heads, d, items;
+  int split;     // 1: L <= 128, the two WGs take different items
+  int n_groups;  // split: ceil(items / 2), else items
+  int na;        // keys of part a = min(lp16, 128)
+  int nb;        // keys of part b = lp16 - na
+  int pingpong;  // 1: the WGs alternate on the MUFU pipe (named barriers 1 / 2)
+  int debug;     // bring-up only (env PC_ATTN6_DEBUG): 2 = no MMA issue (wrong results: timing A/B only)
+  long long* trace;  // bring-up only (env PC_ATTN_TRACE=1): [tile][WG][16] clock64 samples of CTA 0, warp quarter 0, thread 0 of the row
+};
+
+#define TR6(slot)                                                                                              \
+  do {                                                                                                         \
+    if (p.trace != nullptr && blockIdx.x == 0 && quarter == 0 && hf == 0 && lane == 0 && tcount < 8)           \
+      p.trace[(tcount * 2 + w) * 16 + (slot)] = clock64();                                                     \
+  } while (0)
+
+struct Bars6 {
+  uint64_t qk_full[2];     // per stage: Q tiles + K landed
+  uint64_t v_full[2];      // per stage: V landed
+  uint64_t stage_free[2];  // per stage: both WGs' last PV MMA on it retired (2 arrivals)
+  uint64_t s_full[2];      // per WG: S of the tile in TMEM
+  uint64_t pa_full[2];     // per WG: P part a in TMEM (8 warp arrivals)
+  uint64_t pb_full[2];     // per WG: P part b in TMEM (4 warp arrivals: it belongs to the rows' second threads)
+  uint64_t pv_done[2];     // per WG: last PV MMA of the tile retired
+  uint64_t o_free[2];      // per WG: O read out (8 warp arrivals)
+  uint32_t tmem_base;
+};
+
+struct Job6 {
+  bool active;
+  int item;  // b * heads + h
+  int tile;
+};
+__device__ __forceinline__ Job6 job_of(const Params6& p, int g, int w) {
+  Job6 j;
+  if (p.split) {
+    j.item = 2 * g + w;
+    j.tile = 0;
+    j.active = j.item < p.items;
+  } else {
+    j.item = g;
+    j.tile = w;
+    j.active = true;
+  }
+  return j;
+}
+
+__device__ __forceinline__ float lo_f(uint64_t v) { return __uint_as_float(static_cast<uint32_t>(v)); }
+__device__ __forceinline__ float hi_f(uint64_t v) { return __uint_as_float(static_cast<uint32_t>(v >> 32)); }
+__device__ __forceinline__ uint64_t pack_u32x2(uint32_t lo, uint32_t hi) {
+  return static_cast<uint64_t>(lo) | (static_cast<uint64_t>(hi) << 32);
+}
+__device__ __forceinline__ void pair_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+// TMEM column of the fp16 P of score chunk k (16 keys -> 8 columns): in place inside the chunk range of the thread that
+// produced it. Thread 0 of a row owns chunks [0, h0); thread 1 owns [h0, nch): its part-a chunks [h0, 8) are packed from
+// column 16 h0, its part-b chunks from column 128.
+__device__ __forceinline__ int p_col(int k, int h0) {
+  return k < h0 ? 8 * k : k < 8 ? 16 * h0 + 8 * (k - h0) : SB_COL + 8 * (k - 8);
+}
+
+template <int N>
+__device__ __forceinline__ float max_full(const uint32_t (&v)[N], float mx) {
+  float m1 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < N; j += 4) {
+    mx = fmaxf(mx, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+    m1 = fmaxf(m1, fmaxf(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+  }
+  return fmaxf(mx, m1);
+}
+
+// Maximum of this thread's score chunks [k0, k1) (at most 7). Every array is defined unconditionally inside its own
+// scope: a conditionally defined tcgen05.ld destination is live from the kernel entry for ptxas (it cost 80 registers).
+template <bool CAUSAL>
+__device__ __forceinline__ float row_max(uint32_t t_row, int k0, int k1, int L, int jmax) {
+  float mx = -INFINITY;
+  const int kf = CAUSAL ? k0 : max(k0, min(k1, L >> 4));  // chunks below kf hold 16 valid keys for every row
+  int k = k0;
+  if (k + 4 <= kf) {
+    uint32_t A[32], B[32];
+    tmem_ld_32x32(t_row + 16 * k, A);
+    tmem_ld_32x32(t_row + 16 * k + 32, B);
+    tmem_wait_ld();
+    mx = max_full<32>(A, mx);
+    mx = max_full<32>(B, mx);
+    k += 4;
+  }
+  if (k + 3 <= kf) {  // 4 + 3 chunks: the first thread of a ViT-B/16 row in two rounds
+    uint32_t A[32], B[16];
+    tmem_ld_32x32(t_row + 16 * k, A);
+    tmem_ld_32x16(t_row + 16 * k + 32, B);
+    tmem_wait_ld();
+    mx = max_full<32>(A, mx);
+    mx = max_full<16>(B, mx);
+    k += 3;
+  }
+  if (k + 2 <= kf) {
+    uint32_t A[32];
+    tmem_ld_32x32(t_row + 16 * k, A);
+    tmem_wait_ld();
+    mx = max_full<32>(A, mx);
+    k += 2;
+  }
+  if (k < kf) {
+    uint32_t A[16];
+    tmem_ld_32x16(t_row + 16 * k, A);
+    tmem_wait_ld();
+    mx = max_full<16>(A, mx);
+    ++k;
+  }
+#pragma unroll 1
+  for (; k < k1; ++k) {  // masked chunks: the row's last one (or every chunk under the causal mask); also any chunk
+    uint32_t A[16];      // the blocks above left over (they take at most 7)
+    tmem_ld_32x16(t_row + 16 * k, A);
+    tmem_wait_ld();
+    mx = chunk_max<false>(A, jmax - 16 * k, mx);
+  }
+  return mx;
+}
+
+// exp2 on the FMA / ALU pipes for two values at once (MUFU: 16 exp2 / clk / SM): Cody-Waite split x = n + f,
+// n = round(x), f in [-0.5, 0.5]; 2^f by a cubic minimax polynomial (max relative error 7.5e-5, below the fp16
+// rounding of P); 2^n by adding n to the exponent field. x <= 0 here; clamped at -125.
+__device__ __forceinline__ uint64_t exp2_poly_f32x2(uint64_t x2) {
+  const float MAGIC = 12582912.0f;  // 1.5 * 2^23: x + MAGIC has round(x) in its low mantissa bits
+  const uint64_t x = pack_f32x2(fmaxf(lo_f(x2), -125.0f), fmaxf(hi_f(x2), -125.0f));
+  const uint64_t xr = add_f32x2(x, pack_f32x2(MAGIC, MAGIC));
+  const uint64_t n = add_f32x2(xr, pack_f32x2(-MAGIC, -MAGIC));
+  const uint64_t f = fma_f32x2(n, pack_f32x2(-1.0f, -1.0f), x);
+  uint64_t q = fma_f32x2(f, pack_f32x2(0.0551716685f, 0.0551716685f), pack_f32x2(0.2426111251f, 0.2426111251f));
+  q = fma_f32x2(q, f, pack_f32x2(0.6932609677f, 0.6932609677f));
+  q = fma_f32x2(q, f, pack_f32x2(0.9999280572f, 0.9999280572f));
+  const uint32_t r0 = static_cast<uint32_t>(q) + (static_cast<uint32_t>(xr) << 23);
+  const uint32_t r1 = static_cast<uint32_t>(q >> 32) + (static_cast<uint32_t>(xr >> 32) << 23);
+  return pack_u32x2(r0, r1);
+}
+// pairs of a 16-column chunk that take the polynomial (NP of 8), spread over the chunk
+template <int NP>
+__device__ __forceinline__ constexpr bool pair_is_poly(int j) {
+  return NP >= 8 ? true : NP <= 0 ? false : ((j + 1) * NP) / 8 != (j * NP) / 8;
+}
+
+// N (16 or 32) unmasked score columns at s_addr -> N/2 columns of packed fp16 p = exp2(s * sc + nref) at p_addr.
+// Per pair of scores: FFMA2, 2 x MUFU.EX2 (or the polynomial), FADD2 (row sum, two chains), F2FP.
+template <int NP>
+__device__ __forceinline__ void exp_unit32(uint32_t s_addr, uint32_t p_addr, uint64_t sc2, uint64_t nref2, uint64_t& acc_a,
+                                           uint64_t& acc_b) {
+  uint32_t A[32], pk[16];
+  tmem_ld_32x32(s_addr, A);
+  tmem_wait_ld();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const uint64_t t = fma_f32x2(pack_u32x2(A[2 * j], A[2 * j + 1]), sc2, nref2);
+    const uint64_t e = pair_is_poly<NP>(j & 7) ? exp2_poly_f32x2(t) : pack_f32x2(ex2_approx(lo_f(t)), ex2_approx(hi_f(t)));
+    if (j & 1) acc_b = add_f32x2(acc_b, e);
+    else acc_a = add_f32x2(acc_a, e);
+    pk[j] = pack_half2(lo_f(e), hi_f(e));
+  }
+  tmem_st_32x16(p_addr, pk);
+}
+template <int NP>
+__device__ __forceinline__ void exp_unit16(uint32_t s_addr, uint32_t p_addr, uint64_t sc2, uint64_t nref2, uint64_t& acc_a,
+                                           uint64_t& acc_b) {
+  uint32_t A[16], pk[8];
+  tmem_ld_32x16(s_addr, A);
+  tmem_wait_ld();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint64_t t = fma_f32x2(pack_u32x2(A[2 * j], A[2 * j + 1]), sc2, nref2);
+    const uint64_t e = pair_is_poly<NP>(j) ? exp2_poly_f32x2(t) : pack_f32x2(ex2_approx(lo_f(t)), ex2_approx(hi_f(t)));
+    if (j & 1) acc_b = add_f32x2(acc_b, e);
+    else acc_a = add_f32x2(acc_a, e);
+    pk[j] = pack_half2(lo_f(e), hi_f(e));
+  }
+  tmem_st_32x8(p_addr, pk);
+}
+
+// score chunks [k0, k1) of this thread -> P at columns pcol + 8 (k - k0). (A 16-column loop with the next chunk's
+// scores prefetched measured slower than these 32-column units: 33.7 vs 32.1 us at B = 96, L = 197.)
+template <bool CAUSAL, int NP>
+__device__ __forceinline__ void exp_chunks(uint32_t t_row, int k0, int k1, int pcol, int L, int jmax, uint64_t sc2,
+                                           uint64_t nref2, uint64_t& acc_a, uint64_t& acc_b) {
+  const int kf = CAUSAL ? k0 : max(k0, min(k1, L >> 4));  // chunks below kf hold 16 valid keys for every row
+  int k = k0;
+#pragma unroll 1
+  for (; k + 2 <= kf; k += 2) exp_unit32<NP>(t_row + 16 * k, t_row + pcol + 8 * (k - k0), sc2, nref2, acc_a, acc_b);
+  if (k < kf) {
+    exp_unit16<NP>(t_row + 16 * k, t_row + pcol + 8 * (k - k0), sc2, nref2, acc_a, acc_b);
+    ++k;
+  }
+#pragma unroll 1
+  for (; k < k1; ++k) {  // masked chunks
+    uint32_t A[16], pk[8];
+    tmem_ld_32x16(t_row + 16 * k, A);
+    tmem_wait_ld();
+    acc_a = chunk_exp<false>(A, pk, jmax - 16 * k, sc2, nref2, acc_a);
+    tmem_st_32x8(t_row + pcol + 8 * (k - k0), pk);
+  }
+}
+
+template <bool CAUSAL, int NP>
+__global__ void __launch_bounds__(THREADS6, 1)
+attention6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmT,
+                  const __grid_constant__ CUtensorMap tmO, const Params6 p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  Bars6* bars = reinterpret_cast<Bars6*>(smem + OFF_BARS);
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform
+  const int lane = threadIdx.x & 31;
+
+  if (warp == TMA_WARP) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmT);
+      tma_prefetch_desc(&tmO);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&bars->qk_full[i], 1);
+        mbar_init(&bars->v_full[i], 1);
+        mbar_init(&bars->stage_free[i], 2);
+        mbar_init(&bars->s_full[i], 1);
+        mbar_init(&bars->pa_full[i], 8);
+        mbar_init(&bars->pb_full[i], 4);
+        mbar_init(&bars->pv_done[i], 1);
+        mbar_init(&bars->o_free[i], 8);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(&bars->tmem_base, 512);
+    tmem_relinquish();
+  }
+  griddep_launch_dependents();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  griddep_wait();  // qkv is the previous kernel's output
+
+  const int g_stride = gridDim.x;
+  const int nch = p.lp16 >> 4;    // 16-key score chunks per row
+  const int h0 = (nch + 1) >> 1;  // chunks [0, h0) belong to thread 0 of a row, [h0, nch) to thread 1 (h0 <= 7)
+  if (warp == TMA_WARP) {
+    // ---------------------------------------------------------------------------------- producer
+    uint32_t u = 0;
+    for (int g = blockIdx.x; g < p.n_groups; g += g_stride, ++u) {
+      const int st = u & 1;
+      uint8_t* stage = smem + st * STAGE_BYTES;
+      mbar_wait(&bars->stage_free[st], ((u >> 1) & 1) ^ 1);
+      if (elect_one()) {
+        uint64_t* qk = &bars->qk_full[st];
+        uint64_t* vf = &bars->v_full[st];
+        if (p.split) {
+          const Job6 j1 = job_of(p, g, 1);
+          const int n_act = j1.active ? 2 : 1;
+          mbar_arrive_expect_tx(qk, static_cast<uint32_t>(n_act) * (TILE_BYTES + p.na * 128));
+          for (int s = 0; s < n_act; ++s) {
+            const int item = 2 * g + s;
+            const int c0 = (item % p.heads) * HEAD_DIM, r0 = (item / p.heads) * p.L;
+            tma_load_2d(stage + OFF_Q + s * TILE_BYTES, &tmQ, qk, c0, r0);
+            tma_load_2d(stage + OFF_K + s * TILE_BYTES, &tmT, qk, p.d + c0, r0);
+          }
+          mbar_arrive_expect_tx(vf, static_cast<uint32_t>(n_act) * (p.na * 128));
+          for (int s = 0; s < n_act; ++s) {
+            const int item = 2 * g + s;
+            tma_load_2d(stage + OFF_V + s * TILE_BYTES, &tmT, vf, 2 * p.d + (item % p.heads) * HEAD_DIM,
+                        (item / p.heads) * p.L);
+          }
+        } else {
+          const int c0 = (g % p.heads) * HEAD_DIM, r0 = (g / p.heads) * p.L;
+          mbar_arrive_expect_tx(qk, 3 * TILE_BYTES + p.nb * 128);
+          tma_load_2d(stage + OFF_K, &tmQ, qk, p.d + c0, r0);
+          tma_load_2d(stage + OFF_Q, &tmQ, qk, c0, r0);
+          tma_load_2d(stage + OFF_K + TILE_BYTES, &tmT, qk, p.d + c0, r0 + 128);
+          tma_load_2d(stage + OFF_Q + TILE_BYTES, &tmQ, qk, c0, r0 + 128);
+          mbar_arrive_expect_tx(vf, TILE_BYTES + p.nb * 128);
+          tma_load_2d(stage + OFF_V, &tmQ, vf, 2 * p.d + c0, r0);
+          tma_load_2d(stage + OFF_V + TILE_BYTES, &tmT, vf, 2 * p.d + c0, r0 + 128);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == MMA_WARP0 || warp == MMA_WARP0 + 1) {
+    // ---------------------------------------------------------------------------------- MMA issuer of WG w
+    const int w = warp - MMA_WARP0;
+    const uint32_t region = tmem + w * 256;
+    const uint32_t idesc_o = umma_idesc_f16(128, HEAD_DIM, 0, 1);
+    const uint32_t idesc_sa = umma_idesc_f16(128, p.na, 0, 0);
+    const uint32_t idesc_sb = umma_idesc_f16(128, p.nb > 0 ? p.nb : 16, 0, 0);
+    const int kv_off = p.split ? w * TILE_BYTES : 0;
+    const int ka_steps = p.na >> 4;
+    uint32_t u = 0, tcount = 0;
+    for (int g = blockIdx.x; g < p.n_groups; g += g_stride, ++u) {
+      const int st = u & 1;
+      const uint32_t full_par = (u >> 1) & 1;
+      const Job6 j = job_of(p, g, w);
+      if (!j.active) {  // split mode, odd item count: nothing was loaded for this WG; release its share of the stage
+        if (elect_one()) mbar_arrive(&bars->stage_free[st]);
+        __syncwarp();
+        continue;
+      }
+      const uint32_t sbase = smem_u32(smem + st * STAGE_BYTES);
+      const uint64_t q_desc = umma_desc_kmajor_sw128(sbase + OFF_Q + w * TILE_BYTES);
+      const uint64_t k_desc = umma_desc_kmajor_sw128(sbase + OFF_K + kv_off);
+      const uint64_t v_desc = umma_desc_mnmajor_sw128(sbase + OFF_V + kv_off, 1024);
+      mbar_wait(&bars->qk_full[st], full_par);
+      tc_fence_after();
+      // S_a overlaps neither O nor anything the previous tile still reads (its P was consumed by the MMAs issued
+      // before this one: the tensor pipe runs them in order)
+      if (elect_one()) {
+        if (!(p.debug & 2)) {
+#pragma unroll
+          for (int k = 0; k < HEAD_DIM / 16; ++k)
+            umma_f16_ss(region, q_desc + 2 * k, k_desc + 2 * k, idesc_sa, k != 0 ? 1u : 0u);
+        }
+      }
+      __syncwarp();
+      // S_b's last chunk and the first P V MMA overwrite O: the previous tile's O must have been read out. (s_full is
+      // committed behind this wait in split mode too: it orders every softmax thread's read of its partner's
+      // exchange slot before the partner's next write.)
+      mbar_wait(&bars->o_free[w], (tcount & 1) ^ 1);
+      tc_fence_after();
+      if (elect_one()) {
+        if (nch > 8 && !(p.debug & 2)) {
+#pragma unroll
+          for (int k = 0; k < HEAD_DIM / 16; ++k)
+            umma_f16_ss(region + SB_COL, q_desc + 2 * k, k_desc + (TILE_BYTES >> 4) + 2 * k, idesc_sb, k != 0 ? 1u : 0u);
+        }
+        umma_commit(&bars->s_full[w]);
+      }
+      __syncwarp();
+      mbar_wait(&bars->v_full[st], full_par);
+      if (nch > 8) {
+        mbar_wait(&bars->pb_full[w], tcount & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          // O[128, 64] = P_b V_b : P from TMEM (8 columns per 16 keys), V MN-major (16 key rows = 2048 B per step)
+          if (!(p.debug & 2))
+            for (int k = 8; k < nch; ++k)
+              umma_f16_ts(region + O_COL, region + p_col(k, h0), v_desc + 128 * k, idesc_o, k != 8 ? 1u : 0u);
+        }
+        __syncwarp();
+      }
+      mbar_wait(&bars->pa_full[w], tcount & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        if (!(p.debug & 2))
+          for (int k = 0; k < ka_steps; ++k)
+            umma_f16_ts(region + O_COL, region + p_col(k, h0), v_desc + 128 * k, idesc_o, (nch > 8 || k != 0) ? 1u : 0u);
+        umma_commit(&bars->pv_done[w]);
+        umma_commit(&bars->stage_free[st]);
+      }
+      __syncwarp();
+      ++tcount;
+    }
+  } else if (warp < MMA_WARP0) {
+    // ---------------------------------------------------------------------------------- softmax WG w
+    const int w = warp >> 3;
+    const int hf = (warp >> 2) & 1;  // which of the two threads of a row
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;  // row of the tile == TMEM lane
+    const uint32_t t_row = tmem + w * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
+    const float sc = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+    const uint64_t sc2 = pack_f32x2(sc, sc);
+    // this thread's chunks [c0, c1); [c0, ca) belong to part a, [cb, c1) to part b
+    const int c0 = hf ? h0 : 0, c1 = hf ? nch : h0;
+    const int ca = min(c1, 8), cb = max(c0, 8);
+    const int pair_bar = 3 + w * 4 + quarter;  // named barrier of the row's two threads (two warps)
+    uint8_t* stg = smem + OFF_OUT + warp * 2048;
+    float* my_x = reinterpret_cast<float*>(smem + OFF_XCH) + (w * 2 + hf) * 128 + r;
+    const float* other_x = reinterpret_cast<float*>(smem + OFF_XCH) + (w * 2 + (hf ^ 1)) * 128 + r;
+    uint32_t tcount = 0;
+    const int n_iter = (p.n_groups - static_cast<int>(blockIdx.x) + g_stride - 1) / g_stride;
+    if (p.pingpong && w == 1) asm volatile("bar.arrive 1, 512;" ::: "memory");  // WG 0 goes first
+    int it = 0;
+    for (int g = blockIdx.x; g < p.n_groups; g += g_stride, ++it) {
+      const Job6 j = job_of(p, g, w);
+      const bool last_iter = it == n_iter - 1;
+      if (!j.active) {  // keep the hand-over protocol balanced
+        if (p.pingpong) {
+          if (w == 0) {
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            asm volatile("bar.arrive 2, 512;" ::: "memory");
+          } else {
+            asm volatile("bar.sync 2, 512;" ::: "memory");
+            if (!last_iter) asm volatile("bar.arrive 1, 512;" ::: "memory");
+          }
+        }
+        continue;
+      }
+      const int i = j.tile * 128 + r;  // query index inside the sequence
+      const bool warp_live = j.tile * 128 + quarter * 32 < p.L;
+      const int jmax = CAUSAL ? min(i, p.L - 1) : p.L - 1;  // last key this row attends to
+      TR6(0);
+      mbar_wait(&bars->s_full[w], tcount & 1);
+      tc_fence_after();
+      TR6(1);
+      // ---- row maximum: own chunks, then the partner's through shared memory
+      float mx = -INFINITY;
+      if (warp_live) mx = row_max<CAUSAL>(t_row, c0, c1, p.L, jmax);
+      *my_x = mx;
+      pair_bar_sync(pair_bar);
+      mx = fmaxf(mx, *other_x);
+      pair_bar_sync(pair_bar);  // both maxima read: the slots may take the partial sums
+      const float nref = (mx == -INFINITY) ? 0.0f : -mx * sc;
+      const uint64_t nref2 = pack_f32x2(nref, nref);
+      TR6(2);
+      if (p.pingpong) {
+        if (w == 0) asm volatile("bar.sync 1, 512;" ::: "memory");
+        else asm volatile("bar.sync 2, 512;" ::: "memory");
+      }
+      TR6(3);
+      // ---- exponentials: part b first (it frees the columns O overlaps), then part a
+      uint64_t acc_a = 0, acc_b = 0;
+      if (hf == 1 && nch > 8) {
+        if (warp_live) {
+          exp_chunks<CAUSAL, NP>(t_row, cb, c1, p_col(cb, h0), p.L, jmax, sc2, nref2, acc_a, acc_b);
+          tmem_wait_st();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->pb_full[w]);
+      }
+      TR6(4);
+      if (warp_live) {
+        exp_chunks<CAUSAL, NP>(t_row, c0, ca, p_col(c0, h0), p.L, jmax, sc2, nref2, acc_a, acc_b);
+        tmem_wait_st();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->pa_full[w]);
+      if (p.pingpong) {
+        if (w == 0) asm volatile("bar.arrive 2, 512;" ::: "memory");
+        else if (!last_iter) asm volatile("bar.arrive 1, 512;" ::: "memory");
+      }
+      TR6(5);
+      // ---- the row sum is the sum of its two threads' partial sums
+      const float part = (lo_f(acc_a) + hi_f(acc_a)) + (lo_f(acc_b) + hi_f(acc_b));
+      *my_x = part;
+      pair_bar_sync(pair_bar);
+      const float sum = hf ? *other_x + part : part + *other_x;  // same order in both threads
+      // ---- last PV MMA of the tile retired -> O / sum -> fp16 -> out[b, i, h*64 + 32*hf .. +31]
+      mbar_wait(&bars->pv_done[w], tcount & 1);
+      tc_fence_after();
+      TR6(6);
+      if (!warp_live) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->o_free[w]);
+      }
+      if (warp_live) {
+        uint32_t O2[32];
+        tmem_ld_32x32(t_row + O_COL + 32 * hf, O2);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->o_free[w]);  // O may be overwritten by the next tile
+        TR6(7);
+        // fp16 rows into this warp's 2 KB staging block: 32 rows x 64 B, 64B-swizzled (16-byte chunk c of row r at
+        // chunk c ^ ((r >> 1) & 3): conflict-free 128-bit stores), then one TMA store through the [B][L][d] map,
+        // which clips the rows past the sequence end.
+        if (elect_one()) tma_store_wait_read<0>();  // the previous tile's store has drained this block
+        __syncwarp();
+        const float inv = __fdividef(1.0f, sum);
+        uint8_t* my_row = stg + lane * 64;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int e = cc * 8;
+          uint4 x;
+          x.x = pack_half2(__uint_as_float(O2[e + 0]) * inv, __uint_as_float(O2[e + 1]) * inv);
+          x.y = pack_half2(__uint_as_float(O2[e + 2]) * inv, __uint_as_float(O2[e + 3]) * inv);
+          x.z = pack_half2(__uint_as_float(O2[e + 4]) * inv, __uint_as_float(O2[e + 5]) * inv);
+          x.w = pack_half2(__uint_as_float(O2[e + 6]) * inv, __uint_as_float(O2[e + 7]) * inv);
+          *reinterpret_cast<uint4*>(my_row + ((cc ^ ((lane >> 1) & 3)) << 4)) = x;
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (elect_one()) {
+          const int b = j.item / p.heads, h = j.item % p.heads;
+          tma_store_3d(&tmO, stg, h * HEAD_DIM + 32 * hf, j.tile * 128 + quarter * 32, b);
+          tma_store_commit();
+        }
+      }
+      TR6(8);
+      ++tcount;
+    }
+    if (elect_one()) tma_store_wait_all<0>();  // output written before the CTA (and its staging smem) goes away
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+template <bool CAUSAL, int NP>
+int launch_variant6(int grid, int smem_bytes, cudaStream_t stream, const CUtensorMap& tmQ, const CUtensorMap& tmT,
+                    const CUtensorMap& tmO, const Params6& p) {
+  auto kern = attention6_kernel<CAUSAL, NP>;
+  PC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  PC_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS6), smem_bytes, stream, 1, tmQ, tmT, tmO, p));
+  return PC_OK;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+}  // namespace
+
+// L <= 208: the whole score row of a 128-query tile (<= 208 fp32 columns) and its O accumulator (64) fit in half of
+// the SM's tensor memory with S_a clear of O
+bool attention6_supports(int L) {
+  static int impl = -1;
+  if (impl < 0) impl = env_int("PC_ATTN_IMPL", 6);  // A/B switch: 5 = round-1 kernel (attention5.cu), 2 = attention.cu
+  return impl == 6 && L <= 208;
+}
+
+int launch_attention6(const __half* qkv, __half* out, int B, int L, int heads, int causal, cudaStream_t stream) {
+  const int d = heads * HEAD_DIM;
+  Params6 p{};
+  p.L = L;
+  p.lp16 = (L + 15) / 16 * 16;
+  p.heads = heads;
+  p.d = d;
+  p.items = B * heads;
+  p.split = L <= 128 ? 1 : 0;
+  p.n_groups = p.split ? (p.items + 1) / 2 : p.items;
+  p.na = p.lp16 < 128 ? p.lp16 : 128;
+  p.nb = p.lp16 - p.na;
+  static int pingpong = -1, dbg = -1, tracing = -1, npoly = -1;
+  if (pingpong < 0) pingpong = env_int("PC_ATTN6_PINGPONG", 1);
+  if (dbg < 0) dbg = env_int("PC_ATTN6_DEBUG", 0);
+  if (tracing < 0) tracing = env_int("PC_ATTN_TRACE", 0);
+  if (npoly < 0) npoly = env_int("PC_ATTN6_POLY", 0);  // pairs (of 8 per 16-key chunk) on the FMA-pipe polynomial
+  p.pingpong = pingpong;
+  p.debug = dbg;
+  const int smem_bytes = OFF_BARS + static_cast<int>(sizeof(Bars6));
+  static_assert(OFF_BARS + sizeof(Bars6) <= 227 * 1024, "attention6: shared memory budget");
+  static long long* trace = nullptr;
+  if (tracing) {
+    if (!trace) PC_CHECK_CUDA(cudaMalloc(&trace, 8 * 2 * 16 * sizeof(long long)));
+    PC_CHECK_CUDA(cudaMemsetAsync(trace, 0, 8 * 2 * 16 * sizeof(long long), stream));
+    p.trace = trace;
+  }
+  CUtensorMap tmQ, tmT, tmO;
+  const uint64_t rows = static_cast<uint64_t>(B) * L;
+  const int tail_rows = p.split ? p.na : p.nb;  // split: the K / V box of one item; else part b of the shared item
+  PC_TRY(make_tmap_f16_2d(&tmQ, qkv, 3 * d, rows, static_cast<uint64_t>(3 * d) * 2, 64, 128));
+  PC_TRY(make_tmap_f16_2d(&tmT, qkv, 3 * d, rows, static_cast<uint64_t>(3 * d) * 2, 64, tail_rows));
+  PC_TRY(make_tmap_f16_3d(&tmO, out, d, L, B, static_cast<uint64_t>(d) * 2, static_cast<uint64_t>(L) * d * 2, 32, 32));
+  const int sms = device_sm_count();
+  const int grid = p.n_groups < sms ? p.n_groups : sms;
+  if (causal) PC_TRY((launch_variant6<true, 0>(grid, smem_bytes, stream, tmQ, tmT, tmO, p)));
+  else if (npoly == 0) PC_TRY((launch_variant6<false, 0>(grid, smem_bytes, stream, tmQ, tmT, tmO, p)));
+  else if (npoly == 1) PC_TRY((launch_variant6<false, 1>(grid, smem_bytes, stream, tmQ, tmT, tmO, p)));
+  else if (npoly == 2) PC_TRY((launch_variant6<false, 2>(grid, smem_bytes, stream, tmQ, tmT, tmO, p)));
+  else if (npoly == 3) PC_TRY((launch_variant6<false, 3>(grid, smem_bytes, stream, tmQ, tmT, tmO, p)));
+  else PC_TRY((launch_variant6<false, 4>(grid, smem_bytes, stream, tmQ, tmT, tmO, p)));
+  if (tracing) {
+    static int printed = 0;
+    static long long h[8 * 2 * 16];
+    PC_CHECK_CUDA(cudaStreamSynchronize(stream));
+    PC_CHECK_CUDA(cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost));
+    if (printed++ == 3) {
+      const long long t0 = h[0];
+      fprintf(stderr, "[attn6 trace] items=%d L=%d (cycles since WG 0's first tile; CTA 0, warp quarter 0, thread 0 of the row)\n",
+              p.items, L);
+      fprintf(stderr, "tile WG    start | s_full  rowmax  turn    exp_b   exp_a   pv_done o_read  stored\n");
+      for (int t = 0; t < 8; ++t)
+        for (int w = 0; w < 2; ++w) {
+          const long long* r = h + (t * 2 + w) * 16;
+          if (!r[0]) continue;
+          fprintf(stderr, "%3d  %d %8lld | +%5lld  +%5lld  +%5lld  +%5lld  +%5lld  +%5lld  +%5lld  +%5lld\n", t, w, r[0] - t0,
+                  r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4], r[6] - r[5], r[7] - r[6], r[8] - r[7]);
+        }
+    }
+  }
+  return PC_OK;
+}
+
+}  // namespace pc

@@ -56,8 +56,11 @@ int gemm_stats_parts(int M, int N);
 // qkv: [B*L, 3*d] fp16, columns [0,d) = q, [d,2d) = k, [2d,3d) = v, head h at h*64 (nn.MultiheadAttention
 // packed in-proj order). out: [B*L, d] fp16 (heads merged). head_dim is fixed at 64 (all CLIP towers).
 int launch_attention(const __half* qkv, __half* out, int B, int L, int heads, int causal, cudaStream_t stream);
-// attention5.cu: the L <= 256 kernel (four query tiles in flight per SM); launch_attention dispatches to it.
-// PC_ATTN_TWO_TILES=1 keeps every shape on attention.cu's two-tile kernel (A/B timing).
+// attention6.cu: the L <= 256 kernel (whole score row in TMEM, exact softmax, two query tiles in flight per SM);
+// launch_attention dispatches to it. PC_ATTN_IMPL=5 selects the round-1 kernel (attention5.cu: 64-key blocks, online
+// softmax, four tiles in flight), PC_ATTN_IMPL=2 keeps every shape on attention.cu's streaming kernel (A/B timing).
+bool attention6_supports(int L);
+int launch_attention6(const __half* qkv, __half* out, int B, int L, int heads, int causal, cudaStream_t stream);
 bool attention5_supports(int L);
 int launch_attention5(const __half* qkv, __half* out, int B, int L, int heads, int causal, cudaStream_t stream);
 

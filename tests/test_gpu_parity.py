@@ -78,7 +78,12 @@ def test_linear_residual_in_place(nat):
                                               (1, 1, 1, False), (2, 128, 2, True), (2, 129, 2, False),
                                               (1, 50, 1, False), (3, 256, 3, False), (2, 577, 2, False),
                                               (1, 300, 3, True), (3, 193, 1, False), (2, 385, 1, True),
-                                              (40, 197, 12, False), (200, 77, 8, True)])
+                                              (40, 197, 12, False), (200, 77, 8, True),
+                                              # whole-row kernel (attention6.cu): part-b widths 16 .. 128, odd item counts
+                                              # in split mode, the RN50x16 attention pool, causal rows across both parts
+                                              (1, 145, 48, False), (2, 208, 1, False), (2, 200, 2, False), (3, 130, 1, False),
+                                              (2, 144, 1, False), (1, 16, 1, False), (5, 64, 3, True), (3, 127, 1, False),
+                                              (3, 255, 2, True), (1, 256, 1, True), (13, 197, 12, False), (3, 33, 1, True)])
 def test_attention(nat, B, L, heads, causal):
     torch.manual_seed(L)
     d = heads * 64
