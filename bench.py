@@ -31,6 +31,20 @@ N_CLASSES, K_SHOTS, N_TEMPLATES = 1000, 16, 7
 ALPHA, BETA = 0.5, 12.0
 METRIC = "query images/sec, ImageNet 1000-way 16-shot ViT-B/16"
 
+# BASELINE.json `configs`: c2 is the headline (the metric is quoted on it); c3 / c4 / c5 are reported as `secondary`
+# entries of the same JSON line (query path only, random prototypes: the memory-bank build is c2's prelude).
+# alpha / beta: the reference's configs/{imagenet,fewsol_198,sun397}.yml.
+WORKLOADS = {
+    "c2": dict(arch="ViT-B/16", n_classes=1000, adapter="fc", alpha=0.5, beta=12.0, batch=1024, micro_batch=96,
+               name="imagenet 16-shot ViT-B/16 fc adapter, 1000-way eval (configs[1])"),
+    "c3": dict(arch="ViT-L/14", n_classes=198, adapter="conv-3x", alpha=0.2, beta=12.0, batch=512, micro_batch=64,
+               name="fewsol_198 16-shot ViT-L/14 conv-3x adapter, Proto-CLIP-F (configs[2])"),
+    "c4": dict(arch="ViT-L/14@336px", n_classes=1000, adapter="fc", alpha=0.5, beta=12.0, batch=256, micro_batch=32,
+               name="imagenet 16-shot ViT-L/14@336px fc adapter, query batch sharded over the ranks (configs[3])"),
+    "c5": dict(arch="RN50x16", n_classes=397, adapter="conv-2x", alpha=1.0, beta=11.0, batch=256, micro_batch=64,
+               name="sun397 16-shot RN50x16, main.qt.py path, conv-2x adapter (configs[4])"),
+}
+
 
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -48,8 +62,8 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+    def __init__(self, index: int, period: float = 0.2):
+        self.index, self.period, self.rows, self._stop, self._t = index, period, [], threading.Event(), None
 
     def _run(self):
         while not self._stop.is_set():
@@ -59,7 +73,7 @@ class ClockSampler:
                 self.rows.append([c.strip() for c in out.strip().split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(self.period)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -168,6 +182,16 @@ def run_ours(args):
     def step_resident(i):
         return clf.classify(pool_dev[i % 2])[1]
 
+    # ---- roofline legs first, on an idle GPU (rank 0; the others wait at the barrier below): the attention kernel
+    #      alone (burst clocks) and the four Linear launches of a block with the towers' own epilogues (burst loop +
+    #      a 1.5 s loop that reaches the power-capped clocks of the step), CUDA events on the launching stream
+    roof = attn = None
+    g = c["image_resolution"] // c["vision_patch_size"]
+    if rank == 0 and not args.lite:
+        attn = attention_roofline(nat, dev, local_rank, mb or 96, g * g + 1, c["vision_width"] // 64)
+        roof = gemm_roofline(ctx, dev, local_rank, mb or 96, g * g + 1, c["vision_width"])
+    pdist.barrier()
+
     # ---- value: inputs resident in HBM, CUDA events on the launching stream, barrier + sync both sides
     for i in range(args.warmup):
         step_resident(i)
@@ -232,20 +256,20 @@ def run_ours(args):
     ms_e2e = pdist.max_over_ranks(t0.elapsed_time(t1), dev)
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
 
-    # ---- roofline of the dominant kernel family (gemm_tn_kernel: the 4 Linears of a ResidualAttentionBlock at
-    #      the micro-batch's M), timed live with CUDA events on the launching stream
-    roof = None
-    if rank == 0:
-        roof = gemm_roofline(nat, dev, (mb or 96) * (c["image_resolution"] // c["vision_patch_size"]) ** 2 + (mb or 96),
-                             c["vision_width"])
-    attn = None
-    if rank == 0:
-        attn = attention_roofline(nat, dev, mb or 96, (c["image_resolution"] // c["vision_patch_size"]) ** 2 + 1,
-                                  c["vision_width"] // 64)
+    # ---- parity leg at every world size (rank 0, first cpu-sample queries of its batch 0) + the CPU baseline (N = 1)
     cpu = None
     parity = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu, parity = cpu_baseline_and_parity(sd, head, pool_host[0], clf, pool_dev[0], args.cpu_sample)
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu, parity = cpu_baseline_and_parity(sd, head, pool_host[0], clf, pool_dev[0], args.cpu_sample,
+                                              timed=(world == 1))
+    # ---- the other BASELINE.json configs (query path, resident images), same launch / timing rules
+    del clf, pool_dev, stage
+    torch.cuda.empty_cache()
+    secondary = []
+    if not args.no_secondary:
+        for key in args.secondary.split(","):
+            if key and key != "c2":
+                secondary.append(run_workload_lite(key, args.secondary_steps, 2, rank, local_rank, world, dev))
 
     if rank == 0:
         layers = c["vision_layers"]
@@ -260,7 +284,7 @@ def run_ours(args):
             "metric": METRIC, "value": round(value, 1), "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": "imagenet 16-shot ViT-B/16 fc adapter, 1000-way eval (configs[1])",
+            "config": {"workload": WORKLOADS["c2"]["name"],
                        "backbone": ARCH, "n_classes": N_CLASSES, "shots": K_SHOTS, "adapter": "fc", "alpha": ALPHA,
                        "beta": BETA, "batch_per_gpu": B, "micro_batch": mb or 96, "image": "3x224x224 fp32",
                        "l2": "inputs larger than L2 (616 MB per batch, 2 alternating batches)",
@@ -273,98 +297,204 @@ def run_ours(args):
             "model_frac_of_sustained_peak": round(value / world * flops_img / 1e12 / sustained, 4),
             "accuracy_on_synthetic_queries": round(acc, 4),
             "roofline": roof, "roofline_attention": attn, "cpu_baseline": cpu, "parity": parity, "peaks": src,
+            "secondary": secondary,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
 
 
-def gemm_roofline(nat, dev, M, d):
-    """Average device time of the four GEMM launches of one ResidualAttentionBlock (QKV, out-proj, c_fc, c_proj)."""
-    sustained, burst, src = measured_peaks()
-    torch.manual_seed(0)
-    x = (torch.randn(M, d, device=dev) * 0.5).half()
-    h4 = (torch.randn(M, 4 * d, device=dev) * 0.5).half()
-    res = torch.randn(M, d, device=dev).half()
-    w_qkv = (torch.randn(3 * d, d, device=dev) * 0.03).half()
-    w_o = (torch.randn(d, d, device=dev) * 0.03).half()
-    w_fc = (torch.randn(4 * d, d, device=dev) * 0.03).half()
-    w_pr = (torch.randn(d, 4 * d, device=dev) * 0.03).half()
-    b3, b1, b4 = [torch.zeros(n * d, device=dev).half() for n in (3, 1, 4)]
+def flops_per_image(arch: str) -> float:
+    from proto_clip_b200 import synthetic
+    c = synthetic.arch_config(arch)
+    return synthetic.rn_flops_per_image(arch) if isinstance(c["vision_layers"], tuple) else synthetic.vit_flops_per_image(arch)
 
-    def block():
-        nat.linear(x, w_qkv, b3, nat.EPI_BIAS)
-        nat.linear(x, w_o, b1, nat.EPI_BIAS_RESIDUAL, residual=res)
-        nat.linear(x, w_fc, b4, nat.EPI_BIAS_QUICKGELU)
-        nat.linear(h4, w_pr, b1, nat.EPI_BIAS_RESIDUAL, residual=res)
 
-    for _ in range(5):
-        block()
+def run_workload_lite(key: str, steps: int, warmup: int, rank: int, local_rank: int, world: int, dev) -> dict:
+    """One of BASELINE.json's other configs through the same public path (FewShotClassifier.classify: encode_image ->
+    /norm -> adapter -> /norm -> P -> argmax), images resident in HBM, random prototypes. Weak scaling: every rank
+    runs `batch` query images per step; the value is the whole-job aggregate over the max-over-ranks device time."""
+    from proto_clip_b200 import _native as nat
+    from proto_clip_b200 import dist as pdist
+    from proto_clip_b200 import pipeline, synthetic
+    w = WORKLOADS[key]
+    c = synthetic.arch_config(w["arch"])
+    R, D, N = c["image_resolution"], c["embed_dim"], w["n_classes"]
+    sd = synthetic.make_state_dict(w["arch"], 0)
+    ctx = nat.Context(dev)
+    ctx.bind_visual(sd)
+    del sd
+    g = torch.Generator(device=dev).manual_seed(9)
+    V = nat.l2_normalize(torch.randn(N * K_SHOTS, D, generator=g, device=dev).half())
+    T = nat.l2_normalize(torch.randn(N, D, generator=g, device=dev).half())
+    kind = w["adapter"]
+    adapter = synthetic.make_adapter_state_dict("fc" if kind == "fc" else "conv", D, seed=4,
+                                                out_gain=synthetic.trained_like_gain(D))
+    head = pipeline.build_head_state(V, T, N, K_SHOTS, kind, adapter, w["alpha"], w["beta"])
+    clf = pipeline.FewShotClassifier(ctx, head, micro_batch=w["micro_batch"])
+    B = w["batch"]
+    pool = [torch.randn(B, 3, R, R, device=dev, generator=g) for _ in range(2)]  # 2 x >= 115 MB per rank
+    for i in range(warmup):
+        clf.classify(pool[i % 2])
+    torch.cuda.synchronize()
+    pdist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(steps):
+            clf.classify(pool[i % 2])
+        e1.record()
+        torch.cuda.synchronize()
+    pdist.barrier()
+    ms = pdist.max_over_ranks(e0.elapsed_time(e1), dev)
+    value = world * B * steps / (ms / 1e3)
+    sustained, _, src = measured_peaks()
+    fl = flops_per_image(w["arch"])
+    out = {"workload": w["name"], "key": key, "backbone": w["arch"], "n_classes": N, "adapter": kind,
+           "value": round(value, 1), "unit": "images/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+           "batch_per_gpu": B, "micro_batch": w["micro_batch"], "ms_per_step": round(ms / steps, 3),
+           "model_tflops": round(value * fl / 1e12, 1),
+           "model_frac_of_sustained_peak": round(value / world * fl / 1e12 / sustained, 4),
+           "clocks": clocks.summary(), "data": "synthetic, resident in HBM, random prototypes"}
+    del clf, head, ctx, pool
+    torch.cuda.empty_cache()
+    return out
+
+
+def timed_loop(fn, min_ms: float, index: int):
+    """fn back to back for at least min_ms of device time (CUDA events on the launching stream); returns
+    (ms per call, median SM clock sampled by a background nvidia-smi thread while the loop ran, or None when the
+    loop is shorter than the sampling period)."""
+    for _ in range(3):
+        fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    iters = 50
     e0.record()
-    for _ in range(iters):
-        block()
+    for _ in range(10):
+        fn()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
+    iters = max(20, int(min_ms / max(e0.elapsed_time(e1) / 10, 1e-3)))
+    with ClockSampler(index, period=0.05) as clocks:
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters, clocks.summary()["sm_mhz"]
+
+
+def gemm_roofline(ctx, dev, index, B, L, d):
+    """The four Linear launches of one ResidualAttentionBlock exactly as the towers run them
+    (pc_resblock_forward_parts, parts = GEMMs: EPI_LN_BIAS QKV, EPI_BIAS_RES + row statistics out_proj, EPI_LN_QGELU
+    c_fc, EPI_BIAS_RES + statistics c_proj; clip/model.py:187-190) at the micro-batch's M = B*L. Timed twice: a short
+    loop on an idle GPU (burst clocks -> burst peak) and a >= 1.5 s loop (power-capped clocks, as inside the step ->
+    sustained peak). `frac` is the sustained one."""
+    from proto_clip_b200 import _native as nat
+    sustained, burst, src = measured_peaks()
+    torch.manual_seed(0)
+    x = (torch.randn(B * L, d, device=dev) * 0.5).half()
+    x0 = x.clone()
+    ctx.resblock_forward_parts(nat.PC_TOWER_VISUAL, 0, x, B, L, False, parts=3, chained=False)  # leaves valid statistics
+
+    def block():
+        ctx.resblock_forward_parts(nat.PC_TOWER_VISUAL, 0, x, B, L, False, parts=1, chained=True)
+
+    time.sleep(0.5)
+    ms_b, mhz_b = timed_loop(block, 10.0, index)
+    x.copy_(x0)
+    ms_s, mhz_s = timed_loop(block, 1500.0, index)
+    M = B * L
     flops = 24.0 * M * d * d
-    achieved = flops / (ms / 1e3) / 1e12
-    # DRAM read + write bytes of the same four launches (QKV 68.0 MB, out-proj 60.4 MB, c_fc 95.3 MB, c_proj 164.7 MB),
-    # one `ncu --set full` capture with cold caches: profiles/r01_ncu_gemm_summary.txt. Only valid for that shape.
+    tf_b, tf_s = flops / (ms_b / 1e3) / 1e12, flops / (ms_s / 1e3) / 1e12
+    # DRAM read + write bytes of the same four launches from one `ncu --set full` capture with cold caches
+    # (profiles/README.md names the file); only valid for the c2 shape.
     traffic = 388.4e6 if (M, d) == (18912, 768) else None
-    return {"bound": "tensor", "achieved": round(achieved, 1), "peak": sustained, "unit": "TFLOP/s",
-            "frac": round(achieved / sustained, 4), "traffic": traffic,
-            "kernel": f"gemm_tn_kernel<pair,*>: 4 Linear launches of one ResidualAttentionBlock, M={M}, d={d}",
-            "flops_per_4_launches": flops, "ms_per_4_launches": round(ms, 4), "peak_kind": f"bf16 sustained ({src})"}
+    return {"bound": "tensor", "achieved": round(tf_s, 1), "peak": sustained, "unit": "TFLOP/s",
+            "frac": round(tf_s / sustained, 4), "traffic": traffic,
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the four launches, ncu --set full, cold "
+                              "caches (profiles/r02_ncu_gemm_summary.txt); algorithmic bytes 4 launches = 537 MB",
+            "kernel": f"gemm_tn_kernel<pair, EPI_LN_BIAS | EPI_BIAS_RES | EPI_LN_QGELU | EPI_BIAS_RES>: the 4 Linear "
+                      f"launches of one ResidualAttentionBlock as the tower runs them, M={M}, d={d}",
+            "flops_per_4_launches": flops, "ms_per_4_launches": round(ms_s, 4), "sm_mhz": mhz_s,
+            "peak_kind": f"bf16 sustained ({src}); loop of >= 1.5 s, power-capped clocks like the step",
+            "burst": {"achieved": round(tf_b, 1), "peak": burst, "frac": round(tf_b / burst, 4),
+                      "ms_per_4_launches": round(ms_b, 4), "sm_mhz": mhz_b,
+                      "peak_kind": f"bf16 burst ({src}); 10 ms loop on an idle GPU"}}
 
 
-def attention_roofline(nat, dev, B, L, heads):
-    """attention_kernel alone at the micro-batch's shape: algorithmic 4*B*heads*L^2*64 flop per launch (QK^T + PV)."""
+def attention_roofline(nat, dev, index, B, L, heads):
+    """The attention kernel alone at the micro-batch's shape: algorithmic 4*B*heads*L^2*64 flop per launch (QK^T + PV).
+    Timed on an idle GPU before the step loops (a kernel timed alone -> burst peak); the SM clock during the loop is
+    recorded: right after the GEMM-heavy step the power-capped clock (1.4 GHz) would inflate the time by a third."""
     sustained, burst, src = measured_peaks()
     torch.manual_seed(1)
     qkv = torch.randn(B * L, 3 * heads * 64, device=dev).half()
-    for _ in range(5):
-        nat.attention(qkv, B, L, heads, False)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    iters = 100
-    e0.record()
-    for _ in range(iters):
-        nat.attention(qkv, B, L, heads, False)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
+    time.sleep(0.5)
+    ms, mhz = timed_loop(lambda: nat.attention(qkv, B, L, heads, False), 300.0, index)
     flops = 4.0 * B * heads * L * L * 64
     achieved = flops / (ms / 1e3) / 1e12
     exps = float(B) * heads * L * L
+    name = "attention6_kernel (whole-row S in TMEM, L <= 208)" if L <= 208 else "attention_kernel (64-key blocks)"
     return {"bound": "tensor", "achieved": round(achieved, 1), "peak": burst, "unit": "TFLOP/s",
             "frac": round(achieved / burst, 4), "traffic": None,
-            "kernel": f"{'attention5_kernel' if L <= 256 else 'attention_kernel'}<causal=false>: B={B}, L={L}, heads={heads}, head_dim=64",
-            "flops_per_launch": flops, "us_per_launch": round(ms * 1e3, 2), "peak_kind": f"bf16 burst ({src})",
-            "note": "softmax-bound at head_dim 64: one exp2 per 256 tensor flops; the MUFU pipe (16 exp2/clk/SM) "
-                    "caps this shape at about 0.55 of the tensor peak",
+            "kernel": f"{name}<causal=false>: B={B}, L={L}, heads={heads}, head_dim=64",
+            "flops_per_launch": flops, "us_per_launch": round(ms * 1e3, 2), "sm_mhz": mhz,
+            "peak_kind": f"bf16 burst ({src})",
+            "note": "head_dim 64: one exp2 per 256 tensor flops; the MUFU pipe (16 exp2/clk/SM) alone bounds this shape "
+                    "at 9.9 us = 0.69 of the tensor peak, the M = 128 / N <= 208 UMMA shapes at 0.55",
             "gexp_per_s": round(exps / (ms / 1e3) / 1e9, 1)}
 
 
-def cpu_baseline_and_parity(sd, head, host_images, clf, dev_images, sample):
-    """The reference algorithm (oracle port, fp32 like clip.load(device='cpu')) on this box's host cores, on the
-    first `sample` queries of batch 0; also the argmax parity of the CUDA path on exactly those queries."""
+def reference_step_fn(sd, asd, D, zi, zt, alpha, beta):
+    """(step(images) -> (p, argmax), kind): the reference's OWN modules on the CPU when they can be imported
+    (/root/reference, or the byte-for-byte snapshot oracle/make_ref.py left in oracle/_ref/): clip/model.py build_model
+    + encode_image (clip/model.py:338-339, fp32 like clip.load(device='cpu'), clip/clip.py:137-138), utils.py:351-352
+    normalisation, model.py:81-95 Adapter_FC, utils.py:225-244 P, main.py:438 argmax. Else the oracle port."""
     from oracle import protoclip_oracle as O
+    from oracle import reference_shims
+    if reference_shims.available():
+        ref = reference_shims.reference()
+        model = ref.clip_model.build_model({k: v.clone() for k, v in sd.items()}).float()
+        adapter = ref.model.Adapter_FC(D, dtype=torch.float32)
+        adapter.load_state_dict({k: v.float() for k, v in asd.items()})
+
+        def step(images):
+            f = model.encode_image(images)
+            f = f / f.norm(dim=-1, keepdim=True)
+            q = adapter(f)
+            q = q / q.norm(dim=-1, keepdim=True)
+            p = ref.utils.P(q, zi, zt, alpha, beta)
+            return p, p.max(1)[1]
+        where = "oracle/_ref snapshot of the reference" if reference_shims.is_snapshot() else reference_shims.REFERENCE_ROOT
+        return step, "reference", f"clip/model.py + model.py + utils.py of {where}"
+
+    def step(images):
+        p, pr, _ = O.classify_queries(sd, asd, "fc", images, zi, zt, alpha, beta, "fp32")
+        return p, pr
+    return step, "port", "oracle/protoclip_oracle.py"
+
+
+def cpu_baseline_and_parity(sd, head, host_images, clf, dev_images, sample, timed=True):
+    """The reference path (fp32 like clip.load(device='cpu')) on this box's host cores, on the first `sample` queries
+    of batch 0; also the argmax parity of the CUDA path on exactly those queries."""
     torch.set_num_threads(os.cpu_count() or 1)
     zi, zt = head.z_img.float().cpu(), head.z_txt.float().cpu()
     asd = {k: v.cpu() for k, v in head.adapter.items()}
+    step, kind, what = reference_step_fn(sd, asd, zi.shape[1], zi, zt, ALPHA, BETA)
     imgs = host_images[:sample].clone()
     bs = 32
     with torch.no_grad():
-        O.classify_queries(sd, asd, "fc", imgs[:bs], zi, zt, ALPHA, BETA, "fp32")  # warm-up
+        if timed:
+            step(imgs[:bs])  # warm-up
         best, preds, ps = float("inf"), [], []
-        for rep in range(2):
+        for rep in range(2 if timed else 1):
             t = time.perf_counter()
             preds, ps = [], []
             for i in range(0, sample, bs):
-                p, pr, _ = O.classify_queries(sd, asd, "fc", imgs[i:i + bs], zi, zt, ALPHA, BETA, "fp32")
+                p, pr = step(imgs[i:i + bs])
                 preds.append(pr)
                 ps.append(p)
             best = min(best, time.perf_counter() - t)
@@ -372,9 +502,11 @@ def cpu_baseline_and_parity(sd, head, host_images, clf, dev_images, sample):
     p_gpu, pred_gpu, _ = clf.classify(dev_images[:sample], want_p=True)
     top2 = p_cpu.topk(2, dim=1).values
     mism = int((pred_gpu.cpu() != pred_cpu).sum())
-    cpu = {"value": round(sample / best, 2), "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
-           "sample": f"first {sample} queries of batch 0, batch 32, fp32, best of 2 after 1 warm-up (oracle/protoclip_oracle.py)"}
-    parity = {"checked": sample, "argmax_mismatches": mism,
+    cpu = None
+    if timed:
+        cpu = {"value": round(sample / best, 2), "unit": "images/s", "cores": os.cpu_count(), "kind": kind,
+               "sample": f"first {sample} queries of batch 0, batch 32, fp32, best of 2 after 1 warm-up ({what})"}
+    parity = {"checked": sample, "against": kind, "argmax_mismatches": mism,
               "max_abs_dp": round((p_gpu.cpu() - p_cpu).abs().max().item(), 6),
               "min_top1_top2_margin_ref": round((top2[:, 0] - top2[:, 1]).min().item(), 6)}
     return cpu, parity
@@ -402,23 +534,10 @@ def run_reference(args):
     bs = args.ref_batch
     bases = synthetic.class_bases(8, R, seed=1)
     imgs = synthetic.class_structured_images(bases, torch.arange(bs) % 8, seed=3)
-    kind = "port"
-    if reference_shims.available():
-        ref = reference_shims.reference()
-        model = ref.clip_model.build_model({k: v.clone() for k, v in sd.items()}).float()  # clip/clip.py:137-138
-        adapter = ref.model.Adapter_FC(D, dtype=torch.float32)
-        adapter.load_state_dict({k: v.float() for k, v in asd.items()})
-        kind = "reference"
+    step_fn, kind, what = reference_step_fn(sd, asd, D, zi, zt, ALPHA, BETA)
 
-        def step():
-            f = model.encode_image(imgs)
-            f = f / f.norm(dim=-1, keepdim=True)
-            q = adapter(f)
-            q = q / q.norm(dim=-1, keepdim=True)
-            return ref.utils.P(q, zi, zt, ALPHA, BETA).max(1)[1]
-    else:
-        def step():
-            return O.classify_queries(sd, asd, "fc", imgs, zi, zt, ALPHA, BETA, "fp32")[1]
+    def step():
+        return step_fn(imgs)[1]
 
     for _ in range(max(1, min(args.warmup, 2))):
         step()
@@ -428,7 +547,7 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t
     v = round(bs * steps / dt, 2)
-    sample = f"{steps} steps of {bs} synthetic queries, fp32, {os.cpu_count()} threads ({kind})"
+    sample = f"{steps} steps of {bs} synthetic queries, fp32, {os.cpu_count()} threads ({what})"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": round(dt / steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
@@ -451,6 +570,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=128, help="queries timed on the host CPU for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lite", action="store_true", help="profiling mode: random head state, value arm only")
+    ap.add_argument("--secondary", default="c3,c4,c5", help="other BASELINE.json configs reported in `secondary`")
+    ap.add_argument("--secondary-steps", type=int, default=3)
+    ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--ref-batch", type=int, default=32)
     ap.add_argument("--ref-max-steps", type=int, default=6)
     args = ap.parse_args()

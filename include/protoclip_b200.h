@@ -173,6 +173,13 @@ int pc_encode_text(pc_ctx* ctx, const int64_t* tokens, int P, void* out, int l2n
 size_t pc_resblock_workspace_bytes(const pc_ctx* ctx, int tower, int B, int L);
 int pc_resblock_forward(pc_ctx* ctx, int tower, int layer, void* x, int B, int L, int causal, void* workspace,
                         size_t workspace_bytes, void* stream);
+/* Measurement entry (bench.py's roofline legs): the same block, restricted to `parts` (bit 0: its four Linear launches
+ * with the epilogues the towers use -- LayerNorm-folded QKV / c_fc, residual + row statistics for out_proj / c_proj,
+ * clip/model.py:187-190; bit 1: the attention launch, clip/model.py:183-185). chained = 1: the LayerNorm statistics
+ * left in the workspace by the previous call's c_proj are used (as between the blocks of a tower) instead of a fresh
+ * row-statistics pass. Results are only meaningful for parts = 3. */
+int pc_resblock_forward_parts(pc_ctx* ctx, int tower, int layer, void* x, int B, int L, int causal, int parts,
+                              int chained, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Building blocks, exposed because the reference's nn.Modules are (and the parity tests probe them):
  * nn.Linear / F.linear: out[M,N] = x[M,K] @ w[N,K]^T (+ bias) with the epilogues above. */

@@ -1,8 +1,9 @@
-"""Import the REAL reference (read-only tree at /root/reference) on a CPU-only box.  TEST INFRASTRUCTURE ONLY.
+"""Import the REAL reference (read-only tree at /root/reference, else the byte-for-byte snapshot of its hot-path
+files that oracle/make_ref.py leaves in oracle/_ref/) on a CPU-only box.  TEST INFRASTRUCTURE ONLY.
 
 Used by tests/golden/make_golden.py (fixture generation), by tests that pin oracle/protoclip_oracle.py against
-the live reference when the tree is present, and by bench.py --impl reference / cpu_baseline when the tree is
-present. /root/reference does not exist on the GPU box, so nothing in the `-m gpu` tests needs this.
+the live reference, and by bench.py --impl reference / cpu_baseline. /root/reference does not exist on the GPU box;
+the snapshot (git-ignored, not gpurun-ignored) travels there, so the CPU arm times the reference's own modules.
 
 The shims follow SURVEY.md §8(c): four stub modules for packages that are not installed here (ftfy,
 matplotlib, info_nce, gdown) — none of them touches the hot path's arithmetic (ftfy.fix_text is the identity
@@ -16,11 +17,26 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("PROTOCLIP_REFERENCE_ROOT", "/root/reference")
+SNAPSHOT_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _pick_root() -> str:
+    full = os.environ.get("PROTOCLIP_REFERENCE_ROOT", "/root/reference")
+    if os.path.isfile(os.path.join(full, "clip", "model.py")):
+        return full
+    return SNAPSHOT_ROOT
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def available() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "clip", "model.py"))
+
+
+def is_snapshot() -> bool:
+    """True when the modules come from oracle/_ref/ (hot-path files only) rather than a full checkout."""
+    return os.path.abspath(REFERENCE_ROOT) == os.path.abspath(SNAPSHOT_ROOT)
 
 
 def _stub(name: str, **attrs) -> types.ModuleType:

@@ -25,6 +25,7 @@ SYMBOLS = [
     "pc_text_bind_weights", "pc_rn_bind_weights", "pc_linear_shift_relu_forward",
     "pc_preprocess_workspace_bytes", "pc_preprocess_image", "pc_preprocess_batch_workspace_bytes", "pc_preprocess_batch", "pc_encode_image_workspace_bytes", "pc_encode_image",
     "pc_encode_text_workspace_bytes", "pc_encode_text", "pc_resblock_workspace_bytes", "pc_resblock_forward",
+    "pc_resblock_forward_parts",
     "pc_linear_forward", "pc_layernorm_forward", "pc_attention_forward", "pc_l2_normalize",
     "pc_adapter_fc_workspace_bytes", "pc_adapter_fc_forward", "pc_adapter_conv_forward", "pc_build_prototypes",
     "pc_proto_classify_workspace_bytes", "pc_proto_classify", "pc_proto_grid_search",
@@ -119,6 +120,7 @@ def load_library() -> C.CDLL:
     lib.pc_resblock_workspace_bytes.argtypes = [vp, i, i, i]
     lib.pc_resblock_workspace_bytes.restype = sz
     lib.pc_resblock_forward.argtypes = [vp, i, i, vp, i, i, i, vp, sz, vp]
+    lib.pc_resblock_forward_parts.argtypes = [vp, i, i, vp, i, i, i, i, i, vp, sz, vp]
     lib.pc_linear_forward.argtypes = [vp, i, vp, i, vp, vp, i, vp, i, i, i, i, i, vp]
     lib.pc_linear_shift_relu_forward.argtypes = [vp, i, vp, i, vp, vp, i, vp, i, i, i, i, i, i, vp]
     lib.pc_layernorm_forward.argtypes = [vp, vp, vp, vp, i, i, vp]
@@ -547,6 +549,19 @@ class Context:
             check(self.lib.pc_resblock_forward(self.handle, tower, layer, x.data_ptr(), B, L, int(causal),
                                                ws.data_ptr(), ws.numel(), stream_ptr(self.device)),
                   "pc_resblock_forward")
+        return x
+
+    def resblock_forward_parts(self, tower: int, layer: int, x: torch.Tensor, B: int, L: int, causal: bool,
+                               parts: int, chained: bool) -> torch.Tensor:
+        """Measurement entry (bench.py roofline legs): the block restricted to its four Linear launches (parts bit 0,
+        the towers' own LayerNorm-folded / residual + statistics epilogues) and / or its attention launch (bit 1)."""
+        x = require_cuda(x, torch.float16, "x")
+        nbytes = self.lib.pc_resblock_workspace_bytes(self.handle, tower, B, L)
+        ws = workspace(self.device, "tower", nbytes)
+        with torch.cuda.device(self.device):
+            check(self.lib.pc_resblock_forward_parts(self.handle, tower, layer, x.data_ptr(), B, L, int(causal),
+                                                     int(parts), int(chained), ws.data_ptr(), ws.numel(),
+                                                     stream_ptr(self.device)), "pc_resblock_forward_parts")
         return x
 
 

@@ -219,8 +219,9 @@ int build_folds(Tower& t) {
 //   out: s1 = gemm_stats_parts(rows, d) partial pairs of the new x (ready for the next block's ln_1)
 // QKV reads x directly with the gamma-scaled in_proj; out_proj writes the statistics of the row segments it
 // produces into s2; c_fc reads them (ln_2); c_proj writes the new s1. No atomics: results are bit-reproducible.
+// `parts` (measurement only, pc_resblock_forward_parts): bit 0 = the four GEMM launches, bit 1 = the attention launch.
 int resblock_fused(const Tower& t, int layer, __half* x, __half* h, __half* big, float* s1, int parts_in, float* s2,
-                   int B, int L, int causal, cudaStream_t s) {
+                   int B, int L, int causal, cudaStream_t s, int parts = 3) {
   const pc_resblock_weights& w = t.blocks[layer];
   const int d = t.width, rows = B * L;
   GemmArgs g{};
@@ -229,8 +230,9 @@ int resblock_fused(const Tower& t, int layer, __half* x, __half* h, __half* big,
   g.W = t.qkv_ln[layer].w; g.ldw = d;
   g.C = big; g.ldc = 3 * d;
   g.ln_stats = s1; g.ln_parts = parts_in; g.ln_s = t.qkv_ln[layer].s; g.ln_c = t.qkv_ln[layer].c;
-  PC_TRY(launch_gemm(g, EPI_LN_BIAS, s));
-  PC_TRY(launch_attention(big, h, B, L, t.heads, causal, s));
+  if (parts & 1) PC_TRY(launch_gemm(g, EPI_LN_BIAS, s));
+  if (parts & 2) PC_TRY(launch_attention(big, h, B, L, t.heads, causal, s));
+  if (!(parts & 1)) return PC_OK;
   g = GemmArgs{};
   g.M = rows; g.N = d; g.K = d;
   g.A = h; g.lda = d;
@@ -265,8 +267,11 @@ struct TowerWs {
   int* idx;
   float *s1, *s2;  // LayerNorm statistics [rows][parts][2] (ln_1 / ln_2 inputs)
 };
-// partial pairs per row: at most one per 64 output columns of a residual GEMM (gemm_stats_parts)
-size_t stats_bytes(int rows, int d) { return align_up(static_cast<size_t>(rows) * ((d + 63) / 64) * 8, 256); }
+// partial pairs per row: gemm_stats_parts() = 2 per column tile of the residual GEMM; sized for the worst case, the
+// 128-column tiles of the single-CTA kernel (2 * ceil(d / 128); d = 64 -> 2 pairs, not d / 64 = 1)
+size_t stats_bytes(int rows, int d) {
+  return align_up(static_cast<size_t>(rows) * (2 * ((d + 127) / 128)) * 8, 256);
+}
 size_t tower_ws_bytes(int rows, int d, int mb) {
   return align_up(static_cast<size_t>(rows) * d * 2, 256) * 2 + align_up(static_cast<size_t>(rows) * d * 8, 256) +
          align_up(static_cast<size_t>(mb) * 4, 256) + 2 * stats_bytes(rows, d);
@@ -795,6 +800,26 @@ int pc_resblock_forward(pc_ctx* ctx, int tower, int layer, void* x, int B, int L
     return resblock_fused(t, layer, static_cast<__half*>(x), ws.h, ws.big, ws.s1, 1, ws.s2, B, L, causal, s);
   }
   return resblock(t, layer, static_cast<__half*>(x), ws.h, ws.big, B, L, causal, s);
+}
+
+int pc_resblock_forward_parts(pc_ctx* ctx, int tower, int layer, void* x, int B, int L, int causal, int parts,
+                              int chained, void* workspace, size_t workspace_bytes, void* stream) {
+  PC_TRY(use_device(ctx));
+  PC_REQUIRE(tower == PC_TOWER_VISUAL || tower == PC_TOWER_TEXT, PC_ERR_ARG, "pc_resblock_forward_parts: tower %d", tower);
+  const Tower& t = tower == PC_TOWER_TEXT ? ctx->txt : ctx->vis;
+  PC_REQUIRE(t.bound, PC_ERR_STATE, "pc_resblock_forward_parts: tower %d is not bound", tower);
+  PC_REQUIRE(layer >= 0 && layer < t.layers, PC_ERR_ARG, "pc_resblock_forward_parts: layer %d of %d", layer, t.layers);
+  PC_REQUIRE(x && B > 0 && L > 0 && parts >= 1 && parts <= 3, PC_ERR_ARG, "pc_resblock_forward_parts: bad arguments");
+  PC_REQUIRE(fused_ln_enabled(), PC_ERR_STATE, "pc_resblock_forward_parts: needs the LayerNorm-folded path (PC_NO_FUSED_LN unset)");
+  PC_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, PC_ERR_ALIGN,
+             "pc_resblock_forward_parts: workspace must be 256-byte aligned");
+  PC_REQUIRE(workspace_bytes >= tower_ws_bytes(B * L, t.width, 1), PC_ERR_WORKSPACE,
+             "pc_resblock_forward_parts: workspace %zu < %zu", workspace_bytes, tower_ws_bytes(B * L, t.width, 1));
+  const TowerWs ws = carve(workspace, B * L, t.width, 1);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!chained) PC_TRY(launch_row_stats(static_cast<const __half*>(x), ws.s1, B * L, t.width, s));
+  return resblock_fused(t, layer, static_cast<__half*>(x), ws.h, ws.big, ws.s1,
+                        chained ? gemm_stats_parts(B * L, t.width) : 1, ws.s2, B, L, causal, s, parts);
 }
 
 int pc_linear_forward(const void* x, int ldx, const void* w, int ldw, const void* bias, const void* residual,

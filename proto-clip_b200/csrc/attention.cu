@@ -465,12 +465,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 template <bool CAUSAL>
 int launch_variant(int grid, int smem_bytes, cudaStream_t stream, const CUtensorMap& tmQ, const CUtensorMap& tmKV,
                    const CUtensorMap& tmO, const AttnParams& p) {
-  static int configured_bytes = 0;
+  static int configured[kMaxDevices];
   auto kern = attention_kernel<CAUSAL>;
-  if (smem_bytes > configured_bytes) {
-    PC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    configured_bytes = smem_bytes;
-  }
+  PC_CHECK_CUDA(ensure_dynamic_smem(kern, smem_bytes, configured));
   PC_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(ATT_THREADS), smem_bytes, stream, 1, tmQ, tmKV, tmO, p));
   return PC_OK;
 }

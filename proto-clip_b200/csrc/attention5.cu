@@ -407,12 +407,9 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 template <bool CAUSAL>
 int launch_variant5(int grid, int smem_bytes, cudaStream_t stream, const CUtensorMap& tmQ, const CUtensorMap& tmKV,
                     const CUtensorMap& tmKVt, const CUtensorMap& tmO, const Params5& p) {
-  static int configured_bytes = 0;
+  static int configured[kMaxDevices];
   auto kern = attention5_kernel<CAUSAL>;
-  if (smem_bytes > configured_bytes) {
-    PC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    configured_bytes = smem_bytes;
-  }
+  PC_CHECK_CUDA(ensure_dynamic_smem(kern, smem_bytes, configured));
   PC_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS5), smem_bytes, stream, 1, tmQ, tmKV, tmKVt, tmO, p));
   return PC_OK;
 }

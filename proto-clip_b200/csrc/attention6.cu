@@ -560,8 +560,9 @@ attention6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 template <bool CAUSAL, int NP>
 int launch_variant6(int grid, int smem_bytes, cudaStream_t stream, const CUtensorMap& tmQ, const CUtensorMap& tmT,
                     const CUtensorMap& tmO, const Params6& p) {
+  static int configured[kMaxDevices];
   auto kern = attention6_kernel<CAUSAL, NP>;
-  PC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  PC_CHECK_CUDA(ensure_dynamic_smem(kern, smem_bytes, configured));
   PC_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS6), smem_bytes, stream, 1, tmQ, tmT, tmO, p));
   return PC_OK;
 }

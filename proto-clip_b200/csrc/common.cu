@@ -145,12 +145,20 @@ bool pdl_enabled() {
   return v == 1;
 }
 
-int device_sm_count() {
-  static int n = 0;
-  if (n) return n;
+int current_device() {
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  return dev;
+}
+
+int device_sm_count() {
+  static int cache[kMaxDevices];  // 0 = unknown; racing writers store the same value
+  const int dev = current_device();
+  if (dev < 0) return 148;
+  if (dev < kMaxDevices && cache[dev]) return cache[dev];
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  if (dev < kMaxDevices) cache[dev] = n;
   return n;
 }
 

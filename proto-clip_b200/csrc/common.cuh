@@ -54,7 +54,22 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint32_t elem_bytes, uint64
 int make_tmap_f16_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t dim1, uint64_t dim2,
                      uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box_inner, uint32_t box_rows);
 
-int device_sm_count();
+int device_sm_count();  // SM count of the CURRENT device (cached per device)
+
+// The opt-in dynamic shared-memory limit (cudaFuncSetAttribute) is per device and a process may hold one pc_ctx per
+// GPU: remember the largest size configured for (kernel, device) so that the attribute call stays off the launch path.
+// `slots` is a zero-initialised static array of kMaxDevices atomics owned by the call site.
+constexpr int kMaxDevices = 64;
+int current_device();
+template <typename Kern>
+cudaError_t ensure_dynamic_smem(Kern kern, int bytes, int* slots) {
+  const int dev = current_device();
+  int* slot = &slots[dev < 0 || dev >= kMaxDevices ? 0 : dev];
+  if (bytes <= __atomic_load_n(slot, __ATOMIC_ACQUIRE) && dev >= 0 && dev < kMaxDevices) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) __atomic_store_n(slot, bytes, __ATOMIC_RELEASE);
+  return e;
+}
 
 // Programmatic dependent launch (PDL): kernels launched through launch_pdl() may be scheduled while the previous
 // kernel of the stream is still draining; they run their prologue (barrier init, TMEM allocation, descriptor

@@ -535,12 +535,9 @@ int launch_impl(const GemmArgs& a0, cudaStream_t stream) {
   using Smem = SmemT<EPI>;
   constexpr int BN = PAIR ? 256 : 128;
   constexpr int TILE_M = PAIR ? 256 : 128;
-  static bool configured = false;
+  static int configured[kMaxDevices];
   auto kern = gemm_tn_kernel<PAIR, EPI>;
-  if (!configured) {
-    PC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::TOTAL));
-    configured = true;
-  }
+  PC_CHECK_CUDA(ensure_dynamic_smem(kern, Smem::TOTAL, configured));
   GemmArgs a = a0;
   a.debug = debug_flags();
   CUtensorMap tmA, tmW, tmC, tmR;

@@ -375,11 +375,8 @@ int launch_proto_grid(const float* dots, int ld, const __half* q, int D, const f
              PC_ERR_ARG, "proto_grid: bad args");
   const int smem = 4 * N * static_cast<int>(sizeof(float));
   PC_REQUIRE(smem <= 200 * 1024, PC_ERR_ARG, "proto_grid: N=%d needs %d B smem", N, smem);
-  static int configured = 0;
-  if (smem > configured && smem > 48 * 1024) {
-    PC_CHECK_CUDA(cudaFuncSetAttribute(proto_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
-  }
+  static int configured[kMaxDevices];
+  if (smem > 48 * 1024) PC_CHECK_CUDA(ensure_dynamic_smem(proto_grid_kernel, smem, configured));
   proto_grid_kernel<<<Q, 256, smem, stream>>>(dots, ld, q, D, zi_n2, zt_n2, N, labels, alphas, n_alpha, betas, n_beta,
                                               counts);
   PC_CHECK_CUDA(cudaGetLastError());
@@ -424,11 +421,8 @@ int launch_adapter_conv(const AdapterConvW& w, int three_x, const __half* q, __h
   while (S * S < D) ++S;  // ceil(sqrt(D)) (model.py:27)
   const int smem = (1 + 32) * S * S * static_cast<int>(sizeof(__half));
   PC_REQUIRE(smem <= 200 * 1024, PC_ERR_ARG, "adapter_conv: D=%d needs %d B smem", D, smem);
-  static int configured = 0;
-  if (smem > configured) {
-    PC_CHECK_CUDA(cudaFuncSetAttribute(adapter_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
-  }
+  static int configured[kMaxDevices];
+  PC_CHECK_CUDA(ensure_dynamic_smem(adapter_conv_kernel, smem, configured));
   adapter_conv_kernel<<<Q, 256, smem, stream>>>(w, three_x, q, out, D, S);
   PC_CHECK_CUDA(cudaGetLastError());
   return PC_OK;

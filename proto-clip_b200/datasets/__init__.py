@@ -65,13 +65,18 @@ class _SyntheticLoader:
         return (len(self.split) + self.batch_size - 1) // self.batch_size
 
     def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
+        return self.iter_range(0, len(self))
+
+    def iter_range(self, lo: int, hi: int) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
+        """Batches [lo, hi) only (dist.sharded_batches): a batch's images depend on its index alone, so a rank that
+        starts in the middle of the split draws exactly what the single-process run draws there."""
         try:
             from .. import synthetic
         except ImportError:  # pragma: no cover
             from proto_clip_b200 import synthetic
         dev = torch.device("cuda", torch.cuda.current_device())
         bases = synthetic.class_bases(self.split.num_classes, _resolution, seed=1, device=dev)
-        for i in range(0, len(self.split), self.batch_size):
+        for i in range(lo * self.batch_size, min(hi * self.batch_size, len(self.split)), self.batch_size):
             labels = self.split.labels[i:i + self.batch_size]
             images = synthetic.class_structured_images(bases, labels.to(dev), seed=1000 * self.split.seed + i)
             yield images, labels

@@ -10,8 +10,13 @@ memory-bank / feature / hyper-parameter-search file formats, and printed accurac
   * episodic training (main.py:216-381) is outside the inference hot path: with `only_test: False` the run stops
     after the training-free evaluation and says so. Testing a trained Proto-CLIP-F needs its `_v/_t/_a.pt` files
     exactly as in the reference (main.py:385-398);
-  * every encoder / adapter / P call runs on libprotoclip_b200 (sm_100a); with torchrun the query features are
-    sharded across ranks (dist.py) after one broadcast of the prototype memory.
+  * every encoder / adapter / P call runs on libprotoclip_b200 (sm_100a);
+  * multi-GPU: `torchrun --nproc-per-node N proto-clip_b200/main.py ...` (the reference is single-GPU, README.md:44).
+    One process per GPU (dist.py): the memory-bank builders and pre_load_features shard their loader batches / prompts
+    over the ranks and meet in one all-gather each (utils.py), rank 0 alone writes the cache files, the prototype
+    memory is built on rank 0 and shipped in ONE broadcast, every rank scores its contiguous slice of the query
+    features (grid-search hit counts are summed, predictions gathered in query order). Results are identical to the
+    single-process run (tests/test_gpu_parity.py::test_cli_two_ranks_equal_one_rank).
 """
 from __future__ import annotations
 
@@ -30,6 +35,7 @@ if os.path.dirname(_HERE) not in sys.path:
     sys.path.insert(0, os.path.dirname(_HERE))
 
 from proto_clip_b200 import clip  # noqa: E402
+from proto_clip_b200 import dist as pdist  # noqa: E402
 from proto_clip_b200.model import Adapter, Adapter_FC  # noqa: E402
 from proto_clip_b200.utils import (P, beautify, build_cache_model, build_prototypes, get_model_dir_root,  # noqa: E402
                                    get_seed, get_textual_memory_bank, load, pre_load_features, predict, save)
@@ -107,17 +113,30 @@ def alpha_beta_lists():
     return alpha_list, beta_list
 
 
+def my_slice(n):
+    """This rank's contiguous share [lo, hi) of n query rows (everything for a single process)."""
+    rank, _, world = pdist.env_rank()
+    return pdist.shard_bounds(n, rank, world) if pdist.active() else (0, n)
+
+
 def grid_accuracy(features, labels, z_img_proto, z_text_proto):
     """[319, 3] float64 rows (alpha, beta, accuracy) — the format of zero_shot_hp_search_*.pkl (main.py:187-207)."""
     from proto_clip_b200 import _native as nat
     alpha_list, beta_list = alpha_beta_lists()
-    # one fused pass instead of 319 P() calls on identical matmuls: counts[a, b] = #correct at (alpha_a, beta_b)
-    q = features.half().contiguous()
+    # one fused pass instead of 319 P() calls on identical matmuls: counts[a, b] = #correct at (alpha_a, beta_b);
+    # every rank scores its slice of the queries, the integer hit counts are summed over the ranks
+    total = features.shape[0]
+    lo, hi = my_slice(total)
+    q = features[lo:hi].half().contiguous()
     zi, zt = z_img_proto.half().contiguous(), z_text_proto.half().contiguous()
-    counts = nat.proto_grid_search(q, zi, zt, zi.float().pow(2).sum(-1), zt.float().pow(2).sum(-1),
-                                   labels.to(q.device).long().contiguous(), alpha_list, beta_list)
+    if hi > lo:
+        counts = nat.proto_grid_search(q, zi, zt, zi.float().pow(2).sum(-1), zt.float().pow(2).sum(-1),
+                                       labels[lo:hi].to(q.device).long().contiguous(), alpha_list, beta_list)
+    else:
+        counts = torch.zeros((len(alpha_list), len(beta_list)), dtype=torch.int32, device=features.device)
+    counts = pdist.all_reduce_sum(counts)
     # `(pred == labels).float().mean()` of the reference: an fp32 division of an exactly representable count
-    acc = (counts.float() / float(q.shape[0])).cpu().numpy().astype(np.float64)
+    acc = (counts.float() / float(total)).cpu().numpy().astype(np.float64)
     rows = [[alpha, beta, acc[i, j]] for i, alpha in enumerate(alpha_list) for j, beta in enumerate(beta_list)]
     return np.array(rows)
 
@@ -142,7 +161,10 @@ def run_proto_clip(cfg, visual_memory_keys, visual_memory_values, val_features, 
     adapter = make_adapter(cfg, ndim)
 
     # ---- training-free evaluation: (alpha, beta) grid with zero-shot prototypes (main.py:166-207)
-    if all(os.path.exists(p) for p in paths.values()):
+    pdist.barrier()  # every rank sees the same cache state
+    cached = all(os.path.exists(p) for p in paths.values())
+    pdist.barrier()
+    if cached:
         val_acc = load(paths["val"], "hp based on val set")
         test_acc = load(paths["test"], "hp based on test set")
         train_acc = load(paths["train"], "hp based on test set")
@@ -152,6 +174,7 @@ def run_proto_clip(cfg, visual_memory_keys, visual_memory_values, val_features, 
             from proto_clip_b200 import _native as nat
             z_img_proto, _ = nat.build_prototypes(keys_t.half(), N, K, per_shot_norm=False)  # main.py:173-176
             z_text_proto = nat.l2_normalize(textual_memory_bank.t().contiguous().half())
+            z_img_proto, z_text_proto = pdist.broadcast_tensors([z_img_proto, z_text_proto])  # rank 0's prototypes
             train_features = nat.l2_normalize(keys_t.half())
             val_acc = grid_accuracy(nat.l2_normalize(val_features), val_labels, z_img_proto, z_text_proto)
             test_acc = grid_accuracy(nat.l2_normalize(test_features), test_labels, z_img_proto, z_text_proto)
@@ -161,19 +184,20 @@ def run_proto_clip(cfg, visual_memory_keys, visual_memory_values, val_features, 
         save(train_acc, paths["train"], "hp based on test set")
     za, zb, zacc = best_alpha_beta(val_acc)
     i = int(np.argmax(val_acc[:, 2]))
-    print(f"**** Zero-shot Proto-CLIP: best val accuracy {zacc * 100:.2f}% at alpha={za}, beta={zb}; "
+    log(f"**** Zero-shot Proto-CLIP: best val accuracy {zacc * 100:.2f}% at alpha={za}, beta={zb}; "
           f"test accuracy there {test_acc[i, 2] * 100:.2f}% ****")
 
     best_alpha, best_beta = cfg["alpha"], cfg["beta"]  # main.py:213-214
     if not cfg["only_test"]:
-        print("Episodic training of the memory banks / adapter (reference main.py:216-381) is outside this "
+        log("Episodic training of the memory banks / adapter (reference main.py:216-381) is outside this "
               "inference build; stopping after the training-free evaluation. Re-run with only_test once "
               "trained `_v/_t/_a.pt` files exist.")
-        return {"zero_shot_val_acc": zacc, "zero_shot_alpha": za, "zero_shot_beta": zb}
+        return {"zero_shot_val_acc": zacc, "zero_shot_alpha": za, "zero_shot_beta": zb, "val_grid": val_acc,
+                "test_grid": test_acc}
 
     # ---- testing a trained Proto-CLIP-F (main.py:383-455)
     with torch.no_grad():
-        print("Testing...")
+        log("Testing...")
         ab_dir = "alpha-beta" if VARIANT == "main" else "best-alpha-beta"  # main.py:385 / main.qt.py:327
         model_dir = f"{model_dir_root}/{ab_dir}/{best_alpha}-{best_beta}"
         model_prefix = f"best_lr_{cfg['lr']}_aug_{cfg['augment_epoch']}_epochs_{cfg['train_epoch']}"
@@ -185,6 +209,7 @@ def run_proto_clip(cfg, visual_memory_keys, visual_memory_values, val_features, 
         except Exception:
             raise FileNotFoundError(f"File does not exist: {pv} and {pt}")
         z_img_proto, z_text_proto = build_prototypes(embeddings_v.data.cuda(), embeddings_t.data.cuda(), K)
+        z_img_proto, z_text_proto = pdist.broadcast_tensors([z_img_proto, z_text_proto])  # rank 0's prototypes
         from proto_clip_b200 import _native as nat
         test_f = nat.l2_normalize(adapter(test_features))                      # main.py:407-409
         train_f = nat.l2_normalize(adapter(visual_memory_keys.t().contiguous()))
@@ -192,17 +217,31 @@ def run_proto_clip(cfg, visual_memory_keys, visual_memory_values, val_features, 
         val_acc = grid_accuracy(val_f_adapt, val_labels, z_img_proto, z_text_proto)
         test_acc_grid = grid_accuracy(test_f, test_labels, z_img_proto, z_text_proto)
         grid_accuracy(train_f, train_labels, z_img_proto, z_text_proto)
-        p = P(test_f, z_img_proto, z_text_proto, best_alpha, best_beta)
-        test_acc = (p.max(1)[1] == test_labels).float().mean()
-        print("**** Fixed-alp-beta: Proto-CLIP's test accuracy: {:.2f}% ****\n".format(test_acc * 100))
-        print("fixed_best_alpha", best_alpha, "fixed_best_beta", best_beta)
+        lo, hi = my_slice(test_f.shape[0])
+
+        def predictions(alpha, beta):
+            """P(...).max(1)[1] (main.py:436-438) on this rank's query slice, gathered in query order."""
+            mine = P(test_f[lo:hi], z_img_proto, z_text_proto, alpha, beta).max(1)[1] if hi > lo else \
+                torch.empty(0, dtype=torch.int64, device=test_f.device)
+            return pdist.all_gather_rows(mine, test_f.shape[0])
+
+        test_pred = predictions(best_alpha, best_beta)
+        test_acc = (test_pred == test_labels).float().mean()
+        log("**** Fixed-alp-beta: Proto-CLIP's test accuracy: {:.2f}% ****\n".format(test_acc * 100))
+        log("fixed_best_alpha", best_alpha, "fixed_best_beta", best_beta)
         ha, hb, _ = best_alpha_beta(val_acc)
-        p = P(test_f, z_img_proto, z_text_proto, ha, hb)
-        hp_acc = (p.max(1)[1] == test_labels).float().mean()
-        print("**** HP-search: Proto-CLIP's test accuracy: {:.2f}% ****\n".format(hp_acc * 100))
-        print("hp_search_best_alpha", ha, "hp_search_best_beta", hb)
+        hp_pred = predictions(ha, hb)
+        hp_acc = (hp_pred == test_labels).float().mean()
+        log("**** HP-search: Proto-CLIP's test accuracy: {:.2f}% ****\n".format(hp_acc * 100))
+        log("hp_search_best_alpha", ha, "hp_search_best_beta", hb)
     return {"test_acc": float(test_acc), "hp_test_acc": float(hp_acc), "hp_alpha": ha, "hp_beta": hb,
-            "test_acc_grid": test_acc_grid}
+            "test_acc_grid": test_acc_grid, "val_grid": val_acc, "test_pred": test_pred.cpu(), "hp_pred": hp_pred.cpu()}
+
+
+def log(*a, **k):
+    """print on rank 0 only (every rank computes the same numbers)."""
+    if pdist.is_main():
+        print(*a, **k)
 
 
 def seed_worker(worker_id):
@@ -218,11 +257,17 @@ def main(argv=None):
     if args.dataset is None:
         raise SystemExit("Please provide alias of dataset")
     cfg = populate_cfg_using_args(cfg, args)
+    rank, local_rank, world = pdist.init()       # torchrun: one process per GPU; a plain launch is rank 0 of 1
+    if torch.cuda.is_available():
+        torch.cuda.set_device(pdist.device_for(local_rank))
     cache_dir = os.path.join("./caches", cfg["dataset"])
     os.makedirs(cache_dir, exist_ok=True)
     cfg["cache_dir"] = cache_dir
-    print("\nRunning configs.")
-    print(cfg, "\n")
+    log("\nRunning configs.")
+    log(cfg, "\n")
+    if world > 1:
+        log(f"{world} ranks: loader batches / prompts / query features are sharded, one all-gather per bank, "
+            f"one broadcast of the prototypes")
 
     clip_model, preprocess = clip.load(cfg["backbone"])
     clip_model.eval()
@@ -234,7 +279,7 @@ def main(argv=None):
     torch.cuda.manual_seed_all(seed)
     n_workers, train_bs, val_bs, test_bs = 8, 1024, 1024, 1024
 
-    print("Preparing dataset.")
+    log("Preparing dataset.")
     from proto_clip_b200 import datasets
     datasets.configure(clip_model.visual.input_resolution)
     if cfg["dataset"] == "imagenet":
@@ -254,15 +299,17 @@ def main(argv=None):
         test_loader = datasets.build_data_loader(data_source=dataset.test, batch_size=test_bs, is_train=False,
                                                  tfm=preprocess, shuffle=False)
 
-    print("Constructing memory bank by few-shot visual and textual features.")
+    log("Constructing memory bank by few-shot visual and textual features.")
     visual_memory_keys, visual_memory_values = build_cache_model(cfg, clip_model, train_loader_cache)
     text_prompts, textual_memory_bank = get_textual_memory_bank(cfg, dataset.classnames, dataset.template, clip_model)
-    print("Loading visual features and labels from val set.")
+    log("Loading visual features and labels from val set.")
     val_features, val_labels = pre_load_features(cfg, "val", clip_model, val_loader)
-    print("Loading visual features and labels from test set.")
+    log("Loading visual features and labels from test set.")
     test_features, test_labels = pre_load_features(cfg, "test", clip_model, test_loader)
-    return run_proto_clip(cfg, visual_memory_keys, visual_memory_values, val_features, val_labels, test_features,
-                          test_labels, textual_memory_bank, clip_model, text_prompts)
+    out = run_proto_clip(cfg, visual_memory_keys, visual_memory_values, val_features, val_labels, test_features,
+                         test_labels, textual_memory_bank, clip_model, text_prompts)
+    pdist.barrier()
+    return out
 
 
 if __name__ == "__main__":

@@ -20,13 +20,24 @@ from tqdm import tqdm
 try:
     from . import _native as nat
     from . import clip
+    from . import dist as pdist
 except ImportError:  # pragma: no cover - top-level import when main.py runs as a script
     from proto_clip_b200 import _native as nat
     from proto_clip_b200 import clip
+    from proto_clip_b200 import dist as pdist
+
+# Multi-GPU (torchrun --nproc-per-node N main.py ...; dist.py): the three builders below shard their loader batches /
+# prompts over the ranks, meet in ONE all-gather each (per-row arithmetic does not depend on the shard, so the result
+# is bit-identical to the single-process run), and only rank 0 writes the cache files, between two barriers.
 
 
 def get_seed():
     return 1
+
+
+def _here():
+    """map_location of the cache files: this rank's device (they were written from rank 0's)."""
+    return f"cuda:{torch.cuda.current_device()}"
 
 
 def dir_exists(path):
@@ -34,6 +45,8 @@ def dir_exists(path):
 
 
 def save(obj, filepath, msg):
+    if not pdist.is_main():  # one writer per cache file
+        return
     print(f"Saving {msg} to {filepath}")
     with open(filepath, "wb") as handle:
         pickle.dump(obj, handle, protocol=pickle.HIGHEST_PROTOCOL)
@@ -92,8 +105,12 @@ def clip_classifier(classnames, template, clip_model):
         for classname in classnames:
             classname = classname.replace("_", " ")
             prompts += [t.format(classname) for t in template]
-        texts = clip.tokenize(prompts).cuda()
-        emb = nat.l2_normalize(clip_model.encode_text(texts))                    # utils.py:266-267
+        texts = clip.tokenize(prompts)
+        rank, _, world = pdist.env_rank()
+        lo, hi = pdist.shard_bounds(texts.shape[0], rank, world) if pdist.active() else (0, texts.shape[0])
+        emb = nat.l2_normalize(clip_model.encode_text(texts[lo:hi].cuda())) if hi > lo else \
+            torch.empty((0, clip_model.text_projection.shape[1]), dtype=torch.float16, device="cuda")  # utils.py:266-267
+        emb = pdist.all_gather_rows(emb, texts.shape[0])
         emb = emb.view(len(classnames), len(template), -1)
         mean = emb.float().mean(dim=1).half()                                    # fp16 mean, fp32 accumulation
         clip_weights = nat.l2_normalize(mean).t().contiguous()                   # utils.py:268-271
@@ -105,10 +122,13 @@ def get_textual_memory_bank(cfg, classnames, template, clip_model):
     model_dir_root = get_model_dir_root(cfg)
     os.makedirs(model_dir_root, exist_ok=True)
     path = os.path.join(model_dir_root, f"text_mb_{beautify(cfg['backbone'])}_K_{cfg['shots']}.pkl")
+    pdist.barrier()  # every rank sees the same cache state
     if dir_exists(path):
         return classnames, load(path, msg)
+    pdist.barrier()
     text_prompts, textual_memory_bank = clip_classifier(classnames, template, clip_model)
     save(textual_memory_bank, path, msg)
+    pdist.barrier()
     return text_prompts, textual_memory_bank
 
 
@@ -122,26 +142,36 @@ def build_cache_model(cfg, clip_model, train_loader_cache):
         return f"{model_dir_root}/visual_mb_{kind}_aug_{cfg['augment_epoch']}_{cfg['shots']}_shots.pt"
 
     key_path, value_path = get_filename("keys"), get_filename("values")
+    pdist.barrier()  # every rank sees the same cache state
     if dir_exists(key_path) and dir_exists(value_path):
-        return torch.load(key_path), torch.load(value_path)
+        return torch.load(key_path, map_location=_here()), torch.load(value_path, map_location=_here())
+    pdist.barrier()
     cache_keys, cache_values = [], []
+    D = clip_model.visual.output_dim
     with torch.no_grad():
         for augment_idx in range(cfg["augment_epoch"]):
             train_features = []
-            print("Augment Epoch: {:} / {:}".format(augment_idx, cfg["augment_epoch"]))
-            for images, target in tqdm(train_loader_cache):
+            if pdist.is_main():
+                print("Augment Epoch: {:} / {:}".format(augment_idx, cfg["augment_epoch"]))
+            for images, target in tqdm(pdist.sharded_batches(train_loader_cache), disable=not pdist.is_main()):
                 train_features.append(clip_model.encode_image(images.cuda()))
                 if augment_idx == 0:
                     cache_values.append(target.cuda())
-            cache_keys.append(torch.cat(train_features, dim=0).unsqueeze(0))
+            train_features = torch.cat(train_features, dim=0) if train_features else \
+                torch.empty((0, D), dtype=torch.float16, device="cuda")
+            cache_keys.append(train_features.unsqueeze(0))
     cache_keys = torch.cat(cache_keys, dim=0).float().mean(dim=0).half()       # fp16 mean over augment epochs
+    cache_values = torch.cat(cache_values, dim=0) if cache_values else torch.empty(0, dtype=torch.int64, device="cuda")
+    cache_keys = pdist.all_gather_varlen(cache_keys)                           # the ranks' batch ranges, in order
+    cache_values = pdist.all_gather_varlen(cache_values)
     cache_keys = nat.l2_normalize(cache_keys).permute(1, 0)
-    cache_values = torch.cat(cache_values, dim=0)
     index = torch.argsort(cache_values)
     cache_values = F.one_hot(cache_values[index])
     cache_keys = cache_keys[:, index]
-    torch.save(cache_keys, key_path)
-    torch.save(cache_values, value_path)
+    if pdist.is_main():
+        torch.save(cache_keys, key_path)
+        torch.save(cache_values, value_path)
+    pdist.barrier()
     return cache_keys, cache_values
 
 
@@ -150,19 +180,28 @@ def pre_load_features(cfg, split, clip_model, loader):
     (utils.py:335-361). The normalisation is fused into the encoder call."""
     root_dir_prefix = f"{get_model_dir_root(cfg)}/{split}"
     feature_path, label_path = f"{root_dir_prefix}_features.pt", f"{root_dir_prefix}_labels.pt"
+    pdist.barrier()  # every rank sees the same cache state
     if dir_exists(feature_path) and dir_exists(label_path):
-        print(f"Loading cached features and labels from {root_dir_prefix}")
-        return torch.load(feature_path), torch.load(label_path)
-    print(f"Creating cached (features, labels) and saving to {root_dir_prefix}")
+        if pdist.is_main():
+            print(f"Loading cached features and labels from {root_dir_prefix}")
+        return torch.load(feature_path, map_location=_here()), torch.load(label_path, map_location=_here())
+    pdist.barrier()
+    if pdist.is_main():
+        print(f"Creating cached (features, labels) and saving to {root_dir_prefix}")
     features, labels = [], []
     with torch.no_grad():
-        for images, target in tqdm(loader):
+        for images, target in tqdm(pdist.sharded_batches(loader), disable=not pdist.is_main()):
             features.append(nat.l2_normalize(clip_model.encode_image(images.cuda())))
             labels.append(target.cuda())
-    features, labels = torch.cat(features), torch.cat(labels)
-    os.makedirs(os.path.dirname(feature_path), exist_ok=True)
-    torch.save(features, feature_path)
-    torch.save(labels, label_path)
+    features = torch.cat(features) if features else \
+        torch.empty((0, clip_model.visual.output_dim), dtype=torch.float16, device="cuda")
+    labels = torch.cat(labels) if labels else torch.empty(0, dtype=torch.int64, device="cuda")
+    features, labels = pdist.all_gather_varlen(features), pdist.all_gather_varlen(labels)
+    if pdist.is_main():
+        os.makedirs(os.path.dirname(feature_path), exist_ok=True)
+        torch.save(features, feature_path)
+        torch.save(labels, label_path)
+    pdist.barrier()
     return features, labels
 
 

@@ -519,6 +519,36 @@ def test_main_cli_end_to_end_on_synthetic_dataset(nat, tmp_path, monkeypatch, ba
     assert abs(res["test_acc"] - acc_o) < 1e-6 and acc_o > (0.9 if adapter == "fc" else 2.0 / N)
 
 
+def test_cli_two_ranks_equal_one_rank(nat, tmp_path):
+    """`torchrun --nproc-per-node 2 main.py ...` (loader batches, prompts and query features
+    sharded over the ranks; one all-gather per bank, one broadcast of the prototypes, hit counts summed, predictions
+    gathered) produces EXACTLY what the single-process run produces: memory banks, cached features, both (alpha, beta)
+    grids and every prediction. Two GPUs -> NCCL; a single-GPU box runs the two ranks on cuda:0 over gloo (the
+    collectives are staged through the host, the CUDA kernels are the same)."""
+    import subprocess
+    import sys
+    import numpy as np
+    runner = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cli_ranks_runner.py")
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    r1 = subprocess.run([sys.executable, runner, str(tmp_path / "one")], env=env, capture_output=True, text=True, timeout=600)
+    assert r1.returncode == 0 and "RUNNER OK 1" in r1.stdout, r1.stderr[-3000:]
+    if torch.cuda.device_count() < 2:
+        env["PROTOCLIP_DIST_BACKEND"] = "gloo"
+    port = 29700 + (os.getpid() % 200)
+    r2 = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                         "--master-addr", "127.0.0.1", "--master-port", str(port), runner, str(tmp_path / "two")],
+                        env=env, capture_output=True, text=True, timeout=900)
+    assert r2.returncode == 0 and "RUNNER OK 2" in r2.stdout, (r2.stdout[-1500:], r2.stderr[-3000:])
+    a = torch.load(tmp_path / "one" / "result.pt", weights_only=False)
+    b = torch.load(tmp_path / "two" / "result.pt", weights_only=False)
+    assert a["world"] == 1 and b["world"] == 2
+    for k in ("keys", "values", "text_mb", "test_features", "test_labels", "test_pred", "hp_pred"):
+        assert torch.equal(a[k], b[k]), k
+    for k in ("zero_val_grid", "zero_test_grid", "val_grid", "test_acc_grid"):
+        assert a[k].shape == (319, 3) and np.array_equal(a[k], b[k]), k
+    assert a["test_acc"] == b["test_acc"] and a["test_acc"] > 0.9
+
+
 def test_toolkit_callers_top_k_and_ood(nat, tmp_path, monkeypatch):
     """ProtoClipClassifier.classify_objects (top-k names / probabilities) and test_ood_performance through the toolkit
     shells, on a trained-model file set in the reference's formats, against the oracle."""

@@ -166,6 +166,24 @@ a, b = pdist.shard_bounds(37, rank, world)
 full = pdist.all_gather_rows(rows[a:b].clone(), 37)
 assert torch.equal(full, rows), full
 t = pdist.max_over_ranks(float(rank + 1), torch.device("cpu"))
+# the CLI's collectives (main.py / utils.py under torchrun): contiguous BATCH ranges of a loader gathered in order
+# (ranks may hold no batch at all), integer hit counts summed, the prototypes in one broadcast
+loader = [(torch.full((n, 3), float(i)), torch.full((n,), i, dtype=torch.int64)) for i, n in enumerate([4, 4, 4, 2])]
+mine = list(pdist.sharded_batches(loader))
+feats = torch.cat([b[0] for b in mine]) if mine else torch.empty((0, 3))
+labs = torch.cat([b[1] for b in mine]) if mine else torch.empty(0, dtype=torch.int64)
+assert torch.equal(pdist.all_gather_varlen(feats), torch.cat([b[0] for b in loader]))
+assert torch.equal(pdist.all_gather_varlen(labs), torch.cat([b[1] for b in loader]))
+one = [(torch.ones(5, 2), torch.zeros(5, dtype=torch.int64))]              # fewer batches than ranks
+got = list(pdist.sharded_batches(one))
+assert len(got) == (1 if rank == 0 else 0)
+assert pdist.all_gather_varlen(got[0][0] if got else torch.empty((0, 2))).shape == (5, 2)
+counts = pdist.all_reduce_sum(torch.full((11, 29), rank + 1, dtype=torch.int32))
+assert int(counts[0, 0]) == world * (world + 1) // 2
+za, zb = torch.full((4, 8), float(rank)).half(), torch.full((4, 8), float(10 + rank)).half()
+za, zb = pdist.broadcast_tensors([za, zb])
+assert float(za[0, 0]) == 0.0 and float(zb[3, 7]) == 10.0 and za.shape == (4, 8)
+assert pdist.active() and pdist.is_main() == (rank == 0)
 pdist.barrier()
 if rank == 0:
     ref = (q @ head.z_img.float().t()).argmax(1)
