@@ -35,13 +35,13 @@ METRIC = "query images/sec, ImageNet 1000-way 16-shot ViT-B/16"
 # entries of the same JSON line (query path only, random prototypes: the memory-bank build is c2's prelude).
 # alpha / beta: the reference's configs/{imagenet,fewsol_198,sun397}.yml.
 WORKLOADS = {
-    "c2": dict(arch="ViT-B/16", n_classes=1000, adapter="fc", alpha=0.5, beta=12.0, batch=1024, micro_batch=96,
+    "c2": dict(arch="ViT-B/16", n_classes=1000, adapter="fc", alpha=0.5, beta=12.0, batch=1024, micro_batch=512,
                name="imagenet 16-shot ViT-B/16 fc adapter, 1000-way eval (configs[1])"),
-    "c3": dict(arch="ViT-L/14", n_classes=198, adapter="conv-3x", alpha=0.2, beta=12.0, batch=512, micro_batch=64,
+    "c3": dict(arch="ViT-L/14", n_classes=198, adapter="conv-3x", alpha=0.2, beta=12.0, batch=512, micro_batch=0,
                name="fewsol_198 16-shot ViT-L/14 conv-3x adapter, Proto-CLIP-F (configs[2])"),
-    "c4": dict(arch="ViT-L/14@336px", n_classes=1000, adapter="fc", alpha=0.5, beta=12.0, batch=256, micro_batch=32,
+    "c4": dict(arch="ViT-L/14@336px", n_classes=1000, adapter="fc", alpha=0.5, beta=12.0, batch=256, micro_batch=0,
                name="imagenet 16-shot ViT-L/14@336px fc adapter, query batch sharded over the ranks (configs[3])"),
-    "c5": dict(arch="RN50x16", n_classes=397, adapter="conv-2x", alpha=1.0, beta=11.0, batch=256, micro_batch=64,
+    "c5": dict(arch="RN50x16", n_classes=397, adapter="conv-2x", alpha=1.0, beta=11.0, batch=256, micro_batch=0,
                name="sun397 16-shot RN50x16, main.qt.py path, conv-2x adapter (configs[4])"),
 }
 
@@ -187,9 +187,10 @@ def run_ours(args):
     #      a 1.5 s loop that reaches the power-capped clocks of the step), CUDA events on the launching stream
     roof = attn = None
     g = c["image_resolution"] // c["vision_patch_size"]
+    eff_mb = effective_micro_batch(B, g * g + 1, mb, dev)
     if rank == 0 and not args.lite:
-        attn = attention_roofline(nat, dev, local_rank, mb or 96, g * g + 1, c["vision_width"] // 64)
-        roof = gemm_roofline(ctx, dev, local_rank, mb or 96, g * g + 1, c["vision_width"])
+        attn = attention_roofline(nat, dev, local_rank, eff_mb, g * g + 1, c["vision_width"] // 64)
+        roof = gemm_roofline(ctx, dev, local_rank, eff_mb, g * g + 1, c["vision_width"])
     pdist.barrier()
 
     # ---- value: inputs resident in HBM, CUDA events on the launching stream, barrier + sync both sides
@@ -273,7 +274,7 @@ def run_ours(args):
 
     if rank == 0:
         layers = c["vision_layers"]
-        n_mb = math.ceil(B / (mb or 96))
+        n_mb = math.ceil(B / eff_mb)
         # per micro-batch: patchify, conv1 GEMM, embed+ln_pre, row_stats; per block 4 GEMMs (LayerNorm folded into two
         # of them) + attention; ln_post, proj GEMM, l2norm. Per step: adapter (2 GEMMs, 2 LN kernels), l2norm,
         # 2 similarity GEMMs + softmax/argmax.
@@ -286,7 +287,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": WORKLOADS["c2"]["name"],
                        "backbone": ARCH, "n_classes": N_CLASSES, "shots": K_SHOTS, "adapter": "fc", "alpha": ALPHA,
-                       "beta": BETA, "batch_per_gpu": B, "micro_batch": mb or 96, "image": "3x224x224 fp32",
+                       "beta": BETA, "batch_per_gpu": B, "micro_batch": eff_mb, "image": "3x224x224 fp32",
                        "l2": "inputs larger than L2 (616 MB per batch, 2 alternating batches)",
                        "parallelism": f"dp{world} (query shards; one-off memory-bank build sharded with 2 all-gathers, then 1 NCCL broadcast of the head state; no collective in the timed step)"},
             "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": int(pool_host[0].numel() * 4),
@@ -302,6 +303,17 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def effective_micro_batch(B: int, L: int, mb: int, dev) -> int:
+    """Images per encoder pass: the caller's --micro-batch, else the library's policy (csrc/api.cu pick_micro_batch: at
+    most 6 row-block waves of the CTA-pair GEMM per pass, the batch cut into equal passes)."""
+    if mb > 0:
+        return mb
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    cap = 6 * max(1, (sms // 2) * 256 // L)
+    passes = max(1, math.ceil(B / cap))
+    return math.ceil(B / passes)
 
 
 def flops_per_image(arch: str) -> float:
@@ -386,6 +398,10 @@ def timed_loop(fn, min_ms: float, index: int):
     return e0.elapsed_time(e1) / iters, clocks.summary()["sm_mhz"]
 
 
+# (M, d) -> dram__bytes_read.sum + dram__bytes_write.sum of the block's four Linear launches (ncu --set full, cold caches)
+GEMM_TRAFFIC = {(18912, 768): 388.4e6}
+
+
 def gemm_roofline(ctx, dev, index, B, L, d):
     """The four Linear launches of one ResidualAttentionBlock exactly as the towers run them
     (pc_resblock_forward_parts, parts = GEMMs: EPI_LN_BIAS QKV, EPI_BIAS_RES + row statistics out_proj, EPI_LN_QGELU
@@ -397,10 +413,10 @@ def gemm_roofline(ctx, dev, index, B, L, d):
     torch.manual_seed(0)
     x = (torch.randn(B * L, d, device=dev) * 0.5).half()
     x0 = x.clone()
-    ctx.resblock_forward_parts(nat.PC_TOWER_VISUAL, 0, x, B, L, False, parts=3, chained=False)  # leaves valid statistics
+    ctx.resblock_forward_parts(nat.PC_TOWER_VISUAL, 0, x, B, L, False, parts=31, chained=False)  # leaves valid statistics
 
     def block():
-        ctx.resblock_forward_parts(nat.PC_TOWER_VISUAL, 0, x, B, L, False, parts=1, chained=True)
+        ctx.resblock_forward_parts(nat.PC_TOWER_VISUAL, 0, x, B, L, False, parts=29, chained=True)
 
     time.sleep(0.5)
     ms_b, mhz_b = timed_loop(block, 10.0, index)
@@ -410,12 +426,13 @@ def gemm_roofline(ctx, dev, index, B, L, d):
     flops = 24.0 * M * d * d
     tf_b, tf_s = flops / (ms_b / 1e3) / 1e12, flops / (ms_s / 1e3) / 1e12
     # DRAM read + write bytes of the same four launches from one `ncu --set full` capture with cold caches
-    # (profiles/README.md names the file); only valid for the c2 shape.
-    traffic = 388.4e6 if (M, d) == (18912, 768) else None
+    # (profiles/README.md names the file); only valid for the shape it was captured at.
+    traffic = GEMM_TRAFFIC.get((M, d))
     return {"bound": "tensor", "achieved": round(tf_s, 1), "peak": sustained, "unit": "TFLOP/s",
             "frac": round(tf_s / sustained, 4), "traffic": traffic,
             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the four launches, ncu --set full, cold "
-                              "caches (profiles/r02_ncu_gemm_summary.txt); algorithmic bytes 4 launches = 537 MB",
+                              "caches (profiles/README.md names the capture); null when no capture exists for this M",
+            "algorithmic_bytes_per_4_launches": 2.0 * (M * d * (1 + 3 + 1 + 1 + 1 + 1 + 4 + 4 + 1 + 1) + 12 * d * d),
             "kernel": f"gemm_tn_kernel<pair, EPI_LN_BIAS | EPI_BIAS_RES | EPI_LN_QGELU | EPI_BIAS_RES>: the 4 Linear "
                       f"launches of one ResidualAttentionBlock as the tower runs them, M={M}, d={d}",
             "flops_per_4_launches": flops, "ms_per_4_launches": round(ms_s, 4), "sm_mhz": mhz_s,

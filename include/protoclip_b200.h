@@ -173,11 +173,18 @@ int pc_encode_text(pc_ctx* ctx, const int64_t* tokens, int P, void* out, int l2n
 size_t pc_resblock_workspace_bytes(const pc_ctx* ctx, int tower, int B, int L);
 int pc_resblock_forward(pc_ctx* ctx, int tower, int layer, void* x, int B, int L, int causal, void* workspace,
                         size_t workspace_bytes, void* stream);
-/* Measurement entry (bench.py's roofline legs): the same block, restricted to `parts` (bit 0: its four Linear launches
- * with the epilogues the towers use -- LayerNorm-folded QKV / c_fc, residual + row statistics for out_proj / c_proj,
- * clip/model.py:187-190; bit 1: the attention launch, clip/model.py:183-185). chained = 1: the LayerNorm statistics
- * left in the workspace by the previous call's c_proj are used (as between the blocks of a tower) instead of a fresh
- * row-statistics pass. Results are only meaningful for parts = 3. */
+/* Measurement entry (bench.py's roofline legs): the same block, restricted to the launches named by `parts` (a mask of
+ * PC_PART_*), each with the epilogue the towers use -- LayerNorm-folded QKV / c_fc, residual + row statistics for
+ * out_proj / c_proj (clip/model.py:187-190), the attention core (clip/model.py:183-185). chained = 1: the LayerNorm
+ * statistics left in the workspace by the previous call's c_proj are used (as between the blocks of a tower) instead
+ * of a fresh row-statistics pass. Results are only meaningful for parts = PC_PART_ALL. */
+#define PC_PART_QKV 1
+#define PC_PART_ATTN 2
+#define PC_PART_OUT 4
+#define PC_PART_FC 8
+#define PC_PART_PROJ 16
+#define PC_PART_GEMMS 29
+#define PC_PART_ALL 31
 int pc_resblock_forward_parts(pc_ctx* ctx, int tower, int layer, void* x, int B, int L, int causal, int parts,
                               int chained, void* workspace, size_t workspace_bytes, void* stream);
 

@@ -553,8 +553,8 @@ class Context:
 
     def resblock_forward_parts(self, tower: int, layer: int, x: torch.Tensor, B: int, L: int, causal: bool,
                                parts: int, chained: bool) -> torch.Tensor:
-        """Measurement entry (bench.py roofline legs): the block restricted to its four Linear launches (parts bit 0,
-        the towers' own LayerNorm-folded / residual + statistics epilogues) and / or its attention launch (bit 1)."""
+        """Measurement entry (bench.py roofline legs): the block restricted to the launches in `parts` (mask: 1 QKV,
+        2 attention, 4 out_proj, 8 c_fc, 16 c_proj; 29 = the four Linears with the towers' own epilogues, 31 = all)."""
         x = require_cuda(x, torch.float16, "x")
         nbytes = self.lib.pc_resblock_workspace_bytes(self.handle, tower, B, L)
         ws = workspace(self.device, "tower", nbytes)

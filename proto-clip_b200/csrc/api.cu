@@ -58,13 +58,25 @@ struct RnTower {
 };
 constexpr int kRnMicroBatch = 64;
 
-// Default micro-batch: as many sequences as fill ONE row-block wave of the CTA-pair GEMM (sm_count / 2 pairs x 256
-// rows): ViT-B/16 (L = 197) -> 96 images = 18 912 rows = 73.9 of 74 row blocks; ViT-L/14 -> 73; @336px -> 32.
-// Keeps every Linear at an integer number of waves and the activations (x, h, qkv / MLP hidden) L2-resident.
-inline int default_micro_batch(int L) {
+// Micro-batching. One row-block WAVE of the CTA-pair GEMM is sm_count / 2 pairs x 256 rows: ViT-B/16 (L = 197) -> 96
+// images = 18 912 rows = 73.9 of 74 row blocks; ViT-L/14 -> 73; @336px -> 32. Round 1 ran one wave per pass (activations
+// L2-resident); measured on B200, longer passes win: every launch pays ~2 us of launch gap plus the fill of its first
+// tile and the un-overlapped epilogue of its last one, and the Linears stay compute-bound from HBM (ViT-B/16, batch
+// 1024: 26.1 k img/s at 96 per pass, 26.7 k at 288, 27.3 k at 512). Default: at most kMaxWaves waves per pass, and the
+// batch cut into EQUAL passes (1024 -> 2 x 512, not 576 + 448): tiles, not row blocks, are what the workers balance.
+constexpr int kMaxWaves = 6;
+inline int wave_images(int L) {
   const int rows = (device_sm_count() / 2) * 256;
   const int mb = rows / (L > 0 ? L : 1);
   return mb > 0 ? mb : 1;
+}
+inline int default_micro_batch(int L) { return kMaxWaves * wave_images(L); }  // workspace sizing: the largest pass
+// images per pass for a batch of B (micro_batch > 0: the caller's choice)
+inline int pick_micro_batch(int L, int B, int micro_batch) {
+  if (micro_batch > 0) return micro_batch;
+  const int cap = default_micro_batch(L);
+  const int passes = (B + cap - 1) / cap;
+  return passes > 0 ? (B + passes - 1) / passes : cap;
 }
 constexpr int kClassifyChunk = 8192;    // queries per P() pass: [8192, 2N] fp32 dots stay L2-resident
 
@@ -219,9 +231,9 @@ int build_folds(Tower& t) {
 //   out: s1 = gemm_stats_parts(rows, d) partial pairs of the new x (ready for the next block's ln_1)
 // QKV reads x directly with the gamma-scaled in_proj; out_proj writes the statistics of the row segments it
 // produces into s2; c_fc reads them (ln_2); c_proj writes the new s1. No atomics: results are bit-reproducible.
-// `parts` (measurement only, pc_resblock_forward_parts): bit 0 = the four GEMM launches, bit 1 = the attention launch.
+// `parts` (measurement only, pc_resblock_forward_parts): which launches run -- PC_PART_QKV | ATTN | OUT | FC | PROJ.
 int resblock_fused(const Tower& t, int layer, __half* x, __half* h, __half* big, float* s1, int parts_in, float* s2,
-                   int B, int L, int causal, cudaStream_t s, int parts = 3) {
+                   int B, int L, int causal, cudaStream_t s, int parts = 31) {
   const pc_resblock_weights& w = t.blocks[layer];
   const int d = t.width, rows = B * L;
   GemmArgs g{};
@@ -232,7 +244,6 @@ int resblock_fused(const Tower& t, int layer, __half* x, __half* h, __half* big,
   g.ln_stats = s1; g.ln_parts = parts_in; g.ln_s = t.qkv_ln[layer].s; g.ln_c = t.qkv_ln[layer].c;
   if (parts & 1) PC_TRY(launch_gemm(g, EPI_LN_BIAS, s));
   if (parts & 2) PC_TRY(launch_attention(big, h, B, L, t.heads, causal, s));
-  if (!(parts & 1)) return PC_OK;
   g = GemmArgs{};
   g.M = rows; g.N = d; g.K = d;
   g.A = h; g.lda = d;
@@ -241,14 +252,14 @@ int resblock_fused(const Tower& t, int layer, __half* x, __half* h, __half* big,
   g.bias = static_cast<const __half*>(w.out_proj_bias);
   g.residual = x; g.ldr = d;
   g.stats_out = s2;
-  PC_TRY(launch_gemm(g, EPI_BIAS_RES, s));
+  if (parts & 4) PC_TRY(launch_gemm(g, EPI_BIAS_RES, s));
   g = GemmArgs{};
   g.M = rows; g.N = 4 * d; g.K = d;
   g.A = x; g.lda = d;
   g.W = t.fc_ln[layer].w; g.ldw = d;
   g.C = big; g.ldc = 4 * d;
   g.ln_stats = s2; g.ln_parts = gemm_stats_parts(rows, d); g.ln_s = t.fc_ln[layer].s; g.ln_c = t.fc_ln[layer].c;
-  PC_TRY(launch_gemm(g, EPI_LN_QGELU, s));
+  if (parts & 8) PC_TRY(launch_gemm(g, EPI_LN_QGELU, s));
   g = GemmArgs{};
   g.M = rows; g.N = d; g.K = 4 * d;
   g.A = big; g.lda = 4 * d;
@@ -257,7 +268,7 @@ int resblock_fused(const Tower& t, int layer, __half* x, __half* h, __half* big,
   g.bias = static_cast<const __half*>(w.c_proj_bias);
   g.residual = x; g.ldr = d;
   g.stats_out = s1;
-  PC_TRY(launch_gemm(g, EPI_BIAS_RES, s));
+  if (parts & 16) PC_TRY(launch_gemm(g, EPI_BIAS_RES, s));
   return PC_OK;
 }
 
@@ -662,7 +673,7 @@ int pc_encode_image(pc_ctx* ctx, const void* images, int img_dtype, int B, void*
     return PC_OK;
   }
   const Tower& t = ctx->vis;
-  const int mb = micro_batch > 0 ? micro_batch : default_micro_batch(t.L);
+  const int mb = pick_micro_batch(t.L, B, micro_batch);
   PC_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, PC_ERR_ALIGN,
              "pc_encode_image: workspace must be 256-byte aligned");
   PC_REQUIRE(workspace_bytes >= tower_ws_bytes(mb * t.L, t.width, mb), PC_ERR_WORKSPACE,
@@ -737,7 +748,7 @@ int pc_encode_text(pc_ctx* ctx, const int64_t* tokens, int P, void* out, int l2n
   PC_REQUIRE(ctx->txt.bound, PC_ERR_STATE, "pc_encode_text: text weights are not bound");
   PC_REQUIRE(tokens && out && P > 0, PC_ERR_ARG, "pc_encode_text: null buffer or empty batch");
   const Tower& t = ctx->txt;
-  const int mb = micro_batch > 0 ? micro_batch : default_micro_batch(t.L);
+  const int mb = pick_micro_batch(t.L, P, micro_batch);
   PC_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, PC_ERR_ALIGN,
              "pc_encode_text: workspace must be 256-byte aligned");
   PC_REQUIRE(workspace_bytes >= tower_ws_bytes(mb * t.L, t.width, mb), PC_ERR_WORKSPACE,
@@ -809,7 +820,7 @@ int pc_resblock_forward_parts(pc_ctx* ctx, int tower, int layer, void* x, int B,
   const Tower& t = tower == PC_TOWER_TEXT ? ctx->txt : ctx->vis;
   PC_REQUIRE(t.bound, PC_ERR_STATE, "pc_resblock_forward_parts: tower %d is not bound", tower);
   PC_REQUIRE(layer >= 0 && layer < t.layers, PC_ERR_ARG, "pc_resblock_forward_parts: layer %d of %d", layer, t.layers);
-  PC_REQUIRE(x && B > 0 && L > 0 && parts >= 1 && parts <= 3, PC_ERR_ARG, "pc_resblock_forward_parts: bad arguments");
+  PC_REQUIRE(x && B > 0 && L > 0 && parts >= 1 && parts <= 31, PC_ERR_ARG, "pc_resblock_forward_parts: bad arguments");
   PC_REQUIRE(fused_ln_enabled(), PC_ERR_STATE, "pc_resblock_forward_parts: needs the LayerNorm-folded path (PC_NO_FUSED_LN unset)");
   PC_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, PC_ERR_ALIGN,
              "pc_resblock_forward_parts: workspace must be 256-byte aligned");

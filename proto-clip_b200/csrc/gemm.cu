@@ -168,12 +168,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
   griddep_launch_dependents();  // the next kernel of the stream may start its own prologue from here on
+  const long long t_entry = ((g.debug & 16) && threadIdx.x == 0) ? static_cast<long long>(globaltimer_ns()) : 0;
   tc_fence_before();
   if (PAIR) cluster_sync_all();  // barriers of BOTH CTAs initialised before any remote arrive / multicast commit
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
   griddep_wait();  // operands (and the residual / output buffers) belong to the previous kernel until here
+  if ((g.debug & 16) && threadIdx.x == 0) {  // bring-up: per-CTA wall-clock timeline of the whole grid
+    g.trace[3 * blockIdx.x + 0] = t_entry;
+    g.trace[3 * blockIdx.x + 1] = static_cast<long long>(globaltimer_ns());
+  }
 
   if (warp == TMA_WARP) {
     // ------------------------------------------------------------ TMA producer
@@ -504,6 +509,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   if (PAIR) cluster_sync_all();  // no CTA of the pair exits (or frees TMEM) while the other may still signal it
   else __syncthreads();
+  if ((g.debug & 16) && threadIdx.x == 0) g.trace[3 * blockIdx.x + 2] = static_cast<long long>(globaltimer_ns());
   if (warp == MMA_WARP) {
     tc_fence_after();
     if (PAIR) tmem_dealloc_pair(tmem_base, 2 * BN);
@@ -565,8 +571,59 @@ int launch_impl(const GemmArgs& a0, cudaStream_t stream) {
     PC_CHECK_CUDA(cudaMemsetAsync(trace, 0, 64 * 16 * sizeof(long long), stream));
     a.trace = trace;
   }
+  // bring-up (PC_GEMM_DEBUG=16): globaltimer at kernel entry / after griddep_wait / at exit of every CTA, 16 launches deep
+  static long long* trace_all = nullptr;
+  static int launch_no = 0;
+  constexpr int kSlots = 16, kSlotLen = 3 * 304;
+  if (a.debug & 16) {
+    if (!trace_all) {
+      PC_CHECK_CUDA(cudaMalloc(&trace_all, kSlots * kSlotLen * sizeof(long long)));
+      PC_CHECK_CUDA(cudaMemset(trace_all, 0, kSlots * kSlotLen * sizeof(long long)));
+    }
+    a.trace = trace_all + (launch_no % kSlots) * kSlotLen;
+  }
   PC_CHECK_CUDA(launch_pdl(kern, dim3(PAIR ? 2 * workers : workers), dim3(GEMM_THREADS), Smem::TOTAL, stream, PAIR ? 2 : 1,
                            tmA, tmW, tmC, tmR, a));
+  if (a.debug & 16) {
+    static int report_at = -1;
+    if (report_at < 0) {
+      const char* e = getenv("PC_GEMM_TRACE_AT");
+      report_at = e ? atoi(e) : 40;
+    }
+    if (++launch_no == report_at) {
+      static long long h[kSlots * kSlotLen];
+      PC_CHECK_CUDA(cudaStreamSynchronize(stream));
+      PC_CHECK_CUDA(cudaMemcpy(h, trace_all, sizeof(h), cudaMemcpyDeviceToHost));
+      const int ctas = PAIR ? 2 * workers : workers;
+      fprintf(stderr, "[gemm grid trace] M=%d N=%d K=%d pair=%d epi=%d, %d CTAs (ns; launches in stream order)\n", a.M, a.N, a.K,
+              (int)PAIR, EPI, ctas);
+      fprintf(stderr, "launch | first entry  first go   last go | first exit  median exit  last exit | span(go..exit) gap to prev\n");
+      long long prev_end = 0;
+      for (int l = report_at - kSlots + 1; l < report_at; ++l) {  // the slot of launch l (0-based launch index l)
+        if (l < 0) continue;
+        const long long* r = h + (l % kSlots) * kSlotLen;
+        long long e0 = r[0], g0 = r[1], g1 = r[1], x0 = r[2], x1 = r[2];
+        static long long ex[304];
+        for (int c = 0; c < ctas; ++c) {
+          e0 = r[3 * c] < e0 ? r[3 * c] : e0;
+          g0 = r[3 * c + 1] < g0 ? r[3 * c + 1] : g0;
+          g1 = r[3 * c + 1] > g1 ? r[3 * c + 1] : g1;
+          x0 = r[3 * c + 2] < x0 ? r[3 * c + 2] : x0;
+          x1 = r[3 * c + 2] > x1 ? r[3 * c + 2] : x1;
+          ex[c] = r[3 * c + 2];
+        }
+        for (int i = 1; i < ctas; ++i) {  // insertion sort: median exit
+          long long v = ex[i];
+          int j = i - 1;
+          for (; j >= 0 && ex[j] > v; --j) ex[j + 1] = ex[j];
+          ex[j + 1] = v;
+        }
+        fprintf(stderr, "%6d | %11lld %9lld %9lld | %10lld %12lld %10lld | %14lld %11lld\n", l, e0 - g0, 0LL, g1 - g0, x0 - g0,
+                ex[ctas / 2] - g0, x1 - g0, x1 - g0, prev_end ? g0 - prev_end : 0LL);
+        prev_end = x1;
+      }
+    }
+  }
   if (a.debug & 8) {
     static int printed = 0;
     long long h[64 * 16];

@@ -132,6 +132,27 @@ def case_attn(B, L, heads, causal):
     timed_loop(lambda: nat.attention(qkv, B, L, heads, causal), 4.0 * B * heads * L * L * 64, f"attn B{B} L{L}", 0.3)
 
 
+def case_block_parts(B=96, arch="ViT-B/16"):
+    """Each launch of one ResidualAttentionBlock on its own, with the epilogue the tower uses
+    (pc_resblock_forward_parts), next to the plain-epilogue GEMM of the same shape."""
+    import torch
+    from proto_clip_b200 import _native as nat
+    from proto_clip_b200 import synthetic
+    c = synthetic.arch_config(arch)
+    d, L = c["vision_width"], (c["image_resolution"] // c["vision_patch_size"]) ** 2 + 1
+    sd = synthetic.make_state_dict(arch, 0)
+    ctx = nat.Context(torch.device("cuda:0"))
+    ctx.bind_visual(sd)
+    x = (torch.randn(B * L, d, device="cuda") * 0.5).half()
+    ctx.resblock_forward_parts(nat.PC_TOWER_VISUAL, 0, x, B, L, False, 31, False)
+    M = B * L
+    for name, mask, fl in (("qkv   LN_BIAS ", 1, 2.0 * M * 3 * d * d), ("out   RES+stat", 4, 2.0 * M * d * d),
+                           ("c_fc  LN_QGELU", 8, 2.0 * M * 4 * d * d), ("c_proj RES+stat", 16, 2.0 * M * 4 * d * d),
+                           ("4 gemms       ", 29, 24.0 * M * d * d), ("attention     ", 2, 4.0 * B * (d // 64) * L * L * 64)):
+        timed_loop(lambda: ctx.resblock_forward_parts(nat.PC_TOWER_VISUAL, 0, x, B, L, False, mask, True), fl,
+                   f"block {arch} B{B} {name}", 0.5)
+
+
 def case_rows():
     import torch
     from proto_clip_b200 import _native as nat
@@ -228,6 +249,7 @@ CASES = {
     "tower_rn50x16_mb64": lambda: case_tower("RN50x16", 128, 64),
     "tower_rn50": lambda: case_tower("RN50", 512),
     "tower_vitb16": lambda: case_tower("ViT-B/16", 960),
+    "block_parts": case_block_parts,
     "gemm_small": lambda: case_gemm(128, 256, 64),
     "gemm_k": lambda: case_gemm(128, 256, 768),
     "gemm_n128": lambda: case_gemm(300, 128, 512),
