@@ -444,13 +444,28 @@ def gemm_roofline(ctx, dev, index, B, L, d):
 
 def attention_roofline(nat, dev, index, B, L, heads):
     """The attention kernel alone at the micro-batch's shape: algorithmic 4*B*heads*L^2*64 flop per launch (QK^T + PV).
-    Timed on an idle GPU before the step loops (a kernel timed alone -> burst peak); the SM clock during the loop is
-    recorded: right after the GEMM-heavy step the power-capped clock (1.4 GHz) would inflate the time by a third."""
+    Timed on an idle GPU before the step loops. `frac` follows MEASURED_PEAKS.json's burst protocol (a kernel timed
+    alone: best of 10 short groups of launches, CUDA events) against the burst peak; the >= 300 ms back-to-back loop is
+    reported beside it with the SM clock sampled while it ran (right after the GEMM-heavy step the power-capped
+    1.4 GHz clock would inflate either by a third, which is why this leg runs first)."""
     sustained, burst, src = measured_peaks()
     torch.manual_seed(1)
     qkv = torch.randn(B * L, 3 * heads * 64, device=dev).half()
     time.sleep(0.5)
-    ms, mhz = timed_loop(lambda: nat.attention(qkv, B, L, heads, False), 300.0, index)
+    for _ in range(5):
+        nat.attention(qkv, B, L, heads, False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    groups = []
+    for _ in range(10):
+        e0.record()
+        for _ in range(10):
+            nat.attention(qkv, B, L, heads, False)
+        e1.record()
+        torch.cuda.synchronize()
+        groups.append(e0.elapsed_time(e1) / 10)
+    ms = min(groups)
+    ms_loop, mhz = timed_loop(lambda: nat.attention(qkv, B, L, heads, False), 300.0, index)
     flops = 4.0 * B * heads * L * L * 64
     achieved = flops / (ms / 1e3) / 1e12
     exps = float(B) * heads * L * L
@@ -458,10 +473,14 @@ def attention_roofline(nat, dev, index, B, L, heads):
     return {"bound": "tensor", "achieved": round(achieved, 1), "peak": burst, "unit": "TFLOP/s",
             "frac": round(achieved / burst, 4), "traffic": None,
             "kernel": f"{name}<causal=false>: B={B}, L={L}, heads={heads}, head_dim=64",
-            "flops_per_launch": flops, "us_per_launch": round(ms * 1e3, 2), "sm_mhz": mhz,
-            "peak_kind": f"bf16 burst ({src})",
+            "flops_per_launch": flops, "us_per_launch": round(ms * 1e3, 2),
+            "peak_kind": f"bf16 burst ({src}); best of 10 groups of 10 launches on an idle GPU",
+            "loop_300ms": {"us_per_launch": round(ms_loop * 1e3, 2), "achieved": round(flops / (ms_loop / 1e3) / 1e12, 1),
+                           "frac_of_burst_peak": round(flops / (ms_loop / 1e3) / 1e12 / burst, 4), "sm_mhz": mhz},
+            "hbm_bytes_per_launch": float(B * L * heads * 64 * 2 * 4),
             "note": "head_dim 64: one exp2 per 256 tensor flops; the MUFU pipe (16 exp2/clk/SM) alone bounds this shape "
-                    "at 9.9 us = 0.69 of the tensor peak, the M = 128 / N <= 208 UMMA shapes at 0.55",
+                    "at 0.69 of the tensor peak, the M = 128 / N <= 208 UMMA shapes at 0.55; at this batch qkv "
+                    "(B*L*3d fp16) no longer fits the L2 and the kernel also moves hbm_bytes_per_launch",
             "gexp_per_s": round(exps / (ms / 1e3) / 1e9, 1)}
 
 

@@ -80,7 +80,8 @@ struct Params6 {
 struct Bars6 {
   uint64_t qk_full[2];     // per stage: Q tiles + K landed
   uint64_t v_full[2];      // per stage: V landed
-  uint64_t stage_free[2];  // per stage: both WGs' last PV MMA on it retired (2 arrivals)
+  uint64_t qk_free[2];     // per stage: both WGs' S MMAs retired -> Q and K may be overwritten (2 arrivals)
+  uint64_t v_free[2];      // per stage: both WGs' last PV MMA retired -> V may be overwritten (2 arrivals)
   uint64_t s_full[2];      // per WG: S of the tile in TMEM
   uint64_t pa_full[2];     // per WG: P part a in TMEM (8 warp arrivals)
   uint64_t pb_full[2];     // per WG: P part b in TMEM (4 warp arrivals: it belongs to the rows' second threads)
@@ -279,7 +280,8 @@ attention6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       for (int i = 0; i < 2; ++i) {
         mbar_init(&bars->qk_full[i], 1);
         mbar_init(&bars->v_full[i], 1);
-        mbar_init(&bars->stage_free[i], 2);
+        mbar_init(&bars->qk_free[i], 2);
+        mbar_init(&bars->v_free[i], 2);
         mbar_init(&bars->s_full[i], 1);
         mbar_init(&bars->pa_full[i], 8);
         mbar_init(&bars->pb_full[i], 4);
@@ -304,24 +306,41 @@ attention6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   const int h0 = (nch + 1) >> 1;  // chunks [0, h0) belong to thread 0 of a row, [h0, nch) to thread 1 (h0 <= 7)
   if (warp == TMA_WARP) {
     // ---------------------------------------------------------------------------------- producer
+    // Q and K of a stage are released as soon as the item's S MMAs have retired, V only after its last P V MMA: the
+    // Q / K of item i + 2 are on their way while item i is still in its softmax (the kernel is HBM-fed at large batches).
+    // Boxes of lp16 (split) / nb (second tile) rows: the rows of a 128-row tile past the sequence stay whatever the
+    // buffer held (finite or not, they only feed score rows >= L, which are never stored).
     uint32_t u = 0;
     for (int g = blockIdx.x; g < p.n_groups; g += g_stride, ++u) {
       const int st = u & 1;
+      const uint32_t free_par = ((u >> 1) & 1) ^ 1;
       uint8_t* stage = smem + st * STAGE_BYTES;
-      mbar_wait(&bars->stage_free[st], ((u >> 1) & 1) ^ 1);
+      const int n_act = (p.split && !job_of(p, g, 1).active) ? 1 : 2;
+      mbar_wait(&bars->qk_free[st], free_par);
       if (elect_one()) {
         uint64_t* qk = &bars->qk_full[st];
-        uint64_t* vf = &bars->v_full[st];
         if (p.split) {
-          const Job6 j1 = job_of(p, g, 1);
-          const int n_act = j1.active ? 2 : 1;
-          mbar_arrive_expect_tx(qk, static_cast<uint32_t>(n_act) * (TILE_BYTES + p.na * 128));
+          mbar_arrive_expect_tx(qk, static_cast<uint32_t>(n_act) * (2 * p.na * 128));
           for (int s = 0; s < n_act; ++s) {
             const int item = 2 * g + s;
             const int c0 = (item % p.heads) * HEAD_DIM, r0 = (item / p.heads) * p.L;
-            tma_load_2d(stage + OFF_Q + s * TILE_BYTES, &tmQ, qk, c0, r0);
+            tma_load_2d(stage + OFF_Q + s * TILE_BYTES, &tmT, qk, c0, r0);
             tma_load_2d(stage + OFF_K + s * TILE_BYTES, &tmT, qk, p.d + c0, r0);
           }
+        } else {
+          const int c0 = (g % p.heads) * HEAD_DIM, r0 = (g / p.heads) * p.L;
+          mbar_arrive_expect_tx(qk, 2 * TILE_BYTES + 2 * p.nb * 128);
+          tma_load_2d(stage + OFF_K, &tmQ, qk, p.d + c0, r0);
+          tma_load_2d(stage + OFF_Q, &tmQ, qk, c0, r0);
+          tma_load_2d(stage + OFF_K + TILE_BYTES, &tmT, qk, p.d + c0, r0 + 128);
+          tma_load_2d(stage + OFF_Q + TILE_BYTES, &tmT, qk, c0, r0 + 128);
+        }
+      }
+      __syncwarp();
+      mbar_wait(&bars->v_free[st], free_par);
+      if (elect_one()) {
+        uint64_t* vf = &bars->v_full[st];
+        if (p.split) {
           mbar_arrive_expect_tx(vf, static_cast<uint32_t>(n_act) * (p.na * 128));
           for (int s = 0; s < n_act; ++s) {
             const int item = 2 * g + s;
@@ -330,11 +349,6 @@ attention6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           }
         } else {
           const int c0 = (g % p.heads) * HEAD_DIM, r0 = (g / p.heads) * p.L;
-          mbar_arrive_expect_tx(qk, 3 * TILE_BYTES + p.nb * 128);
-          tma_load_2d(stage + OFF_K, &tmQ, qk, p.d + c0, r0);
-          tma_load_2d(stage + OFF_Q, &tmQ, qk, c0, r0);
-          tma_load_2d(stage + OFF_K + TILE_BYTES, &tmT, qk, p.d + c0, r0 + 128);
-          tma_load_2d(stage + OFF_Q + TILE_BYTES, &tmQ, qk, c0, r0 + 128);
           mbar_arrive_expect_tx(vf, TILE_BYTES + p.nb * 128);
           tma_load_2d(stage + OFF_V, &tmQ, vf, 2 * p.d + c0, r0);
           tma_load_2d(stage + OFF_V + TILE_BYTES, &tmT, vf, 2 * p.d + c0, r0 + 128);
@@ -357,7 +371,10 @@ attention6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const uint32_t full_par = (u >> 1) & 1;
       const Job6 j = job_of(p, g, w);
       if (!j.active) {  // split mode, odd item count: nothing was loaded for this WG; release its share of the stage
-        if (elect_one()) mbar_arrive(&bars->stage_free[st]);
+        if (elect_one()) {
+          mbar_arrive(&bars->qk_free[st]);
+          mbar_arrive(&bars->v_free[st]);
+        }
         __syncwarp();
         continue;
       }
@@ -389,6 +406,7 @@ attention6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             umma_f16_ss(region + SB_COL, q_desc + 2 * k, k_desc + (TILE_BYTES >> 4) + 2 * k, idesc_sb, k != 0 ? 1u : 0u);
         }
         umma_commit(&bars->s_full[w]);
+        umma_commit(&bars->qk_free[st]);  // this WG's reads of the stage's Q and K have retired
       }
       __syncwarp();
       mbar_wait(&bars->v_full[st], full_par);
@@ -410,7 +428,7 @@ attention6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           for (int k = 0; k < ka_steps; ++k)
             umma_f16_ts(region + O_COL, region + p_col(k, h0), v_desc + 128 * k, idesc_o, (nch > 8 || k != 0) ? 1u : 0u);
         umma_commit(&bars->pv_done[w]);
-        umma_commit(&bars->stage_free[st]);
+        umma_commit(&bars->v_free[st]);
       }
       __syncwarp();
       ++tcount;

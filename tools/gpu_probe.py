@@ -267,6 +267,7 @@ CASES = {
     "attn_50": lambda: case_attn(3, 50, 12, False),
     "attn_257": lambda: case_attn(2, 257, 16, False),
     "attn_big": lambda: case_attn(96, 197, 12, False),
+    "attn_512": lambda: case_attn(512, 197, 12, False),
     "attn_577": lambda: case_attn(2, 577, 16, False),
     "attn_text_big": lambda: case_attn(192, 77, 8, True),
     "attn_L14_big": lambda: case_attn(48, 257, 16, False),
