@@ -32,6 +32,13 @@ def rel_err(got, ref):
     return ((got - ref).abs().max() / ref.abs().max().clamp_min(1e-12)).item()
 
 
+def mean_rel_err(got, ref):
+    """mean |got - ref| / mean |ref|: unlike rel_err (max error over the reference's RANGE) it does not let a few
+    large components hide errors on the many small ones."""
+    got, ref = got.float().cpu(), ref.float().cpu()
+    return ((got - ref).abs().mean() / ref.abs().mean().clamp_min(1e-12)).item()
+
+
 def golden_images(fx):
     """Regenerate the images a tower fixture was made with (tests/golden/make_golden.py:images_for)."""
     from proto_clip_b200 import synthetic
