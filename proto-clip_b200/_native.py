@@ -32,6 +32,27 @@ SYMBOLS = [
 ]
 
 
+class nvtx_range:
+    """NVTX range around a library call (towers, head): visible in Nsight Systems / `ncu --nvtx`; a no-op cost of two
+    calls when no tool is attached (the reference has no profiler hooks)."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        try:
+            torch.cuda.nvtx.range_push(self.name)
+            self._on = True
+        except Exception:  # nvtx unavailable (CPU-only import)
+            self._on = False
+        return self
+
+    def __exit__(self, *exc):
+        if self._on:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 class NativeError(RuntimeError):
     """A libprotoclip_b200 call returned a negative PC_ERR_* code."""
 
@@ -518,7 +539,7 @@ class Context:
             out = torch.empty((B, self.vis_desc["embed_dim"]), dtype=torch.float16, device=self.device)
         nbytes = self.lib.pc_encode_image_workspace_bytes(self.handle, micro_batch)
         ws = workspace(self.device, "tower", nbytes)
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), nvtx_range("protoclip.encode_image"):
             check(self.lib.pc_encode_image(self.handle, images.data_ptr(),
                                            PC_IMG_F16 if images.dtype == torch.float16 else PC_IMG_F32, B,
                                            out.data_ptr(), int(l2norm), micro_batch, ws.data_ptr(), ws.numel(),
@@ -535,7 +556,7 @@ class Context:
         out = torch.empty((P, self.txt_desc["embed_dim"]), dtype=torch.float16, device=self.device)
         nbytes = self.lib.pc_encode_text_workspace_bytes(self.handle, micro_batch)
         ws = workspace(self.device, "tower", nbytes)
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), nvtx_range("protoclip.encode_text"):
             check(self.lib.pc_encode_text(self.handle, tokens.data_ptr(), P, out.data_ptr(), int(l2norm), micro_batch,
                                           ws.data_ptr(), ws.numel(), stream_ptr(self.device)), "pc_encode_text")
         return out

@@ -695,9 +695,9 @@ int pc_encode_image(pc_ctx* ctx, const void* images, int img_dtype, int B, void*
     g.W = ctx->conv1_p; g.ldw = ctx->Kp;
     g.C = ws.h; g.ldc = d;
     PC_TRY(launch_gemm(g, EPI_BIAS, s));
-    PC_TRY(launch_embed_ln_pre(ws.h, ctx->cls, ctx->vpos, ctx->ln_pre_w, ctx->ln_pre_b, ws.x, n, t.L, d, s));
+    PC_TRY(launch_embed_ln_pre(ws.h, ctx->cls, ctx->vpos, ctx->ln_pre_w, ctx->ln_pre_b, ws.x,
+                               fused_ln_enabled() ? ws.s1 : nullptr, n, t.L, d, s));
     if (fused_ln_enabled()) {
-      PC_TRY(launch_row_stats(ws.x, ws.s1, n * t.L, d, s));
       for (int l = 0; l < t.layers; ++l)
         PC_TRY(resblock_fused(t, l, ws.x, ws.h, ws.big, ws.s1, l == 0 ? 1 : gemm_stats_parts(n * t.L, d), ws.s2, n, t.L, 0, s));
     } else {

@@ -80,8 +80,9 @@ int launch_fold_ln(const __half* W, const float* gamma, const float* beta, const
 int launch_patchify(const void* images, int img_is_f16, __half* out, int B, int R, int p, int Kp,
                     cudaStream_t stream);
 // x[b,0,:] = cls + pos[0]; x[b,1+t,:] = patch[b*g2+t,:] + pos[1+t]; then ln_pre (clip/model.py:222-227).
+// stats (nullable): [B*L][2] fp32 (sum, sum of squares) of the stored rows = launch_row_stats(x) for free.
 int launch_embed_ln_pre(const __half* patch, const float* cls, const float* pos, const float* gamma,
-                        const float* beta, __half* x, int B, int L, int d, cudaStream_t stream);
+                        const float* beta, __half* x, float* stats, int B, int L, int d, cudaStream_t stream);
 // text: x[p,t,:] = f16(tok_emb[tokens[p,t]]) + f16(pos[t]) (clip/model.py:342-344)
 int launch_text_embed(const int64_t* tokens, const float* tok_emb, const float* pos, __half* x, int P, int L,
                       int d, int vocab, cudaStream_t stream);

@@ -45,9 +45,10 @@ __device__ __forceinline__ void load_row_f16(const __half* row, int d, int lane,
 }
 
 // Normalise the row held in `r` (fp32 two-pass mean / biased variance, eps 1e-5) and store fp16.
+// stats (nullable): (sum, sum of squares) of the fp16 values STORED, i.e. what launch_row_stats would compute on `out`.
 template <int NV>
 __device__ __forceinline__ void ln_store(RowF<NV>& r, int d, int lane, const float* gamma, const float* beta,
-                                         __half* out) {
+                                         __half* out, float* stats = nullptr) {
   const int vecs = d >> 3;
   float s = 0.0f;
 #pragma unroll
@@ -66,6 +67,7 @@ __device__ __forceinline__ void ln_store(RowF<NV>& r, int d, int lane, const flo
         q += c * c;
       }
   const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(d) + 1e-5f);
+  float st_s = 0.0f, st_q = 0.0f;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const int vi = lane + k * 32;
@@ -77,11 +79,20 @@ __device__ __forceinline__ void ln_store(RowF<NV>& r, int d, int lane, const flo
       *reinterpret_cast<float4*>(bt) = *reinterpret_cast<const float4*>(beta + vi * 8);
       *reinterpret_cast<float4*>(bt + 4) = *reinterpret_cast<const float4*>(beta + vi * 8 + 4);
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
+      for (int e = 0; e < 4; ++e) {
         pk[e] = pack_half2((r.v[k][2 * e] - mean) * rstd * gm[2 * e] + bt[2 * e],
                            (r.v[k][2 * e + 1] - mean) * rstd * gm[2 * e + 1] + bt[2 * e + 1]);
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&pk[e]));
+        st_s += f.x + f.y;
+        st_q = fmaf(f.x, f.x, fmaf(f.y, f.y, st_q));
+      }
       *reinterpret_cast<uint4*>(out + vi * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
+  }
+  if (stats != nullptr) {
+    st_s = warp_sum(st_s);
+    st_q = warp_sum(st_q);
+    if (lane == 0) *reinterpret_cast<float2*>(stats) = make_float2(st_s, st_q);
   }
 }
 
@@ -229,68 +240,108 @@ fold_ln_kernel(const __half* __restrict__ W, const float* __restrict__ gamma, co
   }
 }
 
-// One thread per (image, channel, patch row i, patch gy, patch gx): p contiguous input pixels -> p contiguous fp16
-// values of patch row (b, gy, gx) at column c*p*p + i*p. Consecutive lanes take consecutive gx, so a warp reads one
-// contiguous stretch of an image row (coalesced) and writes p*2-byte segments. Zero-padding columns [K, Kp) are
-// written by the threads of the last patch row of the last channel.
+// One warp per output row (image b, patch gy, gx): its 3 p segments (channel c, patch row i) of p contiguous input pixels
+// become p contiguous fp16 values at column (c p + i) p; lanes take consecutive segments, so the warp writes the whole
+// Kp-wide row contiguously and reads 3 p full 4 p-byte (p = 16: two sectors) pieces of image rows. (The first version,
+// one thread per segment with consecutive lanes on consecutive PATCHES, wrote 32-byte pieces 1.5 KB apart: 35 % of the
+// HBM copy rate in ncu; see profiles/.) Zero-padding columns [K, Kp) are written by the first lanes.
+// PT: the patch size when it is one of CLIP's (16, 32, 14), so that the per-segment loops unroll and a lane has all of
+// its loads in flight at once; 0 = any even p.
+template <int PT>
 __global__ void __launch_bounds__(256)
-patchify_kernel(const void* __restrict__ images, int img_is_f16, __half* __restrict__ out, int B, int R, int p,
+patchify_kernel(const void* __restrict__ images, int img_is_f16, __half* __restrict__ out, int B, int R, int p_rt,
                 int g, int K, int Kp) {
-  const size_t total = static_cast<size_t>(B) * 3 * p * g * g;
-  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
-       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int gx = static_cast<int>(t % g);
-    size_t r = t / g;
-    const int i = static_cast<int>(r % p);
-    r /= p;
-    const int gy = static_cast<int>(r % g);
-    r /= g;
-    const int c = static_cast<int>(r % 3);
-    const int b = static_cast<int>(r / 3);
-    const size_t src = ((static_cast<size_t>(b) * 3 + c) * R + (gy * p + i)) * R + gx * p;
-    __half* dst = out + (static_cast<size_t>(b) * g * g + gy * g + gx) * Kp + (c * p + i) * p;
-    if (img_is_f16) {
-      const __half2* in2 = reinterpret_cast<const __half2*>(static_cast<const __half*>(images) + src);
-      for (int j = 0; j < (p >> 1); ++j) reinterpret_cast<__half2*>(dst)[j] = in2[j];
-    } else {
-      const float2* in2 = reinterpret_cast<const float2*>(static_cast<const float*>(images) + src);
-      for (int j = 0; j < (p >> 1); ++j) {
-        const float2 f = in2[j];
-        reinterpret_cast<__half2*>(dst)[j] = __floats2half2_rn(f.x, f.y);
+  const int p = PT > 0 ? PT : p_rt;
+  const int lane = threadIdx.x & 31;
+  const int rows = B * g * g, segs = 3 * p;
+  for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += gridDim.x * 8) {
+    const int gx = row % g, gy = (row / g) % g, b = row / (g * g);
+    __half* dst_row = out + static_cast<size_t>(row) * Kp;
+    for (int sg = lane; sg < segs; sg += 32) {
+      const int c = sg / p, i = sg - c * p;
+      const size_t src = ((static_cast<size_t>(b) * 3 + c) * R + (gy * p + i)) * R + gx * p;
+      __half2* dst = reinterpret_cast<__half2*>(dst_row + sg * p);
+      if (img_is_f16) {
+        const __half2* in2 = reinterpret_cast<const __half2*>(static_cast<const __half*>(images) + src);
+#pragma unroll
+        for (int j = 0; j < (p >> 1); ++j) dst[j] = in2[j];
+      } else if ((p & 3) == 0) {  // 16-byte loads (src is a multiple of p floats)
+        const float4* in4 = reinterpret_cast<const float4*>(static_cast<const float*>(images) + src);
+        if (PT > 0) {
+          float4 f[(PT > 0 ? PT : 4) / 4];
+#pragma unroll
+          for (int j = 0; j < PT / 4; ++j) f[j] = __ldg(in4 + j);
+#pragma unroll
+          for (int j = 0; j < PT / 8; ++j) {  // 8 pixels -> one 16-byte store
+            uint4 o;
+            o.x = pack_half2(f[2 * j].x, f[2 * j].y);
+            o.y = pack_half2(f[2 * j].z, f[2 * j].w);
+            o.z = pack_half2(f[2 * j + 1].x, f[2 * j + 1].y);
+            o.w = pack_half2(f[2 * j + 1].z, f[2 * j + 1].w);
+            reinterpret_cast<uint4*>(dst)[j] = o;
+          }
+        } else {
+          for (int j = 0; j < (p >> 2); ++j) {
+            const float4 f = in4[j];
+            dst[2 * j] = __floats2half2_rn(f.x, f.y);
+            dst[2 * j + 1] = __floats2half2_rn(f.z, f.w);
+          }
+        }
+      } else {
+        const float2* in2 = reinterpret_cast<const float2*>(static_cast<const float*>(images) + src);
+#pragma unroll
+        for (int j = 0; j < (p >> 1); ++j) {
+          const float2 f = __ldg(in2 + j);
+          dst[j] = __floats2half2_rn(f.x, f.y);
+        }
       }
     }
-    if (c == 2 && i == p - 1)
-      for (int k = K; k < Kp; ++k) out[(static_cast<size_t>(b) * g * g + gy * g + gx) * Kp + k] = __float2half_rn(0.0f);
+    for (int k = K + lane; k < Kp; k += 32) dst_row[k] = __float2half_rn(0.0f);
   }
 }
 
+// x[b, 0] = cls + pos[0]; x[b, 1 + t] = patch[b, t] + pos[1 + t] (fp16 adds of fp16-cast terms, clip/model.py:225-226),
+// then ln_pre (:227). 16-byte vector loads; also emits the (sum, sum of squares) of the stored fp16 row: the
+// LayerNorm statistics the first block's folded QKV GEMM reads (saves the row_stats pass over x).
 template <int NV>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 embed_ln_pre_kernel(const __half* __restrict__ patch, const float* __restrict__ cls,
                     const float* __restrict__ pos, const float* __restrict__ gamma,
-                    const float* __restrict__ beta, __half* __restrict__ x, int B, int L, int d) {
-  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
-  if (row >= B * L) return;
+                    const float* __restrict__ beta, __half* __restrict__ x, float* __restrict__ stats, int B, int L,
+                    int d) {
   const int lane = threadIdx.x & 31;
-  const int b = row / L, t = row % L;
   const int vecs = d >> 3;
-  RowF<NV> r;
+  for (int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); row < B * L; row += gridDim.x * ROW_WARPS) {
+    const int b = row / L, t = row % L;
+    const __half* prow = patch + (static_cast<size_t>(b) * (L - 1) + (t - 1)) * d;  // t >= 1
+    RowF<NV> r;
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int vi = lane + k * 32;
-    if (vi < vecs) {
+    for (int k = 0; k < NV; ++k) {
+      const int vi = lane + k * 32;
+      if (vi < vecs) {
+        float pe[8], tk[8];
+        *reinterpret_cast<float4*>(pe) = *reinterpret_cast<const float4*>(pos + static_cast<size_t>(t) * d + vi * 8);
+        *reinterpret_cast<float4*>(pe + 4) = *reinterpret_cast<const float4*>(pos + static_cast<size_t>(t) * d + vi * 8 + 4);
+        __half2 tok[4];
+        if (t == 0) {
+          *reinterpret_cast<float4*>(tk) = *reinterpret_cast<const float4*>(cls + vi * 8);
+          *reinterpret_cast<float4*>(tk + 4) = *reinterpret_cast<const float4*>(cls + vi * 8 + 4);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int c = vi * 8 + e;
-        // token value in fp16 (conv output / cast class embedding), fp16 add of the fp16-cast position
-        const __half tok = (t == 0) ? __float2half_rn(cls[c])
-                                    : patch[(static_cast<size_t>(b) * (L - 1) + (t - 1)) * d + c];
-        const __half pe = __float2half_rn(pos[static_cast<size_t>(t) * d + c]);
-        r.v[k][e] = __half2float(__hadd(tok, pe));
+          for (int e = 0; e < 4; ++e) tok[e] = __floats2half2_rn(tk[2 * e], tk[2 * e + 1]);
+        } else {
+          *reinterpret_cast<uint4*>(tok) = *reinterpret_cast<const uint4*>(prow + vi * 8);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(__hadd2(tok[e], __floats2half2_rn(pe[2 * e], pe[2 * e + 1])));
+          r.v[k][2 * e] = f.x;
+          r.v[k][2 * e + 1] = f.y;
+        }
       }
     }
+    ln_store(r, d, lane, gamma, beta, x + static_cast<size_t>(row) * d,
+             stats != nullptr ? stats + 2 * static_cast<size_t>(row) : nullptr);
   }
-  ln_store(r, d, lane, gamma, beta, x + static_cast<size_t>(row) * d);
 }
 
 __global__ void __launch_bounds__(256)
@@ -436,17 +487,21 @@ int launch_patchify(const void* images, int img_is_f16, __half* out, int B, int 
   const int g = R / p;
   const int K = 3 * p * p;
   PC_REQUIRE(Kp >= K && Kp % 8 == 0, PC_ERR_ARG, "patchify: padded K %d < %d or not a multiple of 8", Kp, K);
-  const size_t total = static_cast<size_t>(B) * 3 * p * g * g;
-  patchify_kernel<<<grid_1d(total, 256), 256, 0, stream>>>(images, img_is_f16, out, B, R, p, g, K, Kp);
+  // dst rows start on 16-byte boundaries (Kp % 8 == 0); a segment's 16-byte stores also need p % 8 == 0
+  const int grid = ln_grid(B * g * g);
+  if (p == 16) patchify_kernel<16><<<grid, 256, 0, stream>>>(images, img_is_f16, out, B, R, p, g, K, Kp);
+  else if (p == 32) patchify_kernel<32><<<grid, 256, 0, stream>>>(images, img_is_f16, out, B, R, p, g, K, Kp);
+  else if (p == 14) patchify_kernel<14><<<grid, 256, 0, stream>>>(images, img_is_f16, out, B, R, p, g, K, Kp);
+  else patchify_kernel<0><<<grid, 256, 0, stream>>>(images, img_is_f16, out, B, R, p, g, K, Kp);
   PC_CHECK_CUDA(cudaGetLastError());
   return PC_OK;
 }
 
 int launch_embed_ln_pre(const __half* patch, const float* cls, const float* pos, const float* gamma,
-                        const float* beta, __half* x, int B, int L, int d, cudaStream_t stream) {
+                        const float* beta, __half* x, float* stats, int B, int L, int d, cudaStream_t stream) {
   PC_TRY(check_row_dims("embed_ln_pre", B * L, d));
-#define CALL(NV) embed_ln_pre_kernel<NV><<<(B * L + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, stream>>>( \
-      patch, cls, pos, gamma, beta, x, B, L, d)
+#define CALL(NV) embed_ln_pre_kernel<NV><<<ln_grid(B * L), ROW_WARPS * 32, 0, stream>>>( \
+      patch, cls, pos, gamma, beta, x, stats, B, L, d)
   PC_DISPATCH_NV(d, CALL);
 #undef CALL
   PC_CHECK_CUDA(cudaGetLastError());

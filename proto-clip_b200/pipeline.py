@@ -117,8 +117,9 @@ class FewShotClassifier:
     def classify_features(self, feats: torch.Tensor, want_p: bool = False):
         """feats: L2-normalised image features f16 [Q, D] (what pre_load_features caches)."""
         h = self.head
-        q = self.adapt(feats)
-        return nat.proto_classify(q, h.z_img, h.z_txt, h.zi_n2, h.zt_n2, h.alpha, h.beta, want_p=want_p)
+        with nat.nvtx_range("protoclip.head"):
+            q = self.adapt(feats)
+            return nat.proto_classify(q, h.z_img, h.z_txt, h.zi_n2, h.zt_n2, h.alpha, h.beta, want_p=want_p)
 
     def classify(self, images: torch.Tensor, want_p: bool = False):
         """images: [B,3,R,R] f32/f16 on the context's device. Returns (p or None, argmax int64 [B], pmax)."""

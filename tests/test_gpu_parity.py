@@ -552,6 +552,41 @@ def test_drop_in_shells_reproduce_the_reference_flow(nat, tmp_path, monkeypatch)
     assert (p_o.max(1)[1] == q_labels).float().mean().item() > 0.9
 
 
+def test_clip_classifier_on_real_imagenet_prompts(nat, tmp_path):
+    """a6 with REAL prompts on hardware: the reference's ImageNet class names and its 7 templates
+    (datasets/imagenet.py:26-199, read from the oracle/_ref snapshot), tokenised by this repo's BPE tokenizer with the
+    shipped CLIP vocabulary -- token ids must equal the reference tokenizer's (clip/simple_tokenizer.py:62-132) --
+    then utils.clip_classifier (utils.py:256-273) on the ViT-B/16 text tower against the CPU oracle."""
+    import importlib.util
+    from oracle import reference_shims
+    from proto_clip_b200 import clip, utils
+    src = os.path.join(reference_shims.REFERENCE_ROOT, "datasets", "imagenet.py")
+    if not os.path.isfile(src):
+        pytest.skip("reference snapshot (oracle/_ref, built by __graft_entry__.build()) not present")
+    text = open(src).read()
+    ns = {}
+    exec(text[text.index("imagenet_classes = ["):text.index("class ImageNet")], ns)      # the two lists only
+    classes, templates = ns["imagenet_classes"], ns["imagenet_templates"]
+    assert len(classes) == 1000 and len(templates) == 7
+    pick = classes[::53][:19] + ["tench"]                                                # 20 classes, multi-word names too
+    prompts = [t.format(c.replace("_", " ")) for c in pick for t in templates]
+    tok = clip.tokenize(prompts)
+    ref = reference_shims.reference()
+    assert torch.equal(tok, ref.clip.tokenize(prompts)), "BPE token ids differ from the reference tokenizer"
+    assert tok.shape == (140, 77) and int(tok.max()) == 49407
+    sd = synthetic.make_state_dict("ViT-B/16", 0)
+    path = tmp_path / "vitb16.pt"
+    torch.save(sd, path)
+    model, _ = clip.load(str(path))
+    names, bank = utils.clip_classifier(pick, templates, model)
+    assert names == pick and bank.shape == (512, 20) and bank.dtype == torch.float16
+    te = O.l2_normalize(O.encode_text(sd, tok, "fp32")).view(20, 7, -1).mean(1)
+    want = O.l2_normalize(te).t()
+    print(f"clip_classifier on 140 real ImageNet prompts: range-relative error {rel_err(bank, want):.2e}, "
+          f"mean-relative {mean_rel_err(bank, want):.2e}")
+    assert rel_err(bank, want) < TOWER_TOL and mean_rel_err(bank, want) < MEAN_TOL
+
+
 # ----------------------------------------------------------------------------- properties at full size
 def test_full_size_properties_vit_b16(nat):
     """ViT-B/16 at the benchmark's size: per-image results do not depend on batch position, batch size or

@@ -250,6 +250,7 @@ CASES = {
     "tower_rn50": lambda: case_tower("RN50", 512),
     "tower_vitb16": lambda: case_tower("ViT-B/16", 960),
     "block_parts": case_block_parts,
+    "block_parts_512": lambda: case_block_parts(512),
     "gemm_small": lambda: case_gemm(128, 256, 64),
     "gemm_k": lambda: case_gemm(128, 256, 768),
     "gemm_n128": lambda: case_gemm(300, 128, 512),
