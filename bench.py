@@ -426,6 +426,24 @@ def gemm_roofline(ctx, dev, index, B, L, d):
     M = B * L
     flops = 24.0 * M * d * d
     tf_b, tf_s = flops / (ms_b / 1e3) / 1e12, flops / (ms_s / 1e3) / 1e12
+    # context, not a target: the vendor library (torch.matmul -> cuBLAS, fp16, NO bias / LayerNorm / GELU / residual
+    # epilogue) on the same four problem shapes, same loop. MEASURED_PEAKS' denominators are 8192^3 problems; these
+    # shapes pay a launch, a pipeline fill and an un-overlapped last epilogue every ~100-350 us.
+    a1 = torch.randn(M, d, device=dev).half()
+    a4 = torch.randn(M, 4 * d, device=dev).half()
+    ws_ = [torch.randn(n, k, device=dev).half() * 0.03 for n, k in ((3 * d, d), (d, d), (4 * d, d), (d, 4 * d))]
+    outs = [torch.empty(M, w.shape[0], device=dev, dtype=torch.float16) for w in ws_]
+
+    def lib_block():
+        torch.matmul(a1, ws_[0].t(), out=outs[0])
+        torch.matmul(a1, ws_[1].t(), out=outs[1])
+        torch.matmul(a1, ws_[2].t(), out=outs[2])
+        torch.matmul(a4, ws_[3].t(), out=outs[3])
+
+    time.sleep(0.5)
+    ms_lb, _ = timed_loop(lib_block, 10.0, index)
+    ms_ls, mhz_l = timed_loop(lib_block, 1500.0, index)
+    del a1, a4, ws_, outs
     # DRAM read + write bytes of the same four launches from one `ncu --set full` capture with cold caches
     # (profiles/README.md names the file); only valid for the shape it was captured at.
     traffic = GEMM_TRAFFIC.get((M, d))
@@ -438,6 +456,9 @@ def gemm_roofline(ctx, dev, index, B, L, d):
                       f"launches of one ResidualAttentionBlock as the tower runs them, M={M}, d={d}",
             "flops_per_4_launches": flops, "ms_per_4_launches": round(ms_s, 4), "sm_mhz": mhz_s,
             "peak_kind": f"bf16 sustained ({src}); loop of >= 1.5 s, power-capped clocks like the step",
+            "cublas_same_shapes_no_epilogue": {"achieved_sustained": round(flops / (ms_ls / 1e3) / 1e12, 1),
+                                               "achieved_burst": round(flops / (ms_lb / 1e3) / 1e12, 1),
+                                               "ms_per_4_launches": round(ms_ls, 4), "sm_mhz": mhz_l},
             "burst": {"achieved": round(tf_b, 1), "peak": burst, "frac": round(tf_b / burst, 4),
                       "ms_per_4_launches": round(ms_b, 4), "sm_mhz": mhz_b,
                       "peak_kind": f"bf16 burst ({src}); 10 ms loop on an idle GPU"}}

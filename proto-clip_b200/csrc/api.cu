@@ -432,20 +432,30 @@ int rn_forward(const RnTower& t, const void* img, int img_is_f16, int n, __half*
     __half* sw = x; x = y; y = sw;
     h = ho;
   }
-  // AttentionPool2d (:67-92): tokens, packed q/k/v projection, attention, c_proj of the mean token's row
+  // AttentionPool2d (:67-92) returns token 0 only: k / v projections of every token, the q projection and the
+  // attention of the mean token alone (the reference computes all HW + 1 query rows and drops the rest), then c_proj
   const int E = t.embed, L = t.tokens;
   PC_TRY(launch_attnpool_tokens(x, t.pos, t1, n, h * h, E, s));
   GemmArgs g{};
-  g.M = n * L; g.N = 3 * E; g.K = E;
+  g.M = n * L; g.N = 2 * E; g.K = E;
   g.A = t1; g.lda = E;
+  g.W = t.qkv_w + static_cast<size_t>(E) * E; g.ldw = E;  // rows [E, 3E): k_proj, v_proj
+  g.C = t2; g.ldc = 2 * E;
+  g.bias = t.qkv_b + E;
+  PC_TRY(launch_gemm(g, EPI_BIAS, s));
+  __half* q0 = t3;                                   // [n, E]
+  __half* pooled = t3 + static_cast<size_t>(n) * E;  // [n, E]
+  g = GemmArgs{};
+  g.M = n; g.N = E; g.K = E;
+  g.A = t1; g.lda = L * E;  // token 0 of every image
   g.W = t.qkv_w; g.ldw = E;
-  g.C = t2; g.ldc = 3 * E;
+  g.C = q0; g.ldc = E;
   g.bias = t.qkv_b;
   PC_TRY(launch_gemm(g, EPI_BIAS, s));
-  PC_TRY(launch_attention(t2, t3, n, L, t.heads, 0, s));
+  PC_TRY(launch_attnpool_query0(q0, t2, pooled, n, L, t.heads, s));
   g = GemmArgs{};
   g.M = n; g.N = t.out_dim; g.K = E;
-  g.A = t3; g.lda = L * E;  // row 0 of every image
+  g.A = pooled; g.lda = E;
   g.W = t.c_w; g.ldw = E;
   g.C = feat; g.ldc = t.out_dim;
   g.bias = t.c_b;

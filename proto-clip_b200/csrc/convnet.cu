@@ -5,6 +5,7 @@
 // fp32 per-channel shift at bind time, ReLU and the identity add run in the GEMM epilogue. What is left for this
 // file is HBM-bound data movement: 16-byte vector loads / stores, one 8-channel vector per thread, grid-stride.
 #include "kernels.cuh"
+#include "ptx.cuh"
 
 namespace pc {
 namespace {
@@ -269,6 +270,86 @@ int launch_avgpool_nhwc(const __half* x, __half* y, int B, int H, int W, int C, 
              "avgpool: B=%d H=%d W=%d C=%d s=%d", B, H, W, C, s);
   avgpool_nhwc_kernel<<<grid_for(static_cast<size_t>(B) * (H / s) * (W / s) * (C / 8)), CT, 0, stream>>>(
       x, y, B, H, W, C, s, in_bordered ? 1 : 0);
+  PC_CHECK_CUDA(cudaGetLastError());
+  return PC_OK;
+}
+
+// AttentionPool2d returns token 0 only (clip/model.py:72-92 computes all HW + 1 query rows and drops the rest): ONE
+// query row per (image, head). One warp per (image, head): lanes take keys for the scores (64-wide dot products of
+// 128-byte rows), the probabilities go through shared memory, then lanes take two head-dim columns each for P V.
+// q: [B, E] (token 0's projected query, bias included), kv: [B*L, 2E] (k | v, biases included), out: [B, E] fp16.
+constexpr int POOL_WARPS = 4;
+__global__ void __launch_bounds__(POOL_WARPS * 32)
+attnpool_query0_kernel(const __half* __restrict__ q, const __half* __restrict__ kv, __half* __restrict__ out, int B,
+                       int L, int heads) {
+  extern __shared__ float pool_smem[];  // [POOL_WARPS][64 + Lp]
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int Lp = (L + 31) & ~31;
+  float* qs = pool_smem + wib * (64 + Lp);
+  float* ps = qs + 64;
+  const int E = heads * 64;
+  for (int item = blockIdx.x * POOL_WARPS + wib; item < B * heads; item += gridDim.x * POOL_WARPS) {
+    const int b = item / heads, h = item % heads;
+    __syncwarp();
+    {  // q * head_dim^-0.5 (clip/model.py:78-79 -> F.multi_head_attention_forward scales the query)
+      const __half2 qq = *reinterpret_cast<const __half2*>(q + static_cast<size_t>(b) * E + h * 64 + 2 * lane);
+      const float2 f = __half22float2(qq);
+      qs[2 * lane] = f.x * 0.125f;
+      qs[2 * lane + 1] = f.y * 0.125f;
+    }
+    __syncwarp();
+    const __half* kbase = kv + static_cast<size_t>(b) * L * 2 * E + h * 64;
+    float mx = -INFINITY;
+    for (int j = lane; j < Lp; j += 32) {
+      float sc = -INFINITY;
+      if (j < L) {
+        const uint4* kr = reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(j) * 2 * E);
+        float acc = 0.0f;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          const uint4 u = kr[v];
+          const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(h2[e]);
+            acc = fmaf(f.x, qs[8 * v + 2 * e], fmaf(f.y, qs[8 * v + 2 * e + 1], acc));
+          }
+        }
+        sc = acc;
+      }
+      ps[j] = sc;
+      mx = fmaxf(mx, sc);
+    }
+    mx = warp_max(mx);
+    float sum = 0.0f;
+    for (int j = lane; j < Lp; j += 32) {
+      const float pj = (j < L) ? __expf(ps[j] - mx) : 0.0f;
+      ps[j] = pj;
+      sum += pj;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    const __half* vbase = kbase + E;
+    float o0 = 0.0f, o1 = 0.0f;
+    for (int j = 0; j < L; ++j) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(vbase + static_cast<size_t>(j) * 2 * E + 2 * lane));
+      const float pj = ps[j];
+      o0 = fmaf(pj, f.x, o0);
+      o1 = fmaf(pj, f.y, o1);
+    }
+    const float inv = 1.0f / sum;
+    *reinterpret_cast<__half2*>(out + static_cast<size_t>(b) * E + h * 64 + 2 * lane) = __floats2half2_rn(o0 * inv, o1 * inv);
+  }
+}
+
+int launch_attnpool_query0(const __half* q, const __half* kv, __half* out, int B, int L, int heads, cudaStream_t stream) {
+  PC_REQUIRE(q && kv && out && B > 0 && L > 0 && heads > 0, PC_ERR_ARG, "attnpool_query0: bad arguments");
+  const int Lp = (L + 31) & ~31;
+  const size_t smem = static_cast<size_t>(POOL_WARPS) * (64 + Lp) * sizeof(float);
+  PC_REQUIRE(smem <= 48 * 1024, PC_ERR_ARG, "attnpool_query0: %d tokens need %zu B of shared memory", L, smem);
+  const int items = B * heads;
+  const int want = (items + POOL_WARPS - 1) / POOL_WARPS, cap = device_sm_count() * 8;
+  attnpool_query0_kernel<<<want < cap ? want : cap, POOL_WARPS * 32, smem, stream>>>(q, kv, out, B, L, heads);
   PC_CHECK_CUDA(cudaGetLastError());
   return PC_OK;
 }

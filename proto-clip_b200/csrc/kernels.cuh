@@ -113,6 +113,8 @@ int launch_avgpool_nhwc(const __half* x, __half* y, int B, int H, int W, int C, 
                         cudaStream_t stream);
 // AttentionPool2d tokens: [B,HW,C] -> [B,HW+1,C] = [mean; pixels] + pos (clip/model.py:68-70)
 int launch_attnpool_tokens(const __half* x, const float* pos, __half* tok, int B, int HW, int C, cudaStream_t stream);
+// AttentionPool2d's single live query row (token 0, clip/model.py:72-92): q [B, E], kv [B*L, 2E] = k | v -> out [B, E]
+int launch_attnpool_query0(const __half* q, const __half* kv, __half* out, int B, int L, int heads, cudaStream_t stream);
 
 // ---------------------------------------------------------------- preprocess.cu (clip/clip.py:77-84 `_transform`)
 // B same-size RGB uint8 images [B, H, W, 3] (device) -> [B, 3, n_px, n_px] fp32 / fp16: bicubic antialiased resize of the shorter side
