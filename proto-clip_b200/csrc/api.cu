@@ -131,6 +131,15 @@ int check_blocks(const pc_resblock_weights* b, int layers) {
   return PC_OK;
 }
 
+bool planar_qkv_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PC_NO_PLANAR_QKV");  // A/B switch: 1 keeps the packed [rows, 3d] qkv layout
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int use_device(const pc_ctx* ctx) {
   PC_REQUIRE(ctx != nullptr, PC_ERR_ARG, "null context");
   PC_CHECK_CUDA(cudaSetDevice(ctx->device));
@@ -242,8 +251,12 @@ int resblock_fused(const Tower& t, int layer, __half* x, __half* h, __half* big,
   g.W = t.qkv_ln[layer].w; g.ldw = d;
   g.C = big; g.ldc = 3 * d;
   g.ln_stats = s1; g.ln_parts = parts_in; g.ln_s = t.qkv_ln[layer].s; g.ln_c = t.qkv_ln[layer].c;
+  // L <= 208: the projection writes q / k / v as 3 * heads contiguous [rows, 64] planes -- an item's Q, K and V are three
+  // contiguous 25 KB blocks for the attention kernel's TMA loads instead of 128-byte pieces at a 6 d-byte stride
+  const int planar = attention6_supports(L) && planar_qkv_enabled() ? 1 : 0;
+  g.c_planar = planar;
   if (parts & 1) PC_TRY(launch_gemm(g, EPI_LN_BIAS, s));
-  if (parts & 2) PC_TRY(launch_attention(big, h, B, L, t.heads, causal, s));
+  if (parts & 2) PC_TRY(launch_attention_layout(big, planar, h, B, L, t.heads, causal, s));
   g = GemmArgs{};
   g.M = rows; g.N = d; g.K = d;
   g.A = h; g.lda = d;

@@ -474,10 +474,18 @@ int launch_variant(int grid, int smem_bytes, cudaStream_t stream, const CUtensor
 
 }  // namespace
 
+int launch_attention_layout(const __half* qkv, int qkv_planar, __half* out, int B, int L, int heads, int causal,
+                            cudaStream_t stream) {
+  PC_REQUIRE(qkv && out && B > 0 && L > 0 && heads > 0, PC_ERR_ARG, "attention: bad arguments");
+  if (attention6_supports(L)) return launch_attention6(qkv, qkv_planar, out, B, L, heads, causal, stream);
+  PC_REQUIRE(!qkv_planar, PC_ERR_ARG, "attention: the planar qkv layout is only read by the L <= 208 kernel (L = %d)", L);
+  return launch_attention(qkv, out, B, L, heads, causal, stream);
+}
+
 int launch_attention(const __half* qkv, __half* out, int B, int L, int heads, int causal,
                      cudaStream_t stream) {
   PC_REQUIRE(qkv && out && B > 0 && L > 0 && heads > 0, PC_ERR_ARG, "attention: bad arguments");
-  if (attention6_supports(L)) return launch_attention6(qkv, out, B, L, heads, causal, stream);  // whole-row S in TMEM
+  if (attention6_supports(L)) return launch_attention6(qkv, 0, out, B, L, heads, causal, stream);  // whole-row S in TMEM
   if (attention5_supports(L)) return launch_attention5(qkv, out, B, L, heads, causal, stream);  // round-1 kernel (A/B)
   const int d = heads * HEAD_DIM;
   AttnParams p{};

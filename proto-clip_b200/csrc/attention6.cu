@@ -323,17 +323,17 @@ attention6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           mbar_arrive_expect_tx(qk, static_cast<uint32_t>(n_act) * (2 * p.na * 128));
           for (int s = 0; s < n_act; ++s) {
             const int item = 2 * g + s;
-            const int c0 = (item % p.heads) * HEAD_DIM, r0 = (item / p.heads) * p.L;
-            tma_load_2d(stage + OFF_Q + s * TILE_BYTES, &tmT, qk, c0, r0);
-            tma_load_2d(stage + OFF_K + s * TILE_BYTES, &tmT, qk, p.d + c0, r0);
+            const int hd = item % p.heads, r0 = (item / p.heads) * p.L;
+            tma_load_3d(stage + OFF_Q + s * TILE_BYTES, &tmT, qk, 0, r0, hd);
+            tma_load_3d(stage + OFF_K + s * TILE_BYTES, &tmT, qk, 0, r0, p.heads + hd);
           }
         } else {
-          const int c0 = (g % p.heads) * HEAD_DIM, r0 = (g / p.heads) * p.L;
+          const int hd = g % p.heads, r0 = (g / p.heads) * p.L;
           mbar_arrive_expect_tx(qk, 2 * TILE_BYTES + 2 * p.nb * 128);
-          tma_load_2d(stage + OFF_K, &tmQ, qk, p.d + c0, r0);
-          tma_load_2d(stage + OFF_Q, &tmQ, qk, c0, r0);
-          tma_load_2d(stage + OFF_K + TILE_BYTES, &tmT, qk, p.d + c0, r0 + 128);
-          tma_load_2d(stage + OFF_Q + TILE_BYTES, &tmT, qk, c0, r0 + 128);
+          tma_load_3d(stage + OFF_K, &tmQ, qk, 0, r0, p.heads + hd);
+          tma_load_3d(stage + OFF_Q, &tmQ, qk, 0, r0, hd);
+          tma_load_3d(stage + OFF_K + TILE_BYTES, &tmT, qk, 0, r0 + 128, p.heads + hd);
+          tma_load_3d(stage + OFF_Q + TILE_BYTES, &tmT, qk, 0, r0 + 128, hd);
         }
       }
       __syncwarp();
@@ -344,14 +344,13 @@ attention6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           mbar_arrive_expect_tx(vf, static_cast<uint32_t>(n_act) * (p.na * 128));
           for (int s = 0; s < n_act; ++s) {
             const int item = 2 * g + s;
-            tma_load_2d(stage + OFF_V + s * TILE_BYTES, &tmT, vf, 2 * p.d + (item % p.heads) * HEAD_DIM,
-                        (item / p.heads) * p.L);
+            tma_load_3d(stage + OFF_V + s * TILE_BYTES, &tmT, vf, 0, (item / p.heads) * p.L, 2 * p.heads + item % p.heads);
           }
         } else {
-          const int c0 = (g % p.heads) * HEAD_DIM, r0 = (g / p.heads) * p.L;
+          const int hd = g % p.heads, r0 = (g / p.heads) * p.L;
           mbar_arrive_expect_tx(vf, TILE_BYTES + p.nb * 128);
-          tma_load_2d(stage + OFF_V, &tmQ, vf, 2 * p.d + c0, r0);
-          tma_load_2d(stage + OFF_V + TILE_BYTES, &tmT, vf, 2 * p.d + c0, r0 + 128);
+          tma_load_3d(stage + OFF_V, &tmQ, vf, 0, r0, 2 * p.heads + hd);
+          tma_load_3d(stage + OFF_V + TILE_BYTES, &tmT, vf, 0, r0 + 128, 2 * p.heads + hd);
         }
       }
       __syncwarp();
@@ -600,7 +599,10 @@ bool attention6_supports(int L) {
   return impl == 6 && L <= 208;
 }
 
-int launch_attention6(const __half* qkv, __half* out, int B, int L, int heads, int causal, cudaStream_t stream) {
+// qkv: packed [B*L, 3d] (nn.MultiheadAttention in-proj order) or planar [3 * heads][B*L][64] (GemmArgs::c_planar).
+// Either way the kernel sees a 3-D tensor [plane = 3 * heads][row = B*L][64]: only the strides differ.
+int launch_attention6(const __half* qkv, int qkv_planar, __half* out, int B, int L, int heads, int causal,
+                      cudaStream_t stream) {
   const int d = heads * HEAD_DIM;
   Params6 p{};
   p.L = L;
@@ -630,8 +632,10 @@ int launch_attention6(const __half* qkv, __half* out, int B, int L, int heads, i
   CUtensorMap tmQ, tmT, tmO;
   const uint64_t rows = static_cast<uint64_t>(B) * L;
   const int tail_rows = p.split ? p.na : p.nb;  // split: the K / V box of one item; else part b of the shared item
-  PC_TRY(make_tmap_f16_2d(&tmQ, qkv, 3 * d, rows, static_cast<uint64_t>(3 * d) * 2, 64, 128));
-  PC_TRY(make_tmap_f16_2d(&tmT, qkv, 3 * d, rows, static_cast<uint64_t>(3 * d) * 2, 64, tail_rows));
+  const uint64_t row_pitch = qkv_planar ? 128 : static_cast<uint64_t>(3 * d) * 2;
+  const uint64_t plane_pitch = qkv_planar ? rows * 128 : 128;
+  PC_TRY(make_tmap_f16_3d(&tmQ, qkv, 64, rows, 3 * heads, row_pitch, plane_pitch, 64, 128));
+  PC_TRY(make_tmap_f16_3d(&tmT, qkv, 64, rows, 3 * heads, row_pitch, plane_pitch, 64, tail_rows));
   PC_TRY(make_tmap_f16_3d(&tmO, out, d, L, B, static_cast<uint64_t>(d) * 2, static_cast<uint64_t>(L) * d * 2, 32, 32));
   const int sms = device_sm_count();
   const int grid = p.n_groups < sms ? p.n_groups : sms;

@@ -487,7 +487,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         fence_async_smem();  // generic-proxy writes -> visible to the TMA store
         __syncwarp();
         if (elect_one()) {
-          if (!(g.debug & 1) && gcol0 < g.N && m0 + row_off < g.M) tma_store_2d(&tmC, stg, gcol0, m0 + row_off);
+          if (!(g.debug & 1) && gcol0 < g.N && m0 + row_off < g.M) {
+            if (g.c_planar) tma_store_3d(&tmC, stg, 0, m0 + row_off, gcol0 / GRP_COLS);  // plane = 64-column block
+            else tma_store_2d(&tmC, stg, gcol0, m0 + row_off);
+          }
           tma_store_commit();
         }
       }
@@ -552,6 +555,8 @@ int launch_impl(const GemmArgs& a0, cudaStream_t stream) {
                       128));
   if (EPI == EPI_F32) {
     PC_TRY(make_tmap_2d(&tmC, a.C, 4, a.N, a.M, static_cast<uint64_t>(a.ldc) * 4, 32, 32));
+  } else if (a.c_planar) {
+    PC_TRY(make_tmap_f16_3d(&tmC, a.C, 64, a.M, a.N / 64, 128, static_cast<uint64_t>(a.M) * 128, 64, 32));
   } else {
     PC_TRY(make_tmap_2d(&tmC, a.C, 2, a.N, a.M, static_cast<uint64_t>(a.ldc) * 2, 64, 32));
   }
@@ -693,6 +698,8 @@ int launch_gemm(const GemmArgs& a, int epilogue, cudaStream_t stream) {
   const int chunk = (epilogue == EPI_F32) ? 4 : 8;
   PC_REQUIRE(a.ldc % chunk == 0 && a.ldc >= a.N && (reinterpret_cast<uintptr_t>(a.C) & 15) == 0, PC_ERR_ALIGN,
              "gemm: output needs a 16-byte aligned C and ldc (%d) >= N (%d), a multiple of %d", a.ldc, a.N, chunk);
+  PC_REQUIRE(!a.c_planar || (epilogue != EPI_F32 && epilogue != EPI_BIAS_RES && a.N % 64 == 0), PC_ERR_ARG,
+             "gemm: planar output needs an fp16 non-residual epilogue and N %% 64 == 0 (N = %d)", a.N);
   if (epilogue == EPI_BIAS_RES) {
     PC_REQUIRE(a.residual != nullptr && a.ldr % 8 == 0 && a.ldr >= a.N &&
                    (reinterpret_cast<uintptr_t>(a.residual) & 15) == 0,

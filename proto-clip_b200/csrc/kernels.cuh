@@ -25,6 +25,9 @@ struct GemmArgs {
   const __half* A; int lda;   // [M, K] row-major, lda elements
   const __half* W; int ldw;   // [N, K] row-major
   void* C; int ldc;           // [M, N] fp16 (fp32 for EPI_F32)
+  int c_planar;               // 1 (fp16 epilogues, N % 64 == 0): C is written as N/64 planes [N/64][M][64] -- column block j
+                              // of the result is a contiguous [M, 64] matrix. The QKV projection uses it so that one
+                              // head's q / k / v rows are contiguous 128-byte rows for the attention kernel's TMA loads.
   const __half* bias;         // [N] or nullptr
   const float* bias_f32;      // [N] fp32 bias used instead of `bias` when non-null (folded BatchNorm shift)
   // 3x3 / stride 1 / padding 1 convolution as an implicit GEMM over a ZERO-BORDERED NHWC activation
@@ -56,11 +59,15 @@ int gemm_stats_parts(int M, int N);
 // qkv: [B*L, 3*d] fp16, columns [0,d) = q, [d,2d) = k, [2d,3d) = v, head h at h*64 (nn.MultiheadAttention
 // packed in-proj order). out: [B*L, d] fp16 (heads merged). head_dim is fixed at 64 (all CLIP towers).
 int launch_attention(const __half* qkv, __half* out, int B, int L, int heads, int causal, cudaStream_t stream);
+// qkv_planar = 1: qkv is [3 * heads][B*L][64] (GemmArgs::c_planar); only attention6 shapes (attention6_supports(L))
+int launch_attention_layout(const __half* qkv, int qkv_planar, __half* out, int B, int L, int heads, int causal,
+                            cudaStream_t stream);
 // attention6.cu: the L <= 256 kernel (whole score row in TMEM, exact softmax, two query tiles in flight per SM);
 // launch_attention dispatches to it. PC_ATTN_IMPL=5 selects the round-1 kernel (attention5.cu: 64-key blocks, online
 // softmax, four tiles in flight), PC_ATTN_IMPL=2 keeps every shape on attention.cu's streaming kernel (A/B timing).
 bool attention6_supports(int L);
-int launch_attention6(const __half* qkv, __half* out, int B, int L, int heads, int causal, cudaStream_t stream);
+int launch_attention6(const __half* qkv, int qkv_planar, __half* out, int B, int L, int heads, int causal,
+                      cudaStream_t stream);
 bool attention5_supports(int L);
 int launch_attention5(const __half* qkv, __half* out, int B, int L, int heads, int causal, cudaStream_t stream);
 
