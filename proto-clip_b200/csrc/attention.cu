@@ -462,6 +462,104 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
 }
 
+// The last L % 128 query rows of every sequence when that remainder is tiny (ViT-L/14: L = 257 = 2 x 128 + 1): a third
+// 128-row tile would cost a whole pass of its warpgroup over every key block for one live row (measured: 192 TFLOP/s
+// at L = 257 against 320 at L = 577). One CTA per (sequence, head, row), one warp per 32 keys: a lane scores one key
+// (a 64-wide dot product of a 128-byte row), the warp forms its partial (max, sum, P V) with the 32 V-row loads in
+// flight at once, the partials meet in shared memory (online-softmax merge). fp32 throughout.
+constexpr int TAIL_MAX_ROWS = 8;
+constexpr int TAIL_MAX_WARPS = 32;
+__global__ void __launch_bounds__(TAIL_MAX_WARPS * 32)
+attention_tail_rows_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int B, int L, int heads, int row0,
+                           int causal) {
+  __shared__ float qs[64];
+  __shared__ float part[TAIL_MAX_WARPS][66];  // per warp: max, sum, o[64]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int d = heads * HEAD_DIM, nrows = L - row0;
+  griddep_launch_dependents();
+  griddep_wait();
+  const int item = blockIdx.x;
+  const int i = row0 + item % nrows, bh = item / nrows, b = bh / heads, h = bh % heads;
+  const int nkeys = causal ? i + 1 : L;
+  if (w == 0) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(
+        qkv + (static_cast<size_t>(b) * L + i) * 3 * d + h * HEAD_DIM + 2 * lane));
+    qs[2 * lane] = f.x * 0.125f;
+    qs[2 * lane + 1] = f.y * 0.125f;
+  }
+  __syncthreads();
+  const __half* kbase = qkv + static_cast<size_t>(b) * L * 3 * d + d + h * HEAD_DIM;
+  const __half* vbase = kbase + d;
+  // scores of keys [32 w, 32 w + 32): eight lanes share a key row (16 bytes each: every load instruction reads four
+  // whole 128-byte rows), eight rounds of four keys; the 8-lane partial dot products meet by shuffles
+  __shared__ float sc_s[TAIL_MAX_WARPS][32];
+  const int part8 = lane & 7, kq = lane >> 3;
+  float qv[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) qv[e] = qs[8 * part8 + e];
+  uint4 kk[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const int jj = min(32 * w + 4 * t + kq, nkeys - 1);
+    kk[t] = *(reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(jj) * 3 * d) + part8);
+  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const __half2* h2 = reinterpret_cast<const __half2*>(&kk[t]);
+    float acc = 0.0f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(h2[e]);
+      acc = fmaf(f.x, qv[2 * e], fmaf(f.y, qv[2 * e + 1], acc));
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (part8 == 0) sc_s[w][4 * t + kq] = acc;
+  }
+  __syncwarp();
+  const int j = 32 * w + lane;
+  const float sc = (j < nkeys) ? sc_s[w][lane] : -INFINITY;
+  const float mw = warp_max(sc);
+  const float pj = (j < nkeys) ? __expf(sc - mw) : 0.0f;
+  const float lw = warp_sum(pj);
+  float o0 = 0.0f, o1 = 0.0f;
+  if (32 * w < nkeys) {
+    __half2 vv[32];
+#pragma unroll
+    for (int u = 0; u < 32; ++u)
+      vv[u] = *reinterpret_cast<const __half2*>(vbase + static_cast<size_t>(min(32 * w + u, nkeys - 1)) * 3 * d + 2 * lane);
+#pragma unroll
+    for (int u = 0; u < 32; ++u) {
+      const float pu = __shfl_sync(0xffffffffu, pj, u);  // 0 for keys past nkeys
+      const float2 f = __half22float2(vv[u]);
+      o0 = fmaf(pu, f.x, o0);
+      o1 = fmaf(pu, f.y, o1);
+    }
+  }
+  if (lane == 0) {
+    part[w][0] = mw;
+    part[w][1] = lw;
+  }
+  part[w][2 + 2 * lane] = o0;
+  part[w][3 + 2 * lane] = o1;
+  __syncthreads();
+  if (w == 0) {
+    float m = -INFINITY;
+    for (int k = 0; k < nwarps; ++k) m = fmaxf(m, part[k][0]);
+    float l = 0.0f, a0 = 0.0f, a1 = 0.0f;
+    for (int k = 0; k < nwarps; ++k) {
+      const float sck = (part[k][0] == -INFINITY) ? 0.0f : __expf(part[k][0] - m);
+      l = fmaf(part[k][1], sck, l);
+      a0 = fmaf(part[k][2 + 2 * lane], sck, a0);
+      a1 = fmaf(part[k][3 + 2 * lane], sck, a1);
+    }
+    const float inv = 1.0f / l;
+    *reinterpret_cast<__half2*>(out + (static_cast<size_t>(b) * L + i) * d + h * HEAD_DIM + 2 * lane) =
+        __floats2half2_rn(a0 * inv, a1 * inv);
+  }
+}
+
 template <bool CAUSAL>
 int launch_variant(int grid, int smem_bytes, cudaStream_t stream, const CUtensorMap& tmQ, const CUtensorMap& tmKV,
                    const CUtensorMap& tmO, const AttnParams& p) {
@@ -495,6 +593,16 @@ int launch_attention(const __half* qkv, __half* out, int B, int L, int heads, in
   p.d = d;
   p.items = B * heads;
   p.m_tiles = (L + 127) / 128;
+  // a tiny last tile goes to attention_tail_rows_kernel instead (see there); PC_ATTN_NO_TAIL=1 switches that off
+  static int no_tail = -1;
+  if (no_tail < 0) {
+    const char* e = getenv("PC_ATTN_NO_TAIL");
+    no_tail = e ? atoi(e) : 0;  // 1: third tile in the main kernel; 2 (timing only, wrong results): tail rows skipped
+  }
+  const int tail_rows = (L > 256 && L % 128 >= 1 && L % 128 <= TAIL_MAX_ROWS && no_tail != 1) ? L % 128 : 0;
+  const int tail_warps = (L + 31) / 32;  // one warp per 32 keys
+  const bool use_tail = tail_rows > 0 && tail_warps <= TAIL_MAX_WARPS;
+  if (use_tail) p.m_tiles -= 1;
   p.split = p.m_tiles == 1 ? 1 : 0;
   p.ppi = (p.m_tiles + 1) / 2;
   p.n_groups = p.split ? (p.items + 1) / 2 : p.items * p.ppi;
@@ -536,6 +644,10 @@ int launch_attention(const __half* qkv, __half* out, int B, int L, int heads, in
   }
   PC_TRY(causal ? launch_variant<true>(grid, smem_bytes, stream, tmQ, tmKV, tmO, p)
                 : launch_variant<false>(grid, smem_bytes, stream, tmQ, tmKV, tmO, p));
+  if (use_tail && no_tail != 2) {
+    PC_CHECK_CUDA(launch_pdl(attention_tail_rows_kernel, dim3(B * heads * tail_rows), dim3(tail_warps * 32), 0, stream, 1,
+                             qkv, out, B, L, heads, L - tail_rows, causal));
+  }
   if (tracing) {
     static int printed = 0;
     long long h[32 * 2 * 8];

@@ -331,11 +331,18 @@ attnpool_query0_kernel(const __half* __restrict__ q, const __half* __restrict__ 
     __syncwarp();
     const __half* vbase = kbase + E;
     float o0 = 0.0f, o1 = 0.0f;
-    for (int j = 0; j < L; ++j) {
-      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(vbase + static_cast<size_t>(j) * 2 * E + 2 * lane));
-      const float pj = ps[j];
-      o0 = fmaf(pj, f.x, o0);
-      o1 = fmaf(pj, f.y, o1);
+    for (int j0 = 0; j0 < L; j0 += 32) {  // 32 independent row loads in flight, then the FMAs
+      __half2 vv[32];
+#pragma unroll
+      for (int u = 0; u < 32; ++u)
+        vv[u] = *reinterpret_cast<const __half2*>(vbase + static_cast<size_t>(min(j0 + u, L - 1)) * 2 * E + 2 * lane);
+#pragma unroll
+      for (int u = 0; u < 32; ++u) {
+        const float2 f = __half22float2(vv[u]);
+        const float pj = (j0 + u < L) ? ps[j0 + u] : 0.0f;
+        o0 = fmaf(pj, f.x, o0);
+        o1 = fmaf(pj, f.y, o1);
+      }
     }
     const float inv = 1.0f / sum;
     *reinterpret_cast<__half2*>(out + static_cast<size_t>(b) * E + h * 64 + 2 * lane) = __floats2half2_rn(o0 * inv, o1 * inv);

@@ -86,7 +86,9 @@ def test_linear_residual_in_place(nat):
                                               # in split mode, the RN50x16 attention pool, causal rows across both parts
                                               (1, 145, 48, False), (2, 208, 1, False), (2, 200, 2, False), (3, 130, 1, False),
                                               (2, 144, 1, False), (1, 16, 1, False), (5, 64, 3, True), (3, 127, 1, False),
-                                              (3, 255, 2, True), (1, 256, 1, True), (13, 197, 12, False), (3, 33, 1, True)])
+                                              (3, 255, 2, True), (1, 256, 1, True), (13, 197, 12, False), (3, 33, 1, True),
+                                              # L = k * 128 + few rows: the last rows go to attention_tail_rows_kernel
+                                              (3, 257, 16, False), (2, 260, 2, True), (2, 392, 1, False), (5, 264, 3, False)])
 def test_attention(nat, B, L, heads, causal):
     torch.manual_seed(L)
     d = heads * 64
