@@ -145,16 +145,13 @@ def run_ours(args):
         # (SURVEY f2): 16 000 support images (augment_epoch 1) and N x 7 prompts. A random-init text tower is not
         # class-aligned, so its output is timed / exercised only: the classifier's textual memory is the aligned
         # synthetic bank below.
-        sup_lo, sup_hi = pdist.shard_bounds(N_CLASSES * K_SHOTS, rank, world)
-        feats = []
-        for n0 in range(sup_lo, sup_hi, 1024):
-            labels = torch.arange(n0, min(n0 + 1024, sup_hi), device=dev) // K_SHOTS
-            imgs = synthetic.class_structured_images(bases, labels, seed=2 + n0)
-            feats.append(ctx.encode_image(imgs, l2norm=True, micro_batch=mb))   # utils.py:310,319
-        V = pdist.all_gather_rows(torch.cat(feats), N_CLASSES * K_SHOTS)
-        tok_lo, tok_hi = pdist.shard_bounds(N_CLASSES * N_TEMPLATES, rank, world)
-        tokens = synthetic_tokens(N_CLASSES * N_TEMPLATES, c["context_length"], c["vocab_size"], 5)[tok_lo:tok_hi].to(dev)
-        te = pdist.all_gather_rows(ctx.encode_text(tokens, l2norm=True), N_CLASSES * N_TEMPLATES)  # utils.py:266-267
+        def support_slice(lo, hi):
+            labels = torch.arange(lo, hi, device=dev) // K_SHOTS
+            return synthetic.class_structured_images(bases, labels, seed=2 + lo)
+
+        tokens = synthetic_tokens(N_CLASSES * N_TEMPLATES, c["context_length"], c["vocab_size"], 5)
+        V, te = pipeline.build_memory_sharded(ctx, support_slice, tokens, micro_batch=mb,
+                                              num_support=N_CLASSES * K_SHOTS)        # utils.py:310,319 / 266-267
         if rank == 0:
             _ = nat.l2_normalize(te.view(N_CLASSES, N_TEMPLATES, D).float().mean(dim=1).half())   # utils.py:268-269
             T = synthetic.aligned_text_memory(V, N_CLASSES, K_SHOTS, seed=6)

@@ -127,22 +127,30 @@ class FewShotClassifier:
         return self.classify_features(feats, want_p=want_p)
 
 
-def build_memory_sharded(ctx: "nat.Context", support_images: torch.Tensor, prompt_tokens: Optional[torch.Tensor],
-                         micro_batch: int = 0) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+def build_memory_sharded(ctx: "nat.Context", support_images, prompt_tokens: Optional[torch.Tensor],
+                         micro_batch: int = 0, num_support: Optional[int] = None,
+                         chunk: int = 1024) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """Memory-bank construction sharded across ranks (utils.py:284-332 and 256-273 run it on one
-    GPU): every rank encodes its contiguous slice of the label-sorted support images ([N*K, 3, R, R], same tensor on
-    every rank or at least the rank's own slice filled) and of the prompt rows ([N*T, ctx] int64), then ONE
-    all-gather per bank. Returns (V [N*K, D] f16 L2-normalised, text features [N*T, D] f16 L2-normalised or None),
-    identical on every rank and identical to the single-GPU result (per-row arithmetic does not depend on the shard).
-    """
+    GPU): every rank encodes its contiguous slice of the label-sorted support set and of the prompt rows
+    ([N*T, ctx] int64), then ONE all-gather per bank. `support_images` is either a tensor [N*K, 3, R, R] (the same on
+    every rank, or at least the rank's own slice filled) or a callable `(lo, hi) -> images [hi - lo, 3, R, R]` that
+    produces a slice on demand (bench.py draws its synthetic support set that way; `num_support` = N*K then).
+    Returns (V [N*K, D] f16 L2-normalised, text features [N*T, D] f16 L2-normalised or None), identical on every rank
+    and identical to the single-GPU result (per-row arithmetic does not depend on the shard or on `chunk`)."""
     from . import dist as pdist
     rank, _, world = pdist.env_rank()
-    total = support_images.shape[0]
+    if not pdist.active():
+        rank, world = 0, 1
+    total = int(num_support) if callable(support_images) else support_images.shape[0]
     lo, hi = pdist.shard_bounds(total, rank, world)
     dev = ctx.device
     D = ctx.vis_desc["embed_dim"]
-    local = ctx.encode_image(support_images[lo:hi].to(dev), l2norm=True, micro_batch=micro_batch) if hi > lo else \
-        torch.empty((0, D), dtype=torch.float16, device=dev)
+    feats = []
+    for c0 in range(lo, hi, chunk):
+        c1 = min(c0 + chunk, hi)
+        imgs = support_images(c0, c1) if callable(support_images) else support_images[c0:c1]
+        feats.append(ctx.encode_image(imgs.to(dev), l2norm=True, micro_batch=micro_batch))
+    local = torch.cat(feats) if feats else torch.empty((0, D), dtype=torch.float16, device=dev)
     V = pdist.all_gather_rows(local, total)
     T = None
     if prompt_tokens is not None:

@@ -66,6 +66,22 @@ def get_model_dir_root(cfg):
     return f"{cfg['cache_dir']}/models/{beautify(cfg['backbone'])}/K-{cfg['shots']}"
 
 
+_n2_cache = {}
+
+
+def _norm2(z):
+    """||z_n||^2 [N] fp32 of a prototype matrix, remembered per (storage, shape, version): main.py calls P() / predict()
+    hundreds of times on the same prototypes (main.py:419-448)."""
+    key = (z.data_ptr(), tuple(z.shape), z._version, str(z.device))
+    hit = _n2_cache.get(key)
+    if hit is None:
+        if len(_n2_cache) > 16:
+            _n2_cache.clear()
+        hit = z.float().pow(2).sum(-1)
+        _n2_cache[key] = hit
+    return hit
+
+
 def P(zq_imgs_flat, z_img_proto, z_text_proto, alpha, beta):
     """p = alpha * softmax(-beta * ||q - c_img||^2) + (1 - alpha) * softmax(-beta * ||q - c_txt||^2), fp32 [Q, N].
 
@@ -74,8 +90,8 @@ def P(zq_imgs_flat, z_img_proto, z_text_proto, alpha, beta):
     q = zq_imgs_flat.half().contiguous()
     zi = z_img_proto.half().contiguous()
     zt = z_text_proto.half().contiguous()
-    p, _, _ = nat.proto_classify(q, zi, zt, zi.float().pow(2).sum(-1), zt.float().pow(2).sum(-1), float(alpha),
-                                 float(beta), want_p=True, want_argmax=False)
+    p, _, _ = nat.proto_classify(q, zi, zt, _norm2(zi), _norm2(zt), float(alpha), float(beta), want_p=True,
+                                 want_argmax=False)
     return p
 
 
@@ -84,8 +100,8 @@ def predict(zq_imgs_flat, z_img_proto, z_text_proto, alpha, beta):
     q = zq_imgs_flat.half().contiguous()
     zi = z_img_proto.half().contiguous()
     zt = z_text_proto.half().contiguous()
-    _, am, _ = nat.proto_classify(q, zi, zt, zi.float().pow(2).sum(-1), zt.float().pow(2).sum(-1), float(alpha),
-                                  float(beta), want_p=False, want_argmax=True)
+    _, am, _ = nat.proto_classify(q, zi, zt, _norm2(zi), _norm2(zt), float(alpha), float(beta), want_p=False,
+                                  want_argmax=True)
     return am
 
 

@@ -55,6 +55,20 @@ if rank == 0:
     torch.save({k: v.cuda() for k, v in asd.items()}, prefix + "_a.pt")
 pdist.barrier()
 res = M.main(argv + ["--only_test"])
+# the tensor-in / tensor-out sharded builder bench.py's prelude uses (pipeline.build_memory_sharded), both input forms
+from proto_clip_b200 import _native as nat  # noqa: E402
+from proto_clip_b200 import pipeline  # noqa: E402
+dev = torch.device("cuda", torch.cuda.current_device())
+ctx = nat.Context(dev)
+sd_small = synthetic.make_state_dict("small", 0)
+ctx.bind_visual(sd_small)
+ctx.bind_text(sd_small)
+bases = synthetic.class_bases(N, c["image_resolution"], seed=1, device=dev)
+sup_labels = torch.arange(N * 3, device=dev) // 3
+sup = synthetic.class_structured_images(bases, sup_labels, seed=2)
+V_t, T_t = pipeline.build_memory_sharded(ctx, sup, tok, num_support=None, chunk=5)
+V_c, _ = pipeline.build_memory_sharded(ctx, lambda lo, hi: sup[lo:hi], None, num_support=N * 3, chunk=4)
+assert torch.equal(V_t, V_c)
 if rank == 0:
     text_mb = utils.load(f"{root}/text_mb_{utils.beautify(backbone)}_K_{K}.pkl", "text memory")
     torch.save({"world": world, "zero_val_grid": out["val_grid"], "zero_test_grid": out["test_grid"],
@@ -64,6 +78,7 @@ if rank == 0:
                 "test_features": torch.load(f"{root}/test_features.pt").cpu(),
                 "test_labels": torch.load(f"{root}/test_labels.pt").cpu(),
                 "val_grid": res["val_grid"], "test_acc_grid": res["test_acc_grid"], "test_pred": res["test_pred"],
-                "hp_pred": res["hp_pred"], "test_acc": res["test_acc"]}, "result.pt")
+                "hp_pred": res["hp_pred"], "test_acc": res["test_acc"], "sharded_V": V_t.cpu(), "sharded_T": T_t.cpu()},
+               "result.pt")
     print("RUNNER OK", world)
 pdist.barrier()

@@ -724,7 +724,7 @@ def test_cli_two_ranks_equal_one_rank(nat, tmp_path):
     a = torch.load(tmp_path / "one" / "result.pt", weights_only=False)
     b = torch.load(tmp_path / "two" / "result.pt", weights_only=False)
     assert a["world"] == 1 and b["world"] == 2
-    for k in ("keys", "values", "text_mb", "test_features", "test_labels", "test_pred", "hp_pred"):
+    for k in ("keys", "values", "text_mb", "test_features", "test_labels", "test_pred", "hp_pred", "sharded_V", "sharded_T"):
         assert torch.equal(a[k], b[k]), k
     for k in ("zero_val_grid", "zero_test_grid", "val_grid", "test_acc_grid"):
         assert a[k].shape == (319, 3) and np.array_equal(a[k], b[k]), k
