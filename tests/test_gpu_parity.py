@@ -307,6 +307,40 @@ def test_layernorm_folding_under_outliers_and_offsets(nat):
         assert e_cuda.max().item() <= 3.0 * e_ref.max().item() + 1e-3
 
 
+@pytest.mark.parametrize("arch,micro_batch,P", [("tiny", 3, 7), ("tiny", 16, 16), ("small", 5, 9)])
+def test_exactly_sized_workspace_is_not_overrun(nat, arch, micro_batch, P):
+    """The towers stay inside the workspace the ABI asks for (pc_encode_*_workspace_bytes), including the LayerNorm
+    statistics block sized for the single-CTA GEMM's two partial pairs per 128 columns (the d = 64 text tower of
+    'tiny' wrote past a d/64-pair buffer in round 1): exactly-sized buffer, 64 KB of canary bytes on either side."""
+    sd = synthetic.make_state_dict(arch, 0)
+    c = synthetic.arch_config(arch)
+    ctx = nat.Context(torch.device(DEV))
+    ctx.bind_visual(sd)
+    ctx.bind_text(sd)
+    lib, guard = ctx.lib, 65536
+    tok = torch.zeros(P, c["context_length"], dtype=torch.int64)
+    tok[:, 0], tok[:, 1], tok[:, 2] = c["vocab_size"] - 2, torch.arange(P) % (c["vocab_size"] - 3) + 1, c["vocab_size"] - 1
+    imgs = torch.randn(P, 3, c["image_resolution"], c["image_resolution"], device=DEV)
+    want_t = ctx.encode_text(tok.to(DEV), micro_batch=micro_batch)
+    want_i = ctx.encode_image(imgs, micro_batch=micro_batch)
+    for kind in ("text", "image"):
+        nbytes = (lib.pc_encode_text_workspace_bytes if kind == "text" else lib.pc_encode_image_workspace_bytes)(
+            ctx.handle, micro_batch)
+        buf = torch.full((guard + nbytes + guard + 256,), 0xA5, dtype=torch.uint8, device=DEV)
+        off = (-buf.data_ptr() - guard) % 256 + guard               # 256-byte aligned workspace start inside the buffer
+        out = torch.empty((P, c["embed_dim"]), dtype=torch.float16, device=DEV)
+        if kind == "text":
+            t = tok.to(DEV)
+            nat.check(lib.pc_encode_text(ctx.handle, t.data_ptr(), P, out.data_ptr(), 0, micro_batch,
+                                         buf.data_ptr() + off, nbytes, nat.stream_ptr(torch.device(DEV))), "pc_encode_text")
+        else:
+            nat.check(lib.pc_encode_image(ctx.handle, imgs.data_ptr(), 0, P, out.data_ptr(), 0, micro_batch,
+                                          buf.data_ptr() + off, nbytes, nat.stream_ptr(torch.device(DEV))), "pc_encode_image")
+        torch.cuda.synchronize()
+        assert bool((buf[:off] == 0xA5).all()) and bool((buf[off + nbytes:] == 0xA5).all()), f"{kind}: workspace overrun"
+        assert torch.equal(out, want_t if kind == "text" else want_i)
+
+
 def test_towers_without_layernorm_folding(nat):
     """PC_NO_FUSED_LN=1 (separate LayerNorm kernels, plain GEMM epilogues: csrc/api.cu resblock()) must pass the same
     tower / block goldens: the fallback stays a tested path, and the two paths stay interchangeable."""
