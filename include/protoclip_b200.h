@@ -54,6 +54,11 @@ const char* pc_last_error(void);
  * `clip.load(...)` + `.cuda()` (clip/clip.py:92-139, main.py:495-496). */
 int pc_ctx_create(int device, pc_ctx** out);
 void pc_ctx_destroy(pc_ctx* ctx);
+/* VisionTransformer.forward returns x[:, 0, :] of the last block (clip/model.py:232-236). By default pc_encode_image runs
+ * that block's attention query, out_proj, ln_2 and MLP on the CLS rows only (K / V still come from every token): same
+ * features, 6 % fewer flop for ViT-B/16. full = 1 computes every token of the last block like the reference does
+ * (A/B timing; bench.py reports both), 0 the CLS rows only, -1 follows the environment (PC_FULL_LAST_BLOCK=1). */
+int pc_ctx_set_full_last_block(pc_ctx* ctx, int full);
 
 /* Parameters of one ResidualAttentionBlock, in the reference state-dict layout and dtype
  * (clip/model.py:169-181; fp16 Linear/MHA tensors, fp32 LayerNorm tensors after convert_weights). */
@@ -204,6 +209,11 @@ int pc_layernorm_forward(const void* x, void* y, const void* gamma, const void* 
                          void* stream);
 /* nn.MultiheadAttention core (clip/model.py:173,183-185): packed qkv f16 [B*L, 3d] -> f16 [B*L, d]. */
 int pc_attention_forward(const void* qkv, void* out, int B, int L, int heads, int causal, void* stream);
+/* The same attention for query rows [row0, row0 + nrows) of every sequence only (keys / values: all L tokens);
+ * out is compact f16 [B*nrows, d]. This is what x[:, 0, :] after the last block needs (clip/model.py:232-236, row0 = 0,
+ * nrows = 1) and what the attention pool's query token needs (clip/model.py:70-92). nrows < L <= 1024. */
+int pc_attention_rows_forward(const void* qkv, void* out, int B, int L, int heads, int row0, int nrows, int causal,
+                              void* stream);
 /* x / x.norm(dim=-1, keepdim=True) on f16 rows (utils.py:267,319,352; main.py:400-409). */
 int pc_l2_normalize(const void* x, void* y, int rows, int d, void* stream);
 

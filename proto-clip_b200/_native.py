@@ -21,12 +21,13 @@ EPI_BIAS, EPI_BIAS_QUICKGELU, EPI_BIAS_RESIDUAL, EPI_F32 = 0, 1, 2, 3
 
 # every symbol include/protoclip_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
-    "pc_version", "pc_last_error", "pc_ctx_create", "pc_ctx_destroy", "pc_vit_bind_weights",
+    "pc_version", "pc_last_error", "pc_ctx_create", "pc_ctx_destroy", "pc_ctx_set_full_last_block", "pc_vit_bind_weights",
     "pc_text_bind_weights", "pc_rn_bind_weights", "pc_linear_shift_relu_forward",
     "pc_preprocess_workspace_bytes", "pc_preprocess_image", "pc_preprocess_batch_workspace_bytes", "pc_preprocess_batch", "pc_encode_image_workspace_bytes", "pc_encode_image",
     "pc_encode_text_workspace_bytes", "pc_encode_text", "pc_resblock_workspace_bytes", "pc_resblock_forward",
     "pc_resblock_forward_parts",
-    "pc_linear_forward", "pc_layernorm_forward", "pc_attention_forward", "pc_l2_normalize",
+    "pc_linear_forward", "pc_layernorm_forward", "pc_attention_forward", "pc_attention_rows_forward",
+    "pc_l2_normalize",
     "pc_adapter_fc_workspace_bytes", "pc_adapter_fc_forward", "pc_adapter_conv_forward", "pc_build_prototypes",
     "pc_proto_classify_workspace_bytes", "pc_proto_classify", "pc_proto_grid_search",
 ]
@@ -123,6 +124,7 @@ def load_library() -> C.CDLL:
     lib.pc_ctx_create.argtypes = [i, C.POINTER(vp)]
     lib.pc_ctx_destroy.argtypes = [vp]
     lib.pc_ctx_destroy.restype = None
+    lib.pc_ctx_set_full_last_block.argtypes = [vp, i]
     lib.pc_vit_bind_weights.argtypes = [vp, C.POINTER(VitWeights)]
     lib.pc_text_bind_weights.argtypes = [vp, C.POINTER(TextWeights)]
     lib.pc_rn_bind_weights.argtypes = [vp, C.POINTER(RnWeights)]
@@ -146,6 +148,7 @@ def load_library() -> C.CDLL:
     lib.pc_linear_shift_relu_forward.argtypes = [vp, i, vp, i, vp, vp, i, vp, i, i, i, i, i, i, vp]
     lib.pc_layernorm_forward.argtypes = [vp, vp, vp, vp, i, i, vp]
     lib.pc_attention_forward.argtypes = [vp, vp, i, i, i, i, vp]
+    lib.pc_attention_rows_forward.argtypes = [vp, vp, i, i, i, i, i, i, vp]
     lib.pc_l2_normalize.argtypes = [vp, vp, i, i, vp]
     lib.pc_adapter_fc_workspace_bytes.argtypes = [i, i, i]
     lib.pc_adapter_fc_workspace_bytes.restype = sz
@@ -271,6 +274,18 @@ def attention(qkv: torch.Tensor, B: int, L: int, heads: int, causal: bool) -> to
     with torch.cuda.device(qkv.device):
         check(lib.pc_attention_forward(qkv.data_ptr(), out.data_ptr(), B, L, heads, int(causal),
                                        stream_ptr(qkv.device)), "pc_attention_forward")
+    return out
+
+
+def attention_rows(qkv: torch.Tensor, B: int, L: int, heads: int, row0: int, nrows: int, causal: bool = False) -> torch.Tensor:
+    """Attention output of query rows [row0, row0 + nrows) of every sequence, compact [B*nrows, d]
+    (pc_attention_rows_forward; clip/model.py:232-236 keeps row 0 of the last block)."""
+    lib = load_library()
+    d = heads * 64
+    out = torch.empty((B * nrows, d), dtype=torch.float16, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        check(lib.pc_attention_rows_forward(qkv.data_ptr(), out.data_ptr(), B, L, heads, row0, nrows, int(causal),
+                                            stream_ptr(qkv.device)), "pc_attention_rows_forward")
     return out
 
 
@@ -560,6 +575,12 @@ class Context:
             check(self.lib.pc_encode_text(self.handle, tokens.data_ptr(), P, out.data_ptr(), int(l2norm), micro_batch,
                                           ws.data_ptr(), ws.numel(), stream_ptr(self.device)), "pc_encode_text")
         return out
+
+    def set_full_last_block(self, full: Optional[bool]) -> None:
+        """True: the last visual block computes every token like the reference (clip/model.py:232-233 then keeps the
+        CLS row); False: CLS rows only (default); None: follow PC_FULL_LAST_BLOCK."""
+        check(self.lib.pc_ctx_set_full_last_block(self.handle, -1 if full is None else int(bool(full))),
+              "pc_ctx_set_full_last_block")
 
     def resblock_forward(self, tower: int, layer: int, x: torch.Tensor, B: int, L: int, causal: bool) -> torch.Tensor:
         """In place on x: f16 [B*L, d] token-major."""

@@ -86,6 +86,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct pc_ctx {
   int device = 0;
+  int full_last_block = -1;  // -1: follow PC_FULL_LAST_BLOCK; 0 / 1: pc_ctx_set_full_last_block
   Tower vis, txt;
   RnTower rn;  // bound instead of `vis` for ModifiedResNet checkpoints
   // visual stem
@@ -282,6 +283,67 @@ int resblock_fused(const Tower& t, int layer, __half* x, __half* h, __half* big,
   g.residual = x; g.ldr = d;
   g.stats_out = s1;
   if (parts & 16) PC_TRY(launch_gemm(g, EPI_BIAS_RES, s));
+  return PC_OK;
+}
+
+// The LAST block of the visual tower, CLS rows only. VisionTransformer.forward keeps x[:, 0, :] after the last block
+// (clip/model.py:232-233): of that block only K / V of every token and the CLS row of everything else can reach the
+// output. QKV projection for all tokens (the folded GEMM as usual; its q columns of the other tokens are the only
+// unused work left), attention of the CLS query alone, then out_proj + residual, ln_2 (folded), c_fc, QuickGELU,
+// c_proj + residual on B rows instead of B * L: 18 (L - 1) d^2 + 4 L (L - 1) d of the block's 24 L d^2 + 4 L^2 d flop
+// never run (6.3 % of a ViT-B/16 tower). Per-row arithmetic is the towers' own (same GEMM kernel and epilogues; the
+// single-row attention keeps P in fp32). xc_out: compact [B, d] rows of the block output (in `h`).
+// PC_FULL_LAST_BLOCK=1 runs the whole block like the reference (A/B, and the figure bench.py reports beside).
+bool cls_only_last_block_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PC_FULL_LAST_BLOCK");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+int resblock_cls_only(const Tower& t, int layer, __half* x, __half* h, __half* big, float* s1, int parts_in, float* s2,
+                      int B, int L, __half** xc_out, cudaStream_t s) {
+  const pc_resblock_weights& w = t.blocks[layer];
+  const int d = t.width, rows = B * L;
+  GemmArgs g{};
+  g.M = rows; g.N = 3 * d; g.K = d;
+  g.A = x; g.lda = d;
+  g.W = t.qkv_ln[layer].w; g.ldw = d;
+  g.C = big; g.ldc = 3 * d;
+  g.ln_stats = s1; g.ln_parts = parts_in; g.ln_s = t.qkv_ln[layer].s; g.ln_c = t.qkv_ln[layer].c;
+  const int planar = attention6_supports(L) && planar_qkv_enabled() ? 1 : 0;
+  g.c_planar = planar;
+  PC_TRY(launch_gemm(g, EPI_LN_BIAS, s));
+  __half* attn = h;                                // [B, d]  CLS rows of the attention output
+  __half* xc = h + static_cast<size_t>(B) * d;     // [B, d]  CLS rows of the residual stream
+  __half* hid = big + static_cast<size_t>(rows) * 3 * d;  // [B, 4d] behind qkv (rows * d elements are free there)
+  PC_TRY(launch_attention_rows(big, planar, attn, B, L, t.heads, 0, 1, 0, s));
+  g = GemmArgs{};
+  g.M = B; g.N = d; g.K = d;
+  g.A = attn; g.lda = d;
+  g.W = static_cast<const __half*>(w.out_proj_weight); g.ldw = d;
+  g.C = xc; g.ldc = d;
+  g.bias = static_cast<const __half*>(w.out_proj_bias);
+  g.residual = x; g.ldr = L * d;  // row b of the residual = the CLS row of sequence b
+  g.stats_out = s2;
+  PC_TRY(launch_gemm(g, EPI_BIAS_RES, s));
+  g = GemmArgs{};
+  g.M = B; g.N = 4 * d; g.K = d;
+  g.A = xc; g.lda = d;
+  g.W = t.fc_ln[layer].w; g.ldw = d;
+  g.C = hid; g.ldc = 4 * d;
+  g.ln_stats = s2; g.ln_parts = gemm_stats_parts(B, d); g.ln_s = t.fc_ln[layer].s; g.ln_c = t.fc_ln[layer].c;
+  PC_TRY(launch_gemm(g, EPI_LN_QGELU, s));
+  g = GemmArgs{};
+  g.M = B; g.N = d; g.K = 4 * d;
+  g.A = hid; g.lda = 4 * d;
+  g.W = static_cast<const __half*>(w.c_proj_weight); g.ldw = 4 * d;
+  g.C = xc; g.ldc = d;
+  g.bias = static_cast<const __half*>(w.c_proj_bias);
+  g.residual = xc; g.ldr = d;
+  PC_TRY(launch_gemm(g, EPI_BIAS_RES, s));
+  *xc_out = xc;
   return PC_OK;
 }
 
@@ -503,6 +565,12 @@ int pc_ctx_create(int device, pc_ctx** out) {
   return PC_OK;
 }
 
+int pc_ctx_set_full_last_block(pc_ctx* ctx, int full) {
+  PC_REQUIRE(ctx != nullptr, PC_ERR_ARG, "pc_ctx_set_full_last_block: null context");
+  ctx->full_last_block = full < 0 ? -1 : (full ? 1 : 0);
+  return PC_OK;
+}
+
 void pc_ctx_destroy(pc_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
@@ -720,17 +788,26 @@ int pc_encode_image(pc_ctx* ctx, const void* images, int img_dtype, int B, void*
     PC_TRY(launch_gemm(g, EPI_BIAS, s));
     PC_TRY(launch_embed_ln_pre(ws.h, ctx->cls, ctx->vpos, ctx->ln_pre_w, ctx->ln_pre_b, ws.x,
                                fused_ln_enabled() ? ws.s1 : nullptr, n, t.L, d, s));
+    __half* cls_rows = nullptr;  // compact CLS rows when the last block ran on them alone
     if (fused_ln_enabled()) {
-      for (int l = 0; l < t.layers; ++l)
+      const bool want_cls_only = ctx->full_last_block < 0 ? cls_only_last_block_enabled() : ctx->full_last_block == 0;
+      const bool cls_only = want_cls_only && t.L >= 4 && t.L <= 1024;
+      const int full_layers = cls_only ? t.layers - 1 : t.layers;
+      for (int l = 0; l < full_layers; ++l)
         PC_TRY(resblock_fused(t, l, ws.x, ws.h, ws.big, ws.s1, l == 0 ? 1 : gemm_stats_parts(n * t.L, d), ws.s2, n, t.L, 0, s));
+      if (cls_only)
+        PC_TRY(resblock_cls_only(t, t.layers - 1, ws.x, ws.h, ws.big, ws.s1,
+                                 t.layers == 1 ? 1 : gemm_stats_parts(n * t.L, d), ws.s2, n, t.L, &cls_rows, s));
     } else {
       for (int l = 0; l < t.layers; ++l) PC_TRY(resblock(t, l, ws.x, ws.h, ws.big, n, t.L, 0, s));
     }
     // ln_post on the CLS rows, then @ proj (clip/model.py:233-236)
-    PC_TRY(launch_layernorm(ws.x, ws.h, ctx->ln_post_w, ctx->ln_post_b, n, d, t.L, s));
+    __half* post = cls_rows ? cls_rows + static_cast<size_t>(n) * d : ws.h;  // h: [attn | xc | ln_post(xc)] or [ln_post]
+    if (cls_rows) PC_TRY(launch_layernorm(cls_rows, post, ctx->ln_post_w, ctx->ln_post_b, n, d, 1, s));
+    else PC_TRY(launch_layernorm(ws.x, post, ctx->ln_post_w, ctx->ln_post_b, n, d, t.L, s));
     g = GemmArgs{};
     g.M = n; g.N = t.embed; g.K = d;
-    g.A = ws.h; g.lda = d;
+    g.A = post; g.lda = d;
     g.W = t.proj_t; g.ldw = d;
     g.C = feat + static_cast<size_t>(b0) * t.embed; g.ldc = t.embed;
     PC_TRY(launch_gemm(g, EPI_BIAS, s));
@@ -894,6 +971,12 @@ int pc_layernorm_forward(const void* x, void* y, const void* gamma, const void* 
 int pc_attention_forward(const void* qkv, void* out, int B, int L, int heads, int causal, void* stream) {
   return launch_attention(static_cast<const __half*>(qkv), static_cast<__half*>(out), B, L, heads, causal,
                           static_cast<cudaStream_t>(stream));
+}
+
+int pc_attention_rows_forward(const void* qkv, void* out, int B, int L, int heads, int row0, int nrows, int causal,
+                              void* stream) {
+  return launch_attention_rows(static_cast<const __half*>(qkv), 0, static_cast<__half*>(out), B, L, heads, row0, nrows,
+                               causal, static_cast<cudaStream_t>(stream));
 }
 
 int pc_l2_normalize(const void* x, void* y, int rows, int d, void* stream) {

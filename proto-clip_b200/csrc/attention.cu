@@ -471,25 +471,29 @@ constexpr int TAIL_MAX_ROWS = 8;
 constexpr int TAIL_MAX_WARPS = 32;
 __global__ void __launch_bounds__(TAIL_MAX_WARPS * 32)
 attention_tail_rows_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int B, int L, int heads, int row0,
-                           int causal) {
+                           int nrows, int causal, size_t plane_stride, int row_pitch, int out_seq_rows) {
   __shared__ float qs[64];
   __shared__ float part[TAIL_MAX_WARPS][66];  // per warp: max, sum, o[64]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int d = heads * HEAD_DIM, nrows = L - row0;
+  // q / k / v of head h: plane (w * heads + h) at plane_stride elements, row r at r * row_pitch inside it. Packed
+  // [B*L, 3d]: plane_stride 64, row_pitch 3d; planar [3 * heads][B*L][64]: plane_stride B*L*64, row_pitch 64.
+  // Output row of (sequence b, query i): b * out_seq_rows + (i - row0) when out_seq_rows < L (compact), else b*L + i.
+  const int d = heads * HEAD_DIM;
   griddep_launch_dependents();
   griddep_wait();
   const int item = blockIdx.x;
   const int i = row0 + item % nrows, bh = item / nrows, b = bh / heads, h = bh % heads;
   const int nkeys = causal ? i + 1 : L;
+  const size_t seq0 = static_cast<size_t>(b) * L;
   if (w == 0) {
     const float2 f = __half22float2(*reinterpret_cast<const __half2*>(
-        qkv + (static_cast<size_t>(b) * L + i) * 3 * d + h * HEAD_DIM + 2 * lane));
+        qkv + static_cast<size_t>(h) * plane_stride + (seq0 + i) * row_pitch + 2 * lane));
     qs[2 * lane] = f.x * 0.125f;
     qs[2 * lane + 1] = f.y * 0.125f;
   }
   __syncthreads();
-  const __half* kbase = qkv + static_cast<size_t>(b) * L * 3 * d + d + h * HEAD_DIM;
-  const __half* vbase = kbase + d;
+  const __half* kbase = qkv + static_cast<size_t>(heads + h) * plane_stride + seq0 * row_pitch;
+  const __half* vbase = qkv + static_cast<size_t>(2 * heads + h) * plane_stride + seq0 * row_pitch;
   // scores of keys [32 w, 32 w + 32): eight lanes share a key row (16 bytes each: every load instruction reads four
   // whole 128-byte rows), eight rounds of four keys; the 8-lane partial dot products meet by shuffles
   __shared__ float sc_s[TAIL_MAX_WARPS][32];
@@ -501,7 +505,7 @@ attention_tail_rows_kernel(const __half* __restrict__ qkv, __half* __restrict__ 
 #pragma unroll
   for (int t = 0; t < 8; ++t) {
     const int jj = min(32 * w + 4 * t + kq, nkeys - 1);
-    kk[t] = *(reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(jj) * 3 * d) + part8);
+    kk[t] = *(reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(jj) * row_pitch) + part8);
   }
 #pragma unroll
   for (int t = 0; t < 8; ++t) {
@@ -528,7 +532,7 @@ attention_tail_rows_kernel(const __half* __restrict__ qkv, __half* __restrict__ 
     __half2 vv[32];
 #pragma unroll
     for (int u = 0; u < 32; ++u)
-      vv[u] = *reinterpret_cast<const __half2*>(vbase + static_cast<size_t>(min(32 * w + u, nkeys - 1)) * 3 * d + 2 * lane);
+      vv[u] = *reinterpret_cast<const __half2*>(vbase + static_cast<size_t>(min(32 * w + u, nkeys - 1)) * row_pitch + 2 * lane);
 #pragma unroll
     for (int u = 0; u < 32; ++u) {
       const float pu = __shfl_sync(0xffffffffu, pj, u);  // 0 for keys past nkeys
@@ -555,8 +559,8 @@ attention_tail_rows_kernel(const __half* __restrict__ qkv, __half* __restrict__ 
       a1 = fmaf(part[k][3 + 2 * lane], sck, a1);
     }
     const float inv = 1.0f / l;
-    *reinterpret_cast<__half2*>(out + (static_cast<size_t>(b) * L + i) * d + h * HEAD_DIM + 2 * lane) =
-        __floats2half2_rn(a0 * inv, a1 * inv);
+    const size_t orow = out_seq_rows < L ? static_cast<size_t>(b) * out_seq_rows + (i - row0) : seq0 + i;
+    *reinterpret_cast<__half2*>(out + orow * d + h * HEAD_DIM + 2 * lane) = __floats2half2_rn(a0 * inv, a1 * inv);
   }
 }
 
@@ -571,6 +575,22 @@ int launch_variant(int grid, int smem_bytes, cudaStream_t stream, const CUtensor
 }
 
 }  // namespace
+
+// Attention of query rows [row0, row0 + nrows) of every sequence only (nrows small), against all L keys; out is compact
+// [B * nrows, d]. The last ViT block needs the CLS row alone (clip/model.py:233 keeps x[:, 0, :]).
+int launch_attention_rows(const __half* qkv, int qkv_planar, __half* out, int B, int L, int heads, int row0, int nrows,
+                          int causal, cudaStream_t stream) {
+  const int warps = (L + 31) / 32;
+  PC_REQUIRE(qkv && out && B > 0 && L > 0 && heads > 0 && nrows >= 1 && row0 >= 0 && row0 + nrows <= L && nrows < L &&
+                 warps <= TAIL_MAX_WARPS,
+             PC_ERR_ARG, "attention_rows: bad arguments (L = %d, rows [%d, %d))", L, row0, row0 + nrows);
+  const int d = heads * HEAD_DIM;
+  const size_t plane_stride = qkv_planar ? static_cast<size_t>(B) * L * HEAD_DIM : HEAD_DIM;
+  const int row_pitch = qkv_planar ? HEAD_DIM : 3 * d;
+  PC_CHECK_CUDA(launch_pdl(attention_tail_rows_kernel, dim3(B * heads * nrows), dim3(warps * 32), 0, stream, 1, qkv, out,
+                           B, L, heads, row0, nrows, causal, plane_stride, row_pitch, nrows));
+  return PC_OK;
+}
 
 int launch_attention_layout(const __half* qkv, int qkv_planar, __half* out, int B, int L, int heads, int causal,
                             cudaStream_t stream) {
@@ -646,7 +666,7 @@ int launch_attention(const __half* qkv, __half* out, int B, int L, int heads, in
                 : launch_variant<false>(grid, smem_bytes, stream, tmQ, tmKV, tmO, p));
   if (use_tail && no_tail != 2) {
     PC_CHECK_CUDA(launch_pdl(attention_tail_rows_kernel, dim3(B * heads * tail_rows), dim3(tail_warps * 32), 0, stream, 1,
-                             qkv, out, B, L, heads, L - tail_rows, causal));
+                             qkv, out, B, L, heads, L - tail_rows, tail_rows, causal, static_cast<size_t>(HEAD_DIM), 3 * d, L));
   }
   if (tracing) {
     static int printed = 0;

@@ -62,6 +62,9 @@ int launch_attention(const __half* qkv, __half* out, int B, int L, int heads, in
 // qkv_planar = 1: qkv is [3 * heads][B*L][64] (GemmArgs::c_planar); only attention6 shapes (attention6_supports(L))
 int launch_attention_layout(const __half* qkv, int qkv_planar, __half* out, int B, int L, int heads, int causal,
                             cudaStream_t stream);
+// query rows [row0, row0 + nrows) of every sequence only, all L keys (L <= 1024); out: compact [B * nrows, d]
+int launch_attention_rows(const __half* qkv, int qkv_planar, __half* out, int B, int L, int heads, int row0, int nrows,
+                          int causal, cudaStream_t stream);
 // attention6.cu: the L <= 256 kernel (whole score row in TMEM, exact softmax, two query tiles in flight per SM);
 // launch_attention dispatches to it. PC_ATTN_IMPL=5 selects the round-1 kernel (attention5.cu: 64-key blocks, online
 // softmax, four tiles in flight), PC_ATTN_IMPL=2 keeps every shape on attention.cu's streaming kernel (A/B timing).

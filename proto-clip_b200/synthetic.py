@@ -48,6 +48,19 @@ def vit_flops_per_image(name: str) -> float:
     return c["vision_layers"] * (24.0 * L * d * d + 4.0 * L * L * d) + 2.0 * g * g * 3 * p * p * d + 2.0 * d * c["embed_dim"]
 
 
+def vit_executed_flops_per_image(name: str, full_last_block: bool = False) -> float:
+    """2*MAC count this library executes for one encode_image: the reference's count minus what the last block never
+    computes when it runs on the CLS rows alone (out_proj, c_fc, c_proj and the attention queries of the other L - 1
+    tokens: 18 (L - 1) d^2 + 4 L (L - 1) d; csrc/api.cu resblock_cls_only)."""
+    full = vit_flops_per_image(name)
+    if full_last_block:
+        return full
+    c = arch_config(name)
+    g = c["image_resolution"] // c["vision_patch_size"]
+    L, d = g * g + 1, c["vision_width"]
+    return full - (18.0 * (L - 1) * d * d + 4.0 * L * (L - 1) * d)
+
+
 def _blocks(sd, prefix: str, width: int, layers: int, gen: torch.Generator):
     attn_std = width ** -0.5
     proj_std = (width ** -0.5) * ((2 * layers) ** -0.5)

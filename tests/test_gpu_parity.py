@@ -102,6 +102,27 @@ def test_attention(nat, B, L, heads, causal):
     assert rel_err(got, ref) < 2e-3
 
 
+@pytest.mark.parametrize("B,L,heads,row0,nrows,causal", [(5, 197, 12, 0, 1, False), (3, 50, 12, 0, 1, False),
+                                                         (2, 257, 16, 0, 1, False), (2, 577, 16, 0, 1, False),
+                                                         (3, 77, 8, 76, 1, True), (2, 77, 2, 30, 5, True),
+                                                         (2, 1024, 1, 1000, 3, False), (4, 4, 1, 0, 1, False),
+                                                         (600, 197, 12, 0, 1, False)])
+def test_attention_rows(nat, B, L, heads, row0, nrows, causal):
+    """pc_attention_rows_forward: the query rows the last visual block keeps (clip/model.py:232-236), compact output."""
+    torch.manual_seed(L + row0)
+    d = heads * 64
+    qkv = torch.randn(B * L, 3 * d, device=DEV).half()
+    got = nat.attention_rows(qkv, B, L, heads, row0, nrows, causal)
+    q, k, v = [t.reshape(B, L, heads, 64).permute(0, 2, 1, 3).float() for t in qkv.split(d, dim=1)]
+    s = (q @ k.transpose(-1, -2)) * 0.125
+    if causal:
+        s = s + torch.full((L, L), float("-inf"), device=DEV).triu(1)
+    ref = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3)[:, row0:row0 + nrows].reshape(B * nrows, d)
+    assert rel_err(got, ref) < 2e-3
+    with pytest.raises(nat.NativeError):
+        nat.attention_rows(qkv, B, L, heads, L - 1, 2, causal)   # rows past the sequence
+
+
 @pytest.mark.parametrize("B,L,heads,causal,gain", [(3, 197, 2, False, 6.0), (2, 77, 2, True, 6.0), (2, 577, 1, False, 4.0),
                                                     (2, 300, 2, True, 5.0)])
 def test_attention_large_logits(nat, B, L, heads, causal, gain):
@@ -161,6 +182,29 @@ def test_towers_match_reference_goldens(nat, name):
     assert cos > 0.99999
     # fp16 image input gives the same features as fp32 input (the reference casts at clip/model.py:339)
     assert torch.equal(ctx.encode_image(images.half()), f)
+
+
+@pytest.mark.parametrize("name", ["small", "ViT_B_16", "ViT_L_14_336px"])
+def test_last_block_on_cls_rows_equals_full_last_block(nat, name):
+    """VisionTransformer.forward keeps x[:, 0, :] of the last block (clip/model.py:232-236); by default the library
+    computes that block's query / out_proj / MLP for the CLS rows only (csrc/api.cu resblock_cls_only). Both modes must
+    meet the reference's goldens, and agree with each other to fp16 rounding."""
+    fx = load_golden(f"tower_{name}.pt")
+    sd = synthetic.make_state_dict(fx["arch"], fx["seed"])
+    ctx = nat.Context(torch.device(DEV))
+    ctx.bind_visual(sd)
+    images = golden_images(fx).to(DEV)
+    ctx.set_full_last_block(False)
+    f_cls = ctx.encode_image(images)
+    ctx.set_full_last_block(True)
+    f_full = ctx.encode_image(images)
+    ctx.set_full_last_block(None)
+    ref = fx["image_features_fp32"]
+    for f in (f_cls, f_full):
+        assert rel_err(f, ref) < TOWER_TOL and mean_rel_err(f, ref) < MEAN_TOL
+    print(f"{name}: CLS-only vs full last block: max-rel {rel_err(f_cls, f_full):.2e}, mean-rel {mean_rel_err(f_cls, f_full):.2e}")
+    assert rel_err(f_cls, f_full) < 2e-3 and mean_rel_err(f_cls, f_full) < 1.5e-3
+    assert not torch.equal(f_cls, f_full) or fx["B"] < 2   # two different instruction streams really ran
 
 
 @pytest.mark.parametrize("name", ["rn_tiny", "rn_small", "RN50", "RN50x16"])
