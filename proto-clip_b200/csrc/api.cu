@@ -446,6 +446,20 @@ int conv3x3_gemm(const ConvBn& c, const __half* xp, __half* out, int n, int h, c
   return launch_gemm(g, EPI_BIAS, s);
 }
 
+// the same on plain NHWC tensors x [n, h, h, cin] -> out [n, h, h, cout] (GemmArgs patch mode; conv_patch_supported(h, h))
+int conv3x3_patch_gemm(const ConvBn& c, const __half* x, __half* out, int n, int h, cudaStream_t s) {
+  GemmArgs g{};
+  g.N = c.cout; g.K = c.cin;
+  g.A = x; g.lda = c.cin;
+  g.W = c.w; g.ldw = c.Kp;
+  g.C = out; g.ldc = c.cout;
+  g.bias_f32 = c.shift;
+  g.relu = 1;
+  g.conv_taps = 9;
+  g.conv_h = h; g.conv_w = h; g.conv_n = n;
+  return launch_gemm(g, EPI_BIAS, s);
+}
+
 // largest activation / staging operand per image along the forward below
 void rn_plan(RnTower& t) {
   size_t act = 0, col = 0;
@@ -478,21 +492,34 @@ int rn_forward(const RnTower& t, const void* img, int img_is_f16, int n, __half*
   // im2col; conv2 / conv3 are implicit GEMMs chained in the bordered layout (frame re-zeroed in between)
   PC_TRY(launch_stem_im2col(img, img_is_f16, ws.col, n, t.res, s));
   PC_TRY(conv_gemm(t.stem[0], ws.col, t1, n * h * h, nullptr, 1, s));
-  PC_TRY(launch_pad_nhwc(t1, ws.col, n, h, h, t.stem[1].cin, s));
-  PC_TRY(conv3x3_gemm(t.stem[1], ws.col, t2, n, h, s));
-  PC_TRY(launch_zero_border(t2, n, h, h, t.stem[2].cin, s));
-  PC_TRY(conv3x3_gemm(t.stem[2], t2, t1, n, h, s));
-  PC_TRY(launch_avgpool_nhwc(t1, x, n, h, h, t.stem[2].cout, 2, 1, s));
+  if (conv_patch_supported(h, h)) {  // 3x3 convolutions straight on the NHWC tensors (padding = TMA zero fill)
+    PC_TRY(conv3x3_patch_gemm(t.stem[1], t1, t2, n, h, s));
+    PC_TRY(conv3x3_patch_gemm(t.stem[2], t2, t1, n, h, s));
+    PC_TRY(launch_avgpool_nhwc(t1, x, n, h, h, t.stem[2].cout, 2, 0, s));
+  } else {
+    PC_TRY(launch_pad_nhwc(t1, ws.col, n, h, h, t.stem[1].cin, s));
+    PC_TRY(conv3x3_gemm(t.stem[1], ws.col, t2, n, h, s));
+    PC_TRY(launch_zero_border(t2, n, h, h, t.stem[2].cin, s));
+    PC_TRY(conv3x3_gemm(t.stem[2], t2, t1, n, h, s));
+    PC_TRY(launch_avgpool_nhwc(t1, x, n, h, h, t.stem[2].cout, 2, 1, s));
+  }
   h /= 2;
   // layer1..layer4 (:146-149), Bottleneck.forward (:40-53)
   for (const RnBlock& b : t.blocks) {
     const int ho = h / b.stride;
     PC_TRY(conv_gemm(b.c1, x, t1, n * h * h, nullptr, 1, s));
-    PC_TRY(launch_pad_nhwc(t1, ws.col, n, h, h, b.planes, s));
-    PC_TRY(conv3x3_gemm(b.c2, ws.col, t2, n, h, s));
-    // interior of the bordered conv2 output -> t1, through the anti-aliasing avgpool when the block strides (:45)
-    if (b.stride > 1) PC_TRY(launch_avgpool_nhwc(t2, t1, n, h, h, b.planes, b.stride, 1, s));
-    else PC_TRY(launch_unpad_nhwc(t2, t1, n, h, h, b.planes, s));
+    const __half* c3_in = t1;
+    if (conv_patch_supported(h, h)) {
+      PC_TRY(conv3x3_patch_gemm(b.c2, t1, t2, n, h, s));
+      if (b.stride > 1) PC_TRY(launch_avgpool_nhwc(t2, t1, n, h, h, b.planes, b.stride, 0, s));  // anti-aliasing (:45)
+      else c3_in = t2;
+    } else {
+      PC_TRY(launch_pad_nhwc(t1, ws.col, n, h, h, b.planes, s));
+      PC_TRY(conv3x3_gemm(b.c2, ws.col, t2, n, h, s));
+      // interior of the bordered conv2 output -> t1, through the anti-aliasing avgpool when the block strides (:45)
+      if (b.stride > 1) PC_TRY(launch_avgpool_nhwc(t2, t1, n, h, h, b.planes, b.stride, 1, s));
+      else PC_TRY(launch_unpad_nhwc(t2, t1, n, h, h, b.planes, s));
+    }
     const __half* identity = x;
     if (b.has_down) {  // :34-38, :48-49
       const __half* src = x;
@@ -500,10 +527,11 @@ int rn_forward(const RnTower& t, const void* img, int img_is_f16, int n, __half*
         PC_TRY(launch_avgpool_nhwc(x, t3, n, h, h, b.inplanes, b.stride, 0, s));
         src = t3;
       }
-      PC_TRY(conv_gemm(b.down, src, t2, n * ho * ho, nullptr, 0, s));
-      identity = t2;
+      __half* down_out = b.stride > 1 ? t2 : t3;  // t2 may hold conv2's result (c3_in), t3 the pooled x
+      PC_TRY(conv_gemm(b.down, src, down_out, n * ho * ho, nullptr, 0, s));
+      identity = down_out;
     }
-    PC_TRY(conv_gemm(b.c3, t1, y, n * ho * ho, identity, 1, s));
+    PC_TRY(conv_gemm(b.c3, c3_in, y, n * ho * ho, identity, 1, s));
     __half* sw = x; x = y; y = sw;
     h = ho;
   }

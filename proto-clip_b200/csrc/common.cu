@@ -131,6 +131,41 @@ int make_tmap_f16_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_
   return PC_OK;
 }
 
+int make_tmap_f16_nhwc(CUtensorMap* out, const void* base, uint64_t channels, uint64_t w, uint64_t h, uint64_t n,
+                       uint64_t pixel_stride_bytes, uint32_t box_w, uint32_t box_h, uint32_t box_n) {
+  struct Key4 {
+    const void* base;
+    uint64_t c, w, h, n, ps;
+    uint32_t bw, bh, bn;
+  };
+  static thread_local std::vector<std::pair<Key4, CUtensorMap>> cache;
+  for (const auto& e : cache) {
+    const Key4& k = e.first;
+    if (k.base == base && k.c == channels && k.w == w && k.h == h && k.n == n && k.ps == pixel_stride_bytes &&
+        k.bw == box_w && k.bh == box_h && k.bn == box_n) {
+      *out = e.second;
+      return PC_OK;
+    }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  PC_REQUIRE(fn != nullptr, PC_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  PC_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (pixel_stride_bytes & 15) == 0, PC_ERR_ALIGN,
+             "TMA NHWC map: base / pixel stride must be multiples of 16 bytes");
+  PC_REQUIRE(box_w >= 1 && box_h >= 1 && box_n >= 1 && box_w * box_h * box_n <= 256, PC_ERR_ARG,
+             "TMA NHWC box %ux%ux%u unsupported", box_w, box_h, box_n);
+  cuuint64_t dims[4] = {channels, w, h, n};
+  cuuint64_t strides[3] = {pixel_stride_bytes, pixel_stride_bytes * w, pixel_stride_bytes * w * h};
+  cuuint32_t box[4] = {64, box_w, box_h, box_n};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PC_REQUIRE(r == CUDA_SUCCESS, PC_ERR_CUDA, "cuTensorMapEncodeTiled (NHWC) failed with CUresult %d", (int)r);
+  if (cache.size() > 256) cache.clear();
+  cache.emplace_back(Key4{base, channels, w, h, n, pixel_stride_bytes, box_w, box_h, box_n}, *out);
+  return PC_OK;
+}
+
 int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows,
                      uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows) {
   return make_tmap_2d(out, base, 2, inner, rows, row_stride_bytes, box_inner, box_rows);

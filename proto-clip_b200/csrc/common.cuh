@@ -54,6 +54,12 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint32_t elem_bytes, uint64
 int make_tmap_f16_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t dim1, uint64_t dim2,
                      uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box_inner, uint32_t box_rows);
 
+// 4-D fp16 map over an NHWC activation [n][h][w][channels] (pixel stride in bytes >= 2 * channels), box
+// {64 channels, box_w, box_h, box_n}, 128B swizzle: a rectangular pixel patch lands in shared memory as box_w*box_h*box_n
+// consecutive 128-byte rows (x fastest); coordinates outside the image are zero-filled on load and clipped on store.
+int make_tmap_f16_nhwc(CUtensorMap* out, const void* base, uint64_t channels, uint64_t w, uint64_t h, uint64_t n,
+                       uint64_t pixel_stride_bytes, uint32_t box_w, uint32_t box_h, uint32_t box_n);
+
 int device_sm_count();  // SM count of the CURRENT device (cached per device)
 
 // The opt-in dynamic shared-memory limit (cudaFuncSetAttribute) is per device and a process may hold one pc_ctx per

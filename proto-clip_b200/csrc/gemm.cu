@@ -104,6 +104,16 @@ __device__ __forceinline__ uint32_t relu_f16x2(uint32_t a) {
     if ((g.debug & 8) && blockIdx.x == 0 && tidx < 64) g.trace[tidx * 16 + (slot)] = (val); \
   } while (0)
 
+// Columns the MMA of the tile at column n0 computes: the tile width clipped to N, rounded up to the instruction's
+// granularity (16; at least 32 for the 256-row pair shape). W rows past N are zero-filled by TMA. A launch that also
+// accumulates row statistics over whole 64-column groups keeps full tiles (stale accumulator columns must not enter).
+__device__ __forceinline__ int mma_cols(const GemmArgs& g, int n0, int bn, bool pair) {
+  if (g.stats_out != nullptr) return bn;
+  int n = (g.N - n0 + 15) & ~15;
+  if (pair && n < 32) n = 32;
+  return n < bn ? n : bn;
+}
+
 template <bool PAIR, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
@@ -191,7 +201,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int tidx = 0;
       for (int tile = worker; tile < num_tiles; tile += num_workers, ++tidx) {
         const int m0 = (tile / n_blks) * TILE_M + rank * BM;
-        const int n0 = (tile % n_blks) * BN + rank * 128;
+        // the pair's B operand is split evenly: this CTA stages rows [rank * n_mma / 2, +n_mma / 2) of the W tile
+        const int n0 = (tile % n_blks) * BN + (PAIR ? rank * (mma_cols(g, (tile % n_blks) * BN, BN, PAIR) >> 1) : 0);
+        int px0 = 0, py0 = 0, pn0 = 0;  // patch mode: first pixel / image of this CTA's 128 rows
+        if (g.conv_w > 0) {
+          const int patch = m0 >> 7;
+          const int t2 = patch / g.px;
+          px0 = (patch - t2 * g.px) * g.pw;
+          pn0 = t2 / g.py;
+          py0 = (t2 - pn0 * g.py) * g.ph;
+          pn0 *= g.pn;
+        }
         long long w_empty = 0;
         for (int kb = 0; kb < k_blks; ++kb) {
           const long long tw = (g.debug & 8) ? clock64() : 0;
@@ -206,7 +226,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             w_col = tap * g.K + kc;
             a_row = m0 + (tap / 3 - 1) * g.conv_pitch + (tap % 3 - 1);
           }
-          if (elect_one()) {
+          if (g.conv_w > 0) {
+            if (elect_one()) {
+              const int tap = kb / kb_per_tap;
+              if (PAIR) {
+                if (leader) mbar_arrive_expect_tx(&bars->full[stage], TX_BYTES);
+                tma_load_4d_pair(sA, &tmA, &bars->full[stage], a_col, px0 + tap % 3 - 1, py0 + tap / 3 - 1, pn0, kEvictNormal);
+                tma_load_2d_pair(sB, &tmW, &bars->full[stage], w_col, n0, kEvictLast);
+              } else {
+                mbar_arrive_expect_tx(&bars->full[stage], TX_BYTES);
+                tma_load_4d_hint(sA, &tmA, &bars->full[stage], a_col, px0 + tap % 3 - 1, py0 + tap / 3 - 1, pn0, kEvictNormal);
+                tma_load_2d_hint(sB, &tmW, &bars->full[stage], w_col, n0, kEvictLast);
+              }
+            }
+          } else if (elect_one()) {
             if (g.debug & 2) {
               if (leader) mbar_arrive(&bars->full[stage]);
             } else if (PAIR) {
@@ -234,7 +267,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == MMA_WARP) {
     // ------------------------------------------------------------ MMA issuer (PAIR: leader CTA only)
     if (leader) {
-      constexpr uint32_t idesc = umma_idesc_f16(TILE_M, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -250,7 +282,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) TRACE(1, clock64());
         long long w_full = 0;
         const uint32_t d_tmem = tmem_base + as * BN;
+        // instruction shape: only the columns this tile really has (N = 96 / 192 / 384 convolution widths)
+        const uint32_t idesc = umma_idesc_f16(TILE_M, mma_cols(g, (tile % n_blks) * BN, BN, PAIR), 0, 0);
         for (int kb = 0; kb < k_blks; ++kb) {
+          // k-steps of this block that hold real columns (K = 96 per tap: the second block is half empty)
+          const int k_left = g.K - (kb % kb_per_tap) * BK;
+          const int ksteps = k_left >= BK ? BK / 16 : (k_left + 15) >> 4;
           const long long tw = (g.debug & 8) ? clock64() : 0;
           mbar_wait(&bars->full[stage], phase);
           if (g.debug & 8) w_full += clock64() - tw;
@@ -263,9 +300,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint64_t db = umma_desc_kmajor_sw128(b_addr);
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {
-                // advancing 16 fp16 along K inside the 128-byte swizzle row = +32 B = +2 in the address field
-                if (PAIR) umma_f16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                else umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                if (k < ksteps) {
+                  // advancing 16 fp16 along K inside the 128-byte swizzle row = +32 B = +2 in the address field
+                  if (PAIR) umma_f16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                  else umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
               }
             }
             // frees this smem stage (in both CTAs) once the MMAs above retire
@@ -488,7 +527,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         if (elect_one()) {
           if (!(g.debug & 1) && gcol0 < g.N && m0 + row_off < g.M) {
-            if (g.c_planar) tma_store_3d(&tmC, stg, 0, m0 + row_off, gcol0 / GRP_COLS);  // plane = 64-column block
+            if (g.conv_w > 0) {  // patch mode: this warp's 32 rows are a sub-box of the CTA's pixel patch
+              const int patch = (m0 + rank * BM) >> 7;
+              const int t2 = patch / g.px;
+              const int tn = t2 / g.py;
+              const int r0 = quarter * 32 / g.pw;  // patch rows (of pw pixels) before this warp's first row
+              tma_store_4d(&tmC, stg, gcol0, (patch - t2 * g.px) * g.pw, (t2 - tn * g.py) * g.ph + r0 % g.ph,
+                           tn * g.pn + r0 / g.ph);
+            } else if (g.c_planar) tma_store_3d(&tmC, stg, 0, m0 + row_off, gcol0 / GRP_COLS);  // plane = 64-column block
             else tma_store_2d(&tmC, stg, gcol0, m0 + row_off);
           }
           tma_store_commit();
@@ -539,6 +585,17 @@ bool force_single_cta() {
   return v == 1;
 }
 
+// 128-pixel patch (bw x bh pixels of bn images) for the patch-mode convolution: bw divides 32 (a warp's 32 staging rows
+// are whole patch rows), the patches tile the image exactly.
+bool pick_patch(int h, int w, int* bw, int* bh, int* bn) {
+  if (h <= 0 || w <= 0) return false;
+  if (w % 32 == 0 && h % 4 == 0) { *bw = 32; *bh = 4; *bn = 1; return true; }
+  if (w % 16 == 0 && h % 8 == 0) { *bw = 16; *bh = 8; *bn = 1; return true; }
+  if (w % 8 == 0 && h % 8 == 0) { *bw = 8; *bh = 8; *bn = 2; return true; }
+  if (w % 4 == 0 && h % 4 == 0) { *bw = 4; *bh = 4; *bn = 8; return true; }
+  return false;
+}
+
 template <bool PAIR, int EPI>
 int launch_impl(const GemmArgs& a0, cudaStream_t stream) {
   using Smem = SmemT<EPI>;
@@ -550,11 +607,26 @@ int launch_impl(const GemmArgs& a0, cudaStream_t stream) {
   GemmArgs a = a0;
   a.debug = debug_flags();
   CUtensorMap tmA, tmW, tmC, tmR;
-  PC_TRY(make_tmap_2d(&tmA, a.A, 2, a.K, a.M, static_cast<uint64_t>(a.lda) * 2, BK, BM));
+  if (a.conv_w > 0 && (EPI != EPI_BIAS || a.c_planar)) {
+    set_error("gemm: the patch-mode convolution has the bias (+ ReLU) epilogue only");
+    return PC_ERR_ARG;
+  } else if (a.conv_w > 0) {
+    PC_REQUIRE(pick_patch(a.conv_h, a.conv_w, &a.pw, &a.ph, &a.pn), PC_ERR_ARG,
+               "gemm: a %d x %d activation cannot be cut into 128-pixel patches", a.conv_h, a.conv_w);
+    a.px = a.conv_w / a.pw;
+    a.py = a.conv_h / a.ph;
+    a.M = a.px * a.py * ((a.conv_n + a.pn - 1) / a.pn) * BM;
+    PC_TRY(make_tmap_f16_nhwc(&tmA, a.A, a.K, a.conv_w, a.conv_h, a.conv_n, static_cast<uint64_t>(a.lda) * 2, a.pw, a.ph, a.pn));
+  } else {
+    PC_TRY(make_tmap_2d(&tmA, a.A, 2, a.K, a.M, static_cast<uint64_t>(a.lda) * 2, BK, BM));
+  }
   PC_TRY(make_tmap_2d(&tmW, a.W, 2, a.conv_taps > 0 ? a.conv_taps * a.K : a.K, a.N, static_cast<uint64_t>(a.ldw) * 2, BK,
                       128));
   if (EPI == EPI_F32) {
     PC_TRY(make_tmap_2d(&tmC, a.C, 4, a.N, a.M, static_cast<uint64_t>(a.ldc) * 4, 32, 32));
+  } else if (a.conv_w > 0) {  // a warp's 32 staging rows = pw x (32 / pw) pixels of (32 / pw) / ph ... images
+    const int sw = a.pw, sh = (32 / sw) < a.ph ? (32 / sw) : a.ph, sn = 32 / (sw * sh);
+    PC_TRY(make_tmap_f16_nhwc(&tmC, a.C, a.N, a.conv_w, a.conv_h, a.conv_n, static_cast<uint64_t>(a.ldc) * 2, sw, sh, sn));
   } else if (a.c_planar) {
     PC_TRY(make_tmap_f16_3d(&tmC, a.C, 64, a.M, a.N / 64, 128, static_cast<uint64_t>(a.M) * 128, 64, 32));
   } else {
@@ -684,13 +756,23 @@ static int pair_min_n() {
 }
 static bool use_pair(int M, int N) { return M >= 256 && N >= pair_min_n() && !force_single_cta(); }
 
+bool conv_patch_supported(int h, int w) {
+  static int off = -1;
+  if (off < 0) {
+    const char* e = getenv("PC_NO_CONV_PATCH");  // 1: every 3x3 convolution through the bordered copy (A/B timing)
+    off = (e && e[0] == '1') ? 1 : 0;
+  }
+  int bw, bh, bn;
+  return !off && pick_patch(h, w, &bw, &bh, &bn);
+}
+
 int gemm_stats_parts(int M, int N) {
   const int bn = use_pair(M, N) ? 256 : 128;
   return 2 * ((N + bn - 1) / bn);
 }
 
 int launch_gemm(const GemmArgs& a, int epilogue, cudaStream_t stream) {
-  PC_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, PC_ERR_ARG, "gemm: empty problem %dx%dx%d", a.M, a.N, a.K);
+  PC_REQUIRE((a.M > 0 || a.conv_w > 0) && a.N > 0 && a.K > 0, PC_ERR_ARG, "gemm: empty problem %dx%dx%d", a.M, a.N, a.K);
   PC_REQUIRE(a.A && a.W && a.C, PC_ERR_ARG, "gemm: null operand");
   PC_REQUIRE(a.K % 8 == 0 && a.lda % 8 == 0 && a.ldw % 8 == 0, PC_ERR_ALIGN,
              "gemm: K/lda/ldw (%d/%d/%d) must be multiples of 8 fp16 (16-byte TMA rows)", a.K, a.lda, a.ldw);
@@ -708,6 +790,12 @@ int launch_gemm(const GemmArgs& a, int epilogue, cudaStream_t stream) {
   if (epilogue == EPI_LN_BIAS || epilogue == EPI_LN_QGELU) {
     PC_REQUIRE(a.ln_stats != nullptr && a.ln_s != nullptr && a.ln_c != nullptr && a.ln_parts >= 1, PC_ERR_ARG,
                "gemm: the LayerNorm-folded epilogues need ln_stats (ln_parts >= 1), ln_s and ln_c");
+  }
+  if (a.conv_w > 0) {
+    PC_REQUIRE(a.conv_taps == 9 && a.conv_h > 0 && a.conv_n > 0 && a.ldw >= 9 * a.K, PC_ERR_ARG,
+               "gemm: patch-mode convolution needs 9 taps, h / w / n and W [N, 9*K]");
+    return use_pair(a.conv_n * a.conv_h * a.conv_w, a.N) ? dispatch_epi<true>(a, epilogue, stream)
+                                                         : dispatch_epi<false>(a, epilogue, stream);
   }
   PC_REQUIRE(a.conv_taps == 0 || (a.conv_taps == 9 && a.conv_pitch >= 3 && a.ldw >= 9 * a.K), PC_ERR_ARG,
              "gemm: implicit convolution needs 9 taps, a row pitch and W [N, 9*K] (taps %d, pitch %d, ldw %d)",

@@ -36,6 +36,12 @@ struct GemmArgs {
   // [tap*C + c0, +64) of W [N, 9*C]; output rows are in the same bordered layout (border rows hold garbage).
   int conv_taps;              // 0 = plain GEMM, 9 = 3x3 taps
   int conv_pitch;             // W + 2
+  // PATCH mode (conv_taps = 9, conv_w > 0; conv_patch_supported(h, w)): A = [n, h, w, K] and C = [n, h, w, N] are plain
+  // (un-bordered) NHWC tensors. A tile's 128 rows are a rectangular patch bw x bh of bn images, loaded per tap with a
+  // 4-D TMA box shifted by (dx, dy): the padding is TMA's out-of-bounds zero fill, no bordered copy, no frame rows in
+  // the MMA work, and the result is stored through the same patch geometry. M is ignored (derived from the patches).
+  int conv_h, conv_w, conv_n;
+  int pw, ph, pn, px, py;     // filled by launch_gemm: patch box (bw, bh, bn) and patches per image row / column
   int relu;                   // 1: ReLU on the fp16 result (after the residual add for EPI_BIAS_RES): the conv + BN
                               // (+ identity) + ReLU of a Bottleneck (clip/model.py:43-52); EPI_BIAS / EPI_BIAS_RES only
   const __half* residual; int ldr;  // [M, N] fp16 (EPI_BIAS_RES); may alias C
@@ -52,6 +58,8 @@ struct GemmArgs {
   long long* trace;           // [tiles][16] clock64 samples when debug & 8
 };
 int launch_gemm(const GemmArgs& a, int epilogue, cudaStream_t stream);
+// true when an h x w activation can be cut into 128-pixel patches (GemmArgs patch mode)
+bool conv_patch_supported(int h, int w);
 // partial (sum, sum^2) pairs per row that an EPI_BIAS_RES launch of this shape writes into stats_out
 int gemm_stats_parts(int M, int N);
 
