@@ -594,9 +594,10 @@ int env_int(const char* name, int dflt) {
 // L <= 208: the whole score row of a 128-query tile (<= 208 fp32 columns) and its O accumulator (64) fit in half of
 // the SM's tensor memory with S_a clear of O
 bool attention6_supports(int L) {
-  static int impl = -1;
+  static int impl = -1, max_l = -1;
   if (impl < 0) impl = env_int("PC_ATTN_IMPL", 6);  // A/B switch: 5 = round-1 kernel (attention5.cu), 2 = attention.cu
-  return impl == 6 && L <= 208;
+  if (max_l < 0) max_l = env_int("PC_ATTN6_MAX_L", 256);
+  return impl == 6 && L <= max_l && L <= 256;
 }
 
 // qkv: packed [B*L, 3d] (nn.MultiheadAttention in-proj order) or planar [3 * heads][B*L][64] (GemmArgs::c_planar).

@@ -772,6 +772,15 @@ int gemm_stats_parts(int M, int N) {
 }
 
 int launch_gemm(const GemmArgs& a, int epilogue, cudaStream_t stream) {
+  static int log_shapes = -1;  // PC_GEMM_LOG=1: one stderr line per launch (joined with an ncu launch list by tools/rn_breakdown.py)
+  if (log_shapes < 0) {
+    const char* e = getenv("PC_GEMM_LOG");
+    log_shapes = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (log_shapes)
+    fprintf(stderr, "[gemm] M=%d N=%d K=%d epi=%d taps=%d patch=%d res=%d\n",
+            a.conv_w > 0 ? a.conv_n * a.conv_h * a.conv_w : a.M, a.N, a.K, epilogue, a.conv_taps, a.conv_w > 0 ? 1 : 0,
+            a.residual != nullptr ? 1 : 0);
   PC_REQUIRE((a.M > 0 || a.conv_w > 0) && a.N > 0 && a.K > 0, PC_ERR_ARG, "gemm: empty problem %dx%dx%d", a.M, a.N, a.K);
   PC_REQUIRE(a.A && a.W && a.C, PC_ERR_ARG, "gemm: null operand");
   PC_REQUIRE(a.K % 8 == 0 && a.lda % 8 == 0 && a.ldw % 8 == 0, PC_ERR_ALIGN,

@@ -87,6 +87,9 @@ def test_linear_residual_in_place(nat):
                                               (1, 145, 48, False), (2, 208, 1, False), (2, 200, 2, False), (3, 130, 1, False),
                                               (2, 144, 1, False), (1, 16, 1, False), (5, 64, 3, True), (3, 127, 1, False),
                                               (3, 255, 2, True), (1, 256, 1, True), (13, 197, 12, False), (3, 33, 1, True),
+                                              # 208 < L <= 256: S_b grows over the whole O range
+                                              (4, 209, 3, False), (2, 224, 1, True), (2, 240, 2, False), (5, 256, 16, False),
+                                              (3, 250, 2, True),
                                               # L = k * 128 + few rows: the last rows go to attention_tail_rows_kernel
                                               (3, 257, 16, False), (2, 260, 2, True), (2, 392, 1, False), (5, 264, 3, False)])
 def test_attention(nat, B, L, heads, causal):

@@ -270,6 +270,9 @@ CASES = {
     "attn_big": lambda: case_attn(96, 197, 12, False),
     "attn_512": lambda: case_attn(512, 197, 12, False),
     "attn_577": lambda: case_attn(2, 577, 16, False),
+    "attn_256_big": lambda: case_attn(192, 256, 16, False),
+    "attn_257_big": lambda: case_attn(192, 257, 16, False),
+    "attn_577_big": lambda: case_attn(64, 577, 16, False),
     "attn_text_big": lambda: case_attn(192, 77, 8, True),
     "attn_L14_big": lambda: case_attn(48, 257, 16, False),
     "attn_336_big": lambda: case_attn(16, 577, 16, False),
