@@ -35,7 +35,8 @@
 //   warp 16 / 17     MMA issuer of WG 0 / 1 (whole warp in the loop, one elected lane issues)
 //   warp 18          TMA producer: a STAGE holds everything an item needs (Q tile 0, Q tile 1, K, V: 96 KB); two
 //                    stages, so the next item's operands land while the current one is computed
-//   warp 19          idle (warpgroup padding)
+//   warp 19          idle (warpgroup padding); in extra-key mode (L = 257) it computes query row 256 of every item on the
+//                    CUDA cores from the K / V tiles in shared memory
 #include <stdlib.h>
 
 #include "attn_common.cuh"
@@ -56,12 +57,19 @@ constexpr int OFF_V = 4 * TILE_BYTES;
 constexpr int STAGE_BYTES = 6 * TILE_BYTES;   // 96 KB
 constexpr int OFF_OUT = 2 * STAGE_BYTES;      // 16 x 2 KB output staging blocks (one per softmax warp: 32 rows x 64 B)
 constexpr int OFF_XCH = OFF_OUT + 16 * 2048;  // row maximum / partial row sum exchange [tile][thread of the row][row] fp32
-constexpr int OFF_BARS = OFF_XCH + 2 * 2 * 128 * 4;
+constexpr int OFF_XROW = OFF_XCH + 2 * 2 * 128 * 4;  // extra-key mode, per stage: k_256 | v_256 | q_256 (128 B each, linear)
+constexpr int XROW_BYTES = 3 * 128;
+constexpr int OFF_BARS = OFF_XROW + 2 * XROW_BYTES;
+constexpr int HELPER_WARP = 19;
 constexpr int O_COL = 192;   // O accumulator inside a tile's 256-column TMEM region
 constexpr int SB_COL = 128;  // S_b
 
 struct Params6 {
-  int L, lp16, heads, d, items;
+  int L, lp16, heads, d, items;  // L = rows of a sequence in memory
+  int Lm;        // query rows / keys this kernel runs through the tensor cores (= L, or 256 in extra-key mode)
+  const __half* qkv;            // extra-key mode: element pointer + pitches of the [plane][row][64] view
+  long long row_pitch, plane_pitch;
+  __half* out;                  // extra-key mode: [B][L][d], row 256 of every sequence is written by the helper warp
   int split;     // 1: L <= 128, the two WGs take different items
   int n_groups;  // split: ceil(items / 2), else items
   int na;        // keys of part a = min(lp16, 128)
@@ -263,7 +271,13 @@ __device__ __forceinline__ void exp_chunks(uint32_t t_row, int k0, int k1, int p
   }
 }
 
-template <bool CAUSAL, int NP>
+// XKEY (L = 257 = 2 x 128 + 1, ViT-L/14): the tensor cores see 256 queries x 256 keys. The producer also drops rows
+// k_256, v_256 and q_256 of the item into shared memory (three 128-byte bulk copies). Key 256 is folded in by the softmax
+// threads themselves: its score is a 64-long dot product per row (half per thread of the row, q from the Q tile in
+// shared memory), it joins the row maximum and the row sum, and its p * v row is added to O in the epilogue. Query row
+// 256 is computed by the spare warp on the CUDA cores from the K / V tiles in shared memory (257 dot products, one
+// softmax, 257 axpys per item): a separate pass over K and V for that one row cost 57 us of 175 at 192 images.
+template <bool CAUSAL, int NP, bool XKEY>
 __global__ void __launch_bounds__(THREADS6, 1)
 attention6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmT,
                   const __grid_constant__ CUtensorMap tmO, const Params6 p) {
@@ -280,8 +294,8 @@ attention6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       for (int i = 0; i < 2; ++i) {
         mbar_init(&bars->qk_full[i], 1);
         mbar_init(&bars->v_full[i], 1);
-        mbar_init(&bars->qk_free[i], 2);
-        mbar_init(&bars->v_free[i], 2);
+        mbar_init(&bars->qk_free[i], XKEY ? 2 + 16 + 1 : 2);  // XKEY: the softmax warps and the helper read the stage too
+        mbar_init(&bars->v_free[i], XKEY ? 2 + 16 + 1 : 2);
         mbar_init(&bars->s_full[i], 1);
         mbar_init(&bars->pa_full[i], 8);
         mbar_init(&bars->pb_full[i], 4);
@@ -329,7 +343,13 @@ attention6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           }
         } else {
           const int hd = g % p.heads, r0 = (g / p.heads) * p.L;
-          mbar_arrive_expect_tx(qk, 2 * TILE_BYTES + 2 * p.nb * 128);
+          mbar_arrive_expect_tx(qk, 2 * TILE_BYTES + 2 * p.nb * 128 + (XKEY ? 256 : 0));
+          if (XKEY) {
+            uint8_t* xr = smem + OFF_XROW + st * XROW_BYTES;
+            const __half* row = p.qkv + static_cast<long long>(r0 + p.Lm) * p.row_pitch;
+            bulk_load(xr, row + (p.heads + hd) * p.plane_pitch, 128, qk);
+            bulk_load(xr + 256, row + hd * p.plane_pitch, 128, qk);
+          }
           tma_load_3d(stage + OFF_K, &tmQ, qk, 0, r0, p.heads + hd);
           tma_load_3d(stage + OFF_Q, &tmQ, qk, 0, r0, hd);
           tma_load_3d(stage + OFF_K + TILE_BYTES, &tmT, qk, 0, r0 + 128, p.heads + hd);
@@ -348,7 +368,10 @@ attention6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           }
         } else {
           const int hd = g % p.heads, r0 = (g / p.heads) * p.L;
-          mbar_arrive_expect_tx(vf, TILE_BYTES + p.nb * 128);
+          mbar_arrive_expect_tx(vf, TILE_BYTES + p.nb * 128 + (XKEY ? 128 : 0));
+          if (XKEY)
+            bulk_load(smem + OFF_XROW + st * XROW_BYTES + 128,
+                      p.qkv + static_cast<long long>(r0 + p.Lm) * p.row_pitch + (2 * p.heads + hd) * p.plane_pitch, 128, vf);
           tma_load_3d(stage + OFF_V, &tmQ, vf, 0, r0, 2 * p.heads + hd);
           tma_load_3d(stage + OFF_V + TILE_BYTES, &tmT, vf, 0, r0 + 128, 2 * p.heads + hd);
         }
@@ -468,15 +491,46 @@ attention6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         continue;
       }
       const int i = j.tile * 128 + r;  // query index inside the sequence
-      const bool warp_live = j.tile * 128 + quarter * 32 < p.L;
-      const int jmax = CAUSAL ? min(i, p.L - 1) : p.L - 1;  // last key this row attends to
+      const bool warp_live = j.tile * 128 + quarter * 32 < p.Lm;
+      const int jmax = CAUSAL ? min(i, p.Lm - 1) : p.Lm - 1;  // last key this row attends to (through the MMAs)
       TR6(0);
+      float s_x = 0.0f;  // XKEY: q_i . k_256 (this thread's 32 of the 64 dimensions until the exchange below)
+      const int xst = it & 1;
+      if (XKEY) {
+        mbar_wait(&bars->qk_full[xst], (it >> 1) & 1);
+        const uint8_t* qrow = smem + xst * STAGE_BYTES + OFF_Q + w * TILE_BYTES + r * 128;
+        const uint8_t* xk = smem + OFF_XROW + xst * XROW_BYTES + 64 * hf;
+        float d0 = 0.0f, d1 = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint4 a = *reinterpret_cast<const uint4*>(qrow + (((4 * hf + c) ^ (r & 7)) << 4));
+          const uint4 b = *reinterpret_cast<const uint4*>(xk + 16 * c);
+          const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&aw[e]));
+            const float2 fb = __half22float2(*reinterpret_cast<const __half2*>(&bw[e]));
+            d0 = fmaf(fa.x, fb.x, d0);
+            d1 = fmaf(fa.y, fb.y, d1);
+          }
+        }
+        s_x = d0 + d1;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->qk_free[xst]);  // this warp's reads of the stage's Q tile and k_256 are done
+      }
       mbar_wait(&bars->s_full[w], tcount & 1);
       tc_fence_after();
       TR6(1);
+      if (XKEY) {  // the two halves of the dot product meet (slot writes are ordered behind s_full, see the MMA warp)
+        *my_x = s_x;
+        pair_bar_sync(pair_bar);
+        s_x = hf ? *other_x + s_x : s_x + *other_x;  // same order in both threads
+        pair_bar_sync(pair_bar);
+      }
       // ---- row maximum: own chunks, then the partner's through shared memory
       float mx = -INFINITY;
-      if (warp_live) mx = row_max<CAUSAL>(t_row, c0, c1, p.L, jmax);
+      if (warp_live) mx = row_max<CAUSAL>(t_row, c0, c1, p.Lm, jmax);
+      if (XKEY) mx = fmaxf(mx, s_x);
       *my_x = mx;
       pair_bar_sync(pair_bar);
       mx = fmaxf(mx, *other_x);
@@ -493,7 +547,7 @@ attention6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       uint64_t acc_a = 0, acc_b = 0;
       if (hf == 1 && nch > 8) {
         if (warp_live) {
-          exp_chunks<CAUSAL, NP>(t_row, cb, c1, p_col(cb, h0), p.L, jmax, sc2, nref2, acc_a, acc_b);
+          exp_chunks<CAUSAL, NP>(t_row, cb, c1, p_col(cb, h0), p.Lm, jmax, sc2, nref2, acc_a, acc_b);
           tmem_wait_st();
         }
         tc_fence_before();
@@ -502,7 +556,7 @@ attention6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
       TR6(4);
       if (warp_live) {
-        exp_chunks<CAUSAL, NP>(t_row, c0, ca, p_col(c0, h0), p.L, jmax, sc2, nref2, acc_a, acc_b);
+        exp_chunks<CAUSAL, NP>(t_row, c0, ca, p_col(c0, h0), p.Lm, jmax, sc2, nref2, acc_a, acc_b);
         tmem_wait_st();
       }
       tc_fence_before();
@@ -517,11 +571,26 @@ attention6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const float part = (lo_f(acc_a) + hi_f(acc_a)) + (lo_f(acc_b) + hi_f(acc_b));
       *my_x = part;
       pair_bar_sync(pair_bar);
-      const float sum = hf ? *other_x + part : part + *other_x;  // same order in both threads
+      float sum = hf ? *other_x + part : part + *other_x;  // same order in both threads
+      float p_x = 0.0f;
+      uint4 vx[4];
+      if (XKEY) {
+        const float e = ex2_approx(fmaf(s_x, sc, nref));
+        sum += e;
+        p_x = __half2float(__float2half_rn(e));  // P is fp16 for the tensor cores: the same rounding for this key
+      }
       // ---- last PV MMA of the tile retired -> O / sum -> fp16 -> out[b, i, h*64 + 32*hf .. +31]
       mbar_wait(&bars->pv_done[w], tcount & 1);
       tc_fence_after();
       TR6(6);
+      if (XKEY) {
+        mbar_wait(&bars->v_full[xst], (it >> 1) & 1);  // long complete (the P V MMAs waited for it): orders the reads below
+        const uint8_t* xv = smem + OFF_XROW + xst * XROW_BYTES + 128 + 64 * hf;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) vx[c] = *reinterpret_cast<const uint4*>(xv + 16 * c);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->v_free[xst]);
+      }
       if (!warp_live) {
         tc_fence_before();
         __syncwarp();
@@ -534,6 +603,18 @@ attention6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->o_free[w]);  // O may be overwritten by the next tile
+        if (XKEY) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t vw[4] = {vx[c].x, vx[c].y, vx[c].z, vx[c].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 fv = __half22float2(*reinterpret_cast<const __half2*>(&vw[e]));
+              O2[8 * c + 2 * e] = __float_as_uint(fmaf(p_x, fv.x, __uint_as_float(O2[8 * c + 2 * e])));
+              O2[8 * c + 2 * e + 1] = __float_as_uint(fmaf(p_x, fv.y, __uint_as_float(O2[8 * c + 2 * e + 1])));
+            }
+          }
+        }
         TR6(7);
         // fp16 rows into this warp's 2 KB staging block: 32 rows x 64 B, 64B-swizzled (16-byte chunk c of row r at
         // chunk c ^ ((r >> 1) & 3): conflict-free 128-bit stores), then one TMA store through the [B][L][d] map,
@@ -565,6 +646,128 @@ attention6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
     if (elect_one()) tma_store_wait_all<0>();  // output written before the CTA (and its staging smem) goes away
   }
+  if (XKEY && warp == HELPER_WARP) {
+    // ---------------------------------------------------------------------------------- query row 256 of every item
+    // One warp, warp-level tensor-core instructions (mma.sync m16n8k16) in the transposed form, so that the operand that
+    // carries a single useful vector is the 8-wide B side: S^T = K q^T (16 keys per instruction, A through ldmatrix from
+    // the swizzled K tiles), key 256 by hand, one softmax across the 8 lanes that hold column 0, O^T = V^T P^T (A through
+    // ldmatrix.trans from the V tiles, P moved into B-fragment position by shuffles). 128 mma + 128 ldmatrix per item.
+    const float sc = 0.125f * 1.4426950408889634f;
+    const int g4 = lane >> 2, t4 = lane & 3;
+    int it = 0;
+    for (int g = blockIdx.x; g < p.n_groups; g += g_stride, ++it) {
+      const int st = it & 1;
+      const uint32_t par = (it >> 1) & 1;
+      const uint8_t* stage = smem + st * STAGE_BYTES;
+      const uint8_t* xr = smem + OFF_XROW + st * XROW_BYTES;
+      mbar_wait(&bars->qk_full[st], par);
+      if (p.debug & 4) {  // bring-up (wrong row 256): barrier traffic only
+        mbar_wait(&bars->v_full[st], par);
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&bars->qk_free[st]);
+          mbar_arrive(&bars->v_free[st]);
+        }
+        continue;
+      }
+      // ---- S^T = K q^T: A fragments = 16 keys x 16 dims of the K tile (ldmatrix), B = q in column 0 (lanes 0..3)
+      uint32_t qb0[4], qb1[4];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        qb0[ks] = g4 == 0 ? *reinterpret_cast<const uint32_t*>(xr + 256 + (16 * ks + 2 * t4) * 2) : 0u;
+        qb1[ks] = g4 == 0 ? *reinterpret_cast<const uint32_t*>(xr + 256 + (16 * ks + 8 + 2 * t4) * 2) : 0u;
+      }
+      // ldmatrix row of this lane: matrix i = lane >> 3 -> keys + 8 (i & 1), dim chunk + (i >> 1); row lane & 7
+      const int lk = (lane & 7) + 8 * ((lane >> 3) & 1), lc = lane >> 4;
+      float sv[32];  // lanes with t4 == 0: scores of keys 16 mt + g4 (sv[2 mt]) and 16 mt + 8 + g4 (sv[2 mt + 1])
+#pragma unroll
+      for (int mt = 0; mt < 16; ++mt) {
+        const int key = 16 * mt + lk;
+        const uint32_t krow = smem_u32(stage + OFF_K + (key >> 7) * TILE_BYTES + (key & 127) * 128);
+        float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t a0, a1, a2, a3;
+          ldmatrix_x4(a0, a1, a2, a3, krow + (((2 * ks + lc) ^ (key & 7)) << 4));
+          mma_m16n8k16_f16(c0, c1, c2, c3, a0, a1, a2, a3, qb0[ks], qb1[ks]);
+        }
+        sv[2 * mt] = c0;
+        sv[2 * mt + 1] = c2;
+      }
+      // key 256: lanes 0..3 hold q; the four partial dot products meet, lane 0 broadcasts
+      float sx = 0.0f;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const float2 q0 = __half22float2(*reinterpret_cast<const __half2*>(&qb0[ks]));
+        const float2 q1 = __half22float2(*reinterpret_cast<const __half2*>(&qb1[ks]));
+        const float2 k0 = __half22float2(*reinterpret_cast<const __half2*>(xr + (16 * ks + 2 * t4) * 2));
+        const float2 k1 = __half22float2(*reinterpret_cast<const __half2*>(xr + (16 * ks + 8 + 2 * t4) * 2));
+        sx = fmaf(q0.x, k0.x, fmaf(q0.y, k0.y, fmaf(q1.x, k1.x, fmaf(q1.y, k1.y, sx))));
+      }
+      sx += __shfl_xor_sync(0xffffffffu, sx, 1);
+      sx += __shfl_xor_sync(0xffffffffu, sx, 2);
+      sx = __shfl_sync(0xffffffffu, sx, 0);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->qk_free[st]);
+      // ---- softmax over the 8 lanes with t4 == 0 (the other lanes hold columns 1..7 of S^T: zeros, harmless)
+      float mx = sx;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) mx = fmaxf(mx, sv[e]);
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+      float sum = 0.0f;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        sv[e] = ex2_approx((sv[e] - mx) * sc);
+        sum += sv[e];
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+      const float ex = ex2_approx((sx - mx) * sc);
+      sum += ex;
+      const float px = __half2float(__float2half_rn(ex));
+      // ---- O^T = V^T P^T: A fragments = 16 dims x 16 keys of the V tile (ldmatrix.trans), B = P in column 0
+      mbar_wait(&bars->v_full[st], par);
+      float o[4][4];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.0f;
+      // ldmatrix.trans row of this lane: matrix i -> dim chunk + (i & 1), keys + 8 (i >> 1); row (= key) lane & 7
+      const int vk = (lane & 7) + 8 * (lane >> 4), vc = (lane >> 3) & 1;
+#pragma unroll
+      for (int kt = 0; kt < 16; ++kt) {
+        // P of keys 16 kt + 2 t4 (+1) and + 8: they live in lanes 4 g (t4 == 0) with g = key % 8
+        const float p00 = __shfl_sync(0xffffffffu, sv[2 * kt], 8 * t4), p01 = __shfl_sync(0xffffffffu, sv[2 * kt], 8 * t4 + 4);
+        const float p10 = __shfl_sync(0xffffffffu, sv[2 * kt + 1], 8 * t4),
+                    p11 = __shfl_sync(0xffffffffu, sv[2 * kt + 1], 8 * t4 + 4);
+        const uint32_t b0 = g4 == 0 ? pack_half2(p00, p01) : 0u, b1 = g4 == 0 ? pack_half2(p10, p11) : 0u;
+        const int key = 16 * kt + vk;
+        const uint32_t vrow = smem_u32(stage + OFF_V + (key >> 7) * TILE_BYTES + (key & 127) * 128);
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+          uint32_t a0, a1, a2, a3;
+          ldmatrix_x4_trans(a0, a1, a2, a3, vrow + (((2 * mt + vc) ^ (key & 7)) << 4));
+          mma_m16n8k16_f16(o[mt][0], o[mt][1], o[mt][2], o[mt][3], a0, a1, a2, a3, b0, b1);
+        }
+      }
+      const float inv = __fdividef(1.0f, sum);
+      const long long b = g / p.heads, h = g % p.heads;
+      __half* orow = p.out + (b * p.L + p.Lm) * p.d + h * HEAD_DIM;
+      if (t4 == 0) {  // column 0 of O^T: dims 16 mt + g4 (c0) and 16 mt + 8 + g4 (c2)
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+          const int d0 = 16 * mt + g4, d1 = d0 + 8;
+          const float v0 = __half2float(*reinterpret_cast<const __half*>(xr + 128 + 2 * d0));
+          const float v1 = __half2float(*reinterpret_cast<const __half*>(xr + 128 + 2 * d1));
+          orow[d0] = __float2half_rn(fmaf(px, v0, o[mt][0]) * inv);
+          orow[d1] = __float2half_rn(fmaf(px, v1, o[mt][2]) * inv);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->v_free[st]);
+    }
+  }
 
   tc_fence_before();
   __syncthreads();
@@ -574,11 +777,11 @@ attention6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
 }
 
-template <bool CAUSAL, int NP>
+template <bool CAUSAL, int NP, bool XKEY = false>
 int launch_variant6(int grid, int smem_bytes, cudaStream_t stream, const CUtensorMap& tmQ, const CUtensorMap& tmT,
                     const CUtensorMap& tmO, const Params6& p) {
   static int configured[kMaxDevices];
-  auto kern = attention6_kernel<CAUSAL, NP>;
+  auto kern = attention6_kernel<CAUSAL, NP, XKEY>;
   PC_CHECK_CUDA(ensure_dynamic_smem(kern, smem_bytes, configured));
   PC_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS6), smem_bytes, stream, 1, tmQ, tmT, tmO, p));
   return PC_OK;
@@ -602,16 +805,31 @@ bool attention6_supports(int L) {
 
 // qkv: packed [B*L, 3d] (nn.MultiheadAttention in-proj order) or planar [3 * heads][B*L][64] (GemmArgs::c_planar).
 // Either way the kernel sees a 3-D tensor [plane = 3 * heads][row = B*L][64]: only the strides differ.
+// L = 257 (ViT-L/14), no mask: 256 x 256 on the tensor cores + key 256 in the softmax threads (XKEY); the caller adds
+// query row 256 (attention_tail_rows_kernel). PC_ATTN6_XKEY=0 keeps that length on the streaming kernel (A/B).
+bool attention6_supports_xkey(int L, int causal) {
+  static int on = -1;
+  if (on < 0) on = env_int("PC_ATTN6_XKEY", 1);
+  return on && attention6_supports(256) && L == 257 && !causal;
+}
+
 int launch_attention6(const __half* qkv, int qkv_planar, __half* out, int B, int L, int heads, int causal,
                       cudaStream_t stream) {
   const int d = heads * HEAD_DIM;
+  const bool xkey = L == 257;
+  PC_REQUIRE(!xkey || (!causal && !qkv_planar), PC_ERR_ARG, "attention6: the extra-key mode takes packed, unmasked qkv");
   Params6 p{};
   p.L = L;
-  p.lp16 = (L + 15) / 16 * 16;
+  p.Lm = xkey ? 256 : L;
+  p.qkv = qkv;
+  p.out = out;
+  p.row_pitch = 3 * d;
+  p.plane_pitch = HEAD_DIM;
+  p.lp16 = (p.Lm + 15) / 16 * 16;
   p.heads = heads;
   p.d = d;
   p.items = B * heads;
-  p.split = L <= 128 ? 1 : 0;
+  p.split = p.Lm <= 128 ? 1 : 0;
   p.n_groups = p.split ? (p.items + 1) / 2 : p.items;
   p.na = p.lp16 < 128 ? p.lp16 : 128;
   p.nb = p.lp16 - p.na;
@@ -640,7 +858,8 @@ int launch_attention6(const __half* qkv, int qkv_planar, __half* out, int B, int
   PC_TRY(make_tmap_f16_3d(&tmO, out, d, L, B, static_cast<uint64_t>(d) * 2, static_cast<uint64_t>(L) * d * 2, 32, 32));
   const int sms = device_sm_count();
   const int grid = p.n_groups < sms ? p.n_groups : sms;
-  if (causal) PC_TRY((launch_variant6<true, 0>(grid, smem_bytes, stream, tmQ, tmT, tmO, p)));
+  if (xkey) PC_TRY((launch_variant6<false, 0, true>(grid, smem_bytes, stream, tmQ, tmT, tmO, p)));
+  else if (causal) PC_TRY((launch_variant6<true, 0>(grid, smem_bytes, stream, tmQ, tmT, tmO, p)));
   else if (npoly == 0) PC_TRY((launch_variant6<false, 0>(grid, smem_bytes, stream, tmQ, tmT, tmO, p)));
   else if (npoly == 1) PC_TRY((launch_variant6<false, 1>(grid, smem_bytes, stream, tmQ, tmT, tmO, p)));
   else if (npoly == 2) PC_TRY((launch_variant6<false, 2>(grid, smem_bytes, stream, tmQ, tmT, tmO, p)));

@@ -77,6 +77,7 @@ int launch_attention_rows(const __half* qkv, int qkv_planar, __half* out, int B,
 // launch_attention dispatches to it. PC_ATTN_IMPL=5 selects the round-1 kernel (attention5.cu: 64-key blocks, online
 // softmax, four tiles in flight), PC_ATTN_IMPL=2 keeps every shape on attention.cu's streaming kernel (A/B timing).
 bool attention6_supports(int L);
+bool attention6_supports_xkey(int L, int causal);  // L = 257: launch_attention6 + one tail query row
 int launch_attention6(const __half* qkv, int qkv_planar, __half* out, int B, int L, int heads, int causal,
                       cudaStream_t stream);
 bool attention5_supports(int L);
