@@ -425,7 +425,7 @@ def timed_loop(fn, min_ms: float, index: int):
 
 # (M, d) -> dram__bytes_read.sum + dram__bytes_write.sum of the block's four Linear launches (ncu --set full, cold caches)
 GEMM_TRAFFIC = {(18912, 768): 388.4e6,      # profiles/r01_ncu_gemm_summary.txt (plain epilogues)
-                (100864, 768): 2674.4e6}   # profiles/r02_ncu_block_summary.txt (the towers' epilogues, 2 x 512 images)
+                (100864, 768): 2689.3e6}   # profiles/r02_ncu_block_summary.txt (the towers' epilogues, 2 x 512 images)
 
 
 def gemm_roofline(ctx, dev, index, B, L, d):

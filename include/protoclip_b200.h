@@ -204,6 +204,15 @@ int pc_linear_forward(const void* x, int ldx, const void* w, int ldw, const void
 int pc_linear_shift_relu_forward(const void* x, int ldx, const void* w, int ldw, const float* shift,
                                  const void* residual, int ldr, void* out, int ldo, int M, int N, int K, int epilogue,
                                  int relu, void* stream);
+/* 3x3 / stride 1 / padding 1 Conv2d + eval BatchNorm2d + ReLU of a Bottleneck or of the stem (clip/model.py:21-23,
+ * 109-114, 44 / 139-141) on plain NHWC tensors: x f16 [n, h, w, cin], w f16 [cout, 9 * cin (ldw)] with column
+ * (ky * 3 + kx) * cin + c (the BatchNorm scale already folded in), shift f32 [cout] (nullable), out f16 [n, h, w, cout].
+ * Implicit GEMM: a tile's 128 rows are a rectangular pixel patch, loaded per tap through a 4-D TMA box shifted by
+ * (kx - 1, ky - 1); the zero padding is TMA's out-of-bounds fill. cin % 8 == 0, cout % 8 == 0; h x w must be cut by
+ * one of the patch shapes (32x4, 16x8, 8x8 of 2 images, 4x4 of 8 images), else PC_ERR_ARG (the towers then fall back
+ * to a zero-bordered copy). */
+int pc_conv3x3_shift_relu_forward(const void* x, const void* w, int ldw, const float* shift, void* out, int n, int h,
+                                  int width, int cin, int cout, int relu, void* stream);
 /* clip.model.LayerNorm.forward (clip/model.py:155-161): f16 in/out, f32 gamma/beta, eps 1e-5. */
 int pc_layernorm_forward(const void* x, void* y, const void* gamma, const void* beta, int rows, int d,
                          void* stream);

@@ -23,6 +23,7 @@ EPI_BIAS, EPI_BIAS_QUICKGELU, EPI_BIAS_RESIDUAL, EPI_F32 = 0, 1, 2, 3
 SYMBOLS = [
     "pc_version", "pc_last_error", "pc_ctx_create", "pc_ctx_destroy", "pc_ctx_set_full_last_block", "pc_vit_bind_weights",
     "pc_text_bind_weights", "pc_rn_bind_weights", "pc_linear_shift_relu_forward",
+    "pc_conv3x3_shift_relu_forward",
     "pc_preprocess_workspace_bytes", "pc_preprocess_image", "pc_preprocess_batch_workspace_bytes", "pc_preprocess_batch", "pc_encode_image_workspace_bytes", "pc_encode_image",
     "pc_encode_text_workspace_bytes", "pc_encode_text", "pc_resblock_workspace_bytes", "pc_resblock_forward",
     "pc_resblock_forward_parts",
@@ -146,6 +147,7 @@ def load_library() -> C.CDLL:
     lib.pc_resblock_forward_parts.argtypes = [vp, i, i, vp, i, i, i, i, i, vp, sz, vp]
     lib.pc_linear_forward.argtypes = [vp, i, vp, i, vp, vp, i, vp, i, i, i, i, i, vp]
     lib.pc_linear_shift_relu_forward.argtypes = [vp, i, vp, i, vp, vp, i, vp, i, i, i, i, i, i, vp]
+    lib.pc_conv3x3_shift_relu_forward.argtypes = [vp, vp, i, vp, vp, i, i, i, i, i, i, vp]
     lib.pc_layernorm_forward.argtypes = [vp, vp, vp, vp, i, i, vp]
     lib.pc_attention_forward.argtypes = [vp, vp, i, i, i, i, vp]
     lib.pc_attention_rows_forward.argtypes = [vp, vp, i, i, i, i, i, i, vp]
@@ -274,6 +276,27 @@ def attention(qkv: torch.Tensor, B: int, L: int, heads: int, causal: bool) -> to
     with torch.cuda.device(qkv.device):
         check(lib.pc_attention_forward(qkv.data_ptr(), out.data_ptr(), B, L, heads, int(causal),
                                        stream_ptr(qkv.device)), "pc_attention_forward")
+    return out
+
+
+def conv3x3_shift_relu(x: torch.Tensor, weight: torch.Tensor, shift: Optional[torch.Tensor] = None,
+                       relu: bool = True) -> torch.Tensor:
+    """3x3 / pad 1 Conv2d (+ per-channel fp32 shift = folded eval BatchNorm) (+ ReLU) on an NHWC fp16 tensor
+    (clip/model.py:21-23,44,109-114). weight: the module's [cout, cin, 3, 3] fp16 tensor (re-laid out here to the
+    [cout, (ky, kx, c)] matrix the implicit GEMM reads). Returns NHWC fp16 [n, h, w, cout]."""
+    lib = load_library()
+    if not x.is_cuda:
+        raise NativeError("conv3x3_shift_relu: CUDA tensors only; there is no CPU path")
+    n, h, w, cin = x.shape
+    cout = weight.shape[0]
+    wm = weight.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous().half()
+    x = x.contiguous().half()
+    out = torch.empty((n, h, w, cout), dtype=torch.float16, device=x.device)
+    sh = shift.float().contiguous() if shift is not None else None
+    with torch.cuda.device(x.device):
+        check(lib.pc_conv3x3_shift_relu_forward(x.data_ptr(), wm.data_ptr(), 9 * cin, sh.data_ptr() if sh is not None else None,
+                                                out.data_ptr(), n, h, w, cin, cout, int(relu), stream_ptr(x.device)),
+              "pc_conv3x3_shift_relu_forward")
     return out
 
 

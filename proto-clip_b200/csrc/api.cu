@@ -989,6 +989,24 @@ int pc_linear_shift_relu_forward(const void* x, int ldx, const void* w, int ldw,
   return launch_gemm(g, epilogue, static_cast<cudaStream_t>(stream));
 }
 
+int pc_conv3x3_shift_relu_forward(const void* x, const void* w, int ldw, const float* shift, void* out, int n, int h,
+                                  int width, int cin, int cout, int relu, void* stream) {
+  PC_REQUIRE(x && w && out && n > 0 && h > 0 && width > 0 && cin > 0 && cout > 0, PC_ERR_ARG,
+             "pc_conv3x3_shift_relu_forward: null buffer or empty problem");
+  PC_REQUIRE(cin % 8 == 0 && cout % 8 == 0 && ldw % 8 == 0, PC_ERR_ALIGN,
+             "pc_conv3x3_shift_relu_forward: cin / cout / ldw (%d / %d / %d) must be multiples of 8", cin, cout, ldw);
+  GemmArgs g{};
+  g.N = cout; g.K = cin;
+  g.A = static_cast<const __half*>(x); g.lda = cin;
+  g.W = static_cast<const __half*>(w); g.ldw = ldw;
+  g.C = out; g.ldc = cout;
+  g.bias_f32 = shift;
+  g.relu = relu ? 1 : 0;
+  g.conv_taps = 9;
+  g.conv_h = h; g.conv_w = width; g.conv_n = n;
+  return launch_gemm(g, EPI_BIAS, static_cast<cudaStream_t>(stream));
+}
+
 int pc_layernorm_forward(const void* x, void* y, const void* gamma, const void* beta, int rows, int d,
                          void* stream) {
   PC_REQUIRE(x && y && gamma && beta, PC_ERR_ARG, "pc_layernorm_forward: null buffer");

@@ -606,6 +606,7 @@ int launch_attention(const __half* qkv, __half* out, int B, int L, int heads, in
   if (attention6_supports(L)) return launch_attention6(qkv, 0, out, B, L, heads, causal, stream);  // whole-row S in TMEM
   // ViT-L/14 (L = 257): 256 x 256 whole-row + key 256 in the softmax threads + query row 256 in the kernel's spare warp
   if (attention6_supports_xkey(L, causal)) return launch_attention6(qkv, 0, out, B, L, heads, causal, stream);
+  if (attention7_supports(L, causal)) return launch_attention7(qkv, out, B, L, heads, stream);  // 192-key blocks, O in TMEM
   if (attention5_supports(L)) return launch_attention5(qkv, out, B, L, heads, causal, stream);  // round-1 kernel (A/B)
   const int d = heads * HEAD_DIM;
   AttnParams p{};

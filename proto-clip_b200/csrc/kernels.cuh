@@ -80,6 +80,10 @@ bool attention6_supports(int L);
 bool attention6_supports_xkey(int L, int causal);  // L = 257: launch_attention6 + one tail query row
 int launch_attention6(const __half* qkv, int qkv_planar, __half* out, int B, int L, int heads, int causal,
                       cudaStream_t stream);
+// attention7.cu: unmasked L > 257 (ViT-L/14@336px: 577): 192-key blocks through the same softmax machinery, O resident
+// in TMEM, online softmax with a lazy rescale, L % 192 == 1 through the extra-key trick
+bool attention7_supports(int L, int causal);
+int launch_attention7(const __half* qkv, __half* out, int B, int L, int heads, cudaStream_t stream);
 bool attention5_supports(int L);
 int launch_attention5(const __half* qkv, __half* out, int B, int L, int heads, int causal, cudaStream_t stream);
 

@@ -60,6 +60,31 @@ def test_linear(nat, M, N, K, epi):
     assert rel_err(got, ref) < (2e-5 if epi == "f32" else 2e-3)
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout", [(3, 96, 96, 96, 96), (2, 192, 192, 48, 48), (5, 48, 48, 192, 192),
+                                            (3, 24, 24, 384, 384), (5, 12, 12, 768, 768), (9, 12, 12, 64, 200),
+                                            (1, 8, 8, 8, 8), (2, 16, 32, 40, 72), (3, 56, 56, 64, 64), (1, 4, 4, 16, 16),
+                                            (7, 28, 28, 128, 128)])
+def test_conv3x3_patch_mode(nat, n, h, w, cin, cout):
+    """pc_conv3x3_shift_relu_forward (4-D TMA patches, zero padding by out-of-bounds fill) against F.conv2d: every
+    patch shape (32x4, 16x8, 8x8x2 images, 4x4x8 images), image counts that do not fill the last patch, channel counts
+    below / across the 64-wide k-block and the MMA's column granularity."""
+    torch.manual_seed(n * h + cin)
+    x = torch.randn(n, cin, h, w, device=DEV).half()
+    wt = (torch.randn(cout, cin, 3, 3, device=DEV) * (2.0 / (9 * cin)) ** 0.5).half()
+    shift = torch.randn(cout, device=DEV) * 0.3
+    ref = torch.relu(torch.nn.functional.conv2d(x.float(), wt.float(), padding=1) + shift.view(1, -1, 1, 1))
+    got = nat.conv3x3_shift_relu(x.permute(0, 2, 3, 1), wt, shift, relu=True).permute(0, 3, 1, 2)
+    assert rel_err(got, ref) < 2e-3 and mean_rel_err(got, ref) < 2e-3
+    lin = nat.conv3x3_shift_relu(x.permute(0, 2, 3, 1), wt, None, relu=False).permute(0, 3, 1, 2)
+    assert rel_err(lin, torch.nn.functional.conv2d(x.float(), wt.float(), padding=1)) < 2e-3
+
+
+def test_conv3x3_patch_mode_rejects_shapes_no_patch_cuts(nat):
+    x = torch.randn(2, 14, 14, 16, device=DEV).half()
+    with pytest.raises(nat.NativeError):
+        nat.conv3x3_shift_relu(x, torch.randn(16, 16, 3, 3, device=DEV).half())
+
+
 def test_linear_residual_in_place(nat):
     torch.manual_seed(0)
     x = torch.randn(500, 256, device=DEV).half()

@@ -1,6 +1,6 @@
 """Per-kernel counts of the SASS mnemonics that prove a Blackwell-native path (B200_PROFILING.md): UTC*MMA
 (tcgen05.mma), LDTM / STTM (tcgen05.ld / st), UTMALDG / UTMASTG (TMA), UTCBAR (tcgen05.commit), SYNCS (mbarrier),
-MUFU, HMMA (legacy mma.sync: must be 0).   python tools/sass_ops.py [lib.so] > profiles/r02_sass_ops.txt"""
+MUFU, HMMA (legacy mma.sync: only the one-row helper warp of attention6's L = 257 variant may use it).   python tools/sass_ops.py [lib.so] > profiles/r02_sass_ops.txt"""
 import re
 import subprocess
 import sys
