@@ -1,29 +1,34 @@
 // Multi-head self-attention core for long unmasked sequences (L > 257: ViT-L/14@336px has 577 tokens), round 2.
 //
 // attention6.cu keeps the WHOLE score row of a query tile in tensor memory, which ends at 256 keys. This kernel keeps
-// that kernel's softmax machinery (attn_wholerow.cuh: two threads per query row, in-place packed fp16 P, lean
-// exponential units) and streams the keys through it in BLOCKS OF 96 with a DOUBLE-BUFFERED S per query tile: the 256
-// TMEM columns of a tile hold S slot 0 at [0,96), S slot 1 at [96,192) and the O accumulator at [192,256). While the
-// softmax threads work on block j in one slot, S_{j+1} already sits in the other; when they hand P_j over, the MMA warp
-// issues P V_j and then S_{j+2} into the slot P_j occupied (the tensor pipe runs in order). The softmax never waits for
-// an MMA round trip in steady state. (The first version used 192-key blocks with one S slot: every block paid
-// S -> softmax -> P V -> S serially, 6.3 k cycles per block, 207 us at 64 images x 16 heads x 577.)
+// that kernel's softmax machinery (attn_wholerow.cuh: two threads per query row, in-place packed fp16 P, part b first,
+// lean exponential units) and streams the keys through it in BLOCKS OF 192: per 128-query tile the 256 TMEM columns hold
+// S_a = Q K[0:128]^T at [0,128), S_b = Q K[128:192]^T at [128,192) and the O accumulator at [192,256) -- nothing
+// aliases, O stays resident over the key blocks and the P V MMAs accumulate onto it. The softmax is the online one with
+// a LAZY rescale: a row's reference maximum moves only when a block's maximum exceeds it by more than 2^8 (P stays far
+// inside fp16, the row sum is fp32), and only then are the row's 64 O columns read, scaled and written back; for real
+// score distributions that happens in the first block or two of a row and never again.
 //
-// O stays resident over the key blocks and the P V MMAs accumulate onto it. The softmax is the online one with a LAZY
-// rescale: a row's reference maximum moves only when a block's maximum exceeds it by more than 2^8 (P stays far inside
-// fp16, the row sum is fp32), and only then are the row's 64 O columns read, scaled and written back (after the
-// previous block's P V has retired: one mbarrier per warpgroup counts them); for real score distributions that happens
-// in the first block or two of a row and never again.
+// 577 = 3 x 192 + 1: a fourth key block for one key would cost a whole S -> softmax -> P V hop, so the last key is folded
+// in by the softmax threads themselves (the extra-key trick of attention6's L = 257 mode: k_x, v_x rows dropped into
+// shared memory by the producer, q . k_x as a 64-long dot product split over the row's two threads, p_x v_x added to O
+// in the epilogue). Any other remainder is a shorter, masked last block.
 //
-// 577 = 6 x 96 + 1: another key block for one key would cost a whole softmax hop, so the last key is folded in by the
-// softmax threads themselves (the extra-key trick of attention6's L = 257 mode: k_x, v_x rows dropped into shared
-// memory by the producer, q . k_x as a 64-long dot product split over the row's two threads, p_x v_x added to O in the
-// epilogue). Any other remainder is a shorter, masked last block.
+// What bounds it (measured at 64 images x 16 heads x 577, 204 us = 427 TFLOP/s against 273 us for the round-1 kernel):
+// the P V instruction. M = 128, N = 64 (the head dimension), K = 16 with A from tensor memory costs ~ 140 cycles in the
+// kernel, 12 of them per 192-key block and tile; with the four N = 192 score instructions a block costs 2.4 k tensor
+// cycles, i.e. 126 us for the whole launch with the softmax switched off. Two variants that rearranged the chain did
+// not beat this one and were not kept (git history): 96-key blocks with a double-buffered S slot per warpgroup (the
+// softmax never waits for an MMA round trip, but the N = 96 score instructions sit on the 110-cycle shared-memory-operand
+// floor: 220 us), and one tile per CTA with four threads per row, 192-key double-buffered S and two O buffers (all 16
+// softmax warps in the same phase at the same time: 24.5 k exponentials per block are 1.5 k MUFU cycles that nothing
+// else overlaps: 234 us).
 //
 // One CTA per SM, persistent over PASSES = (image, head, pair of query tiles); the two warpgroups take the two tiles and
-// share the K / V stream (a ring of six 24 KB stages).
+// share the K / V stream (a ring of three 48 KB stages), alternating on the MUFU pipe through named barriers.
 //   warps 0..15   softmax (WG w = warp >> 3, thread hf = (warp >> 2) & 1 of a row, TMEM lane quarter = warp & 3)
-//   warps 16, 17  MMA issuer of WG 0 / 1
+//   warps 16, 17  MMA issuer of WG 0 / 1: per block S_j (after P V_{j-1}: the tensor pipe runs in order, so S_j may
+//                 overwrite P_{j-1}'s columns), then P V_j part b / part a as the softmax hands them over
 //   warp 18       TMA producer (Q tiles of the pass, K / V blocks, the extra rows)
 //   warp 19       idle
 #include <stdlib.h>
@@ -42,10 +47,10 @@ constexpr int HEAD_DIM = 64;
 constexpr int MMA_WARP0 = 16;
 constexpr int TMA_WARP = 18;
 constexpr int THREADS7 = 20 * 32;
-constexpr int KB = 96;                        // keys per block (one S slot)
-constexpr int NST = 6;                        // K / V ring stages
+constexpr int KB = 192;                       // keys per block
+constexpr int NST = 3;                        // K / V ring stages
 constexpr int Q_BYTES = 128 * 128;            // one query tile, 128B-swizzled
-constexpr int KV_BYTES = KB * 128;            // K or V of one block: 12 KB (a multiple of the 1024-byte swizzle atom)
+constexpr int KV_BYTES = KB * 128;            // K or V of one block: 24 KB (a multiple of the 1024-byte swizzle atom)
 constexpr int OFF_Q = 0;                      // Q tile of WG 0, then of WG 1
 constexpr int OFF_KV = 2 * Q_BYTES;           // ring: stage s = K block | V block
 constexpr int STAGE_BYTES = 2 * KV_BYTES;
@@ -61,7 +66,7 @@ struct Params7 {
   int Lk;        // keys streamed through the tensor cores (L, or L - 1 in extra-key mode)
   int xkey;      // 1: key L - 1 is folded in by the softmax threads
   int heads, d, items;
-  int n_blk;     // key blocks per row = ceil(Lk / 96)
+  int n_blk;     // key blocks per row = ceil(Lk / 192)
   int n_tiles;   // query tiles per sequence = ceil(L / 128)
   int ppi;       // passes per item = ceil(n_tiles / 2)
   int n_pass;    // items * ppi
@@ -74,11 +79,9 @@ struct Bars7 {
   uint64_t q_full, q_free;             // Q tiles (+ extra rows) of the pass
   uint64_t k_full[NST], v_full[NST];   // per ring stage
   uint64_t k_free[NST], v_free[NST];   // both WGs' S / P V MMAs of the block retired (2 arrivals)
-  uint64_t s_full[2][2];               // per WG and S slot: S of a block in TMEM
-  uint64_t p_full[2][2];               // per WG and S slot: P of the block in TMEM (8 warps). Per slot: a warp that is
-                                       // done with block j may hand over block j + 1 (its S is already there) while
-                                       // others are still on block j; block j + 2 needs P V_j, i.e. phase j complete
-  uint64_t pv_done[2];                 // per WG: one completion per block's P V MMAs
+  uint64_t s_full[2];                  // per WG: S of the block in TMEM
+  uint64_t pa_full[2], pb_full[2];     // per WG: P part a (8 warps) / part b (4 warps) in TMEM
+  uint64_t pv_done[2];                 // per WG: last P V MMA of the pass retired
   uint64_t o_free[2];                  // per WG: O read out by the epilogue (8 warps)
   uint32_t tmem_base;
 };
@@ -112,10 +115,9 @@ attention7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         mbar_init(&bars->v_free[i], 2);
       }
       for (int i = 0; i < 2; ++i) {
-        mbar_init(&bars->s_full[i][0], 1);
-        mbar_init(&bars->s_full[i][1], 1);
-        mbar_init(&bars->p_full[i][0], 8);
-        mbar_init(&bars->p_full[i][1], 8);
+        mbar_init(&bars->s_full[i], 1);
+        mbar_init(&bars->pa_full[i], 8);
+        mbar_init(&bars->pb_full[i], 4);
         mbar_init(&bars->pv_done[i], 1);
         mbar_init(&bars->o_free[i], 8);
       }
@@ -176,9 +178,9 @@ attention7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int w = warp - MMA_WARP0;
     const uint32_t region = tmem + w * 256;
     const uint32_t idesc_o = umma_idesc_f16(128, HEAD_DIM, 0, 1);
-    const uint32_t idesc_s = umma_idesc_f16(128, KB, 0, 0);
-    // blk: ring position (every pass); bcount / tcount: this WG's own blocks and passes
-    uint32_t pass_no = 0, blk = 0, bcount = 0, tcount = 0;
+    const uint32_t idesc_s = umma_idesc_f16(128, KB, 0, 0);  // one 192-key instruction per k-step: S_a | S_b are contiguous
+    // blk: ring position (every pass); bcount / nb_seen / tcount: this WG's own blocks, blocks with a part b, passes
+    uint32_t pass_no = 0, blk = 0, bcount = 0, nb_seen = 0, tcount = 0;
     for (int g = blockIdx.x; g < p.n_pass; g += g_stride, ++pass_no) {
       const int tp = g % p.ppi;
       if (2 * tp + w >= p.n_tiles) {  // odd tile count: no tile for this WG in the pass; release its share of the buffers
@@ -200,47 +202,49 @@ attention7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
       const uint64_t q_desc = umma_desc_kmajor_sw128(smem_u32(smem + OFF_Q + w * Q_BYTES));
       mbar_wait(&bars->q_full, pass_no & 1);
-      // S of block jj of this pass -> slot (bcount0 + jj) & 1. Issued behind P V of block jj - 2 (the previous tenant of
-      // the slot, possibly of the previous pass): the tensor pipe runs in order. Whole 96-key shape also for a short
-      // last block: rows past the keys are the next image's (or zero-filled), their scores are masked in the softmax.
-      const uint32_t bcount0 = bcount, blk0 = blk;
-      auto issue_s = [&](int jj) {
-        const uint32_t bs = blk0 + jj;
-        const int st = bs % NST;
-        mbar_wait(&bars->k_full[st], (bs / NST) & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t k_desc = umma_desc_kmajor_sw128(smem_u32(smem + OFF_KV + st * STAGE_BYTES));
-          const uint32_t slot = (bcount0 + jj) & 1;
-#pragma unroll
-          for (int k = 0; k < HEAD_DIM / 16; ++k)
-            umma_f16_ss(region + slot * KB, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-          umma_commit(&bars->s_full[w][slot]);
-          umma_commit(&bars->k_free[st]);
-          if (jj == p.n_blk - 1) umma_commit(&bars->q_free);
-        }
-        __syncwarp();
-      };
-      issue_s(0);
-      if (p.n_blk > 1) issue_s(1);
       for (int j = 0; j < p.n_blk; ++j, ++blk, ++bcount) {
         const int st = blk % NST;
+        const uint32_t full_par = (blk / NST) & 1;
         const int nch = block_chunks(p, j), h0 = (nch + 1) >> 1;
-        const uint64_t v_desc = umma_desc_mnmajor_sw128(smem_u32(smem + OFF_KV + st * STAGE_BYTES + KV_BYTES), 1024);
-        const uint32_t slot_col = region + (bcount & 1) * KB;
-        mbar_wait(&bars->v_full[st], (blk / NST) & 1);
-        // the first P V of the pass overwrites O: the previous pass's epilogue must have read it
-        if (j == 0) mbar_wait(&bars->o_free[w], (tcount & 1) ^ 1);
-        mbar_wait(&bars->p_full[w][bcount & 1], (bcount >> 1) & 1);
+        const uint32_t kaddr = smem_u32(smem + OFF_KV + st * STAGE_BYTES);
+        const uint64_t k_desc = umma_desc_kmajor_sw128(kaddr);
+        const uint64_t v_desc = umma_desc_mnmajor_sw128(kaddr + KV_BYTES, 1024);
+        mbar_wait(&bars->k_full[st], full_par);
         tc_fence_after();
+        // S_j overwrites the columns P_{j-1} sat in: P V_{j-1} was issued before it and the tensor pipe runs in order.
+        // Whole 128 / 64 key shapes also for a short last block: the rows past the keys are the next image's (or
+        // zero-filled), their scores are masked in the softmax.
         if (elect_one()) {
-          for (int k = 0; k < nch; ++k)
-            umma_f16_ts(region + O_COL, slot_col + p_col(k, h0), v_desc + 128 * k, idesc_o, (j > 0 || k != 0) ? 1u : 0u);
-          umma_commit(&bars->v_free[st]);
-          umma_commit(&bars->pv_done[w]);
+#pragma unroll
+          for (int k = 0; k < HEAD_DIM / 16; ++k) umma_f16_ss(region, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(&bars->s_full[w]);
+          umma_commit(&bars->k_free[st]);
+          if (j == p.n_blk - 1) umma_commit(&bars->q_free);
         }
         __syncwarp();
-        if (j + 2 < p.n_blk) issue_s(j + 2);
+        mbar_wait(&bars->v_full[st], full_par);
+        // the first P V of the pass overwrites O: the previous pass's epilogue must have read it
+        if (j == 0) mbar_wait(&bars->o_free[w], (tcount & 1) ^ 1);
+        if (nch > 8) {
+          mbar_wait(&bars->pb_full[w], nb_seen & 1);
+          ++nb_seen;
+          tc_fence_after();
+          if (elect_one()) {
+            for (int k = 8; k < nch; ++k)
+              umma_f16_ts(region + O_COL, region + p_col(k, h0), v_desc + 128 * k, idesc_o, (j > 0 || k != 8) ? 1u : 0u);
+          }
+          __syncwarp();
+        }
+        mbar_wait(&bars->pa_full[w], bcount & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const int ka = nch < 8 ? nch : 8;
+          for (int k = 0; k < ka; ++k)
+            umma_f16_ts(region + O_COL, region + p_col(k, h0), v_desc + 128 * k, idesc_o, (j > 0 || nch > 8 || k != 0) ? 1u : 0u);
+          umma_commit(&bars->v_free[st]);
+          if (j == p.n_blk - 1) umma_commit(&bars->pv_done[w]);
+        }
+        __syncwarp();
       }
       ++tcount;
     }
@@ -289,11 +293,11 @@ attention7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       uint64_t acc_a = 0, acc_b = 0;  // this thread's partial row sum, relative to m_run
       for (int j = 0; j < p.n_blk; ++j, ++bcount, ++round) {
         const int nch = block_chunks(p, j), h0 = (nch + 1) >> 1;
-        const int c0 = hf ? h0 : 0, c1 = hf ? nch : h0;  // this thread's chunks of the block
-        const int l_blk = min(KB, p.Lk - j * KB);       // valid keys of the block
+        const int c0 = hf ? h0 : 0, c1 = hf ? nch : h0;
+        const int ca = min(c1, 8), cb = max(c0, 8);
+        const int l_blk = min(KB, p.Lk - j * KB);  // valid keys of the block
         const int jmax = l_blk - 1;
         const bool last = j == p.n_blk - 1;
-        const uint32_t s_row = t_row + (bcount & 1) * KB;  // the block's S slot
         if (XKEY && last) {  // q_i . k_x: this thread's 32 of the 64 dimensions (q from the Q tile in shared memory)
           mbar_wait(&bars->q_full, pass_no & 1);
           const uint8_t* qrow = smem + OFF_Q + w * Q_BYTES + r * 128;
@@ -314,9 +318,9 @@ attention7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           }
           s_x = d0 + d1;
         }
-        mbar_wait(&bars->s_full[w][bcount & 1], (bcount >> 1) & 1);
+        mbar_wait(&bars->s_full[w], bcount & 1);
         tc_fence_after();
-        if (XKEY && last) {
+        if (XKEY && last) {  // slot writes are ordered behind s_full (the partner read its previous value before O was freed)
           *my_x = s_x;
           pair_bar_sync(pair_bar);
           s_x = hf ? *other_x + s_x : s_x + *other_x;
@@ -324,7 +328,7 @@ attention7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
         // ---- block maximum: own chunks, the partner's through shared memory, the extra key
         float mx = -INFINITY;
-        if (warp_live) mx = row_max<false>(s_row, c0, c1, l_blk, jmax);
+        if (warp_live) mx = row_max<false>(t_row, c0, c1, l_blk, jmax);
         if (XKEY && last) mx = fmaxf(mx, s_x);
         *my_x = mx;
         pair_bar_sync(pair_bar);
@@ -337,12 +341,7 @@ attention7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           const uint64_t al2 = pack_f32x2(alpha, alpha);
           acc_a = fma_f32x2(acc_a, al2, 0ull);
           acc_b = fma_f32x2(acc_b, al2, 0ull);
-          // O is being accumulated by P V of block j - 1 (issued when this WG handed P_{j-1} over): wait for it to
-          // retire; P V_j cannot be issued before this thread's warp arrives on p_full below. (Parity wait one phase
-          // behind at most: S_j, which this thread has seen, was issued behind P V_{j-2}.)
-          mbar_wait(&bars->pv_done[w], (bcount - 1) & 1);
-          tc_fence_after();
-          if (warp_live) {
+          if (warp_live) {  // P V_{j-1} has retired (S_j was issued behind it): O is quiescent until this block's P V
             uint32_t O2[32];
             tmem_ld_32x32(t_row + O_COL + 32 * hf, O2);
             tmem_wait_ld();
@@ -359,14 +358,23 @@ attention7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           if (w == 0) asm volatile("bar.sync 1, 512;" ::: "memory");
           else asm volatile("bar.sync 2, 512;" ::: "memory");
         }
-        // ---- exponentials, P in place (attn_wholerow.cuh)
+        // ---- exponentials: part b first, then part a (P in place, attn_wholerow.cuh)
+        if (hf == 1 && nch > 8) {
+          if (warp_live) {
+            exp_chunks<false, 0>(t_row, cb, c1, p_col(cb, h0), l_blk, jmax, sc2, nref2, acc_a, acc_b);
+            tmem_wait_st();
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->pb_full[w]);
+        }
         if (warp_live) {
-          exp_chunks<false, 0>(s_row, c0, c1, p_col(c0, h0), l_blk, jmax, sc2, nref2, acc_a, acc_b);
+          exp_chunks<false, 0>(t_row, c0, ca, p_col(c0, h0), l_blk, jmax, sc2, nref2, acc_a, acc_b);
           tmem_wait_st();
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->p_full[w][bcount & 1]);
+        if (lane == 0) mbar_arrive(&bars->pa_full[w]);
         if (p.pingpong) {
           if (w == 0) asm volatile("bar.arrive 2, 512;" ::: "memory");
           else if (round != rounds - 1) asm volatile("bar.arrive 1, 512;" ::: "memory");
@@ -391,10 +399,7 @@ attention7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         sum += e;
         p_x = __half2float(__float2half_rn(e));
       }
-      // The pass's last P V. A parity wait is only meaningful one phase behind: S of the last block was issued behind
-      // P V of block n - 3, so the barrier has reached phase n - 2 at least; observe that one first, then the last.
-      if (p.n_blk > 1) mbar_wait(&bars->pv_done[w], (bcount - 2) & 1);
-      mbar_wait(&bars->pv_done[w], (bcount - 1) & 1);
+      mbar_wait(&bars->pv_done[w], tcount & 1);
       tc_fence_after();
       if (!warp_live) {
         tc_fence_before();
@@ -483,7 +488,7 @@ int launch_attention7(const __half* qkv, __half* out, int B, int L, int heads, c
   const int d = heads * HEAD_DIM;
   Params7 p{};
   p.L = L;
-  p.xkey = (L % KB == 1) ? 1 : 0;  // 577 = 6 x 96 + 1: no seventh block for one key
+  p.xkey = (L % KB == 1) ? 1 : 0;  // 577 = 3 x 192 + 1: no fourth block for one key
   p.Lk = L - p.xkey;
   p.heads = heads;
   p.d = d;
@@ -493,7 +498,7 @@ int launch_attention7(const __half* qkv, __half* out, int B, int L, int heads, c
   p.ppi = (p.n_tiles + 1) / 2;
   p.n_pass = p.items * p.ppi;
   static int pingpong = -1;
-  if (pingpong < 0) pingpong = env_int7("PC_ATTN7_PINGPONG", 0);
+  if (pingpong < 0) pingpong = env_int7("PC_ATTN7_PINGPONG", 1);
   p.pingpong = pingpong;
   p.qkv = qkv;
   p.row_pitch = 3 * d;

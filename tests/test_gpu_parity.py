@@ -116,7 +116,11 @@ def test_linear_residual_in_place(nat):
                                               (4, 209, 3, False), (2, 224, 1, True), (2, 240, 2, False), (5, 256, 16, False),
                                               (3, 250, 2, True),
                                               # L = k * 128 + few rows: the last rows go to attention_tail_rows_kernel
-                                              (3, 257, 16, False), (2, 260, 2, True), (2, 392, 1, False), (5, 264, 3, False)])
+                                              (3, 257, 16, False), (2, 260, 2, True), (2, 392, 1, False), (5, 264, 3, False),
+                                              # unmasked L > 257: 192-key blocks (attention7.cu), odd / even block counts,
+                                              # short last blocks, L % 192 == 1 (extra key), any length
+                                              (2, 288, 1, False), (2, 385, 2, False), (3, 480, 1, False), (9, 577, 16, False),
+                                              (1, 769, 2, False), (1, 5000, 1, False)])
 def test_attention(nat, B, L, heads, causal):
     torch.manual_seed(L)
     d = heads * 64
@@ -167,6 +171,26 @@ def test_attention_large_logits(nat, B, L, heads, causal, gain):
     if causal:
         s = s + torch.full((L, L), float("-inf"), device=DEV).triu(1)
     ref = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B * L, d)
+    assert torch.isfinite(got.float()).all()
+    assert rel_err(got, ref) < 3e-3
+
+
+@pytest.mark.parametrize("B,L,heads", [(3, 577, 2), (2, 480, 1), (2, 769, 1)])
+def test_attention_online_rescale(nat, B, L, heads):
+    """attention7's lazy online softmax: keys of the later 192-key blocks carry much larger scores than the earlier ones
+    (for some rows only), so a row's reference maximum has to move and its O accumulator in TMEM be rescaled mid-row;
+    other rows keep their first reference (no rescale) in the same warp."""
+    torch.manual_seed(L + 7)
+    d = heads * 64
+    qkv = torch.randn(B * L, 3 * d, device=DEV)
+    k = qkv[:, d:2 * d].view(B, L, d)
+    k[:, 200:260] *= 5.0      # second block: clearly above the first for rows aligned with those keys
+    k[:, L - 40:] *= 9.0      # last block: above everything
+    qkv[::3, :d] *= 0.05      # every third query row: tiny scores, its reference never moves
+    qkv = qkv.half()
+    got = nat.attention(qkv, B, L, heads, False)
+    q, k, v = [t.reshape(B, L, heads, 64).permute(0, 2, 1, 3).float() for t in qkv.split(d, dim=1)]
+    ref = (torch.softmax((q @ k.transpose(-1, -2)) * 0.125, -1) @ v).permute(0, 2, 1, 3).reshape(B * L, d)
     assert torch.isfinite(got.float()).all()
     assert rel_err(got, ref) < 3e-3
 
@@ -748,7 +772,7 @@ def test_error_paths(nat):
     with pytest.raises(nat.NativeError):
         nat.linear(torch.zeros(4, 12, device=DEV).half(), torch.zeros(4, 12, device=DEV).half())  # K % 8 != 0
     with pytest.raises(nat.NativeError):
-        nat.attention(torch.zeros(5000, 192, device=DEV).half(), 1, 5000, 1, False)  # L > 4096
+        nat.attention(torch.zeros(5000, 192, device=DEV).half(), 1, 5000, 1, True)  # masked: K / V of a row must fit smem
 
 
 # ----------------------------------------------------------------------------- main.py CLI end to end
