@@ -296,8 +296,8 @@ def run_ours(args):
         n_mb = math.ceil(B / eff_mb)
         # per micro-batch: patchify, conv1 GEMM, embed+ln_pre (+ row statistics); per block 4 GEMMs (LayerNorm folded into two
         # of them) + attention; ln_post, proj GEMM, l2norm. Per step: adapter (2 GEMMs, 2 LN kernels), l2norm,
-        # 2 similarity GEMMs + softmax/argmax.
-        launches = args.steps * (n_mb * (3 + 5 * layers + 3) + 8)
+        # 1 similarity GEMM over the adjacent [z_img; z_txt] banks of the packed head state + softmax/argmax.
+        launches = args.steps * (n_mb * (3 + 5 * layers + 3) + 7)
         sustained, burst, src = measured_peaks()
         head_flops = 4.0 * N_CLASSES * D + 2.0 * D * D / 4 * 2
         flops_ref = synthetic.vit_flops_per_image(ARCH) + head_flops          # what the reference computes per image

@@ -1111,6 +1111,33 @@ size_t pc_proto_classify_workspace_bytes(int Q, int N) {
   return static_cast<size_t>(rows) * 2 * align_up(N, 4) * sizeof(float);
 }
 
+namespace {
+// dots[q, 0:N] = q . z_img^T, dots[q, Np:Np+N] = q . z_txt^T (fp32). When the two banks are adjacent in memory (the packed
+// head state, pipeline.HeadState.pack) and N needs no padding they are ONE [2N, D] matrix: one GEMM launch with N' = 2N
+//  instead of one per bank.
+int bank_dots(const __half* q, const __half* z_img, const __half* z_txt, float* dots, int n, int N, int Np, int D,
+              cudaStream_t s) {
+  GemmArgs g{};
+  g.M = n; g.K = D;
+  g.A = q; g.lda = D;
+  g.ldw = D;
+  g.ldc = 2 * Np;
+  if (z_txt == z_img + static_cast<size_t>(N) * D && Np == N) {
+    g.N = 2 * N;
+    g.W = z_img;
+    g.C = dots;
+    return launch_gemm(g, EPI_F32, s);
+  }
+  for (int bank = 0; bank < 2; ++bank) {
+    g.N = N;
+    g.W = bank == 0 ? z_img : z_txt;
+    g.C = dots + bank * Np;
+    PC_TRY(launch_gemm(g, EPI_F32, s));
+  }
+  return PC_OK;
+}
+}  // namespace
+
 int pc_proto_classify(const void* q, const void* z_img, const void* z_txt, const float* zi_n2, const float* zt_n2,
                       int Q, int N, int D, float alpha, float beta, float* p_out, int64_t* argmax, float* pmax,
                       void* workspace, size_t workspace_bytes, void* stream) {
@@ -1127,14 +1154,8 @@ int pc_proto_classify(const void* q, const void* z_img, const void* z_txt, const
   const __half* qh = static_cast<const __half*>(q);
   for (int q0 = 0; q0 < Q; q0 += kClassifyChunk) {
     const int n = (Q - q0 < kClassifyChunk) ? (Q - q0) : kClassifyChunk;
-    for (int bank = 0; bank < 2; ++bank) {
-      GemmArgs g{};
-      g.M = n; g.N = N; g.K = D;
-      g.A = qh + static_cast<size_t>(q0) * D; g.lda = D;
-      g.W = static_cast<const __half*>(bank == 0 ? z_img : z_txt); g.ldw = D;
-      g.C = dots + bank * Np; g.ldc = 2 * Np;
-      PC_TRY(launch_gemm(g, EPI_F32, s));
-    }
+    PC_TRY(bank_dots(qh + static_cast<size_t>(q0) * D, static_cast<const __half*>(z_img), static_cast<const __half*>(z_txt),
+                     dots, n, N, Np, D, s));
     PC_TRY(launch_proto_softmax(dots, 2 * Np, qh + static_cast<size_t>(q0) * D, D, zi_n2, zt_n2, n, N, alpha, beta,
                                 p_out ? p_out + static_cast<size_t>(q0) * N : nullptr,
                                 argmax ? argmax + q0 : nullptr, pmax ? pmax + q0 : nullptr, s));
@@ -1161,14 +1182,8 @@ int pc_proto_grid_search(const void* q, const void* z_img, const void* z_txt, co
   const __half* qh = static_cast<const __half*>(q);
   for (int q0 = 0; q0 < Q; q0 += kClassifyChunk) {
     const int n = (Q - q0 < kClassifyChunk) ? (Q - q0) : kClassifyChunk;
-    for (int bank = 0; bank < 2; ++bank) {
-      GemmArgs g{};
-      g.M = n; g.N = N; g.K = D;
-      g.A = qh + static_cast<size_t>(q0) * D; g.lda = D;
-      g.W = static_cast<const __half*>(bank == 0 ? z_img : z_txt); g.ldw = D;
-      g.C = dots + bank * Np; g.ldc = 2 * Np;
-      PC_TRY(launch_gemm(g, EPI_F32, s));
-    }
+    PC_TRY(bank_dots(qh + static_cast<size_t>(q0) * D, static_cast<const __half*>(z_img), static_cast<const __half*>(z_txt),
+                     dots, n, N, Np, D, s));
     PC_TRY(launch_proto_grid(dots, 2 * Np, qh + static_cast<size_t>(q0) * D, D, zi_n2, zt_n2, n, N, labels + q0, alphas,
                              n_alpha, betas, n_beta, counts, s));
   }

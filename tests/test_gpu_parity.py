@@ -481,6 +481,27 @@ def test_head_matches_reference_goldens(nat):
         assert torch.allclose(pm.cpu(), ref_p.max(1)[0], atol=1e-5)
 
 
+@pytest.mark.parametrize("N,D", [(1000, 512), (198, 768), (397, 768)])
+def test_proto_classify_adjacent_banks_take_one_gemm(nat, N, D):
+    """When z_img and z_txt are adjacent in memory (the packed head state) and N % 4 == 0 the two similarity GEMMs are
+    one launch over a [2N, D] matrix (csrc/api.cu bank_dots); the result must equal the two-launch path bit for bit,
+    and N % 4 != 0 (397) must keep working through the two-launch path."""
+    torch.manual_seed(N)
+    Q = 300
+    q = nat.l2_normalize(torch.randn(Q, D, device=DEV).half())
+    buf = torch.empty(2 * N, D, device=DEV, dtype=torch.float16)
+    buf[:N] = nat.l2_normalize(torch.randn(N, D, device=DEV).half())
+    buf[N:] = nat.l2_normalize(torch.randn(N, D, device=DEV).half())
+    zi_adj, zt_adj = buf[:N], buf[N:]
+    zi_sep, zt_sep = zi_adj.clone(), zt_adj.clone()
+    n2i, n2t = zi_sep.float().pow(2).sum(-1), zt_sep.float().pow(2).sum(-1)
+    p1, a1, m1 = nat.proto_classify(q, zi_adj, zt_adj, n2i, n2t, 0.5, 12.0)
+    p2, a2, m2 = nat.proto_classify(q, zi_sep, zt_sep, n2i, n2t, 0.5, 12.0)
+    assert torch.equal(p1, p2) and torch.equal(a1, a2) and torch.equal(m1, m2)
+    ref = O.P(q.cpu(), zi_sep.cpu(), zt_sep.cpu(), 0.5, 12.0)
+    assert rel_err(p1, ref) < 1e-4 and torch.equal(a1.cpu(), O.predict(ref))
+
+
 @pytest.mark.parametrize("name", ["ckpt_imagenet_F_16.pt", "ckpt_fewsol_198_F_24.pt"])
 def test_shipped_checkpoint_subsets(nat, name):
     """Real trained Proto-CLIP-F heads (class subsets of pretrained_ckpt/*): predictions identical to the
