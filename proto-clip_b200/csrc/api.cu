@@ -56,7 +56,7 @@ struct RnTower {
   std::vector<void*> owned;
   size_t max_act = 0, max_col = 0;  // per image, in fp16 elements: largest activation / im2col operand
 };
-constexpr int kRnMicroBatch = 64;
+constexpr int kRnMicroBatch = 128;
 
 // Micro-batching. One row-block WAVE of the CTA-pair GEMM is sm_count / 2 pairs x 256 rows: ViT-B/16 (L = 197) -> 96
 // images = 18 912 rows = 73.9 of 74 row blocks; ViT-L/14 -> 73; @336px -> 32. Round 1 ran one wave per pass (activations
