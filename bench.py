@@ -264,6 +264,18 @@ def run_ours(args):
             out_host.copy_(am, non_blocking=True)
         cur.synchronize()
 
+    # the bare pinned-host -> device copy of one batch (context for e2e: when it is longer than the compute of a step,
+    # the end-to-end rate is the PCIe rate, whatever the kernels do)
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(copy_stream):
+        stage[0].copy_(pool_host[0], non_blocking=True)
+        c0.record(copy_stream)
+        for k in range(4):
+            stage[k % 2].copy_(pool_host[k % 2], non_blocking=True)
+        c1.record(copy_stream)
+    torch.cuda.synchronize()
+    h2d_ms = c0.elapsed_time(c1) / 4
     e2e_run(max(2, args.warmup))
     torch.cuda.synchronize()
     pdist.barrier()
@@ -312,7 +324,9 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (616 MB per batch, 2 alternating batches)",
                        "parallelism": f"dp{world} (query shards; one-off memory-bank build sharded with 2 all-gathers, then 1 NCCL broadcast of the head state; no collective in the timed step)"},
             "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": int(pool_host[0].numel() * 4),
-                    "d2h_bytes_per_step": int(B * 8), "ms_per_step": round(ms_e2e / args.steps, 3)},
+                    "d2h_bytes_per_step": int(B * 8), "ms_per_step": round(ms_e2e / args.steps, 3),
+                    "h2d_copy_alone_ms": round(h2d_ms, 3),
+                    "h2d_copy_alone_gbps": round(pool_host[0].numel() * 4 / h2d_ms / 1e6, 1)},
             "gpu_launches": launches,
             "clocks": clocks.summary(),
             "model_tflops": round(value * flops_img / 1e12, 1),
@@ -331,11 +345,11 @@ def run_ours(args):
 
 def effective_micro_batch(B: int, L: int, mb: int, dev) -> int:
     """Images per encoder pass: the caller's --micro-batch, else the library's policy (csrc/api.cu pick_micro_batch: at
-    most 6 row-block waves of the CTA-pair GEMM per pass, the batch cut into equal passes)."""
+    most 12 row-block waves of the CTA-pair GEMM per pass, the batch cut into equal passes)."""
     if mb > 0:
         return mb
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    cap = 6 * max(1, (sms // 2) * 256 // L)
+    cap = 12 * max(1, (sms // 2) * 256 // L)
     passes = max(1, math.ceil(B / cap))
     return math.ceil(B / passes)
 
@@ -425,7 +439,8 @@ def timed_loop(fn, min_ms: float, index: int):
 
 # (M, d) -> dram__bytes_read.sum + dram__bytes_write.sum of the block's four Linear launches (ncu --set full, cold caches)
 GEMM_TRAFFIC = {(18912, 768): 388.4e6,      # profiles/r01_ncu_gemm_summary.txt (plain epilogues)
-                (100864, 768): 2689.3e6}   # profiles/r02_ncu_block_summary.txt (the towers' epilogues, 2 x 512 images)
+                (100864, 768): 2689.3e6,   # profiles/r02_ncu_block_summary.txt (the towers' epilogues, 512 images)
+                (201728, 768): 5513.0e6}   # profiles/r02_ncu_block1024_summary.txt (1024 images in one pass)
 
 
 def gemm_roofline(ctx, dev, index, B, L, d):

@@ -62,9 +62,10 @@ constexpr int kRnMicroBatch = 128;
 // images = 18 912 rows = 73.9 of 74 row blocks; ViT-L/14 -> 73; @336px -> 32. Round 1 ran one wave per pass (activations
 // L2-resident); measured on B200, longer passes win: every launch pays ~2 us of launch gap plus the fill of its first
 // tile and the un-overlapped epilogue of its last one, and the Linears stay compute-bound from HBM (ViT-B/16, batch
-// 1024: 26.1 k img/s at 96 per pass, 26.7 k at 288, 27.3 k at 512). Default: at most kMaxWaves waves per pass, and the
-// batch cut into EQUAL passes (1024 -> 2 x 512, not 576 + 448): tiles, not row blocks, are what the workers balance.
-constexpr int kMaxWaves = 6;
+// 1024: 26.1 k img/s at 96 per pass, 26.7 k at 288, 27.3 k at 512; later in the round 29.4 k at 512 against 29.9 k for
+// the whole 1024 in one pass). Default: at most kMaxWaves waves per pass (1 152 ViT-B/16 images: ~3 GB of workspace), and
+// the batch cut into EQUAL passes (2048 -> 2 x 1024, not 1152 + 896): tiles, not row blocks, are what the workers balance.
+constexpr int kMaxWaves = 12;
 inline int wave_images(int L) {
   const int rows = (device_sm_count() / 2) * 256;
   const int mb = rows / (L > 0 ? L : 1);
