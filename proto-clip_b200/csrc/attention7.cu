@@ -393,6 +393,8 @@ attention7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       *my_x = part;
       pair_bar_sync(pair_bar);
       float sum = hf ? *other_x + part : part + *other_x;
+      pair_bar_sync(pair_bar);  // both partial sums read: the slots may be rewritten (the next pass's S is issued early,
+                                // so unlike in attention6 nothing else orders the partner's read before the next write)
       float p_x = 0.0f;
       if (XKEY) {
         const float e = ex2_approx(fmaf(s_x, sc, nref));
