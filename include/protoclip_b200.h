@@ -165,6 +165,16 @@ int pc_preprocess_image(const uint8_t* rgb, int H, int W, int n_px, void* out, i
 size_t pc_preprocess_batch_workspace_bytes(int B, int H, int W, int n_px);
 int pc_preprocess_batch(const uint8_t* rgb, int B, int H, int W, int n_px, void* out, int out_dtype, void* workspace,
                         size_t workspace_bytes, void* stream);
+/* `get_random_train_tfm()` of datasets/imagenet.py:8-23 (the augmentation build_cache_model's loader applies to the
+ * support images, utils.py:303-310) for ONE image and a GIVEN draw: RandomResizedCrop(n_px, BICUBIC) with the box
+ * (top, left, crop_h, crop_w) -> RandomHorizontalFlip (flip != 0) -> ToTensor -> Normalize(CLIP mean / std). The
+ * random draws stay on the host (torchvision takes them from torch's global generator; the Python shell
+ * `GPUTrainTransform` consumes it identically, so a seed gives the same box / flip as the reference). Byte-exact with
+ * torchvision F.resized_crop + F.hflip on a PIL image: the box is resampled as an image of its own (taps stop at its
+ * edges), both axes scaled independently. rgb: uint8 [H, W, 3] in device memory; out: [3, n_px, n_px] f32 / f16. */
+size_t pc_preprocess_train_workspace_bytes(int crop_h, int crop_w, int n_px);
+int pc_preprocess_train_image(const uint8_t* rgb, int H, int W, int top, int left, int crop_h, int crop_w, int flip,
+                              int n_px, void* out, int out_dtype, void* workspace, size_t workspace_bytes, void* stream);
 
 /* CLIP.encode_text (clip/model.py:341-354). tokens: int64 [P, context_length] (clip.tokenize output,
  * clip/clip.py:194-230); out: f16 [P, embed_dim]. */

@@ -131,3 +131,68 @@ def clip_preprocess(img: np.ndarray, n_px: int) -> np.ndarray:
     mean = np.asarray(CLIP_MEAN, dtype=np.float32)[:, None, None]
     std = np.asarray(CLIP_STD, dtype=np.float32)[:, None, None]
     return ((x - mean) / std).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Training-time augmentation of the support images (reference datasets/imagenet.py:8-23 `get_random_train_tfm`):
+#
+#     Compose([RandomResizedCrop(224, scale=(0.5, 1), interpolation=BICUBIC), RandomHorizontalFlip(0.5),
+#              ToTensor(), Normalize(mean, std)])
+#
+# Third-party arithmetic again: torchvision 0.26 draws the crop box and the flip from torch's global generator
+# (`RandomResizedCrop.get_params`, `RandomHorizontalFlip.forward`), crops the PIL image, and Pillow resamples the
+# CROPPED image (so taps stop at the box edge) to size x size. Pinned by tests/test_preprocess.py against the live
+# transform under the same seed.
+
+TRAIN_SCALE = (0.5, 1.0)              # datasets/imagenet.py:16-17
+TRAIN_RATIO = (3.0 / 4.0, 4.0 / 3.0)  # torchvision default
+
+
+def random_resized_crop_params(height: int, width: int, scale=TRAIN_SCALE, ratio=TRAIN_RATIO):
+    """RandomResizedCrop.get_params: ten tries of (area fraction, log-uniform aspect ratio) from torch's global
+    generator, the first box that fits wins (two more draws place it); else the central fallback. -> (top, left, h, w).
+    Consumes the generator exactly like torchvision, so the same seed gives the same box."""
+    import torch
+    area = height * width
+    log_ratio = torch.log(torch.tensor(ratio))
+    for _ in range(10):
+        target_area = area * torch.empty(1).uniform_(scale[0], scale[1]).item()
+        aspect_ratio = torch.exp(torch.empty(1).uniform_(log_ratio[0], log_ratio[1])).item()
+        w = int(round(math.sqrt(target_area * aspect_ratio)))
+        h = int(round(math.sqrt(target_area / aspect_ratio)))
+        if 0 < w <= width and 0 < h <= height:
+            i = torch.randint(0, height - h + 1, size=(1,)).item()
+            j = torch.randint(0, width - w + 1, size=(1,)).item()
+            return i, j, h, w
+    in_ratio = float(width) / float(height)
+    if in_ratio < min(ratio):
+        w = width
+        h = int(round(w / min(ratio)))
+    elif in_ratio > max(ratio):
+        h = height
+        w = int(round(h * max(ratio)))
+    else:
+        w, h = width, height
+    return (height - h) // 2, (width - w) // 2, h, w
+
+
+def random_flip(p: float = 0.5) -> bool:
+    """RandomHorizontalFlip.forward: one `torch.rand(1)` draw."""
+    import torch
+    return bool(torch.rand(1) < p)
+
+
+def train_transform_u8(img: np.ndarray, top: int, left: int, h: int, w: int, flip: bool, size: int) -> np.ndarray:
+    """F.resized_crop on a PIL image (crop, then Image.resize((size, size), BICUBIC) of the crop) + F.hflip."""
+    crop = np.ascontiguousarray(img[top:top + h, left:left + w])
+    r = resize_bicubic_u8(crop, size, size)
+    return np.ascontiguousarray(r[:, ::-1]) if flip else r
+
+
+def train_transform(img: np.ndarray, top: int, left: int, h: int, w: int, flip: bool, size: int = 224) -> np.ndarray:
+    """`get_random_train_tfm()` for a given box / flip -> float32 [3, size, size]."""
+    u8 = train_transform_u8(img, top, left, h, w, flip, size)
+    x = u8.astype(np.float32).transpose(2, 0, 1) / np.float32(255.0)
+    mean = np.asarray(CLIP_MEAN, dtype=np.float32)[:, None, None]
+    std = np.asarray(CLIP_STD, dtype=np.float32)[:, None, None]
+    return ((x - mean) / std).astype(np.float32)

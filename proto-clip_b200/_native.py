@@ -24,7 +24,8 @@ SYMBOLS = [
     "pc_version", "pc_last_error", "pc_ctx_create", "pc_ctx_destroy", "pc_ctx_set_full_last_block", "pc_vit_bind_weights",
     "pc_text_bind_weights", "pc_rn_bind_weights", "pc_linear_shift_relu_forward",
     "pc_conv3x3_shift_relu_forward",
-    "pc_preprocess_workspace_bytes", "pc_preprocess_image", "pc_preprocess_batch_workspace_bytes", "pc_preprocess_batch", "pc_encode_image_workspace_bytes", "pc_encode_image",
+    "pc_preprocess_workspace_bytes", "pc_preprocess_image", "pc_preprocess_batch_workspace_bytes", "pc_preprocess_batch",
+    "pc_preprocess_train_workspace_bytes", "pc_preprocess_train_image", "pc_encode_image_workspace_bytes", "pc_encode_image",
     "pc_encode_text_workspace_bytes", "pc_encode_text", "pc_resblock_workspace_bytes", "pc_resblock_forward",
     "pc_resblock_forward_parts",
     "pc_linear_forward", "pc_layernorm_forward", "pc_attention_forward", "pc_attention_rows_forward",
@@ -138,6 +139,9 @@ def load_library() -> C.CDLL:
     lib.pc_preprocess_batch_workspace_bytes.argtypes = [i, i, i, i]
     lib.pc_preprocess_batch_workspace_bytes.restype = sz
     lib.pc_preprocess_batch.argtypes = [vp, i, i, i, i, vp, i, vp, sz, vp]
+    lib.pc_preprocess_train_workspace_bytes.argtypes = [i, i, i]
+    lib.pc_preprocess_train_workspace_bytes.restype = sz
+    lib.pc_preprocess_train_image.argtypes = [vp, i, i, i, i, i, i, i, i, vp, i, vp, sz, vp]
     lib.pc_encode_text_workspace_bytes.argtypes = [vp, i]
     lib.pc_encode_text_workspace_bytes.restype = sz
     lib.pc_encode_text.argtypes = [vp, vp, i, vp, i, i, vp, sz, vp]
@@ -335,6 +339,32 @@ def preprocess_image(rgb: torch.Tensor, n_px: int, out: Optional[torch.Tensor] =
         check(lib.pc_preprocess_batch(rgb.data_ptr(), B, H, W, n_px, out.data_ptr(),
                                       PC_IMG_F16 if out.dtype == torch.float16 else PC_IMG_F32, ws.data_ptr(), ws.numel(),
                                       stream_ptr(rgb.device)), "pc_preprocess_batch")
+    return out
+
+
+def preprocess_train_image(rgb: torch.Tensor, box, flip: bool, n_px: int = 224, out: Optional[torch.Tensor] = None,
+                           dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """`get_random_train_tfm()` (datasets/imagenet.py:8-23) on the GPU for a given draw: the `box` = (top, left, h, w)
+    of one RGB uint8 image [H, W, 3] resampled to [3, n_px, n_px] (RandomResizedCrop), mirrored when `flip`
+    (RandomHorizontalFlip), ToTensor, Normalize."""
+    lib = load_library()
+    if not rgb.is_cuda:
+        raise NativeError("preprocess_train_image: the image must be a CUDA uint8 tensor; there is no CPU path")
+    if rgb.dtype != torch.uint8 or rgb.dim() != 3 or rgb.shape[-1] != 3:
+        raise ValueError(f"preprocess_train_image: expected uint8 [H, W, 3], got {rgb.dtype} {tuple(rgb.shape)}")
+    rgb = rgb.contiguous()
+    H, W = int(rgb.shape[0]), int(rgb.shape[1])
+    top, left, ch, cw = (int(v) for v in box)
+    shape = (3, n_px, n_px)
+    if out is None:
+        out = torch.empty(shape, dtype=dtype, device=rgb.device)
+    elif tuple(out.shape) != shape or not out.is_contiguous() or out.dtype not in (torch.float32, torch.float16):
+        raise ValueError(f"preprocess_train_image: out must be a contiguous {shape} f32 / f16 tensor")
+    ws = workspace(rgb.device, "preprocess", lib.pc_preprocess_train_workspace_bytes(ch, cw, n_px))
+    with torch.cuda.device(rgb.device):
+        check(lib.pc_preprocess_train_image(rgb.data_ptr(), H, W, top, left, ch, cw, int(bool(flip)), n_px, out.data_ptr(),
+                                            PC_IMG_F16 if out.dtype == torch.float16 else PC_IMG_F32, ws.data_ptr(),
+                                            ws.numel(), stream_ptr(rgb.device)), "pc_preprocess_train_image")
     return out
 
 

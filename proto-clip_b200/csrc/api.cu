@@ -865,6 +865,20 @@ int pc_preprocess_image(const uint8_t* rgb, int H, int W, int n_px, void* out, i
   return pc_preprocess_batch(rgb, 1, H, W, n_px, out, out_dtype, workspace, workspace_bytes, stream);
 }
 
+size_t pc_preprocess_train_workspace_bytes(int crop_h, int crop_w, int n_px) {
+  return preprocess_train_workspace_bytes(crop_h, crop_w, n_px);
+}
+
+int pc_preprocess_train_image(const uint8_t* rgb, int H, int W, int top, int left, int crop_h, int crop_w, int flip,
+                              int n_px, void* out, int out_dtype, void* workspace, size_t workspace_bytes, void* stream) {
+  PC_REQUIRE(out_dtype == PC_IMG_F32 || out_dtype == PC_IMG_F16, PC_ERR_ARG, "pc_preprocess_train_image: out dtype %d",
+             out_dtype);
+  PC_REQUIRE(workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, PC_ERR_ALIGN,
+             "pc_preprocess_train_image: workspace must be 256-byte aligned");
+  return launch_preprocess_train(rgb, H, W, top, left, crop_h, crop_w, flip, n_px, out, out_dtype == PC_IMG_F16,
+                                 workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
 size_t pc_encode_text_workspace_bytes(const pc_ctx* ctx, int micro_batch) {
   if (!ctx || !ctx->txt.bound) return 0;
   const int mb = micro_batch > 0 ? micro_batch : default_micro_batch(ctx->txt.L);

@@ -145,6 +145,11 @@ int launch_attnpool_query0(const __half* q, const __half* kv, __half* out, int B
 size_t preprocess_workspace_bytes(int B, int H, int W, int n_px);
 int launch_preprocess(const uint8_t* rgb, int B, int H, int W, int n_px, void* out, int out_f16, void* workspace,
                       size_t workspace_bytes, cudaStream_t stream);
+// datasets/imagenet.py:8-23 `get_random_train_tfm` for a given box / flip: the ch x cw box at (top, left) of one image
+// resampled (as a cropped image of its own) to n_px x n_px, mirrored when flip != 0, /255, CLIP mean / std
+size_t preprocess_train_workspace_bytes(int ch, int cw, int n_px);
+int launch_preprocess_train(const uint8_t* rgb, int H, int W, int top, int left, int ch, int cw, int flip, int n_px,
+                            void* out, int out_f16, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 // ---------------------------------------------------------------- head.cu
 int launch_build_prototypes(const __half* V, int N, int K, int D, int per_shot_norm, __half* z, float* zn2,

@@ -9,8 +9,15 @@
 // expression order of precompute_coeffs / normalize_coeffs_8bpc and travel to the device with one small H2D copy; two
 // kernels (horizontal taps -> uint8 rows; vertical taps -> byte -> /255, -mean, /std with correctly rounded fp32 ops,
 // no FMA contraction) write the [3, n_px, n_px] tensor the encoders consume.
+//
+// The training-time augmentation of the support images (reference datasets/imagenet.py:8-23 `get_random_train_tfm`:
+// RandomResizedCrop(224, scale (0.5, 1), BICUBIC) -> RandomHorizontalFlip -> ToTensor -> Normalize) is the same two
+// passes over a different plan: the box drawn on the host is resampled as an image of its own (torchvision crops the
+// PIL image first), both axes scaled independently, and the flip is the horizontal tables in reverse column order.
 #include <math.h>
 
+#include <algorithm>
+#include <utility>
 #include <vector>
 
 #include "kernels.cuh"
@@ -177,31 +184,10 @@ int taps(int in_size, int out_size) {  // ksize of precompute_coeffs
   return static_cast<int>(ceil(2.0 * (scale < 1.0 ? 1.0 : scale))) * 2 + 1;
 }
 
-}  // namespace
-
-size_t preprocess_workspace_bytes(int B, int H, int W, int n_px) {
-  if (B <= 0 || H <= 0 || W <= 0 || n_px <= 0) return 0;
-  const int shrt = W <= H ? W : H, lng = W <= H ? H : W;
-  const int new_long = static_cast<int>(static_cast<double>(n_px) * lng / shrt);
-  // the intermediate image holds at most H source rows of the n_px surviving columns
-  return table_bytes(n_px, taps(W, W <= H ? n_px : new_long), taps(H, W <= H ? new_long : n_px)) +
-         align256(static_cast<size_t>(B) * H * n_px * 3);
-}
-
-int launch_preprocess(const uint8_t* rgb, int B, int H, int W, int n_px, void* out, int out_f16, void* workspace,
-                      size_t workspace_bytes, cudaStream_t stream) {
-  PC_REQUIRE(rgb && out && workspace, PC_ERR_ARG, "preprocess: null buffer");
-  PC_REQUIRE(B > 0 && H > 0 && W > 0 && n_px > 0 && n_px <= 4096 && H <= 32768 && W <= 32768, PC_ERR_ARG,
-             "preprocess: %d images %dx%d -> %d px", B, H, W, n_px);
-  // the filter tables depend on (H, W, n_px) only: the last plan is kept (a loader's images mostly share one size)
-  static thread_local Plan p;
-  static thread_local int pH = 0, pW = 0, pN = 0;
-  if (pH != H || pW != W || pN != n_px) {
-    make_plan(H, W, n_px, &p);
-    pH = H; pW = W; pN = n_px;
-  }
-  PC_REQUIRE(p.new_h >= n_px && p.new_w >= n_px, PC_ERR_ARG, "preprocess: resized image %dx%d smaller than the crop %d",
-             p.new_h, p.new_w, n_px);
+// host tables -> device, then the two passes; `src` points at the first pixel of the resampled window (row pitch W,
+// image pitch H * W), plan.y0 / y1 are rows of that window
+int run_plan(const uint8_t* src, int B, int H, int W, int n_px, const Plan& p, void* out, int out_f16, void* workspace,
+             size_t workspace_bytes, cudaStream_t stream) {
   const int rows = p.y1 - p.y0;
   const size_t tb = table_bytes(n_px, p.ksize_h, p.ksize_v);
   PC_REQUIRE(workspace_bytes >= tb + align256(static_cast<size_t>(B) * rows * n_px * 3), PC_ERR_WORKSPACE,
@@ -223,7 +209,7 @@ int launch_preprocess(const uint8_t* rgb, int B, int H, int W, int n_px, void* o
   const size_t cap = static_cast<size_t>(device_sm_count()) * 32;  // grid-stride beyond 32 blocks per SM
   const int g1 = static_cast<int>(((t1 + 255) / 256 < cap) ? (t1 + 255) / 256 : cap);
   const int g2 = static_cast<int>(((t2 + 255) / 256 < cap) ? (t2 + 255) / 256 : cap);
-  resample_h_kernel<<<g1, 256, 0, stream>>>(rgb, B, H, W, p.y0, rows, n_px, d_bh, d_kh, p.ksize_h, tmp);
+  resample_h_kernel<<<g1, 256, 0, stream>>>(src, B, H, W, p.y0, rows, n_px, d_bh, d_kh, p.ksize_h, tmp);
   PC_CHECK_CUDA(cudaGetLastError());
   if (out_f16)
     resample_v_norm_kernel<__half><<<g2, 256, 0, stream>>>(tmp, B, rows, p.y0, n_px, d_bv, d_kv, p.ksize_v,
@@ -233,6 +219,74 @@ int launch_preprocess(const uint8_t* rgb, int B, int H, int W, int n_px, void* o
                                                           static_cast<float*>(out));
   PC_CHECK_CUDA(cudaGetLastError());
   return PC_OK;
+}
+
+// RandomResizedCrop's resize (torchvision F.resized_crop on a PIL image): the ch x cw box is cropped FIRST, so Pillow
+// resamples an image of that size -- taps stop at the box edge -- to n_px x n_px (both axes scaled independently).
+// RandomHorizontalFlip after it = the horizontal tables in reverse column order.
+void make_plan_window(int ch, int cw, int n_px, int flip, Plan* p) {
+  p->new_h = p->new_w = n_px;
+  p->top = p->left = 0;
+  p->ksize_h = coeffs(cw, n_px, 0, n_px, &p->bh, &p->kh);
+  p->ksize_v = coeffs(ch, n_px, 0, n_px, &p->bv, &p->kv);
+  if (flip) {
+    for (int a = 0, b = n_px - 1; a < b; ++a, --b) {
+      std::swap(p->bh[2 * a], p->bh[2 * b]);
+      std::swap(p->bh[2 * a + 1], p->bh[2 * b + 1]);
+      std::swap_ranges(p->kh.begin() + static_cast<size_t>(a) * p->ksize_h,
+                       p->kh.begin() + static_cast<size_t>(a + 1) * p->ksize_h,
+                       p->kh.begin() + static_cast<size_t>(b) * p->ksize_h);
+    }
+  }
+  p->y0 = p->bv[0];
+  p->y1 = p->bv[2 * (n_px - 1)] + p->bv[2 * (n_px - 1) + 1];
+}
+
+}  // namespace
+
+size_t preprocess_workspace_bytes(int B, int H, int W, int n_px) {
+  if (B <= 0 || H <= 0 || W <= 0 || n_px <= 0) return 0;
+  const int shrt = W <= H ? W : H, lng = W <= H ? H : W;
+  const int new_long = static_cast<int>(static_cast<double>(n_px) * lng / shrt);
+  // the intermediate image holds at most H source rows of the n_px surviving columns
+  return table_bytes(n_px, taps(W, W <= H ? n_px : new_long), taps(H, W <= H ? new_long : n_px)) +
+         align256(static_cast<size_t>(B) * H * n_px * 3);
+}
+
+size_t preprocess_train_workspace_bytes(int ch, int cw, int n_px) {
+  if (ch <= 0 || cw <= 0 || n_px <= 0) return 0;
+  return table_bytes(n_px, taps(cw, n_px), taps(ch, n_px)) + align256(static_cast<size_t>(ch) * n_px * 3);
+}
+
+int launch_preprocess(const uint8_t* rgb, int B, int H, int W, int n_px, void* out, int out_f16, void* workspace,
+                      size_t workspace_bytes, cudaStream_t stream) {
+  PC_REQUIRE(rgb && out && workspace, PC_ERR_ARG, "preprocess: null buffer");
+  PC_REQUIRE(B > 0 && H > 0 && W > 0 && n_px > 0 && n_px <= 4096 && H <= 32768 && W <= 32768, PC_ERR_ARG,
+             "preprocess: %d images %dx%d -> %d px", B, H, W, n_px);
+  // the filter tables depend on (H, W, n_px) only: the last plan is kept (a loader's images mostly share one size)
+  static thread_local Plan p;
+  static thread_local int pH = 0, pW = 0, pN = 0;
+  if (pH != H || pW != W || pN != n_px) {
+    make_plan(H, W, n_px, &p);
+    pH = H; pW = W; pN = n_px;
+  }
+  PC_REQUIRE(p.new_h >= n_px && p.new_w >= n_px, PC_ERR_ARG, "preprocess: resized image %dx%d smaller than the crop %d",
+             p.new_h, p.new_w, n_px);
+  return run_plan(rgb, B, H, W, n_px, p, out, out_f16, workspace, workspace_bytes, stream);
+}
+
+int launch_preprocess_train(const uint8_t* rgb, int H, int W, int top, int left, int ch, int cw, int flip, int n_px,
+                            void* out, int out_f16, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  PC_REQUIRE(rgb && out && workspace, PC_ERR_ARG, "preprocess_train: null buffer");
+  PC_REQUIRE(H > 0 && W > 0 && n_px > 0 && n_px <= 4096 && H <= 32768 && W <= 32768, PC_ERR_ARG,
+             "preprocess_train: image %dx%d -> %d px", H, W, n_px);
+  PC_REQUIRE(top >= 0 && left >= 0 && ch > 0 && cw > 0 && top <= H - ch && left <= W - cw, PC_ERR_ARG,
+             "preprocess_train: box (top %d, left %d, %d x %d) outside the %d x %d image", top, left, ch, cw, H, W);
+  // every call draws a new box: no plan cache (the tables are n_px * (ksize_h + ksize_v) doubles of host work)
+  Plan p;
+  make_plan_window(ch, cw, n_px, flip != 0, &p);
+  const uint8_t* src = rgb + (static_cast<size_t>(top) * W + left) * 3;
+  return run_plan(src, 1, H, W, n_px, p, out, out_f16, workspace, workspace_bytes, stream);
 }
 
 }  // namespace pc

@@ -8,15 +8,18 @@ outside the hot path this repo rebuilds, so it is not re-implemented:
   per split (default 256) of class-structured synthetic images (``synthetic.class_structured_images``),
   generated on the GPU at the bound model's input resolution. It lets ``main.py`` run end to end with no data on disk
   (``--backbone synthetic:<arch>``), which is how the CLI is exercised on the B200 box.
+* ``get_random_train_tfm()`` is the reference's five-line torchvision Compose; ``get_random_train_tfm(device=...)`` /
+  ``GPUTrainTransform`` runs the same augmentation on the GPU for decoded images, bit-identical under the same seed.
 * the reference's eleven aliases (caltech101 ... ucf101, imagenet, fewsol) are delegated, unchanged, to the reference's
   own ``datasets`` package when ``PROTOCLIP_REFERENCE_ROOT`` points at a checkout of it; without one a RuntimeError says so.
 """
 from __future__ import annotations
 
 import importlib.util
+import math
 import os
 import sys
-from typing import Iterator, List, Tuple
+from typing import Iterator, List, Tuple, Union
 
 import torch
 
@@ -127,11 +130,76 @@ def build_data_loader(data_source=None, batch_size=64, input_size=224, tfm=None,
                                                tfm=tfm, is_train=is_train, shuffle=shuffle, **kwargs)
 
 
-def get_random_train_tfm():
-    """datasets/imagenet.py:8-23 (RandomResizedCrop + flip + CLIP normalisation); unused by the synthetic alias."""
-    if "PROTOCLIP_REFERENCE_ROOT" not in os.environ:
-        return None
-    return _ref_sub("imagenet").get_random_train_tfm()
+TRAIN_SCALE = (0.5, 1.0)              # datasets/imagenet.py:16-17
+TRAIN_RATIO = (3.0 / 4.0, 4.0 / 3.0)  # torchvision's RandomResizedCrop default
+
+
+class GPUTrainTransform:
+    """`get_random_train_tfm()` on the GPU (pc_preprocess_train_image): PIL image or HxWx3 uint8 array / tensor -> CUDA
+    tensor [3, size, size], bit-identical to the host Compose under the same torch seed. The draws are taken on the
+    host from torch's global generator in torchvision's order (RandomResizedCrop.get_params: up to ten (area, log-ratio)
+    pairs, two randint for the position; RandomHorizontalFlip: one rand), the pixels never leave the device: Pillow's
+    resampler of the cropped box, the mirror, ToTensor and Normalize are two launches. For callers that hold decoded
+    support images (build_cache_model re-augments the same N*K images `augment_epoch` times, utils.py:303-310)."""
+
+    def __init__(self, size: int = 224, scale=TRAIN_SCALE, ratio=TRAIN_RATIO, p_flip: float = 0.5,
+                 device: Union[str, torch.device] = "cuda", dtype: torch.dtype = torch.float32):
+        self.size, self.scale, self.ratio, self.p_flip = size, tuple(scale), tuple(ratio), p_flip
+        self.device, self.dtype = torch.device(device), dtype
+
+    def get_params(self, height: int, width: int):
+        """torchvision RandomResizedCrop.get_params -> (top, left, h, w)."""
+        area = height * width
+        log_ratio = torch.log(torch.tensor(self.ratio))
+        for _ in range(10):
+            target_area = area * torch.empty(1).uniform_(self.scale[0], self.scale[1]).item()
+            aspect_ratio = torch.exp(torch.empty(1).uniform_(log_ratio[0], log_ratio[1])).item()
+            w = int(round(math.sqrt(target_area * aspect_ratio)))
+            h = int(round(math.sqrt(target_area / aspect_ratio)))
+            if 0 < w <= width and 0 < h <= height:
+                top = torch.randint(0, height - h + 1, size=(1,)).item()
+                left = torch.randint(0, width - w + 1, size=(1,)).item()
+                return top, left, h, w
+        in_ratio = float(width) / float(height)  # central fallback
+        if in_ratio < min(self.ratio):
+            w = width
+            h = int(round(w / min(self.ratio)))
+        elif in_ratio > max(self.ratio):
+            h = height
+            w = int(round(h * max(self.ratio)))
+        else:
+            w, h = width, height
+        return (height - h) // 2, (width - w) // 2, h, w
+
+    def __call__(self, image, out: torch.Tensor = None) -> torch.Tensor:
+        import numpy as np
+        from .. import _native as nat
+        if isinstance(image, torch.Tensor):
+            rgb = image
+        else:
+            if hasattr(image, "convert"):  # PIL.Image; the reference's loader hands over convert("RGB") images
+                if image.mode != "RGB":
+                    raise ValueError(f"GPUTrainTransform handles RGB images; got mode {image.mode!r}")
+            rgb = torch.from_numpy(np.ascontiguousarray(np.asarray(image)))
+        box = self.get_params(int(rgb.shape[0]), int(rgb.shape[1]))
+        flip = bool(torch.rand(1) < self.p_flip)
+        return nat.preprocess_train_image(rgb.to(self.device, non_blocking=True), box, flip, self.size, out=out,
+                                          dtype=self.dtype)
+
+
+def get_random_train_tfm(device: Union[str, torch.device, None] = None):
+    """datasets/imagenet.py:8-23: RandomResizedCrop(224, scale (0.5, 1), BICUBIC) + RandomHorizontalFlip + ToTensor + CLIP
+    normalisation. Without `device` the host Compose the reference hands its DataLoader workers; with one, the same
+    transform on that GPU (`GPUTrainTransform`)."""
+    if device is not None:
+        return GPUTrainTransform(224, device=device)
+    import torchvision.transforms as T
+    return T.Compose([
+        T.RandomResizedCrop(size=224, scale=TRAIN_SCALE, interpolation=T.InterpolationMode.BICUBIC),
+        T.RandomHorizontalFlip(p=0.5),
+        T.ToTensor(),
+        T.Normalize(mean=(0.48145466, 0.4578275, 0.40821073), std=(0.26862954, 0.26130258, 0.27577711)),
+    ])
 
 
 def ImageNet(root_path: str, shots: int, preprocess):

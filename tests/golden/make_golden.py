@@ -205,6 +205,40 @@ def main_preprocess():
     print("preprocess done")
 
 
+def preprocess_train_fixture():
+    """The reference's `get_random_train_tfm()` (datasets/imagenet.py:8-23, the module loaded by file path) on seeded RGB
+    images under `torch.manual_seed(seed)`: inputs (uint8), the seed, and of the reference's fp32 output [3, 224, 224]
+    its bytes (the tensor mapped back through Normalize / ToTensor: exact) + the sha256 of the fp32 tensor itself."""
+    import hashlib
+    import importlib.util
+    import numpy as np
+    from PIL import Image
+    spec = importlib.util.spec_from_file_location("_ref_imagenet", os.path.join(reference_shims.REFERENCE_ROOT, "datasets", "imagenet.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    tf = mod.get_random_train_tfm()  # the real reference function
+    mean = torch.tensor([0.48145466, 0.4578275, 0.40821073]).view(3, 1, 1)
+    std = torch.tensor([0.26862954, 0.26130258, 0.27577711]).view(3, 1, 1)
+    rng = np.random.default_rng(9)
+    cases = []
+    for seed, (h, w) in enumerate(((120, 160), (224, 224), (150, 100), (64, 250), (97, 131))):
+        base = rng.random((h // 4 + 2, w // 4 + 2, 3))
+        img = np.asarray(Image.fromarray((base * 255).astype(np.uint8)).resize((w, h), Image.BILINEAR))
+        img = np.clip(img.astype(np.int32) + rng.integers(-20, 21, img.shape), 0, 255).astype(np.uint8)
+        torch.manual_seed(100 + seed)
+        out = tf(Image.fromarray(img)).clone()
+        u8 = torch.round((out * std + mean) * 255).to(torch.uint8)
+        assert torch.equal(((u8.float() / 255) - mean) / std, out)
+        cases.append({"image": torch.from_numpy(img.copy()), "seed": 100 + seed, "out_u8": u8,
+                      "out_sha256": hashlib.sha256(out.contiguous().numpy().tobytes()).hexdigest()})
+    return {"cases": cases, "pillow": __import__("PIL").__version__, "torchvision": __import__("torchvision").__version__}
+
+
+def main_preprocess_train():
+    torch.save(preprocess_train_fixture(), os.path.join(OUT, "preprocess_train.pt"))
+    print("preprocess_train done")
+
+
 def main_336():
     """ViT-L/14@336px (config C4: L = 577 tokens -> the attention kernel's multi-block path). fp32 reference only."""
     fx = tower_fixture("ViT-L/14@336px", B=2, P=1, with_fp16=False, with_blocks=False)
@@ -219,5 +253,7 @@ if __name__ == "__main__":
         main_rn()
     elif len(sys.argv) > 1 and sys.argv[1] == "preprocess":
         main_preprocess()
+    elif len(sys.argv) > 1 and sys.argv[1] == "preprocess_train":
+        main_preprocess_train()
     else:
         main()

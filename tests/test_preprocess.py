@@ -103,3 +103,106 @@ def test_cuda_preprocess_fixture_and_errors():
         nat.preprocess_image(torch.zeros(8, 8, 3, dtype=torch.uint8), 8)        # CPU tensor: no fallback
     with pytest.raises(ValueError):
         nat.preprocess_image(torch.zeros(8, 8, 4, dtype=torch.uint8, device="cuda"), 8)
+
+
+# ---------------------------------------------------------------- training augmentation (datasets/imagenet.py:8-23)
+TRAIN_SIZES = [(480, 640), (224, 224), (300, 224), (100, 80), (333, 500), (64, 700), (700, 64), (17, 19), (224, 500)]
+
+
+def replay_draw(h, w, seed):
+    """The box / flip torchvision draws for an h x w image under `seed` (oracle restatement of get_params)."""
+    torch.manual_seed(seed)
+    box = PO.random_resized_crop_params(h, w)
+    return box, PO.random_flip()
+
+
+def test_train_oracle_matches_reference_fixture():
+    import hashlib
+    fx = load_golden("preprocess_train.pt")
+    assert len(fx["cases"]) >= 5
+    flips = 0
+    for case in fx["cases"]:
+        img = case["image"].numpy()
+        box, flip = replay_draw(img.shape[0], img.shape[1], case["seed"])
+        flips += flip
+        assert np.array_equal(PO.train_transform_u8(img, *box, flip, 224).transpose(2, 0, 1), case["out_u8"].numpy())
+        got = PO.train_transform(img, *box, flip, 224)
+        assert hashlib.sha256(np.ascontiguousarray(got).tobytes()).hexdigest() == case["out_sha256"]
+    assert 0 < flips < len(fx["cases"])  # both branches of the flip are pinned
+
+
+@pytest.mark.parametrize("h,w", TRAIN_SIZES)
+def test_train_oracle_matches_live_torchvision(h, w):
+    Image = pytest.importorskip("PIL.Image")
+    pytest.importorskip("torchvision.transforms")
+    from proto_clip_b200 import datasets
+    tf = datasets.get_random_train_tfm()  # the reference's Compose, datasets/imagenet.py:14-23
+    img = random_image(h, w, h * 1000 + w + 3)
+    for seed in range(3):
+        torch.manual_seed(seed * 31 + h)
+        ref = tf(Image.fromarray(img)).numpy()
+        after_ref = torch.rand(1)
+        box, flip = replay_draw(h, w, seed * 31 + h)
+        assert torch.equal(torch.rand(1), after_ref), "the oracle consumed the generator differently"
+        assert np.array_equal(PO.train_transform(img, *box, flip, 224), ref), (box, flip)
+
+
+def test_gpu_train_transform_draws_like_torchvision():
+    """The shell's host side (no GPU needed): same box as RandomResizedCrop.get_params for the same seed, including the
+    central fallback for extreme aspect ratios, and the same generator state afterwards."""
+    T = pytest.importorskip("torchvision.transforms")
+    from proto_clip_b200 import datasets
+    tf = datasets.GPUTrainTransform(224)
+    for h, w in TRAIN_SIZES + [(20, 900), (900, 20)]:
+        for seed in range(4):
+            torch.manual_seed(seed)
+            want = T.RandomResizedCrop.get_params(torch.empty(3, h, w), list(datasets.TRAIN_SCALE), list(datasets.TRAIN_RATIO))
+            state = torch.get_rng_state()
+            torch.manual_seed(seed)
+            assert tf.get_params(h, w) == tuple(want)
+            assert torch.equal(torch.get_rng_state(), state)
+    with pytest.raises(ValueError, match="RGB"):
+        tf(__import__("PIL.Image").Image.new("L", (30, 30)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("h,w", TRAIN_SIZES)
+def test_cuda_train_preprocess_bit_exact(h, w):
+    from proto_clip_b200 import _native as nat
+    img = random_image(h, w, h * 1000 + w + 11)
+    dev_img = torch.from_numpy(img).cuda()
+    for seed in range(4):
+        box, flip = replay_draw(h, w, seed)
+        ref = PO.train_transform(img, *box, flip, 224)
+        got = nat.preprocess_train_image(dev_img, box, flip, 224)
+        assert np.array_equal(got.cpu().numpy(), ref), (box, flip)
+    # the whole image as the box, both flips, another output size, fp16
+    for flip in (False, True):
+        ref = PO.train_transform(img, 0, 0, h, w, flip, 96)
+        got = nat.preprocess_train_image(dev_img, (0, 0, h, w), flip, 96)
+        assert np.array_equal(got.cpu().numpy(), ref)
+        got16 = nat.preprocess_train_image(dev_img, (0, 0, h, w), flip, 96, dtype=torch.float16)
+        assert torch.equal(got16.cpu(), torch.from_numpy(ref).half())
+
+
+@pytest.mark.gpu
+def test_cuda_train_transform_fixture_seed_parity_and_errors():
+    """GPUTrainTransform under the fixture's seed = the reference's get_random_train_tfm() output; a box that leaves
+    the image is refused."""
+    import hashlib
+    from proto_clip_b200 import _native as nat
+    from proto_clip_b200 import datasets
+    fx = load_golden("preprocess_train.pt")
+    tf = datasets.get_random_train_tfm(device="cuda")
+    batch = torch.empty(len(fx["cases"]), 3, 224, 224, device="cuda")
+    for i, case in enumerate(fx["cases"]):
+        torch.manual_seed(case["seed"])
+        got = tf(case["image"], out=batch[i])  # straight into a slot of an encoder batch
+        assert got.data_ptr() == batch[i].data_ptr()
+        assert hashlib.sha256(got.cpu().contiguous().numpy().tobytes()).hexdigest() == case["out_sha256"]
+    img = torch.zeros(40, 50, 3, dtype=torch.uint8, device="cuda")
+    for box in ((0, 0, 41, 50), (1, 0, 40, 50), (0, 10, 40, 41), (0, 0, 0, 5), (-1, 0, 5, 5)):
+        with pytest.raises(nat.NativeError):
+            nat.preprocess_train_image(img, box, False, 32)
+    with pytest.raises(nat.NativeError):
+        nat.preprocess_train_image(img.cpu(), (0, 0, 40, 50), False, 32)
