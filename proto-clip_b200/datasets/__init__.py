@@ -180,11 +180,68 @@ class GPUTrainTransform:
             if hasattr(image, "convert"):  # PIL.Image; the reference's loader hands over convert("RGB") images
                 if image.mode != "RGB":
                     raise ValueError(f"GPUTrainTransform handles RGB images; got mode {image.mode!r}")
-            rgb = torch.from_numpy(np.ascontiguousarray(np.asarray(image)))
+            rgb = torch.from_numpy(np.array(image))  # a writable copy
         box = self.get_params(int(rgb.shape[0]), int(rgb.shape[1]))
         flip = bool(torch.rand(1) < self.p_flip)
         return nat.preprocess_train_image(rgb.to(self.device, non_blocking=True), box, flip, self.size, out=out,
                                           dtype=self.dtype)
+
+
+class GPUAugmentedLoader:
+    """The support-image loader of build_cache_model (utils.py:284-332; main.py builds it with `get_random_train_tfm()`,
+    shuffle=False) for a few-shot split that FITS IN HBM: every image is decoded once (PIL on the host, like the
+    reference's `read_image`: `Image.open(path).convert("RGB")`), kept on the device as uint8 [H, W, 3] (ImageNet
+    16-shot: 16 000 images, about 9 GB of the 180), and every pass over the loader -- one per `augment_epoch` -- re-draws
+    the augmentation and runs it on the GPU (`GPUTrainTransform`). Yields (images [b, 3, size, size] on the device,
+    labels int64 [b]) like the reference's loader. The draws come from torch's global generator in image order, so a
+    pass reproduces, bit for bit, the reference's loader at num_workers=0 under the same seed.
+
+    `data_source`: a sequence of Datum-like items (`.impath`, `.label`: datasets/utils.py), or of (image, label) pairs
+    with image a PIL image / HxWx3 uint8 array / tensor."""
+
+    def __init__(self, data_source, batch_size: int = 64, tfm: "GPUTrainTransform" = None,
+                 device: Union[str, torch.device] = "cuda"):
+        self.data_source, self.batch_size = data_source, int(batch_size)
+        self.device = torch.device(device)
+        self.tfm = tfm if tfm is not None else GPUTrainTransform(224, device=self.device)
+        self._pixels: List[torch.Tensor] = []
+        self._labels: List[int] = []
+
+    def __len__(self) -> int:
+        return (len(self.data_source) + self.batch_size - 1) // self.batch_size
+
+    def _decode(self) -> None:
+        import numpy as np
+        for item in self.data_source:
+            if hasattr(item, "impath"):
+                from PIL import Image
+                image, label = Image.open(item.impath).convert("RGB"), item.label
+            else:
+                image, label = item
+            if hasattr(image, "convert"):
+                image = image.convert("RGB")
+            if not isinstance(image, torch.Tensor):
+                image = torch.from_numpy(np.array(image))  # a writable copy
+            if image.dtype != torch.uint8 or image.dim() != 3 or image.shape[-1] != 3:
+                raise ValueError(f"GPUAugmentedLoader: expected RGB uint8 [H, W, 3] images, got {image.dtype} {tuple(image.shape)}")
+            self._pixels.append(image.to(self.device))
+            self._labels.append(int(label))
+
+    def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
+        return self.iter_range(0, len(self))
+
+    def iter_range(self, lo: int, hi: int) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
+        """Batches [lo, hi) (dist.sharded_batches). The draws of the batches before `lo` are not consumed: ranks of a
+        torchrun job draw independently (like DataLoader workers do), a single process reproduces the reference."""
+        if not self._pixels:
+            self._decode()
+        n = len(self._pixels)
+        for i in range(lo * self.batch_size, min(hi * self.batch_size, n), self.batch_size):
+            j = min(i + self.batch_size, n)
+            out = torch.empty((j - i, 3, self.tfm.size, self.tfm.size), dtype=self.tfm.dtype, device=self.device)
+            for k in range(i, j):
+                self.tfm(self._pixels[k], out=out[k - i])
+            yield out, torch.tensor(self._labels[i:j], dtype=torch.int64)
 
 
 def get_random_train_tfm(device: Union[str, torch.device, None] = None):

@@ -206,3 +206,35 @@ def test_cuda_train_transform_fixture_seed_parity_and_errors():
             nat.preprocess_train_image(img, box, False, 32)
     with pytest.raises(nat.NativeError):
         nat.preprocess_train_image(img.cpu(), (0, 0, 40, 50), False, 32)
+
+
+@pytest.mark.gpu
+def test_gpu_augmented_loader_reproduces_the_host_loader():
+    """Two passes (= two augment epochs of build_cache_model) over decoded support images: every batch equals the
+    reference's Compose applied image by image under the same seed (its loader at num_workers=0, shuffle=False)."""
+    Image = pytest.importorskip("PIL.Image")
+    from proto_clip_b200 import datasets
+    sizes = [(90, 120), (224, 224), (150, 100), (64, 250), (97, 131), (300, 200), (240, 320)]
+    source = [(random_image(h, w, 50 + i) if i % 2 else Image.fromarray(random_image(h, w, 50 + i)), i % 3)
+              for i, (h, w) in enumerate(sizes)]
+    host_tf = datasets.get_random_train_tfm()
+    loader = datasets.GPUAugmentedLoader(source, batch_size=3)
+    assert len(loader) == 3
+    torch.manual_seed(1234)
+    want = [[host_tf(im if hasattr(im, "convert") else Image.fromarray(im)) for im, _ in source] for _ in range(2)]
+    torch.manual_seed(1234)
+    for epoch in range(2):
+        seen = 0
+        for images, target in loader:
+            assert images.is_cuda and images.shape[1:] == (3, 224, 224) and target.dtype == torch.int64
+            for k in range(images.shape[0]):
+                assert torch.equal(images[k].cpu(), want[epoch][seen + k]), (epoch, seen + k)
+                assert int(target[k]) == source[seen + k][1]
+            seen += images.shape[0]
+        assert seen == len(source)
+    # a rank's batch range draws for its own images only
+    torch.manual_seed(7)
+    part = list(loader.iter_range(1, 2))
+    assert len(part) == 1 and part[0][0].shape[0] == 3
+    torch.manual_seed(7)
+    assert torch.equal(part[0][0][0].cpu(), host_tf(Image.fromarray(source[3][0])))
