@@ -56,7 +56,15 @@ struct RnTower {
   std::vector<void*> owned;
   size_t max_act = 0, max_col = 0;  // per image, in fp16 elements: largest activation / im2col operand
 };
-constexpr int kRnMicroBatch = 128;
+// ModifiedResNet towers: at most kRnMicroBatch images per pass, the batch cut into equal passes. RN50x16 @384 px on one
+// box (tools/rn_pass_sweep.py, 512 images): 4 496 - 4 510 img/s at 64 per pass, 4 538 at 128, 4 583 - 4 604 at 192,
+// 4 635 - 4 679 at 256, 4 531 - 4 550 at 512 (bit-identical features at every pass size).
+constexpr int kRnMicroBatch = 256;
+inline int pick_rn_micro_batch(int B, int micro_batch) {
+  if (micro_batch > 0) return micro_batch;
+  const int passes = (B + kRnMicroBatch - 1) / kRnMicroBatch;
+  return passes > 0 ? (B + passes - 1) / passes : kRnMicroBatch;
+}
 
 // Micro-batching. One row-block WAVE of the CTA-pair GEMM is sm_count / 2 pairs x 256 rows: ViT-B/16 (L = 197) -> 96
 // images = 18 912 rows = 73.9 of 74 row blocks; ViT-L/14 -> 73; @336px -> 32. Round 1 ran one wave per pass (activations
@@ -774,7 +782,7 @@ int pc_encode_image(pc_ctx* ctx, const void* images, int img_dtype, int B, void*
              img_dtype);
   if (ctx->rn.bound) {  // ModifiedResNet tower (clip/model.py:137-152)
     const RnTower& r = ctx->rn;
-    const int rmb = micro_batch > 0 ? micro_batch : kRnMicroBatch;
+    const int rmb = pick_rn_micro_batch(B, micro_batch);
     PC_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, PC_ERR_ALIGN,
                "pc_encode_image: workspace must be 256-byte aligned");
     PC_REQUIRE(workspace_bytes >= rn_ws_bytes(r, rmb), PC_ERR_WORKSPACE, "pc_encode_image: workspace %zu < %zu",

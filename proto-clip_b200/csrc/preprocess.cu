@@ -8,13 +8,14 @@
 // Integer / byte work, HBM-bound and tiny: the weight tables are built on the host in double precision with the exact
 // expression order of precompute_coeffs / normalize_coeffs_8bpc and travel to the device with one small H2D copy; two
 // kernels (horizontal taps -> uint8 rows; vertical taps -> byte -> /255, -mean, /std with correctly rounded fp32 ops,
-// no FMA contraction) write the [3, n_px, n_px] tensor the encoders consume.
+// tabulated per byte value) write the [3, n_px, n_px] tensor the encoders consume.
 //
 // The training-time augmentation of the support images (reference datasets/imagenet.py:8-23 `get_random_train_tfm`:
 // RandomResizedCrop(224, scale (0.5, 1), BICUBIC) -> RandomHorizontalFlip -> ToTensor -> Normalize) is the same two
 // passes over a different plan: the box drawn on the host is resampled as an image of its own (torchvision crops the
 // PIL image first), both axes scaled independently, and the flip is the horizontal tables in reverse column order.
 #include <math.h>
+#include <string.h>
 
 #include <algorithm>
 #include <utility>
@@ -83,65 +84,92 @@ __device__ __forceinline__ int clip8(int acc) {  // Resample.c clip8
   return v < 0 ? 0 : (v > 255 ? 255 : v);
 }
 
+// Both passes are issue-bound byte work (ncu, round 2: 77 % issue slots at 0.14 - 0.16 of the HBM copy rate with one
+// thread per element of a flat index space: two 64-bit div / mod pairs per element, a rolled tap loop and six IEEE
+// divisions per output pixel). Here a block is a 64 x 4 patch of (column, row) so the index math is a handful of 32-bit
+// operations, the tap loops are unrolled by four, the horizontal weights are stored tap-major (one coalesced load per tap
+// for the 64 columns of a warp pair), and ToTensor + Normalize is a 3 x 256 entry table built on the host with the same
+// correctly rounded fp32 operations (a byte has 256 values).
+constexpr int PP_TX = 64, PP_TY = 4;
+
 // horizontal pass: tmp[b][r][xx][c] for source rows y0 + r, r in [0, rows), and the n_px surviving output columns of
-// every image b of the batch (images [B, H, W, 3], same size)
-__global__ void __launch_bounds__(256)
+// every image b of the batch (images [B, H, W, 3], same size). kk_t is tap-major: kk_t[x * n_px + xx].
+__global__ void __launch_bounds__(PP_TX * PP_TY)
 resample_h_kernel(const uint8_t* __restrict__ src, int B, int H, int W, int y0, int rows, int n_px,
-                  const int* __restrict__ bounds, const int* __restrict__ kk, int ksize, uint8_t* __restrict__ tmp) {
-  const size_t total = static_cast<size_t>(B) * rows * n_px;
-  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
-       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int xx = static_cast<int>(t % n_px);
-    const int r = static_cast<int>((t / n_px) % rows);
-    const size_t b = t / (static_cast<size_t>(n_px) * rows);
-    const int xmin = bounds[2 * xx], n = bounds[2 * xx + 1];
-    const uint8_t* p = src + ((b * H + y0 + r) * W + xmin) * 3;
-    const int* k = kk + xx * ksize;
+                  const int2* __restrict__ bounds, const int* __restrict__ kk_t, uint8_t* __restrict__ tmp) {
+  const int xx = blockIdx.x * PP_TX + threadIdx.x;
+  if (xx >= n_px) return;
+  const int2 bd = bounds[xx];  // (first source column, taps)
+  const int* __restrict__ k = kk_t + xx;
+  const int total_rows = B * rows;
+  for (int row = blockIdx.y * PP_TY + threadIdx.y; row < total_rows; row += gridDim.y * PP_TY) {
+    const int b = row / rows, r = row - b * rows;
+    const uint8_t* __restrict__ p = src + ((static_cast<size_t>(b) * H + y0 + r) * W + bd.x) * 3;
     int a0 = 1 << (PRECISION_BITS - 1), a1 = a0, a2 = a0;
-    for (int x = 0; x < n; ++x) {
-      const int kv = k[x];
+#pragma unroll 4
+    for (int x = 0; x < bd.y; ++x) {
+      const int kv = k[x * n_px];
       a0 += p[3 * x] * kv;
       a1 += p[3 * x + 1] * kv;
       a2 += p[3 * x + 2] * kv;
     }
-    uint8_t* o = tmp + static_cast<size_t>(t) * 3;
+    uint8_t* o = tmp + (static_cast<size_t>(row) * n_px + xx) * 3;
     o[0] = static_cast<uint8_t>(clip8(a0));
     o[1] = static_cast<uint8_t>(clip8(a1));
     o[2] = static_cast<uint8_t>(clip8(a2));
   }
 }
 
-// vertical pass + ToTensor + Normalize: out[c][yy][xx] = ((byte / 255) - mean_c) / std_c, every op rounded to fp32
+// vertical pass + ToTensor + Normalize: out[b][c][yy][xx] = lut[c][byte] with lut[c][v] = ((v / 255) - mean_c) / std_c,
+// every operation rounded to fp32 (norm_lut() below)
 template <typename OutT>
-__global__ void __launch_bounds__(256)
-resample_v_norm_kernel(const uint8_t* __restrict__ tmp, int B, int rows, int y0, int n_px, const int* __restrict__ bounds,
-                       const int* __restrict__ kk, int ksize, OutT* __restrict__ out) {
-  const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};   // clip/clip.py:83
-  const float stdv[3] = {0.26862954f, 0.26130258f, 0.27577711f};
-  const int plane = n_px * n_px;
-  const size_t total = static_cast<size_t>(B) * plane;
-  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
-       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int pix = static_cast<int>(t % plane);
-    const size_t b = t / plane;
-    const int xx = pix % n_px, yy = pix / n_px;
-    const int ymin = bounds[2 * yy] - y0, n = bounds[2 * yy + 1];
-    const int* k = kk + yy * ksize;
-    int a[3] = {1 << (PRECISION_BITS - 1), 1 << (PRECISION_BITS - 1), 1 << (PRECISION_BITS - 1)};
-    for (int y = 0; y < n; ++y) {
-      const uint8_t* p = tmp + ((b * rows + ymin + y) * n_px + xx) * 3;
+__global__ void __launch_bounds__(PP_TX * PP_TY)
+resample_v_norm_kernel(const uint8_t* __restrict__ tmp, int B, int rows, int y0, int n_px, const int2* __restrict__ bounds,
+                       const int* __restrict__ kk, int ksize, const float* __restrict__ lut, OutT* __restrict__ out) {
+  const int xx = blockIdx.x * PP_TX + threadIdx.x;
+  const int yy = blockIdx.y * PP_TY + threadIdx.y;
+  if (xx >= n_px || yy >= n_px) return;
+  const int2 bd = bounds[yy];  // (first source row, taps): the same for the whole warp
+  const int* __restrict__ k = kk + yy * ksize;
+  const int pitch = n_px * 3;
+  const size_t plane = static_cast<size_t>(n_px) * n_px;
+  for (int b = blockIdx.z; b < B; b += gridDim.z) {
+    const uint8_t* __restrict__ p = tmp + ((static_cast<size_t>(b) * rows + (bd.x - y0)) * n_px + xx) * 3;
+    int a0 = 1 << (PRECISION_BITS - 1), a1 = a0, a2 = a0;
+#pragma unroll 4
+    for (int y = 0; y < bd.y; ++y) {
       const int kv = k[y];
-      a[0] += p[0] * kv;
-      a[1] += p[1] * kv;
-      a[2] += p[2] * kv;
+      a0 += p[0] * kv;
+      a1 += p[1] * kv;
+      a2 += p[2] * kv;
+      p += pitch;
     }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float x = __fdiv_rn(static_cast<float>(clip8(a[c])), 255.0f);         // ToTensor
-      const float v = __fdiv_rn(__fsub_rn(x, mean[c]), stdv[c]);                   // Normalize
-      out[(b * 3 + c) * plane + pix] = static_cast<OutT>(v);
-    }
+    OutT* o = out + static_cast<size_t>(b) * 3 * plane + static_cast<size_t>(yy) * n_px + xx;
+    o[0] = static_cast<OutT>(__ldg(lut + clip8(a0)));
+    o[plane] = static_cast<OutT>(__ldg(lut + 256 + clip8(a1)));
+    o[2 * plane] = static_cast<OutT>(__ldg(lut + 512 + clip8(a2)));
   }
+}
+
+// ToTensor (byte / 255) and Normalize ((x - mean) / std) of clip/clip.py:82-83 for every byte value: IEEE single-precision
+// division and subtraction, round to nearest even -- what torch's CPU kernels and the device's __fdiv_rn / __fsub_rn compute
+// (the host compiler keeps float expressions in float: SSE, no fast-math)
+struct NormLut {
+  float v[3 * 256];
+  NormLut() {
+    const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};  // clip/clip.py:83
+    const float stdv[3] = {0.26862954f, 0.26130258f, 0.27577711f};
+    for (int c = 0; c < 3; ++c)
+      for (int b = 0; b < 256; ++b) {
+        volatile float x = static_cast<float>(b) / 255.0f;  // volatile: every intermediate is a rounded fp32 value
+        volatile float d = x - mean[c];
+        v[c * 256 + b] = d / stdv[c];
+      }
+  }
+};
+const float* norm_lut() {
+  static const NormLut lut;  // thread-safe one-time construction
+  return lut.v;
 }
 
 inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
@@ -175,8 +203,9 @@ void make_plan(int H, int W, int n_px, Plan* p) {
   p->y1 = p->bv[2 * (n_px - 1)] + p->bv[2 * (n_px - 1) + 1];
 }
 
+constexpr int LUT_WORDS = 3 * 256;
 size_t table_bytes(int n_px, int ksize_h, int ksize_v) {
-  return align256(static_cast<size_t>(n_px) * (4 + ksize_h + ksize_v) * sizeof(int));
+  return align256((static_cast<size_t>(n_px) * (4 + ksize_h + ksize_v) + LUT_WORDS) * sizeof(int));
 }
 
 int taps(int in_size, int out_size) {  // ksize of precompute_coeffs
@@ -192,31 +221,39 @@ int run_plan(const uint8_t* src, int B, int H, int W, int n_px, const Plan& p, v
   const size_t tb = table_bytes(n_px, p.ksize_h, p.ksize_v);
   PC_REQUIRE(workspace_bytes >= tb + align256(static_cast<size_t>(B) * rows * n_px * 3), PC_ERR_WORKSPACE,
              "preprocess: workspace %zu < %zu", workspace_bytes, tb + align256(static_cast<size_t>(B) * rows * n_px * 3));
-  // one H2D copy of all four tables: [bh | bv | kh | kv]
+  // one H2D copy of all tables: [bh | bv | kh (tap-major) | kv | lut]
   std::vector<int> host;
-  host.reserve(static_cast<size_t>(n_px) * (4 + p.ksize_h + p.ksize_v));
+  host.reserve(static_cast<size_t>(n_px) * (4 + p.ksize_h + p.ksize_v) + LUT_WORDS);
   host.insert(host.end(), p.bh.begin(), p.bh.end());
   host.insert(host.end(), p.bv.begin(), p.bv.end());
-  host.insert(host.end(), p.kh.begin(), p.kh.end());
+  const size_t kh0 = host.size();
+  host.resize(kh0 + static_cast<size_t>(n_px) * p.ksize_h);
+  for (int xx = 0; xx < n_px; ++xx)
+    for (int x = 0; x < p.ksize_h; ++x) host[kh0 + static_cast<size_t>(x) * n_px + xx] = p.kh[static_cast<size_t>(xx) * p.ksize_h + x];
   host.insert(host.end(), p.kv.begin(), p.kv.end());
+  const size_t lut0 = host.size();
+  host.resize(lut0 + LUT_WORDS);
+  memcpy(host.data() + lut0, norm_lut(), LUT_WORDS * sizeof(float));
   int* d_bh = static_cast<int*>(workspace);
   int* d_bv = d_bh + 2 * n_px;
   int* d_kh = d_bv + 2 * n_px;
   int* d_kv = d_kh + static_cast<size_t>(n_px) * p.ksize_h;
+  const float* d_lut = reinterpret_cast<const float*>(d_kv + static_cast<size_t>(n_px) * p.ksize_v);
   uint8_t* tmp = static_cast<uint8_t*>(workspace) + tb;
   PC_CHECK_CUDA(cudaMemcpyAsync(d_bh, host.data(), host.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
-  const size_t t1 = static_cast<size_t>(B) * rows * n_px, t2 = static_cast<size_t>(B) * n_px * n_px;
-  const size_t cap = static_cast<size_t>(device_sm_count()) * 32;  // grid-stride beyond 32 blocks per SM
-  const int g1 = static_cast<int>(((t1 + 255) / 256 < cap) ? (t1 + 255) / 256 : cap);
-  const int g2 = static_cast<int>(((t2 + 255) / 256 < cap) ? (t2 + 255) / 256 : cap);
-  resample_h_kernel<<<g1, 256, 0, stream>>>(src, B, H, W, p.y0, rows, n_px, d_bh, d_kh, p.ksize_h, tmp);
+  const dim3 block(PP_TX, PP_TY);
+  const unsigned gx = static_cast<unsigned>((n_px + PP_TX - 1) / PP_TX);
+  const long long row_blocks = (static_cast<long long>(B) * rows + PP_TY - 1) / PP_TY;
+  const dim3 g1(gx, static_cast<unsigned>(row_blocks < 65535 ? row_blocks : 65535));
+  const dim3 g2(gx, static_cast<unsigned>((n_px + PP_TY - 1) / PP_TY), static_cast<unsigned>(B < 65535 ? B : 65535));
+  resample_h_kernel<<<g1, block, 0, stream>>>(src, B, H, W, p.y0, rows, n_px, reinterpret_cast<const int2*>(d_bh), d_kh, tmp);
   PC_CHECK_CUDA(cudaGetLastError());
   if (out_f16)
-    resample_v_norm_kernel<__half><<<g2, 256, 0, stream>>>(tmp, B, rows, p.y0, n_px, d_bv, d_kv, p.ksize_v,
-                                                           static_cast<__half*>(out));
+    resample_v_norm_kernel<__half><<<g2, block, 0, stream>>>(tmp, B, rows, p.y0, n_px, reinterpret_cast<const int2*>(d_bv),
+                                                             d_kv, p.ksize_v, d_lut, static_cast<__half*>(out));
   else
-    resample_v_norm_kernel<float><<<g2, 256, 0, stream>>>(tmp, B, rows, p.y0, n_px, d_bv, d_kv, p.ksize_v,
-                                                          static_cast<float*>(out));
+    resample_v_norm_kernel<float><<<g2, block, 0, stream>>>(tmp, B, rows, p.y0, n_px, reinterpret_cast<const int2*>(d_bv),
+                                                            d_kv, p.ksize_v, d_lut, static_cast<float*>(out));
   PC_CHECK_CUDA(cudaGetLastError());
   return PC_OK;
 }
