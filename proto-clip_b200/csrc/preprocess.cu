@@ -15,6 +15,7 @@
 // passes over a different plan: the box drawn on the host is resampled as an image of its own (torchvision crops the
 // PIL image first), both axes scaled independently, and the flip is the horizontal tables in reverse column order.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -93,30 +94,70 @@ __device__ __forceinline__ int clip8(int acc) {  // Resample.c clip8
 constexpr int PP_TX = 64, PP_TY = 4;
 
 // horizontal pass: tmp[b][r][xx][c] for source rows y0 + r, r in [0, rows), and the n_px surviving output columns of
-// every image b of the batch (images [B, H, W, 3], same size). kk_t is tap-major: kk_t[x * n_px + xx].
+// every image b of the batch (images [B, H, W, 3], same size). The weights come in two layouts: kk_t tap-major
+// (kk_t[x * n_px + xx], the byte loop) and kk4 in groups of four taps, zero-padded (kk4[g * n_px + xx] = taps 4 g .. 4 g + 3
+// of column xx: one 16-byte load per group).
+//
+// A thread's taps are one contiguous run of 3 n source bytes. Byte loads at the 6.4-byte lane stride of a 2.1x downscale
+// kept the L1 at 88 % of its sector rate (ncu); so the run is read as ALIGNED 32-bit words (a quarter of the requests),
+// realigned with funnel shifts by the run's byte offset, and the twelve bytes of four taps are picked out of three
+// registers. The words of the last tap group may reach up to 16 bytes past the run (zero weights there): they stay inside
+// the buffer on every row but the last one of the last image (`last_row`), which takes the byte loop -- as does row 0 of
+// image 0 when the buffer itself is not word-aligned (`head_unsafe`: the first word would start before it).
+__device__ __forceinline__ int byte_at(uint32_t w, int i) { return static_cast<int>(__byte_perm(w, 0u, 0x4440u | i)); }  // one PRMT
+
+// A block walks `rpt` steps of PP_TY adjacent rows of ONE image (blockIdx.z), so that the per-thread setup (bounds, table
+// pointers, 64-bit address arithmetic: more instructions than the taps of one row) is paid once per rpt rows.
 __global__ void __launch_bounds__(PP_TX * PP_TY)
-resample_h_kernel(const uint8_t* __restrict__ src, int B, int H, int W, int y0, int rows, int n_px,
-                  const int2* __restrict__ bounds, const int* __restrict__ kk_t, uint8_t* __restrict__ tmp) {
+resample_h_kernel(const uint8_t* __restrict__ src, int B, int H, int W, int y0, int rows, int n_px, int rpt,
+                  const int2* __restrict__ bounds, const int* __restrict__ kk_t, const int4* __restrict__ kk4, int last_row,
+                  int head_unsafe, uint8_t* __restrict__ tmp) {
   const int xx = blockIdx.x * PP_TX + threadIdx.x;
   if (xx >= n_px) return;
   const int2 bd = bounds[xx];  // (first source column, taps)
   const int* __restrict__ k = kk_t + xx;
-  const int total_rows = B * rows;
-  for (int row = blockIdx.y * PP_TY + threadIdx.y; row < total_rows; row += gridDim.y * PP_TY) {
-    const int b = row / rows, r = row - b * rows;
-    const uint8_t* __restrict__ p = src + ((static_cast<size_t>(b) * H + y0 + r) * W + bd.x) * 3;
-    int a0 = 1 << (PRECISION_BITS - 1), a1 = a0, a2 = a0;
+  const int groups = (bd.y + 3) >> 2;
+  const int r_first = blockIdx.y * (PP_TY * rpt) + threadIdx.y;
+  const size_t src_step = static_cast<size_t>(PP_TY) * W * 3, out_step = static_cast<size_t>(PP_TY) * n_px * 3;
+  for (int b = blockIdx.z; b < B; b += gridDim.z) {
+    const uint8_t* __restrict__ p = src + ((static_cast<size_t>(b) * H + y0 + r_first) * W + bd.x) * 3;
+    uint8_t* __restrict__ o = tmp + ((static_cast<size_t>(b) * rows + r_first) * n_px + xx) * 3;
+    const int unsafe_from = b == B - 1 ? last_row - y0 : rows;     // rows r >= this take the byte loop
+    const int unsafe_head = (head_unsafe && b == 0) ? -y0 : -1;    // ... and row r == this (source row 0)
+    for (int i = 0, r = r_first; i < rpt && r < rows; ++i, r += PP_TY, p += src_step, o += out_step) {
+      int a0 = 1 << (PRECISION_BITS - 1), a1 = a0, a2 = a0;
+      if (r >= unsafe_from || r == unsafe_head) {  // warp-uniform (a warp is one row)
 #pragma unroll 4
-    for (int x = 0; x < bd.y; ++x) {
-      const int kv = k[x * n_px];
-      a0 += p[3 * x] * kv;
-      a1 += p[3 * x + 1] * kv;
-      a2 += p[3 * x + 2] * kv;
+        for (int x = 0; x < bd.y; ++x) {
+          const int kv = k[x * n_px];
+          a0 += p[3 * x] * kv;
+          a1 += p[3 * x + 1] * kv;
+          a2 += p[3 * x + 2] * kv;
+        }
+      } else {
+        const int off = static_cast<int>(reinterpret_cast<uintptr_t>(p) & 3);
+        const uint32_t* __restrict__ wp = reinterpret_cast<const uint32_t*>(p - off);  // the aligned word the run starts in
+        const int4* __restrict__ k4 = kk4 + xx;
+        const int sh = off * 8;
+        uint32_t w0 = __ldg(wp);
+#pragma unroll 1
+        for (int g = 0; g < groups; ++g) {
+          const uint32_t w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3);
+          const int4 kq = __ldg(k4);  // the weights of taps 4 g .. 4 g + 3 (zero past the run)
+          // bytes 12 g .. 12 g + 11 of the run = taps 4 g .. 4 g + 3, three channels each
+          const uint32_t r0 = __funnelshift_r(w0, w1, sh), r1 = __funnelshift_r(w1, w2, sh), r2 = __funnelshift_r(w2, w3, sh);
+          a0 += byte_at(r0, 0) * kq.x + byte_at(r0, 3) * kq.y + byte_at(r1, 2) * kq.z + byte_at(r2, 1) * kq.w;
+          a1 += byte_at(r0, 1) * kq.x + byte_at(r1, 0) * kq.y + byte_at(r1, 3) * kq.z + byte_at(r2, 2) * kq.w;
+          a2 += byte_at(r0, 2) * kq.x + byte_at(r1, 1) * kq.y + byte_at(r2, 0) * kq.z + byte_at(r2, 3) * kq.w;
+          w0 = w3;
+          wp += 3;
+          k4 += n_px;
+        }
+      }
+      o[0] = static_cast<uint8_t>(clip8(a0));
+      o[1] = static_cast<uint8_t>(clip8(a1));
+      o[2] = static_cast<uint8_t>(clip8(a2));
     }
-    uint8_t* o = tmp + (static_cast<size_t>(row) * n_px + xx) * 3;
-    o[0] = static_cast<uint8_t>(clip8(a0));
-    o[1] = static_cast<uint8_t>(clip8(a1));
-    o[2] = static_cast<uint8_t>(clip8(a2));
   }
 }
 
@@ -148,6 +189,57 @@ resample_v_norm_kernel(const uint8_t* __restrict__ tmp, int B, int rows, int y0,
     o[0] = static_cast<OutT>(__ldg(lut + clip8(a0)));
     o[plane] = static_cast<OutT>(__ldg(lut + 256 + clip8(a1)));
     o[2 * plane] = static_cast<OutT>(__ldg(lut + 512 + clip8(a2)));
+  }
+}
+
+// The same for n_px % 4 == 0 (every CLIP resolution): a thread owns FOUR adjacent pixels = 12 consecutive bytes of the
+// interleaved intermediate row = three aligned 32-bit words per tap instead of twelve byte loads (the byte version is
+// bound by load-instruction issue), and writes one 16-byte (fp16: 8-byte) vector per channel plane.
+template <typename OutT>
+__global__ void __launch_bounds__(PP_TX * PP_TY)
+resample_v_norm_wide_kernel(const uint8_t* __restrict__ tmp, int B, int rows, int y0, int n_px,
+                            const int2* __restrict__ bounds, const int* __restrict__ kk, int ksize,
+                            const float* __restrict__ lut, OutT* __restrict__ out) {
+  const int x4 = blockIdx.x * PP_TX + threadIdx.x;  // pixels 4 x4 .. 4 x4 + 3
+  const int yy = blockIdx.y * PP_TY + threadIdx.y;
+  if (4 * x4 >= n_px || yy >= n_px) return;
+  const int2 bd = bounds[yy];
+  const int* __restrict__ k = kk + yy * ksize;
+  const int pitch_w = (n_px * 3) >> 2;  // words per intermediate row
+  const size_t plane = static_cast<size_t>(n_px) * n_px;
+  for (int b = blockIdx.z; b < B; b += gridDim.z) {
+    const uint32_t* __restrict__ p =
+        reinterpret_cast<const uint32_t*>(tmp + (static_cast<size_t>(b) * rows + (bd.x - y0)) * n_px * 3) + 3 * x4;
+    int a[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) a[i] = 1 << (PRECISION_BITS - 1);
+#pragma unroll 2
+    for (int y = 0; y < bd.y; ++y) {
+      const int kv = k[y];
+      const uint32_t w0 = p[0], w1 = p[1], w2 = p[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        a[i] += byte_at(w0, i) * kv;
+        a[4 + i] += byte_at(w1, i) * kv;
+        a[8 + i] += byte_at(w2, i) * kv;
+      }
+      p += pitch_w;
+    }
+    OutT* o = out + static_cast<size_t>(b) * 3 * plane + static_cast<size_t>(yy) * n_px + 4 * x4;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {  // byte 3 px + c of the group: channel c of pixel px
+      const float v0 = __ldg(lut + 256 * c + clip8(a[c])), v1 = __ldg(lut + 256 * c + clip8(a[3 + c]));
+      const float v2 = __ldg(lut + 256 * c + clip8(a[6 + c])), v3 = __ldg(lut + 256 * c + clip8(a[9 + c]));
+      if (sizeof(OutT) == 4) {
+        *reinterpret_cast<float4*>(o + c * plane) = make_float4(v0, v1, v2, v3);
+      } else {
+        const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
+        uint2 u;
+        u.x = *reinterpret_cast<const uint32_t*>(&h01);
+        u.y = *reinterpret_cast<const uint32_t*>(&h23);
+        *reinterpret_cast<uint2*>(o + c * plane) = u;
+      }
+    }
   }
 }
 
@@ -204,8 +296,9 @@ void make_plan(int H, int W, int n_px, Plan* p) {
 }
 
 constexpr int LUT_WORDS = 3 * 256;
-size_t table_bytes(int n_px, int ksize_h, int ksize_v) {
-  return align256((static_cast<size_t>(n_px) * (4 + ksize_h + ksize_v) + LUT_WORDS) * sizeof(int));
+inline int pad4(int v) { return (v + 3) & ~3; }
+size_t table_bytes(int n_px, int ksize_h, int ksize_v) {  // horizontal taps zero-padded to a multiple of four, two layouts
+  return align256((static_cast<size_t>(n_px) * (4 + 2 * pad4(ksize_h) + ksize_v) + LUT_WORDS) * sizeof(int));
 }
 
 int taps(int in_size, int out_size) {  // ksize of precompute_coeffs
@@ -215,40 +308,65 @@ int taps(int in_size, int out_size) {  // ksize of precompute_coeffs
 
 // host tables -> device, then the two passes; `src` points at the first pixel of the resampled window (row pitch W,
 // image pitch H * W), plan.y0 / y1 are rows of that window
-int run_plan(const uint8_t* src, int B, int H, int W, int n_px, const Plan& p, void* out, int out_f16, void* workspace,
-             size_t workspace_bytes, cudaStream_t stream) {
+// `last_row`: first row (relative to `src`, in the last image) whose tap words could leave the buffer -- the last row, or
+// the last few when a row is shorter than the 16 bytes a run may be over-read by; `head_unsafe`: the buffer does not
+// start on a word boundary
+int run_plan(const uint8_t* src, int B, int H, int W, int n_px, const Plan& p, int last_row, int head_unsafe, void* out,
+             int out_f16, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   const int rows = p.y1 - p.y0;
   const size_t tb = table_bytes(n_px, p.ksize_h, p.ksize_v);
   PC_REQUIRE(workspace_bytes >= tb + align256(static_cast<size_t>(B) * rows * n_px * 3), PC_ERR_WORKSPACE,
              "preprocess: workspace %zu < %zu", workspace_bytes, tb + align256(static_cast<size_t>(B) * rows * n_px * 3));
-  // one H2D copy of all tables: [bh | bv | kh (tap-major) | kv | lut]
+  // one H2D copy of all tables: [bh | bv | kh grouped by four taps | kh tap-major | kv | lut]
   std::vector<int> host;
-  host.reserve(static_cast<size_t>(n_px) * (4 + p.ksize_h + p.ksize_v) + LUT_WORDS);
+  const int khp = pad4(p.ksize_h);
+  host.reserve(static_cast<size_t>(n_px) * (4 + 2 * khp + p.ksize_v) + LUT_WORDS);
   host.insert(host.end(), p.bh.begin(), p.bh.end());
   host.insert(host.end(), p.bv.begin(), p.bv.end());
-  const size_t kh0 = host.size();
-  host.resize(kh0 + static_cast<size_t>(n_px) * p.ksize_h);
+  const size_t k40 = host.size(), kt0 = k40 + static_cast<size_t>(n_px) * khp;
+  host.resize(kt0 + static_cast<size_t>(n_px) * khp, 0);
   for (int xx = 0; xx < n_px; ++xx)
-    for (int x = 0; x < p.ksize_h; ++x) host[kh0 + static_cast<size_t>(x) * n_px + xx] = p.kh[static_cast<size_t>(xx) * p.ksize_h + x];
+    for (int x = 0; x < p.ksize_h; ++x) {
+      const int w = p.kh[static_cast<size_t>(xx) * p.ksize_h + x];
+      host[k40 + (static_cast<size_t>(x >> 2) * n_px + xx) * 4 + (x & 3)] = w;
+      host[kt0 + static_cast<size_t>(x) * n_px + xx] = w;
+    }
   host.insert(host.end(), p.kv.begin(), p.kv.end());
   const size_t lut0 = host.size();
   host.resize(lut0 + LUT_WORDS);
   memcpy(host.data() + lut0, norm_lut(), LUT_WORDS * sizeof(float));
   int* d_bh = static_cast<int*>(workspace);
   int* d_bv = d_bh + 2 * n_px;
-  int* d_kh = d_bv + 2 * n_px;
-  int* d_kv = d_kh + static_cast<size_t>(n_px) * p.ksize_h;
+  int* d_k4 = d_bv + 2 * n_px;  // 16 n_px bytes into a 256-byte aligned buffer: int4-aligned
+  int* d_kh = d_k4 + static_cast<size_t>(n_px) * khp;
+  int* d_kv = d_kh + static_cast<size_t>(n_px) * khp;
   const float* d_lut = reinterpret_cast<const float*>(d_kv + static_cast<size_t>(n_px) * p.ksize_v);
   uint8_t* tmp = static_cast<uint8_t*>(workspace) + tb;
   PC_CHECK_CUDA(cudaMemcpyAsync(d_bh, host.data(), host.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
   const dim3 block(PP_TX, PP_TY);
   const unsigned gx = static_cast<unsigned>((n_px + PP_TX - 1) / PP_TX);
-  const long long row_blocks = (static_cast<long long>(B) * rows + PP_TY - 1) / PP_TY;
-  const dim3 g1(gx, static_cast<unsigned>(row_blocks < 65535 ? row_blocks : 65535));
+  // rows per thread of the horizontal pass: up to 8 once the grid still fills the device several times over
+  const long long row_steps = (static_cast<long long>(rows) + PP_TY - 1) / PP_TY;
+  long long rpt = row_steps * gx * B / (static_cast<long long>(device_sm_count()) * 32);
+  rpt = rpt < 1 ? 1 : (rpt > 8 ? 8 : rpt);
+  const dim3 g1(gx, static_cast<unsigned>((row_steps + rpt - 1) / rpt), static_cast<unsigned>(B < 65535 ? B : 65535));
   const dim3 g2(gx, static_cast<unsigned>((n_px + PP_TY - 1) / PP_TY), static_cast<unsigned>(B < 65535 ? B : 65535));
-  resample_h_kernel<<<g1, block, 0, stream>>>(src, B, H, W, p.y0, rows, n_px, reinterpret_cast<const int2*>(d_bh), d_kh, tmp);
+  resample_h_kernel<<<g1, block, 0, stream>>>(src, B, H, W, p.y0, rows, n_px, static_cast<int>(rpt),
+                                              reinterpret_cast<const int2*>(d_bh), d_kh, reinterpret_cast<const int4*>(d_k4),
+                                              last_row, head_unsafe, tmp);
   PC_CHECK_CUDA(cudaGetLastError());
-  if (out_f16)
+  // four pixels per thread when the rows split into aligned words and the output into aligned vectors
+  static const bool wide_ok = [] { const char* e = getenv("PC_PP_WIDE"); return !(e && e[0] == '0'); }();  // A/B switch
+  const bool wide = wide_ok && (n_px & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (wide) {
+    const dim3 g2w(static_cast<unsigned>((n_px / 4 + PP_TX - 1) / PP_TX), g2.y, g2.z);
+    if (out_f16)
+      resample_v_norm_wide_kernel<__half><<<g2w, block, 0, stream>>>(tmp, B, rows, p.y0, n_px, reinterpret_cast<const int2*>(d_bv),
+                                                                    d_kv, p.ksize_v, d_lut, static_cast<__half*>(out));
+    else
+      resample_v_norm_wide_kernel<float><<<g2w, block, 0, stream>>>(tmp, B, rows, p.y0, n_px, reinterpret_cast<const int2*>(d_bv),
+                                                                   d_kv, p.ksize_v, d_lut, static_cast<float*>(out));
+  } else if (out_f16)
     resample_v_norm_kernel<__half><<<g2, block, 0, stream>>>(tmp, B, rows, p.y0, n_px, reinterpret_cast<const int2*>(d_bv),
                                                              d_kv, p.ksize_v, d_lut, static_cast<__half*>(out));
   else
@@ -309,7 +427,8 @@ int launch_preprocess(const uint8_t* rgb, int B, int H, int W, int n_px, void* o
   }
   PC_REQUIRE(p.new_h >= n_px && p.new_w >= n_px, PC_ERR_ARG, "preprocess: resized image %dx%d smaller than the crop %d",
              p.new_h, p.new_w, n_px);
-  return run_plan(rgb, B, H, W, n_px, p, out, out_f16, workspace, workspace_bytes, stream);
+  return run_plan(rgb, B, H, W, n_px, p, H - 1 - 15 / (3 * W), (reinterpret_cast<uintptr_t>(rgb) & 3) != 0, out, out_f16,
+                  workspace, workspace_bytes, stream);
 }
 
 int launch_preprocess_train(const uint8_t* rgb, int H, int W, int top, int left, int ch, int cw, int flip, int n_px,
@@ -323,7 +442,8 @@ int launch_preprocess_train(const uint8_t* rgb, int H, int W, int top, int left,
   Plan p;
   make_plan_window(ch, cw, n_px, flip != 0, &p);
   const uint8_t* src = rgb + (static_cast<size_t>(top) * W + left) * 3;
-  return run_plan(src, 1, H, W, n_px, p, out, out_f16, workspace, workspace_bytes, stream);
+  return run_plan(src, 1, H, W, n_px, p, H - 1 - top - 15 / (3 * W), (reinterpret_cast<uintptr_t>(rgb) & 3) != 0 && top == 0,
+                  out, out_f16, workspace, workspace_bytes, stream);
 }
 
 }  // namespace pc

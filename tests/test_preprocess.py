@@ -238,3 +238,29 @@ def test_gpu_augmented_loader_reproduces_the_host_loader():
     assert len(part) == 1 and part[0][0].shape[0] == 3
     torch.manual_seed(7)
     assert torch.equal(part[0][0][0].cpu(), host_tf(Image.fromarray(source[3][0])))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shift", [1, 2, 3])
+def test_cuda_preprocess_unaligned_buffers(shift):
+    """The horizontal pass reads aligned 32-bit words around every tap run: image buffers that do not start on a word
+    boundary (a view into a byte buffer) and runs that end with the buffer must give the same bytes."""
+    from proto_clip_b200 import _native as nat
+    for (h, w, n) in ((37, 53, 16), (100, 80, 224), (64, 64, 32), (9, 7, 8), (40, 2, 8)):
+        img = random_image(h, w, 77 + h)
+        flat = torch.zeros(h * w * 3 + shift, dtype=torch.uint8, device="cuda")
+        view = flat[shift:].view(h, w, 3)
+        view.copy_(torch.from_numpy(img))
+        assert view.data_ptr() % 4 == (flat.data_ptr() + shift) % 4
+        assert np.array_equal(nat.preprocess_image(view, n).cpu().numpy(), PO.clip_preprocess(img, n))
+        for box, flip in (((0, 0, h, w), True), ((0, 1, h - 1, w - 1), False), ((1, 0, h - 1, w), False)):
+            got = nat.preprocess_train_image(view, box, flip, 32)
+            assert np.array_equal(got.cpu().numpy(), PO.train_transform(img, *box, flip, 32)), (h, w, box)
+    # a batch: only the last image's last row ends with the buffer
+    imgs = np.stack([random_image(40, 30, s) for s in range(3)])
+    flat = torch.zeros(imgs.size + shift, dtype=torch.uint8, device="cuda")
+    view = flat[shift:].view(3, 40, 30, 3)
+    view.copy_(torch.from_numpy(imgs))
+    got = nat.preprocess_image(view, 24)
+    for i in range(3):
+        assert np.array_equal(got[i].cpu().numpy(), PO.clip_preprocess(imgs[i], 24))
