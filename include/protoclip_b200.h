@@ -145,8 +145,9 @@ int pc_text_bind_weights(pc_ctx* ctx, const pc_text_weights* w);
 /* CLIP.encode_image (clip/model.py:338-339 -> 221-238 for a ViT, -> 137-152 for a ModifiedResNet)
  * [+ the `/= norm` of utils.py:352 when l2norm != 0].
  * images: [B, 3, res, res] f32 or f16 (NCHW, already normalised); feat_out: f16 [B, embed_dim].
- * The batch is walked in micro-batches of `micro_batch` images (0 = library default) so activations stay
- * L2-resident; workspace must hold pc_encode_image_workspace_bytes(ctx, micro_batch). */
+ * The batch is walked in passes of `micro_batch` images; 0 = library default: equal passes of at most twelve row-block
+ * waves of the GEMM for a ViT (ViT-B/16: <= 1152 images), of at most 256 images for a ModifiedResNet. The workspace must
+ * hold pc_encode_image_workspace_bytes(ctx, micro_batch) (0: the largest default pass). Features do not depend on it. */
 size_t pc_encode_image_workspace_bytes(const pc_ctx* ctx, int micro_batch);
 int pc_encode_image(pc_ctx* ctx, const void* images, int img_dtype, int B, void* feat_out, int l2norm,
                     int micro_batch, void* workspace, size_t workspace_bytes, void* stream);
