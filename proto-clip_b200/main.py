@@ -89,6 +89,20 @@ def populate_cfg_using_args(cfg, args):
     return cfg
 
 
+# main.py:74-102: per-dataset (search_scale, search_step) inherited from Tip-Adapter; the reference stores them in cfg
+# and never reads them again on this path -- kept so that a cfg dumped by either program has the same keys
+_SEARCH = {"caltech101": ([12, 5], [200, 20]), "dtd": ([13, 13], [200, 20]), "eurosat": ([12, 10], [200, 20]),
+           "fgvc": ([30, 30], [200, 20]), "food101": ([10, 10], [200, 20]), "imagenet": ([7, 3], [200, 20]),
+           "oxford_flowers": ([50, 50], [200, 20]), "oxford_pets": ([7, 3], [200, 20]),
+           "stanford_cars": ([20, 10], [200, 20]), "sun397": ([12, 10], [200, 20]), "ucf101": ([7, 3], [200, 20]),
+           "fewsol": ([13, 13], [200, 20])}
+
+
+def search_scale_step(cfg):
+    cfg["search_scale"], cfg["search_step"] = _SEARCH.get(cfg["dataset"], (None, None))
+    return cfg
+
+
 def make_adapter(cfg, ndim):
     """Adapter alias dispatch of main.py:118-121: any alias containing 'conv' -> Adapter, exactly 'fc' ->
     Adapter_FC; anything else is an error (the reference dies with an unbound `adapter`)."""
@@ -150,6 +164,7 @@ def best_alpha_beta(val_acc):
 
 def run_proto_clip(cfg, visual_memory_keys, visual_memory_values, val_features, val_labels, test_features,
                    test_labels, textual_memory_bank, clip_model, text_prompts):
+    cfg = search_scale_step(cfg)  # main.py:111
     ndim, NxK = visual_memory_keys.shape
     K = cfg["shots"]
     N = NxK // K

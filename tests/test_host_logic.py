@@ -48,6 +48,20 @@ def test_every_reference_config_exists_with_same_keys():
             assert ref == cfg, f"configs/{n}.yml differs from the reference"
 
 
+def test_search_scale_step_table():
+    """main.py:74-102: cfg gets the per-dataset (search_scale, search_step) pair, None for unknown datasets; the table
+    equals the reference's (read out of its source with ast when the tree is mounted)."""
+    import ast
+    main = load_main()
+    assert main.search_scale_step({"dataset": "imagenet"}) == {"dataset": "imagenet", "search_scale": [7, 3], "search_step": [200, 20]}
+    assert main.search_scale_step({"dataset": "synthetic:8"})["search_scale"] is None
+    ref_main = os.path.join(reference_shims.REFERENCE_ROOT, "main.py")
+    if reference_shims.available() and os.path.isfile(ref_main):
+        fn = next(n for n in ast.parse(open(ref_main).read()).body if isinstance(n, ast.FunctionDef) and n.name == "search_scale_step")
+        table = next(ast.literal_eval(n.value) for n in ast.walk(fn) if isinstance(n, ast.Assign) and isinstance(n.value, ast.Dict))
+        assert {k: (list(v[0]), list(v[1])) for k, v in table.items()} == {k: (v[0], v[1]) for k, v in main._SEARCH.items()}
+
+
 def test_alpha_beta_grid_is_11_by_29():
     main = load_main()
     a, b = main.alpha_beta_lists()
