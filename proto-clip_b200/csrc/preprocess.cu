@@ -111,14 +111,16 @@ __device__ __forceinline__ int byte_at(uint32_t w, int i) { return static_cast<i
 __global__ void __launch_bounds__(PP_TX * PP_TY)
 resample_h_kernel(const uint8_t* __restrict__ src, int B, int H, int W, int y0, int rows, int n_px, int rpt,
                   const int2* __restrict__ bounds, const int* __restrict__ kk_t, const int4* __restrict__ kk4, int last_row,
-                  int head_unsafe, uint8_t* __restrict__ tmp) {
+                  int head_unsafe, size_t src_step, size_t out_step, uint8_t* __restrict__ tmp) {
   const int xx = blockIdx.x * PP_TX + threadIdx.x;
   if (xx >= n_px) return;
   const int2 bd = bounds[xx];  // (first source column, taps)
   const int* __restrict__ k = kk_t + xx;
-  const int groups = (bd.y + 3) >> 2;
-  const int r_first = blockIdx.y * (PP_TY * rpt) + threadIdx.y;
-  const size_t src_step = static_cast<size_t>(PP_TY) * W * 3, out_step = static_cast<size_t>(PP_TY) * n_px * 3;
+  // taps in groups of four; a remainder of one or two taps takes a half group (two words, six bytes), of three a whole one
+  const int groups = (bd.y + 1) >> 2;
+  const bool half_group = static_cast<unsigned>((bd.y & 3) - 1) < 2u;
+  const int4* __restrict__ k4_base = kk4 + xx;
+  const int r_first = blockIdx.y * (PP_TY * rpt) + threadIdx.y;  // src_step / out_step: PP_TY rows of the source / of tmp
   for (int b = blockIdx.z; b < B; b += gridDim.z) {
     const uint8_t* __restrict__ p = src + ((static_cast<size_t>(b) * H + y0 + r_first) * W + bd.x) * 3;
     uint8_t* __restrict__ o = tmp + ((static_cast<size_t>(b) * rows + r_first) * n_px + xx) * 3;
@@ -137,7 +139,7 @@ resample_h_kernel(const uint8_t* __restrict__ src, int B, int H, int W, int y0, 
       } else {
         const int off = static_cast<int>(reinterpret_cast<uintptr_t>(p) & 3);
         const uint32_t* __restrict__ wp = reinterpret_cast<const uint32_t*>(p - off);  // the aligned word the run starts in
-        const int4* __restrict__ k4 = kk4 + xx;
+        const int4* __restrict__ k4 = k4_base;
         const int sh = off * 8;
         uint32_t w0 = __ldg(wp);
 #pragma unroll 1
@@ -152,6 +154,14 @@ resample_h_kernel(const uint8_t* __restrict__ src, int B, int H, int W, int y0, 
           w0 = w3;
           wp += 3;
           k4 += n_px;
+        }
+        if (half_group) {  // the last one or two taps: bytes 0 .. 5 of what is left of the run
+          const uint32_t w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+          const int4 kq = __ldg(k4);  // .y is zero when a single tap is left
+          const uint32_t r0 = __funnelshift_r(w0, w1, sh), r1 = __funnelshift_r(w1, w2, sh);
+          a0 += byte_at(r0, 0) * kq.x + byte_at(r0, 3) * kq.y;
+          a1 += byte_at(r0, 1) * kq.x + byte_at(r1, 0) * kq.y;
+          a2 += byte_at(r0, 2) * kq.x + byte_at(r1, 1) * kq.y;
         }
       }
       o[0] = static_cast<uint8_t>(clip8(a0));
@@ -353,7 +363,8 @@ int run_plan(const uint8_t* src, int B, int H, int W, int n_px, const Plan& p, i
   const dim3 g2(gx, static_cast<unsigned>((n_px + PP_TY - 1) / PP_TY), static_cast<unsigned>(B < 65535 ? B : 65535));
   resample_h_kernel<<<g1, block, 0, stream>>>(src, B, H, W, p.y0, rows, n_px, static_cast<int>(rpt),
                                               reinterpret_cast<const int2*>(d_bh), d_kh, reinterpret_cast<const int4*>(d_k4),
-                                              last_row, head_unsafe, tmp);
+                                              last_row, head_unsafe, static_cast<size_t>(PP_TY) * W * 3,
+                                              static_cast<size_t>(PP_TY) * n_px * 3, tmp);
   PC_CHECK_CUDA(cudaGetLastError());
   // four pixels per thread when the rows split into aligned words and the output into aligned vectors
   static const bool wide_ok = [] { const char* e = getenv("PC_PP_WIDE"); return !(e && e[0] == '0'); }();  // A/B switch
