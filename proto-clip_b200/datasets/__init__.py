@@ -146,14 +146,17 @@ class GPUTrainTransform:
                  device: Union[str, torch.device] = "cuda", dtype: torch.dtype = torch.float32):
         self.size, self.scale, self.ratio, self.p_flip = size, tuple(scale), tuple(ratio), p_flip
         self.device, self.dtype = torch.device(device), dtype
+        lr = torch.log(torch.tensor(self.ratio))  # fp32 like torchvision's; no generator state involved
+        self._log_ratio = (float(lr[0]), float(lr[1]))
+        self._draw = torch.empty(1)
 
     def get_params(self, height: int, width: int):
         """torchvision RandomResizedCrop.get_params -> (top, left, h, w)."""
         area = height * width
-        log_ratio = torch.log(torch.tensor(self.ratio))
+        log_ratio, draw = self._log_ratio, self._draw
         for _ in range(10):
-            target_area = area * torch.empty(1).uniform_(self.scale[0], self.scale[1]).item()
-            aspect_ratio = torch.exp(torch.empty(1).uniform_(log_ratio[0], log_ratio[1])).item()
+            target_area = area * draw.uniform_(self.scale[0], self.scale[1]).item()
+            aspect_ratio = torch.exp(draw.uniform_(log_ratio[0], log_ratio[1])).item()
             w = int(round(math.sqrt(target_area * aspect_ratio)))
             h = int(round(math.sqrt(target_area / aspect_ratio)))
             if 0 < w <= width and 0 < h <= height:
