@@ -264,3 +264,53 @@ def test_cuda_preprocess_unaligned_buffers(shift):
     got = nat.preprocess_image(view, 24)
     for i in range(3):
         assert np.array_equal(got[i].cpu().numpy(), PO.clip_preprocess(imgs[i], 24))
+
+
+def test_augmented_loader_host_logic(tmp_path):
+    """GPUAugmentedLoader without a GPU (a stand-in transform on the CPU): Datum-like items are decoded once from their
+    `impath` like the reference's read_image (RGB), (image, label) pairs are taken as they are, batches keep the source
+    order, `iter_range` serves a rank's batch range, and every pass calls the transform once per image in order."""
+    Image = pytest.importorskip("PIL.Image")
+    from types import SimpleNamespace
+    from proto_clip_b200 import datasets
+
+    class Recorder:
+        size, dtype = 4, torch.float32
+
+        def __init__(self):
+            self.seen = []
+
+        def __call__(self, rgb, out=None):
+            assert rgb.dtype == torch.uint8 and rgb.dim() == 3 and rgb.shape[-1] == 3
+            self.seen.append(rgb.clone())
+            out.fill_(float(rgb[0, 0, 0]))
+            return out
+
+    arrays = [random_image(20 + i, 30 - i, i) for i in range(5)]
+    items = []
+    for i, a in enumerate(arrays):
+        path = tmp_path / f"img{i}.png"
+        Image.fromarray(a if i != 2 else a[:, :, 0]).save(path)  # image 2 is greyscale on disk -> convert("RGB")
+        items.append(SimpleNamespace(impath=str(path), label=i % 2))
+    rec = Recorder()
+    loader = datasets.GPUAugmentedLoader(items, batch_size=2, tfm=rec, device="cpu")
+    assert len(loader) == 3
+    for epoch in range(2):
+        batches = list(loader)
+        assert [b[0].shape[0] for b in batches] == [2, 2, 1]
+        assert torch.cat([b[1] for b in batches]).tolist() == [0, 1, 0, 1, 0]
+    assert len(rec.seen) == 10  # decoded once, transformed once per image per pass, in source order
+    for i, a in enumerate(arrays):
+        want = a if i != 2 else np.repeat(a[:, :, :1], 3, axis=2)
+        assert np.array_equal(rec.seen[i].numpy(), want) and np.array_equal(rec.seen[5 + i].numpy(), want)
+    rec.seen.clear()
+    part = list(loader.iter_range(1, 3))
+    assert [b[0].shape[0] for b in part] == [2, 1] and len(rec.seen) == 3
+    assert np.array_equal(rec.seen[0].numpy(), arrays[2][:, :, :1].repeat(3, axis=2))
+    # (image, label) pairs with a tensor / array / PIL image; anything that is not RGB uint8 is refused
+    mixed = datasets.GPUAugmentedLoader([(torch.from_numpy(arrays[0]), 3), (arrays[1], 4), (Image.fromarray(arrays[3]), 5)],
+                                        batch_size=8, tfm=Recorder(), device="cpu")
+    (images, target), = list(mixed)
+    assert images.shape == (3, 3, 4, 4) and target.tolist() == [3, 4, 5]
+    with pytest.raises(ValueError, match="RGB uint8"):
+        list(datasets.GPUAugmentedLoader([(torch.zeros(4, 4, 3), 0)], tfm=Recorder(), device="cpu"))
