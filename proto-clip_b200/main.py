@@ -61,6 +61,9 @@ def get_arguments(argv=None):
     parser.add_argument("--dataset", dest="dataset",
                         help="dataset alias: [ caltech101, dtd, eurosat, fgvc, food101, imagenet, oxford_flowers, "
                              "oxford_pets, stanford_cars, sun397, ucf101 ]", required=False)
+    parser.add_argument("--gpu_augment", dest="gpu_augment", action="store_true",
+                        help="(not in the reference) keep the decoded support images in HBM and run get_random_train_tfm "
+                             "on the GPU while the visual memory bank is built")
     return parser.parse_args(argv)
 
 
@@ -86,6 +89,8 @@ def populate_cfg_using_args(cfg, args):
         cfg["only_test"] = True
     if args.train_vis_mem_only:
         cfg["train_vis_mem_only"] = True
+    if getattr(args, "gpu_augment", False):
+        cfg["gpu_augment"] = True
     return cfg
 
 
@@ -265,6 +270,19 @@ def seed_worker(worker_id):
     random.seed(worker_seed)
 
 
+def make_support_loader(cfg, dataset, batch_size, generator):
+    """The loader build_cache_model walks `augment_epoch` times (main.py:529-533: `get_random_train_tfm()`, shuffle=False).
+    With `gpu_augment: True` in the YAML (or --gpu_augment) the few-shot split is decoded once, kept in HBM as uint8 and
+    re-augmented on the GPU every pass (`datasets.GPUAugmentedLoader`: same transform, bit-identical to the reference's
+    loader at num_workers=0 under the same seed) instead of going through 8 PIL worker processes."""
+    from proto_clip_b200 import datasets
+    if cfg.get("gpu_augment") and not str(cfg["dataset"]).startswith("synthetic"):
+        return datasets.GPUAugmentedLoader(dataset.train_x, batch_size=batch_size)
+    return datasets.build_data_loader(data_source=dataset.train_x, batch_size=batch_size,
+                                      tfm=datasets.get_random_train_tfm(), is_train=True, shuffle=False,
+                                      worker_init_fn=seed_worker, generator=generator)
+
+
 def main(argv=None):
     args = get_arguments(argv)
     assert os.path.exists(args.config)
@@ -306,9 +324,7 @@ def main(argv=None):
                                                   shuffle=False)
     else:
         dataset = datasets.build_dataset(cfg["dataset"], cfg["root_path"], cfg["shots"])
-        train_loader_cache = datasets.build_data_loader(
-            data_source=dataset.train_x, batch_size=train_bs, tfm=datasets.get_random_train_tfm(), is_train=True,
-            shuffle=False, worker_init_fn=seed_worker, generator=g)
+        train_loader_cache = make_support_loader(cfg, dataset, train_bs, g)
         val_loader = datasets.build_data_loader(data_source=dataset.val, batch_size=val_bs, is_train=False,
                                                 tfm=preprocess, shuffle=False)
         test_loader = datasets.build_data_loader(data_source=dataset.test, batch_size=test_bs, is_train=False,

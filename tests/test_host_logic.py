@@ -62,6 +62,25 @@ def test_search_scale_step_table():
         assert {k: (list(v[0]), list(v[1])) for k, v in table.items()} == {k: (v[0], v[1]) for k, v in main._SEARCH.items()}
 
 
+def test_support_loader_choice(monkeypatch):
+    """main.make_support_loader: the reference's DataLoader + get_random_train_tfm() by default, the HBM-resident GPU
+    loader with `gpu_augment` (never for the synthetic alias, whose images are generated on the device already)."""
+    from types import SimpleNamespace
+    from proto_clip_b200 import datasets
+    main = load_main()
+    a = main.get_arguments(["--config", "x.yml", "--dataset", "dtd", "--gpu_augment"])
+    cfg = main.populate_cfg_using_args({"dataset": "x"}, a)
+    assert cfg["gpu_augment"] is True and cfg["dataset"] == "dtd"
+    calls = {}
+    monkeypatch.setattr(datasets, "build_data_loader", lambda **kw: calls.update(kw) or "host-loader")
+    ds = SimpleNamespace(train_x=[SimpleNamespace(impath="a.jpg", label=0)])
+    assert main.make_support_loader({"dataset": "dtd"}, ds, 64, None) == "host-loader"
+    assert calls["shuffle"] is False and calls["is_train"] is True and calls["tfm"] is not None and calls["batch_size"] == 64
+    loader = main.make_support_loader(cfg, ds, 64, None)
+    assert isinstance(loader, datasets.GPUAugmentedLoader) and loader.batch_size == 64 and len(loader) == 1
+    assert main.make_support_loader({"dataset": "synthetic:4", "gpu_augment": True}, ds, 64, None) == "host-loader"
+
+
 def test_alpha_beta_grid_is_11_by_29():
     main = load_main()
     a, b = main.alpha_beta_lists()
